@@ -1,0 +1,977 @@
+/*
+ * o3d_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C, fp64 restatement of the reference hot path of
+ * leggedrobotics/open3d_slam: the Open3D v0.15.1 routines it calls
+ * (open3d_catkin/CMakeLists.txt:117-118 pins the tag) plus open3d_slam's own
+ * croppers / transform / map-fusion / dense-map code.
+ *
+ * PARITY UNPINNED: the reference holds no test, golden vector or fixture on
+ * this path and Open3D itself is neither under /root/reference
+ * nor installable here, so the [O3D] parts below are restated from the
+ * published v0.15.1 algorithm and cross-checked only against an independent
+ * numpy/scipy restatement (oracle/np_oracle.py) and analytic known answers.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may call into this file.  The product
+ * (open3d_slam_b200/csrc) never links or loads it.
+ *
+ * Each function cites the reference file:line (relative to
+ * /root/reference/open3d_slam/open3d_slam/, abbreviated core/) or the upstream
+ * Open3D file it follows ([O3D] cpp/open3d/...).
+ *
+ * Deterministic choices made where the reference is unspecified:
+ *   - hash-map iteration order  -> first-touch order of the voxel
+ *   - exact distance ties       -> lowest point index wins (nanoflann: unspecified)
+ *   - RandomDownSample seed     -> counter hash of (seed, index) (reference: random_device)
+ *   - OpenMP reduction order    -> fixed 1024-element chunks summed in index order
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------- */
+/*  small helpers                                                             */
+/* ------------------------------------------------------------------------- */
+static inline double sq(double x) { return x * x; }
+
+/* nanoflann L2_Simple_Adaptor accumulates (dx*dx + dy*dy) + dz*dz */
+static inline double dist2(const double* a, const double* b) {
+  double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  return dx * dx + dy * dy + dz * dz;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  KD-tree (stands in for [O3D] KDTreeFlann / nanoflann, leaf size 15)       */
+/*  exact k-NN; ties broken towards the lower index                           */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int left, right;   /* children (node ids) or -1 */
+  int lo, hi;        /* point range [lo,hi) in perm for leaves */
+  int dim;           /* split dimension */
+  double split_lo;   /* max of left child along dim  */
+  double split_hi;   /* min of right child along dim */
+} kd_node;
+
+typedef struct {
+  const double* pts; /* n x 3 */
+  int n;
+  int* perm;
+  kd_node* nodes;
+  int n_nodes, cap_nodes;
+  double bb_min[3], bb_max[3];
+} kd_tree;
+
+#define KD_LEAF 15
+
+static int kd_new_node(kd_tree* t) {
+  if (t->n_nodes == t->cap_nodes) {
+    t->cap_nodes = t->cap_nodes ? 2 * t->cap_nodes : 1024;
+    t->nodes = (kd_node*)realloc(t->nodes, sizeof(kd_node) * (size_t)t->cap_nodes);
+  }
+  return t->n_nodes++;
+}
+
+/* quickselect on perm[lo,hi) by coordinate dim so that perm[mid] is the median */
+static void kd_select(kd_tree* t, int lo, int hi, int mid, int dim) {
+  const double* P = t->pts;
+  int* a = t->perm;
+  while (hi - lo > 1) {
+    /* median of three pivot */
+    int m = lo + (hi - lo) / 2;
+    double v0 = P[3 * a[lo] + dim], v1 = P[3 * a[m] + dim], v2 = P[3 * a[hi - 1] + dim];
+    double pv = (v0 < v1) ? ((v1 < v2) ? v1 : (v0 < v2 ? v2 : v0)) : ((v0 < v2) ? v0 : (v1 < v2 ? v2 : v1));
+    int i = lo, j = hi - 1;
+    while (i <= j) {
+      while (P[3 * a[i] + dim] < pv) i++;
+      while (P[3 * a[j] + dim] > pv) j--;
+      if (i <= j) {
+        int tmp = a[i]; a[i] = a[j]; a[j] = tmp;
+        i++; j--;
+      }
+    }
+    if (mid <= j) hi = j + 1;
+    else if (mid >= i) lo = i;
+    else return;
+  }
+}
+
+static int kd_build_rec(kd_tree* t, int lo, int hi) {
+  int id = kd_new_node(t);
+  kd_node nd;
+  nd.left = nd.right = -1; nd.lo = lo; nd.hi = hi; nd.dim = 0; nd.split_lo = nd.split_hi = 0;
+  if (hi - lo <= KD_LEAF) { t->nodes[id] = nd; return id; }
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = lo; i < hi; i++) {
+    const double* p = t->pts + 3 * t->perm[i];
+    for (int d = 0; d < 3; d++) { if (p[d] < mn[d]) mn[d] = p[d]; if (p[d] > mx[d]) mx[d] = p[d]; }
+  }
+  int dim = 0; double ext = mx[0] - mn[0];
+  for (int d = 1; d < 3; d++) if (mx[d] - mn[d] > ext) { ext = mx[d] - mn[d]; dim = d; }
+  if (!(ext > 0.0)) { t->nodes[id] = nd; return id; } /* all identical: keep as (big) leaf */
+  int mid = lo + (hi - lo) / 2;
+  kd_select(t, lo, hi, mid, dim);
+  double slo = -INFINITY, shi = INFINITY;
+  for (int i = lo; i < mid; i++) { double v = t->pts[3 * t->perm[i] + dim]; if (v > slo) slo = v; }
+  for (int i = mid; i < hi; i++) { double v = t->pts[3 * t->perm[i] + dim]; if (v < shi) shi = v; }
+  nd.dim = dim; nd.split_lo = slo; nd.split_hi = shi;
+  t->nodes[id] = nd;
+  int l = kd_build_rec(t, lo, mid);
+  int r = kd_build_rec(t, mid, hi);
+  t->nodes[id].left = l; t->nodes[id].right = r;
+  return id;
+}
+
+static kd_tree* kd_build(const double* pts, int n) {
+  kd_tree* t = (kd_tree*)calloc(1, sizeof(kd_tree));
+  t->pts = pts; t->n = n;
+  t->perm = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++) t->perm[i] = i;
+  for (int d = 0; d < 3; d++) { t->bb_min[d] = INFINITY; t->bb_max[d] = -INFINITY; }
+  for (int i = 0; i < n; i++) for (int d = 0; d < 3; d++) {
+    double v = pts[3 * i + d];
+    if (v < t->bb_min[d]) t->bb_min[d] = v;
+    if (v > t->bb_max[d]) t->bb_max[d] = v;
+  }
+  if (n > 0) kd_build_rec(t, 0, n);
+  return t;
+}
+
+static void kd_free(kd_tree* t) {
+  if (!t) return;
+  free(t->perm); free(t->nodes); free(t);
+}
+
+/* result set: sorted ascending by (d2, idx), capacity k */
+typedef struct { double* d2; int* idx; int k; int cnt; } kd_result;
+
+static inline int kd_less(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
+
+static inline double kd_worst(const kd_result* r) { return r->cnt < r->k ? INFINITY : r->d2[r->k - 1]; }
+
+static void kd_insert(kd_result* r, double d, int idx) {
+  int i;
+  if (r->cnt < r->k) i = r->cnt++;
+  else {
+    if (!kd_less(d, idx, r->d2[r->k - 1], r->idx[r->k - 1])) return;
+    i = r->k - 1;
+  }
+  while (i > 0 && kd_less(d, idx, r->d2[i - 1], r->idx[i - 1])) {
+    r->d2[i] = r->d2[i - 1]; r->idx[i] = r->idx[i - 1]; i--;
+  }
+  r->d2[i] = d; r->idx[i] = idx;
+}
+
+static void kd_search_rec(const kd_tree* t, int id, const double* q, kd_result* r, double* off, double mindist2) {
+  const kd_node* nd = &t->nodes[id];
+  if (nd->left < 0) {
+    for (int i = nd->lo; i < nd->hi; i++) {
+      int pi = t->perm[i];
+      double d = dist2(q, t->pts + 3 * pi);
+      kd_insert(r, d, pi);
+    }
+    return;
+  }
+  int dim = nd->dim;
+  double v = q[dim];
+  double dl = v - nd->split_lo; if (dl < 0) dl = 0; /* distance along dim to the left child's extent  */
+  double dr = nd->split_hi - v; if (dr < 0) dr = 0; /* distance along dim to the right child's extent */
+  int first, second; double cut;
+  if (dl <= dr) { first = nd->left; second = nd->right; cut = dr; }
+  else { first = nd->right; second = nd->left; cut = dl; }
+  kd_search_rec(t, first, q, r, off, mindist2);
+  double old = off[dim];
+  if (cut < old) cut = old;
+  double nmin = mindist2 - old * old + cut * cut;
+  /* <= so that equal-distance points with a lower index are still seen */
+  if (nmin <= kd_worst(r)) {
+    off[dim] = cut;
+    kd_search_rec(t, second, q, r, off, nmin);
+    off[dim] = old;
+  }
+}
+
+/* exact k nearest neighbours, sorted by (d2, idx). returns count */
+static int kd_knn(const kd_tree* t, const double* q, int k, double* d2, int* idx) {
+  kd_result r; r.d2 = d2; r.idx = idx; r.k = k; r.cnt = 0;
+  if (t->n == 0 || k <= 0) return 0;
+  double off[3]; double md = 0.0;
+  for (int d = 0; d < 3; d++) {
+    off[d] = 0.0;
+    if (q[d] < t->bb_min[d]) off[d] = t->bb_min[d] - q[d];
+    if (q[d] > t->bb_max[d]) off[d] = q[d] - t->bb_max[d];
+    md += off[d] * off[d];
+  }
+  kd_search_rec(t, 0, q, &r, off, md);
+  return r.cnt;
+}
+
+/* [O3D] KDTreeFlann::SearchHybrid (cpp/open3d/geometry/KDTreeFlann.cpp):
+ * knnSearch(max_nn) then keep the prefix with d2 < radius*radius (lower_bound). */
+static int kd_search_hybrid(const kd_tree* t, const double* q, double radius, int max_nn, double* d2, int* idx) {
+  int k = kd_knn(t, q, max_nn, d2, idx);
+  double r2 = radius * radius;
+  int c = 0;
+  while (c < k && d2[c] < r2) c++;
+  return c;
+}
+
+/* exported thin wrappers so tests can exercise the tree directly */
+ORC_EXPORT void* orc_kdtree_build(const double* pts, int n) { return kd_build(pts, n); }
+ORC_EXPORT void orc_kdtree_free(void* t) { kd_free((kd_tree*)t); }
+ORC_EXPORT int orc_kdtree_search_hybrid(void* t, const double* q, double radius, int max_nn, double* d2, int* idx) {
+  return kd_search_hybrid((kd_tree*)t, q, radius, max_nn, d2, idx);
+}
+
+/* ------------------------------------------------------------------------- */
+/*  P1  croppers        core/src/croppers.cpp:76-106 (crop), :121-165 (predicates) */
+/* ------------------------------------------------------------------------- */
+enum { ORC_CROP_NONE = 0, ORC_CROP_MAX_RADIUS = 1, ORC_CROP_MIN_RADIUS = 2, ORC_CROP_MINMAX_RADIUS = 3, ORC_CROP_CYLINDER = 4 };
+
+typedef struct {
+  int32_t kind;
+  int32_t invert;            /* CroppingVolume::isInvertVolume_ (croppers.cpp:57-59) */
+  double rmin, rmax, zmin, zmax;
+  double center[3];          /* pose_.translation(); only the translation is used */
+} orc_cropper;
+
+static int orc_within_impl(const orc_cropper* c, const double* p) {
+  double dx = p[0] - c->center[0], dy = p[1] - c->center[1], dz = p[2] - c->center[2];
+  switch (c->kind) {
+    case ORC_CROP_NONE: return 1;                                   /* croppers.cpp:53-55 */
+    case ORC_CROP_MAX_RADIUS: return sqrt(dx * dx + dy * dy + dz * dz) <= c->rmax;    /* :136-138 */
+    case ORC_CROP_MIN_RADIUS: return sqrt(dx * dx + dy * dy + dz * dz) >= c->rmin;    /* :149-151 */
+    case ORC_CROP_MINMAX_RADIUS: { double d = sqrt(dx * dx + dy * dy + dz * dz); return d <= c->rmax && d >= c->rmin; } /* :121-124 */
+    case ORC_CROP_CYLINDER: return p[2] >= c->zmin && p[2] <= c->zmax && sqrt(dx * dx + dy * dy) <= c->rmax; /* :163-165 */
+    default: return 1;
+  }
+}
+static inline int orc_within(const orc_cropper* c, const double* p) {
+  int w = orc_within_impl(c, p);
+  return c->invert ? !w : w;
+}
+
+/* order-preserving compaction of points (+normals when nrm != NULL) */
+ORC_EXPORT size_t orc_crop(const orc_cropper* c, const double* xyz, const double* nrm, size_t n, double* out_xyz, double* out_nrm) {
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (orc_within(c, xyz + 3 * i)) {
+      memcpy(out_xyz + 3 * m, xyz + 3 * i, 24);
+      if (nrm && out_nrm) memcpy(out_nrm + 3 * m, nrm + 3 * i, 24);
+      m++;
+    }
+  }
+  return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  generic open-addressing voxel hash used by P2 / F1 / F3 restatements      */
+/*  (stands in for std::unordered_map<Eigen::Vector3i, ...>; iteration order  */
+/*   = first-touch order)                                                     */
+/* ------------------------------------------------------------------------- */
+typedef struct { int32_t k[3]; int32_t slot; } vh_entry;
+typedef struct { vh_entry* e; size_t cap; size_t cnt; } vhash;
+
+static void vh_init(vhash* h, size_t expected) {
+  size_t cap = 64; while (cap < 2 * expected + 8) cap <<= 1;
+  h->cap = cap; h->cnt = 0;
+  h->e = (vh_entry*)malloc(sizeof(vh_entry) * cap);
+  for (size_t i = 0; i < cap; i++) h->e[i].slot = -1;
+}
+static void vh_free(vhash* h) { free(h->e); h->e = NULL; }
+static inline uint64_t vh_mix(int32_t x, int32_t y, int32_t z) {
+  uint64_t v = (uint64_t)(uint32_t)x * 0x9E3779B97F4A7C15ull;
+  v ^= ((uint64_t)(uint32_t)y + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+  v ^= ((uint64_t)(uint32_t)z + 0x165667B1ull) * 0xD6E8FEB86659FD93ull;
+  v ^= v >> 29; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 32;
+  return v;
+}
+/* returns slot id (dense, in first-touch order); *is_new set when inserted */
+static int32_t vh_get(vhash* h, int32_t x, int32_t y, int32_t z, int insert, int* is_new) {
+  size_t mask = h->cap - 1;
+  size_t i = (size_t)vh_mix(x, y, z) & mask;
+  for (;;) {
+    vh_entry* e = &h->e[i];
+    if (e->slot < 0) {
+      if (!insert) return -1;
+      e->k[0] = x; e->k[1] = y; e->k[2] = z; e->slot = (int32_t)h->cnt++;
+      if (is_new) *is_new = 1;
+      return e->slot;
+    }
+    if (e->k[0] == x && e->k[1] == y && e->k[2] == z) { if (is_new) *is_new = 0; return e->slot; }
+    i = (i + 1) & mask;
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/*  P2  voxelize -> [O3D] PointCloud::VoxelDownSample                          */
+/*      core/src/helpers.cpp:107-113 ; [O3D] cpp/open3d/geometry/PointCloud.cpp */
+/*  key = floor((p - (minBound - v/2)) / v) ; mean of points (+ normals)      */
+/*  out_keys (optional, 3 x int32 per voxel) lets tests compare as keyed sets */
+/* ------------------------------------------------------------------------- */
+ORC_EXPORT size_t orc_voxel_down_sample(const double* xyz, const double* nrm, size_t n, double voxel,
+                                        double* out_xyz, double* out_nrm, int32_t* out_keys) {
+  if (n == 0) return 0;
+  if (voxel <= 0.0) { /* helpers.cpp:108-110 returns the cloud untouched */
+    memcpy(out_xyz, xyz, 24 * n);
+    if (nrm && out_nrm) memcpy(out_nrm, nrm, 24 * n);
+    return n;
+  }
+  double mn[3] = {xyz[0], xyz[1], xyz[2]};
+  for (size_t i = 1; i < n; i++) for (int d = 0; d < 3; d++) if (xyz[3 * i + d] < mn[d]) mn[d] = xyz[3 * i + d];
+  double vmin[3];
+  for (int d = 0; d < 3; d++) vmin[d] = mn[d] - voxel * 0.5;
+  vhash h; vh_init(&h, n);
+  double* acc = (double*)calloc(n * 6, sizeof(double));
+  int32_t* cnt = (int32_t*)calloc(n, sizeof(int32_t));
+  for (size_t i = 0; i < n; i++) {
+    int32_t k[3];
+    for (int d = 0; d < 3; d++) k[d] = (int32_t)floor((xyz[3 * i + d] - vmin[d]) / voxel);
+    int is_new;
+    int32_t s = vh_get(&h, k[0], k[1], k[2], 1, &is_new);
+    if (is_new && out_keys) { out_keys[3 * s] = k[0]; out_keys[3 * s + 1] = k[1]; out_keys[3 * s + 2] = k[2]; }
+    /* AccumulatedPoint::AddPoint */
+    acc[6 * s + 0] += xyz[3 * i + 0]; acc[6 * s + 1] += xyz[3 * i + 1]; acc[6 * s + 2] += xyz[3 * i + 2];
+    if (nrm) {
+      const double* q = nrm + 3 * i;
+      if (!isnan(q[0]) && !isnan(q[1]) && !isnan(q[2])) { acc[6 * s + 3] += q[0]; acc[6 * s + 4] += q[1]; acc[6 * s + 5] += q[2]; }
+    }
+    cnt[s]++;
+  }
+  size_t m = h.cnt;
+  for (size_t s = 0; s < m; s++) {
+    double c = (double)cnt[s];
+    for (int d = 0; d < 3; d++) out_xyz[3 * s + d] = acc[6 * s + d] / c;
+    if (nrm && out_nrm) for (int d = 0; d < 3; d++) out_nrm[3 * s + d] = acc[6 * s + 3 + d] / c;
+  }
+  free(acc); free(cnt); vh_free(&h);
+  return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  P3  estimateNormalsOrCovariancesIfNeeded   core/src/CloudRegistration.cpp:49-56 */
+/*      [O3D] EstimateNormals(KDTreeSearchParamHybrid) + NormalizeNormals +   */
+/*      OrientNormalsTowardsCameraLocation(0)  (cpp/open3d/geometry/EstimateNormals.cpp, */
+/*      PointCloud.cpp, utility/Eigen.h ComputeCovariance)                    */
+/* ------------------------------------------------------------------------- */
+static void cross3(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+/* A is symmetric, stored full 3x3 row-major */
+static void compute_eigenvector0(const double A[9], double eval0, double* out) {
+  double row0[3] = {A[0] - eval0, A[1], A[2]};
+  double row1[3] = {A[1], A[4] - eval0, A[5]};
+  double row2[3] = {A[2], A[5], A[8] - eval0};
+  double r0xr1[3], r0xr2[3], r1xr2[3];
+  cross3(row0, row1, r0xr1); cross3(row0, row2, r0xr2); cross3(row1, row2, r1xr2);
+  double d0 = dot3(r0xr1, r0xr1), d1 = dot3(r0xr2, r0xr2), d2 = dot3(r1xr2, r1xr2);
+  double dmax = d0; int imax = 0;
+  if (d1 > dmax) { dmax = d1; imax = 1; }
+  if (d2 > dmax) { imax = 2; }
+  const double* v = imax == 0 ? r0xr1 : (imax == 1 ? r0xr2 : r1xr2);
+  double s = sqrt(imax == 0 ? d0 : (imax == 1 ? d1 : d2));
+  out[0] = v[0] / s; out[1] = v[1] / s; out[2] = v[2] / s;
+}
+
+static void compute_eigenvector1(const double A[9], const double* evec0, double eval1, double* out) {
+  double U[3], V[3];
+  if (fabs(evec0[0]) > fabs(evec0[1])) {
+    double inv = 1 / sqrt(evec0[0] * evec0[0] + evec0[2] * evec0[2]);
+    U[0] = -evec0[2] * inv; U[1] = 0; U[2] = evec0[0] * inv;
+  } else {
+    double inv = 1 / sqrt(evec0[1] * evec0[1] + evec0[2] * evec0[2]);
+    U[0] = 0; U[1] = evec0[2] * inv; U[2] = -evec0[1] * inv;
+  }
+  cross3(evec0, U, V);
+  double AU[3] = {A[0] * U[0] + A[1] * U[1] + A[2] * U[2], A[1] * U[0] + A[4] * U[1] + A[5] * U[2], A[2] * U[0] + A[5] * U[1] + A[8] * U[2]};
+  double AV[3] = {A[0] * V[0] + A[1] * V[1] + A[2] * V[2], A[1] * V[0] + A[4] * V[1] + A[5] * V[2], A[2] * V[0] + A[5] * V[1] + A[8] * V[2]};
+  double m00 = dot3(U, AU) - eval1, m01 = dot3(U, AV), m11 = dot3(V, AV) - eval1;
+  double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+  if (a00 >= a11) {
+    double mx = a00 > a01 ? a00 : a01;
+    if (mx > 0) {
+      if (a00 >= a01) { m01 /= m00; m00 = 1 / sqrt(1 + m01 * m01); m01 *= m00; }
+      else { m00 /= m01; m01 = 1 / sqrt(1 + m00 * m00); m00 *= m01; }
+      for (int d = 0; d < 3; d++) out[d] = m01 * U[d] - m00 * V[d];
+    } else { out[0] = U[0]; out[1] = U[1]; out[2] = U[2]; }
+  } else {
+    double mx = a11 > a01 ? a11 : a01;
+    if (mx > 0) {
+      if (a11 >= a01) { m01 /= m11; m11 = 1 / sqrt(1 + m01 * m01); m01 *= m11; }
+      else { m11 /= m01; m01 = 1 / sqrt(1 + m11 * m11); m11 *= m01; }
+      for (int d = 0; d < 3; d++) out[d] = m11 * U[d] - m01 * V[d];
+    } else { out[0] = U[0]; out[1] = U[1]; out[2] = U[2]; }
+  }
+}
+
+/* [O3D] FastEigen3x3 (EstimateNormals.cpp): eigenvector of the smallest eigenvalue */
+ORC_EXPORT void orc_fast_eigen3x3(const double cov[9], double* out) {
+  double A[9]; memcpy(A, cov, sizeof(A));
+  double max_coeff = A[0];
+  for (int i = 1; i < 9; i++) if (A[i] > max_coeff) max_coeff = A[i];
+  if (max_coeff == 0) { out[0] = out[1] = out[2] = 0; return; }
+  for (int i = 0; i < 9; i++) A[i] /= max_coeff;
+  double norm = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+  if (norm > 0) {
+    double eval[3], evec0[3], evec1[3], evec2[3];
+    double q = (A[0] + A[4] + A[8]) / 3;
+    double b00 = A[0] - q, b11 = A[4] - q, b22 = A[8] - q;
+    double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2) / 6);
+    double c00 = b11 * b22 - A[5] * A[5];
+    double c01 = A[1] * b22 - A[5] * A[2];
+    double c02 = A[1] * A[5] - b11 * A[2];
+    double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
+    double half_det = det * 0.5;
+    half_det = fmin(fmax(half_det, -1.0), 1.0);
+    double angle = acos(half_det) / 3.0;
+    const double two_thirds_pi = 2.09439510239319549;
+    double beta2 = cos(angle) * 2;
+    double beta0 = cos(angle + two_thirds_pi) * 2;
+    double beta1 = -(beta0 + beta2);
+    eval[0] = q + p * beta0; eval[1] = q + p * beta1; eval[2] = q + p * beta2;
+    if (half_det >= 0) {
+      compute_eigenvector0(A, eval[2], evec2);
+      if (eval[2] < eval[0] && eval[2] < eval[1]) { memcpy(out, evec2, 24); return; }
+      compute_eigenvector1(A, evec2, eval[1], evec1);
+      if (eval[1] < eval[0] && eval[1] < eval[2]) { memcpy(out, evec1, 24); return; }
+      cross3(evec1, evec2, evec0);
+      memcpy(out, evec0, 24); return;
+    } else {
+      compute_eigenvector0(A, eval[0], evec0);
+      if (eval[0] < eval[1] && eval[0] < eval[2]) { memcpy(out, evec0, 24); return; }
+      compute_eigenvector1(A, evec0, eval[1], evec1);
+      if (eval[1] < eval[0] && eval[1] < eval[2]) { memcpy(out, evec1, 24); return; }
+      cross3(evec0, evec1, evec2);
+      memcpy(out, evec2, 24); return;
+    }
+  } else {
+    /* diagonal matrix (A *= max_coeff in the original leaves the ordering unchanged for max_coeff > 0;
+       for max_coeff < 0 it flips it, so undo the scaling literally) */
+    double a0 = A[0] * max_coeff, a1 = A[4] * max_coeff, a2 = A[8] * max_coeff;
+    if (a0 < a1 && a0 < a2) { out[0] = 1; out[1] = 0; out[2] = 0; }
+    else if (a1 < a0 && a1 < a2) { out[0] = 0; out[1] = 1; out[2] = 0; }
+    else { out[0] = 0; out[1] = 0; out[2] = 1; }
+  }
+}
+
+/* [O3D] utility::ComputeCovariance: single-pass cumulants, neighbours in the order returned by the search */
+static void compute_covariance(const double* pts, const int* idx, int k, double cov[9]) {
+  double c[9] = {0};
+  for (int j = 0; j < k; j++) {
+    const double* p = pts + 3 * idx[j];
+    c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
+    c[3] += p[0] * p[0]; c[4] += p[0] * p[1]; c[5] += p[0] * p[2];
+    c[6] += p[1] * p[1]; c[7] += p[1] * p[2]; c[8] += p[2] * p[2];
+  }
+  for (int j = 0; j < 9; j++) c[j] /= (double)k;
+  cov[0] = c[3] - c[0] * c[0];
+  cov[4] = c[6] - c[1] * c[1];
+  cov[8] = c[8] - c[2] * c[2];
+  cov[1] = cov[3] = c[4] - c[0] * c[1];
+  cov[2] = cov[6] = c[5] - c[0] * c[2];
+  cov[5] = cov[7] = c[7] - c[1] * c[2];
+}
+
+/* full P3: covariances -> normal -> NormalizeNormals -> OrientNormalsTowardsCameraLocation(0,0,0).
+ * The cloud is assumed to have no normals/covariances on entry (true at every reference call site
+ * on this path: ScanToMapRegistration.cpp:38, Odometry.cpp:28 run it right after voxelize()).
+ * out_cov (optional, 9 doubles/pt) exposes the intermediate covariance for tests. */
+ORC_EXPORT void orc_estimate_normals(const double* xyz, size_t n, int knn, double radius, double* out_nrm, double* out_cov) {
+  kd_tree* t = kd_build(xyz, (int)n);
+#pragma omp parallel
+  {
+    double* d2 = (double*)malloc(sizeof(double) * (size_t)(knn > 0 ? knn : 1));
+    int* idx = (int*)malloc(sizeof(int) * (size_t)(knn > 0 ? knn : 1));
+#pragma omp for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+      double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      int k = kd_search_hybrid(t, xyz + 3 * i, radius, knn, d2, idx);
+      if (k >= 3) compute_covariance(xyz, idx, k, cov);
+      if (out_cov) memcpy(out_cov + 9 * i, cov, sizeof(cov));
+      double nr[3];
+      orc_fast_eigen3x3(cov, nr);
+      if (sqrt(dot3(nr, nr)) == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+      /* NormalizeNormals: Eigen normalize() leaves a zero vector untouched; NaN -> (0,0,1) */
+      double z = dot3(nr, nr);
+      if (z > 0) { double s = sqrt(z); nr[0] /= s; nr[1] /= s; nr[2] /= s; }
+      if (isnan(nr[0])) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+      /* OrientNormalsTowardsCameraLocation(camera = 0) */
+      double ref[3] = {-xyz[3 * i], -xyz[3 * i + 1], -xyz[3 * i + 2]};
+      if (sqrt(dot3(nr, nr)) == 0.0) {
+        double rn = sqrt(dot3(ref, ref));
+        if (rn == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+        else { nr[0] = ref[0] / rn; nr[1] = ref[1] / rn; nr[2] = ref[2] / rn; }
+      } else if (dot3(nr, ref) < 0.0) { nr[0] *= -1.0; nr[1] *= -1.0; nr[2] *= -1.0; }
+      out_nrm[3 * i] = nr[0]; out_nrm[3 * i + 1] = nr[1]; out_nrm[3 * i + 2] = nr[2];
+    }
+    free(d2); free(idx);
+  }
+  kd_free(t);
+}
+
+/* ------------------------------------------------------------------------- */
+/*  P4  [O3D] PointCloud::RandomDownSample(ratio)                              */
+/*      called at core/src/ScanToMapRegistration.cpp:39, core/src/Odometry.cpp:29 */
+/*  Reference: shuffle with mt19937(random_device) and keep floor(ratio*n).    */
+/*  Seeded stand-in: keep the floor(ratio*n) points with the smallest          */
+/*  (hash(seed,i), i); output keeps the input order.                           */
+/* ------------------------------------------------------------------------- */
+ORC_EXPORT uint32_t orc_select_hash(uint32_t seed, uint32_t i) {
+  uint32_t x = i * 0x9E3779B1u + seed * 0x85EBCA77u + 0x165667B1u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+typedef struct { uint32_t h; uint32_t i; } hpair;
+static int hpair_cmp(const void* a, const void* b) {
+  const hpair* x = (const hpair*)a; const hpair* y = (const hpair*)b;
+  if (x->h != y->h) return x->h < y->h ? -1 : 1;
+  return x->i < y->i ? -1 : (x->i > y->i ? 1 : 0);
+}
+ORC_EXPORT size_t orc_random_down_sample(const double* xyz, const double* nrm, size_t n, double ratio, uint32_t seed,
+                                         double* out_xyz, double* out_nrm) {
+  size_t k = (size_t)((double)n * ratio); /* [O3D]: size_t(points_.size() * sampling_ratio) */
+  if (k > n) k = n;
+  uint8_t* keep = (uint8_t*)calloc(n ? n : 1, 1);
+  if (k == n) memset(keep, 1, n);
+  else {
+    hpair* hp = (hpair*)malloc(sizeof(hpair) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) { hp[i].h = orc_select_hash(seed, (uint32_t)i); hp[i].i = (uint32_t)i; }
+    qsort(hp, n, sizeof(hpair), hpair_cmp);
+    for (size_t j = 0; j < k; j++) keep[hp[j].i] = 1;
+    free(hp);
+  }
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++) if (keep[i]) {
+    memcpy(out_xyz + 3 * m, xyz + 3 * i, 24);
+    if (nrm && out_nrm) memcpy(out_nrm + 3 * m, nrm + 3 * i, 24);
+    m++;
+  }
+  free(keep);
+  return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  R1-R5  registerClouds -> [O3D] RegistrationICP + TransformationEstimationPointToPlane */
+/*      core/src/CloudRegistration.cpp:44-48 ; [O3D] pipelines/registration/Registration.cpp, */
+/*      TransformationEstimation.cpp, utility/Eigen.cpp                        */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  double T[16];       /* row-major 4x4 */
+  double fitness;
+  double inlier_rmse;
+  int32_t n_corr;
+  int32_t iters;      /* number of ComputeTransformation calls executed */
+} orc_icp_result;
+
+static void mat4_mul(const double* A, const double* B, double* C) {
+  double t[16];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    double s = 0; for (int k = 0; k < 4; k++) s += A[4 * i + k] * B[4 * k + j];
+    t[4 * i + j] = s;
+  }
+  memcpy(C, t, sizeof(t));
+}
+static void mat4_identity(double* T) { memset(T, 0, 128); T[0] = T[5] = T[10] = T[15] = 1.0; }
+
+/* Eigen isIdentity(prec = 1e-12): diagonal ~ 1, off-diagonals much smaller than 1 */
+static int mat4_is_identity(const double* T) {
+  const double prec = 1e-12;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    double v = T[4 * i + j];
+    if (i == j) { if (!(fabs(v - 1.0) <= prec * fmin(fabs(v), 1.0))) return 0; }
+    else { if (!(fabs(v) <= prec)) return 0; }
+  }
+  return 1;
+}
+
+/* [O3D] PointCloud::Transform -> TransformPoints: p = (T*(p,1)).head3 / w */
+static void transform_points(const double* T, double* xyz, size_t n) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; i++) {
+    double* p = xyz + 3 * i;
+    double x = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3];
+    double y = T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7];
+    double z = T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11];
+    double w = T[12] * p[0] + T[13] * p[1] + T[14] * p[2] + T[15];
+    p[0] = x / w; p[1] = y / w; p[2] = z / w;
+  }
+}
+
+/* [O3D] GetRegistrationResultAndCorrespondences: SearchHybrid(p, r, 1) per source point */
+static void icp_correspondences(const kd_tree* t, const double* src, size_t n_src, double r, int* corr, double* d2out,
+                                double* fitness, double* rmse, int* n_corr) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n_src; i++) {
+    double d2; int idx;
+    int k = kd_search_hybrid(t, src + 3 * i, r, 1, &d2, &idx);
+    corr[i] = k > 0 ? idx : -1;
+    d2out[i] = k > 0 ? d2 : 0.0;
+  }
+  /* deterministic chunked reduction (reference: per-thread partial sums merged in a critical section) */
+  double err2 = 0.0; size_t cnt = 0;
+  for (size_t c0 = 0; c0 < n_src; c0 += 1024) {
+    double e = 0.0; size_t c1 = c0 + 1024 < n_src ? c0 + 1024 : n_src;
+    for (size_t i = c0; i < c1; i++) if (corr[i] >= 0) { e += d2out[i]; cnt++; }
+    err2 += e;
+  }
+  *n_corr = (int)cnt;
+  if (cnt == 0) { *fitness = 0.0; *rmse = 0.0; }
+  else { *fitness = (double)cnt / (double)n_src; *rmse = sqrt(err2 / (double)cnt); }
+}
+
+/* Eigen-style LDLT (symmetric diagonal pivoting on the largest |diagonal|) solve of A x = b, A 6x6 symmetric.
+ * [O3D] SolveLinearSystemPSD(JTJ, -JTr) = A.ldlt().solve(b), no det/PSD check on this path. */
+ORC_EXPORT void orc_ldlt6_solve(const double* A_in, const double* b_in, double* x) {
+  double A[36]; memcpy(A, A_in, sizeof(A));
+  int perm[6]; for (int i = 0; i < 6; i++) perm[i] = i;
+  /* in-place LDL^T on the lower triangle with symmetric pivoting: P A P^T = L D L^T */
+  for (int k = 0; k < 6; k++) {
+    int piv = k; double best = fabs(A[7 * k]);
+    for (int i = k + 1; i < 6; i++) if (fabs(A[7 * i]) > best) { best = fabs(A[7 * i]); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < 6; j++) { double t = A[6 * k + j]; A[6 * k + j] = A[6 * piv + j]; A[6 * piv + j] = t; }
+      for (int j = 0; j < 6; j++) { double t = A[6 * j + k]; A[6 * j + k] = A[6 * j + piv]; A[6 * j + piv] = t; }
+      int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+    }
+    double d = A[7 * k];
+    if (d != 0.0) {
+      for (int i = k + 1; i < 6; i++) A[6 * i + k] /= d;
+      for (int i = k + 1; i < 6; i++) for (int j = k + 1; j <= i; j++) {
+        A[6 * i + j] -= A[6 * i + k] * d * A[6 * j + k];
+        A[6 * j + i] = A[6 * i + j];
+      }
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) y[i] = b_in[perm[i]];
+  for (int i = 0; i < 6; i++) for (int j = 0; j < i; j++) y[i] -= A[6 * i + j] * y[j];
+  for (int i = 0; i < 6; i++) { double d = A[7 * i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; } /* Eigen: pseudo-inverse of D */
+  for (int i = 5; i >= 0; i--) for (int j = i + 1; j < 6; j++) y[i] -= A[6 * j + i] * y[j];
+  for (int i = 0; i < 6; i++) x[perm[i]] = y[i];
+}
+
+/* [O3D] TransformVector6dToMatrix4d: R = Rz(x[2]) * Ry(x[1]) * Rx(x[0]), t = x[3..5] */
+ORC_EXPORT void orc_vec6_to_mat4(const double* x, double* T) {
+  double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+  mat4_identity(T);
+  T[0] = cg * cb; T[1] = cg * sb * sa - sg * ca; T[2] = cg * sb * ca + sg * sa;
+  T[4] = sg * cb; T[5] = sg * sb * sa + cg * ca; T[6] = sg * sb * ca - cg * sa;
+  T[8] = -sb;     T[9] = cb * sa;                T[10] = cb * ca;
+  T[3] = x[3]; T[7] = x[4]; T[11] = x[5];
+}
+
+/* [O3D] TransformationEstimationPointToPlane::ComputeTransformation (L2 loss, w = 1).
+ * out_JTJ (36) / out_JTr (6) optional. */
+static void p2plane_update(const double* src, const double* tgt, const double* tgt_nrm, const int* corr, size_t n_src,
+                           double* update, double* out_JTJ, double* out_JTr) {
+  double JTJ[36] = {0}, JTr[6] = {0};
+  size_t ncorr = 0;
+  for (size_t c0 = 0; c0 < n_src; c0 += 1024) {
+    double A[36] = {0}, g[6] = {0};
+    size_t c1 = c0 + 1024 < n_src ? c0 + 1024 : n_src;
+    for (size_t i = c0; i < c1; i++) {
+      int j = corr[i]; if (j < 0) continue;
+      ncorr++;
+      const double* vs = src + 3 * i; const double* vt = tgt + 3 * j; const double* nt = tgt_nrm + 3 * j;
+      double r = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
+      double J[6];
+      J[0] = vs[1] * nt[2] - vs[2] * nt[1]; J[1] = vs[2] * nt[0] - vs[0] * nt[2]; J[2] = vs[0] * nt[1] - vs[1] * nt[0];
+      J[3] = nt[0]; J[4] = nt[1]; J[5] = nt[2];
+      for (int a = 0; a < 6; a++) { for (int b = 0; b < 6; b++) A[6 * a + b] += J[a] * J[b]; g[a] += J[a] * r; }
+    }
+    for (int a = 0; a < 36; a++) JTJ[a] += A[a];
+    for (int a = 0; a < 6; a++) JTr[a] += g[a];
+  }
+  if (out_JTJ) memcpy(out_JTJ, JTJ, sizeof(JTJ));
+  if (out_JTr) memcpy(out_JTr, JTr, sizeof(JTr));
+  if (ncorr == 0) { mat4_identity(update); return; }
+  double nb[6], x[6];
+  for (int a = 0; a < 6; a++) nb[a] = -JTr[a];
+  orc_ldlt6_solve(JTJ, nb, x);
+  orc_vec6_to_mat4(x, update);
+}
+
+/* trace (optional): per evaluation e = 0..iters : fitness, rmse, then JTJ(36)+JTr(6) of the update computed
+ * from it  -> 44 doubles per record, trace_cap records max */
+ORC_EXPORT int orc_registration_icp_p2plane(const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_nrm,
+                                            size_t n_tgt, double max_corr_dist, const double* init, int max_iter,
+                                            double rel_fitness, double rel_rmse, orc_icp_result* out, double* trace,
+                                            int trace_cap) {
+  if (max_corr_dist <= 0.0) return -1;       /* [O3D] LogError */
+  if (!tgt_nrm) return -2;                   /* [O3D] LogError: target needs normals */
+  double T[16]; memcpy(T, init, sizeof(T));
+  kd_tree* t = kd_build(tgt_xyz, (int)n_tgt); /* rebuilt on every call, like the reference */
+  double* pcd = (double*)malloc(24 * (n_src ? n_src : 1));
+  memcpy(pcd, src_xyz, 24 * n_src);
+  if (!mat4_is_identity(init)) transform_points(init, pcd, n_src);
+  int* corr = (int*)malloc(sizeof(int) * (n_src ? n_src : 1));
+  double* d2 = (double*)malloc(sizeof(double) * (n_src ? n_src : 1));
+  double fit, rmse; int nc;
+  icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+  int it = 0;
+  for (int i = 0; i < max_iter; i++) {
+    double upd[16], JTJ[36], JTr[6];
+    p2plane_update(pcd, tgt_xyz, tgt_nrm, corr, n_src, upd, JTJ, JTr);
+    if (trace && i < trace_cap) { trace[44 * i] = fit; trace[44 * i + 1] = rmse; memcpy(trace + 44 * i + 2, JTJ, 288); memcpy(trace + 44 * i + 38, JTr, 48); }
+    mat4_mul(upd, T, T);
+    transform_points(upd, pcd, n_src);
+    double bfit = fit, brmse = rmse;
+    icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+    it = i + 1;
+    if (fabs(bfit - fit) < rel_fitness && fabs(brmse - rmse) < rel_rmse) break;
+  }
+  memcpy(out->T, T, sizeof(T));
+  out->fitness = fit; out->inlier_rmse = rmse; out->n_corr = nc; out->iters = it;
+  free(pcd); free(corr); free(d2); kd_free(t);
+  return 0;
+}
+
+/* Brute-force single evaluation (for cross-checking the tree): fitness/rmse/JTJ/JTr at transform T */
+ORC_EXPORT void orc_icp_evaluate_bruteforce(const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_nrm,
+                                            size_t n_tgt, double r, const double* T, double* fitness, double* rmse,
+                                            double* JTJ, double* JTr, int* corr_out) {
+  double* pcd = (double*)malloc(24 * (n_src ? n_src : 1));
+  memcpy(pcd, src_xyz, 24 * n_src);
+  transform_points(T, pcd, n_src);
+  int* corr = (int*)malloc(sizeof(int) * (n_src ? n_src : 1));
+  double* d2 = (double*)malloc(sizeof(double) * (n_src ? n_src : 1));
+  double r2 = r * r;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n_src; i++) {
+    double best = INFINITY; int bj = -1;
+    for (size_t j = 0; j < n_tgt; j++) {
+      double d = dist2(pcd + 3 * i, tgt_xyz + 3 * j);
+      if (d < best) { best = d; bj = (int)j; }
+    }
+    if (bj >= 0 && best < r2) { corr[i] = bj; d2[i] = best; } else { corr[i] = -1; d2[i] = 0; }
+  }
+  double err2 = 0; size_t cnt = 0;
+  for (size_t c0 = 0; c0 < n_src; c0 += 1024) {
+    double e = 0.0; size_t c1 = c0 + 1024 < n_src ? c0 + 1024 : n_src;
+    for (size_t i = c0; i < c1; i++) if (corr[i] >= 0) { e += d2[i]; cnt++; }
+    err2 += e;
+  }
+  *fitness = cnt ? (double)cnt / (double)n_src : 0.0;
+  *rmse = cnt ? sqrt(err2 / (double)cnt) : 0.0;
+  double upd[16];
+  p2plane_update(pcd, tgt_xyz, tgt_nrm, corr, n_src, upd, JTJ, JTr);
+  if (corr_out) memcpy(corr_out, corr, sizeof(int) * n_src);
+  free(pcd); free(corr); free(d2);
+}
+
+/* ------------------------------------------------------------------------- */
+/*  F0  o3d_slam::transform          core/src/helpers.cpp:273-305              */
+/*  Quirk kept literally: when max|T - I| < 1e-4 the output first receives a    */
+/*  copy of the whole cloud and then ALSO every transformed point (2n points).  */
+/*  out buffers must hold 2n points. Returns the number of points written.     */
+/* ------------------------------------------------------------------------- */
+ORC_EXPORT size_t orc_transform(const double* T, const double* xyz, const double* nrm, size_t n, double* out_xyz, double* out_nrm) {
+  double mx = 0.0;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    double v = fabs(T[4 * i + j] - (i == j ? 1.0 : 0.0)); if (v > mx) mx = v;
+  }
+  size_t m = 0;
+  if (mx < 1e-4) {
+    memcpy(out_xyz, xyz, 24 * n);
+    if (nrm && out_nrm) memcpy(out_nrm, nrm, 24 * n);
+    m = n;
+  }
+  for (size_t i = 0; i < n; i++) {
+    const double* p = xyz + 3 * i;
+    double x = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3] * 1.0;
+    double y = T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7] * 1.0;
+    double z = T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11] * 1.0;
+    double w = T[12] * p[0] + T[13] * p[1] + T[14] * p[2] + T[15] * 1.0;
+    out_xyz[3 * m] = x / w; out_xyz[3 * m + 1] = y / w; out_xyz[3 * m + 2] = z / w;
+    if (nrm && out_nrm) {
+      const double* q = nrm + 3 * i;
+      out_nrm[3 * m] = T[0] * q[0] + T[1] * q[1] + T[2] * q[2];
+      out_nrm[3 * m + 1] = T[4] * q[0] + T[5] * q[1] + T[6] * q[2];
+      out_nrm[3 * m + 2] = T[8] * q[0] + T[9] * q[1] + T[10] * q[2];
+    }
+    m++;
+  }
+  return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  F1  voxelizeWithinCroppingVolume   core/src/helpers.cpp:115-183            */
+/*      (+ AccumulatedPoint :30-70, getVoxelIdx VoxelHashMap.hpp:47-50)        */
+/*  Points inside the cropper are bucketed by floor(p * (1/v)) on the           */
+/*  global-origin grid; the bucket output is the mean of its members (an old   */
+/*  map point counts as ONE member), normals: mean of non-NaN normals then     */
+/*  .normalized(); points outside pass through unchanged and come first.       */
+/*  out_keys (optional): 3 x int32 per output point; pass-through points get    */
+/*  INT32_MIN in all three.                                                    */
+/* ------------------------------------------------------------------------- */
+ORC_EXPORT size_t orc_voxelize_within_cropping_volume(double voxel, const orc_cropper* c, const double* xyz, const double* nrm,
+                                                      size_t n, double* out_xyz, double* out_nrm, int32_t* out_keys) {
+  if (voxel <= 0.0) {
+    memcpy(out_xyz, xyz, 24 * n);
+    if (nrm && out_nrm) memcpy(out_nrm, nrm, 24 * n);
+    return n;
+  }
+  const double inv = 1.0 / voxel;
+  vhash h; vh_init(&h, n);
+  double* acc = (double*)calloc((n ? n : 1) * 6, sizeof(double));
+  int32_t* cnt = (int32_t*)calloc(n ? n : 1, sizeof(int32_t));
+  int32_t* keys = (int32_t*)malloc(sizeof(int32_t) * 3 * (n ? n : 1));
+  size_t m = 0;
+  for (size_t i = 0; i < n; i++) {
+    const double* p = xyz + 3 * i;
+    if (orc_within(c, p)) {
+      int32_t k0 = (int32_t)floor(p[0] * inv), k1 = (int32_t)floor(p[1] * inv), k2 = (int32_t)floor(p[2] * inv);
+      int is_new;
+      int32_t s = vh_get(&h, k0, k1, k2, 1, &is_new);
+      if (is_new) { keys[3 * s] = k0; keys[3 * s + 1] = k1; keys[3 * s + 2] = k2; }
+      acc[6 * s] += p[0]; acc[6 * s + 1] += p[1]; acc[6 * s + 2] += p[2];
+      if (nrm) {
+        const double* q = nrm + 3 * i;
+        if (!isnan(q[0]) && !isnan(q[1]) && !isnan(q[2])) { acc[6 * s + 3] += q[0]; acc[6 * s + 4] += q[1]; acc[6 * s + 5] += q[2]; }
+      }
+      cnt[s]++;
+    } else {
+      memcpy(out_xyz + 3 * m, p, 24);
+      if (nrm && out_nrm) memcpy(out_nrm + 3 * m, nrm + 3 * i, 24);
+      if (out_keys) { out_keys[3 * m] = out_keys[3 * m + 1] = out_keys[3 * m + 2] = INT32_MIN; }
+      m++;
+    }
+  }
+  for (size_t s = 0; s < h.cnt; s++) {
+    double cd = (double)cnt[s];
+    for (int d = 0; d < 3; d++) out_xyz[3 * m + d] = acc[6 * s + d] / cd;
+    if (nrm && out_nrm) {
+      double a[3] = {acc[6 * s + 3] / cd, acc[6 * s + 4] / cd, acc[6 * s + 5] / cd};
+      double z = dot3(a, a);
+      if (z > 0) { double sn = sqrt(z); a[0] /= sn; a[1] /= sn; a[2] /= sn; } /* Eigen normalized() */
+      out_nrm[3 * m] = a[0]; out_nrm[3 * m + 1] = a[1]; out_nrm[3 * m + 2] = a[2];
+    }
+    if (out_keys) { out_keys[3 * m] = keys[3 * s]; out_keys[3 * m + 1] = keys[3 * s + 1]; out_keys[3 * m + 2] = keys[3 * s + 2]; }
+    m++;
+  }
+  free(acc); free(cnt); free(keys); vh_free(&h);
+  return m;
+}
+
+/* Submap::insertScan, sparse map, no carving   core/src/Submap.cpp:39-75
+ * map (n_map points + normals) is updated in place into out_* (capacity >= n_map + 2*n_scan). */
+ORC_EXPORT size_t orc_submap_insert_scan(const double* map_xyz, const double* map_nrm, size_t n_map, const double* scan_xyz,
+                                         const double* scan_nrm, size_t n_scan, const double* T, double map_voxel,
+                                         const orc_cropper* map_builder_cropper_at_sensor, double* out_xyz, double* out_nrm,
+                                         int32_t* out_keys) {
+  if (n_scan == 0) { /* Submap.cpp:41-43 */
+    memcpy(out_xyz, map_xyz, 24 * n_map); memcpy(out_nrm, map_nrm, 24 * n_map); return n_map;
+  }
+  size_t cap = n_map + 2 * n_scan;
+  double* cat_xyz = (double*)malloc(24 * cap);
+  double* cat_nrm = (double*)malloc(24 * cap);
+  memcpy(cat_xyz, map_xyz, 24 * n_map); memcpy(cat_nrm, map_nrm, 24 * n_map);
+  size_t nt = orc_transform(T, scan_xyz, scan_nrm, n_scan, cat_xyz + 3 * n_map, cat_nrm + 3 * n_map); /* :54, :70 */
+  orc_cropper c = *map_builder_cropper_at_sensor;
+  c.center[0] = T[3]; c.center[1] = T[7]; c.center[2] = T[11]; /* :71 setPose(mapToRangeSensor) */
+  size_t m = orc_voxelize_within_cropping_volume(map_voxel, &c, cat_xyz, cat_nrm, n_map + nt, out_xyz, out_nrm, out_keys); /* :72 */
+  free(cat_xyz); free(cat_nrm);
+  return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  F3  VoxelizedPointCloud (dense map)   core/src/Voxel.cpp:18-115            */
+/*  running sum of positions / normals and a count per voxel; key =            */
+/*  floor(p * (1/v)) (VoxelHashMap.hpp:47-50 via getKey :124)                  */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  vhash h;
+  double inv;
+  double* sum;     /* 6 per voxel: position sum, normal sum */
+  int32_t* cnt;
+  int32_t* keys;
+  size_t cap;
+  int has_normals;
+} orc_dense;
+
+ORC_EXPORT void* orc_dense_create(double voxel, size_t max_voxels) {
+  orc_dense* d = (orc_dense*)calloc(1, sizeof(orc_dense));
+  vh_init(&d->h, max_voxels);
+  d->inv = 1.0 / voxel; d->cap = max_voxels;
+  d->sum = (double*)calloc(max_voxels * 6, sizeof(double));
+  d->cnt = (int32_t*)calloc(max_voxels, sizeof(int32_t));
+  d->keys = (int32_t*)calloc(max_voxels * 3, sizeof(int32_t));
+  return d;
+}
+ORC_EXPORT void orc_dense_destroy(void* p) {
+  orc_dense* d = (orc_dense*)p; if (!d) return;
+  vh_free(&d->h); free(d->sum); free(d->cnt); free(d->keys); free(d);
+}
+/* VoxelizedPointCloud::insert  Voxel.cpp:66-88 ; returns -1 when capacity would be exceeded */
+ORC_EXPORT int orc_dense_insert(void* p, const double* xyz, const double* nrm, size_t n) {
+  orc_dense* d = (orc_dense*)p;
+  for (size_t i = 0; i < n; i++) {
+    const double* q = xyz + 3 * i;
+    int32_t k0 = (int32_t)floor(q[0] * d->inv), k1 = (int32_t)floor(q[1] * d->inv), k2 = (int32_t)floor(q[2] * d->inv);
+    if (d->h.cnt >= d->cap && vh_get(&d->h, k0, k1, k2, 0, NULL) < 0) return -1;
+    int is_new;
+    int32_t s = vh_get(&d->h, k0, k1, k2, 1, &is_new);
+    if (is_new) { d->keys[3 * s] = k0; d->keys[3 * s + 1] = k1; d->keys[3 * s + 2] = k2; }
+    d->sum[6 * s] += q[0]; d->sum[6 * s + 1] += q[1]; d->sum[6 * s + 2] += q[2];
+    d->cnt[s]++;
+    if (nrm) { d->sum[6 * s + 3] += nrm[3 * i]; d->sum[6 * s + 4] += nrm[3 * i + 1]; d->sum[6 * s + 5] += nrm[3 * i + 2]; d->has_normals = 1; }
+  }
+  return 0;
+}
+/* VoxelizedPointCloud::toPointCloud  Voxel.cpp:90-115 */
+ORC_EXPORT size_t orc_dense_to_cloud(void* p, double* out_xyz, double* out_nrm, int32_t* out_keys) {
+  orc_dense* d = (orc_dense*)p;
+  size_t m = 0;
+  for (size_t s = 0; s < d->h.cnt; s++) {
+    if (d->cnt[s] <= 0) continue;
+    double c = (double)d->cnt[s];
+    for (int k = 0; k < 3; k++) out_xyz[3 * m + k] = d->sum[6 * s + k] / c;
+    if (out_nrm) for (int k = 0; k < 3; k++) out_nrm[3 * m + k] = d->has_normals ? d->sum[6 * s + 3 + k] / c : 0.0;
+    if (out_keys) { out_keys[3 * m] = d->keys[3 * s]; out_keys[3 * m + 1] = d->keys[3 * s + 1]; out_keys[3 * m + 2] = d->keys[3 * s + 2]; }
+    m++;
+  }
+  return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  S1  ScanToMapIcp::preprocess + processForScanMatchingAndMerging            */
+/*      core/src/ScanToMapRegistration.cpp:35-54 (also Odometry.cpp:25-30)     */
+/*  crop(mapBuilder cropper @ identity) -> voxelize -> normals -> random down   */
+/*  sample = merge_ ; crop(scanMatcher cropper @ identity) of merge_ = match_   */
+/*  All out buffers need capacity n.  Returns 0, or -1 when either is empty.    */
+/* ------------------------------------------------------------------------- */
+ORC_EXPORT int orc_process_scan(const double* raw_xyz, size_t n, const orc_cropper* map_builder_cropper,
+                                const orc_cropper* scan_matcher_cropper, double voxel, int knn, double knn_radius, double ratio,
+                                uint32_t seed, double* merge_xyz, double* merge_nrm, size_t* n_merge, double* match_xyz,
+                                double* match_nrm, size_t* n_match) {
+  double* a = (double*)malloc(24 * (n ? n : 1));
+  double* b = (double*)malloc(24 * (n ? n : 1));
+  double* bn = (double*)malloc(24 * (n ? n : 1));
+  orc_cropper c0 = *map_builder_cropper; c0.center[0] = c0.center[1] = c0.center[2] = 0.0;
+  size_t m = orc_crop(&c0, raw_xyz, NULL, n, a, NULL);
+  m = orc_voxel_down_sample(a, NULL, m, voxel, b, NULL, NULL);
+  if (m > 0) orc_estimate_normals(b, m, knn, knn_radius, bn, NULL);
+  size_t k = orc_random_down_sample(b, bn, m, ratio, seed, merge_xyz, merge_nrm);
+  *n_merge = k;
+  orc_cropper c1 = *scan_matcher_cropper; c1.center[0] = c1.center[1] = c1.center[2] = 0.0;
+  *n_match = orc_crop(&c1, merge_xyz, merge_nrm, k, match_xyz, match_nrm);
+  free(a); free(b); free(bn);
+  return (*n_merge > 0 && *n_match > 0) ? 0 : -1;
+}
+
+ORC_EXPORT int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,265 @@
+"""ctypes front-end of the CPU ORACLE (oracle/o3d_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see the header of o3d_oracle.c): the
+reference has no tests on this path and Open3D v0.15.1 is not available here.
+
+May be imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libo3d_oracle.so")
+
+CROP_NONE, CROP_MAX_RADIUS, CROP_MIN_RADIUS, CROP_MINMAX_RADIUS, CROP_CYLINDER = 0, 1, 2, 3, 4
+_CROP_NAMES = {"None": 0, "MaxRadius": 1, "MinRadius": 2, "MinMaxRadius": 3, "Cylinder": 4}
+
+
+class Cropper(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("invert", C.c_int32), ("rmin", C.c_double), ("rmax", C.c_double),
+                ("zmin", C.c_double), ("zmax", C.c_double), ("center", C.c_double * 3)]
+
+
+def cropper(kind="MinMaxRadius", rmin=0.0, rmax=20.0, zmin=-10.0, zmax=10.0, center=(0.0, 0.0, 0.0), invert=False) -> Cropper:
+    c = Cropper()
+    c.kind = _CROP_NAMES[kind] if isinstance(kind, str) else int(kind)
+    c.invert = int(invert)
+    c.rmin, c.rmax, c.zmin, c.zmax = float(rmin), float(rmax), float(zmin), float(zmax)
+    c.center[0], c.center[1], c.center[2] = (float(v) for v in center)
+    return c
+
+
+class IcpResultC(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("fitness", C.c_double), ("inlier_rmse", C.c_double), ("n_corr", C.c_int32),
+                ("iters", C.c_int32)]
+
+
+@dataclass
+class IcpResult:
+    T: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    n_corr: int
+    iters: int
+    trace: np.ndarray | None = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc -O3 -fopenmp)."""
+    src = os.path.join(_HERE, "o3d_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_crop.restype = C.c_size_t
+        _lib.orc_voxel_down_sample.restype = C.c_size_t
+        _lib.orc_random_down_sample.restype = C.c_size_t
+        _lib.orc_transform.restype = C.c_size_t
+        _lib.orc_voxelize_within_cropping_volume.restype = C.c_size_t
+        _lib.orc_submap_insert_scan.restype = C.c_size_t
+        _lib.orc_dense_create.restype = C.c_void_p
+        _lib.orc_dense_to_cloud.restype = C.c_size_t
+        _lib.orc_kdtree_build.restype = C.c_void_p
+        _lib.orc_select_hash.restype = C.c_uint32
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def crop(c: Cropper, xyz, nrm=None):
+    xyz = _f64(xyz).reshape(-1, 3)
+    n = len(xyz)
+    nrm = None if nrm is None else _f64(nrm).reshape(-1, 3)
+    ox = np.empty((n, 3)); on = np.empty((n, 3)) if nrm is not None else None
+    m = lib().orc_crop(C.byref(c), _p(xyz), _p(nrm), C.c_size_t(n), _p(ox), _p(on))
+    return (ox[:m].copy(), None if on is None else on[:m].copy())
+
+
+def voxel_down_sample(xyz, voxel, nrm=None, return_keys=False):
+    xyz = _f64(xyz).reshape(-1, 3)
+    n = len(xyz)
+    nrm = None if nrm is None else _f64(nrm).reshape(-1, 3)
+    ox = np.empty((n, 3)); on = np.empty((n, 3)) if nrm is not None else None
+    keys = np.empty((n, 3), dtype=np.int32)
+    m = lib().orc_voxel_down_sample(_p(xyz), _p(nrm), C.c_size_t(n), C.c_double(voxel), _p(ox), _p(on), _p(keys))
+    out = (ox[:m].copy(), None if on is None else on[:m].copy())
+    return out + (keys[:m].copy(),) if return_keys else out
+
+
+def estimate_normals(xyz, knn, radius, return_cov=False):
+    xyz = _f64(xyz).reshape(-1, 3)
+    n = len(xyz)
+    on = np.empty((n, 3)); cov = np.empty((n, 9)) if return_cov else None
+    lib().orc_estimate_normals(_p(xyz), C.c_size_t(n), C.c_int(knn), C.c_double(radius), _p(on), _p(cov))
+    return (on, cov.reshape(n, 3, 3)) if return_cov else on
+
+
+def fast_eigen3x3(cov):
+    cov = _f64(cov).reshape(9)
+    out = np.empty(3)
+    lib().orc_fast_eigen3x3(_p(cov), _p(out))
+    return out
+
+
+def random_down_sample(xyz, ratio, seed, nrm=None):
+    xyz = _f64(xyz).reshape(-1, 3)
+    n = len(xyz)
+    nrm = None if nrm is None else _f64(nrm).reshape(-1, 3)
+    ox = np.empty((n, 3)); on = np.empty((n, 3)) if nrm is not None else None
+    m = lib().orc_random_down_sample(_p(xyz), _p(nrm), C.c_size_t(n), C.c_double(ratio), C.c_uint32(seed), _p(ox), _p(on))
+    return (ox[:m].copy(), None if on is None else on[:m].copy())
+
+
+def select_hash(seed, i):
+    return int(lib().orc_select_hash(C.c_uint32(seed), C.c_uint32(i)))
+
+
+def registration_icp_p2plane(src, tgt, tgt_nrm, max_corr_dist, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6,
+                             trace=False) -> IcpResult:
+    src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); tgt_nrm = _f64(tgt_nrm).reshape(-1, 3)
+    init = np.eye(4) if init is None else _f64(init).reshape(4, 4)
+    res = IcpResultC()
+    tr = np.zeros((max(max_iter, 1), 44)) if trace else None
+    rc = lib().orc_registration_icp_p2plane(_p(src), C.c_size_t(len(src)), _p(tgt), _p(tgt_nrm), C.c_size_t(len(tgt)),
+                                            C.c_double(max_corr_dist), _p(init), C.c_int(max_iter), C.c_double(rel_fitness),
+                                            C.c_double(rel_rmse), C.byref(res), _p(tr), C.c_int(max_iter if trace else 0))
+    if rc != 0:
+        raise RuntimeError(f"orc_registration_icp_p2plane failed: {rc}")
+    return IcpResult(np.array(res.T).reshape(4, 4), res.fitness, res.inlier_rmse, res.n_corr, res.iters,
+                     None if tr is None else tr[:res.iters].copy())
+
+
+def icp_evaluate_bruteforce(src, tgt, tgt_nrm, r, T):
+    src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); tgt_nrm = _f64(tgt_nrm).reshape(-1, 3)
+    T = _f64(T).reshape(4, 4)
+    fit = C.c_double(); rm = C.c_double()
+    JTJ = np.empty(36); JTr = np.empty(6); corr = np.empty(len(src), dtype=np.int32)
+    lib().orc_icp_evaluate_bruteforce(_p(src), C.c_size_t(len(src)), _p(tgt), _p(tgt_nrm), C.c_size_t(len(tgt)), C.c_double(r),
+                                      _p(T), C.byref(fit), C.byref(rm), _p(JTJ), _p(JTr), _p(corr))
+    return fit.value, rm.value, JTJ.reshape(6, 6), JTr, corr
+
+
+def ldlt6_solve(A, b):
+    A = _f64(A).reshape(36); b = _f64(b).reshape(6)
+    x = np.empty(6)
+    lib().orc_ldlt6_solve(_p(A), _p(b), _p(x))
+    return x
+
+
+def vec6_to_mat4(x):
+    x = _f64(x).reshape(6)
+    T = np.empty(16)
+    lib().orc_vec6_to_mat4(_p(x), _p(T))
+    return T.reshape(4, 4)
+
+
+def transform(T, xyz, nrm=None):
+    T = _f64(T).reshape(4, 4)
+    xyz = _f64(xyz).reshape(-1, 3)
+    n = len(xyz)
+    nrm = None if nrm is None else _f64(nrm).reshape(-1, 3)
+    ox = np.empty((2 * n, 3)); on = np.empty((2 * n, 3)) if nrm is not None else None
+    m = lib().orc_transform(_p(T), _p(xyz), _p(nrm), C.c_size_t(n), _p(ox), _p(on))
+    return (ox[:m].copy(), None if on is None else on[:m].copy())
+
+
+def voxelize_within_cropping_volume(voxel, c: Cropper, xyz, nrm=None, return_keys=False):
+    xyz = _f64(xyz).reshape(-1, 3)
+    n = len(xyz)
+    nrm = None if nrm is None else _f64(nrm).reshape(-1, 3)
+    ox = np.empty((n, 3)); on = np.empty((n, 3)) if nrm is not None else None
+    keys = np.empty((n, 3), dtype=np.int32)
+    m = lib().orc_voxelize_within_cropping_volume(C.c_double(voxel), C.byref(c), _p(xyz), _p(nrm), C.c_size_t(n), _p(ox), _p(on),
+                                                  _p(keys))
+    out = (ox[:m].copy(), None if on is None else on[:m].copy())
+    return out + (keys[:m].copy(),) if return_keys else out
+
+
+def submap_insert_scan(map_xyz, map_nrm, scan_xyz, scan_nrm, T, map_voxel, c: Cropper, return_keys=False):
+    map_xyz = _f64(map_xyz).reshape(-1, 3); map_nrm = _f64(map_nrm).reshape(-1, 3)
+    scan_xyz = _f64(scan_xyz).reshape(-1, 3); scan_nrm = _f64(scan_nrm).reshape(-1, 3)
+    T = _f64(T).reshape(4, 4)
+    cap = len(map_xyz) + 2 * len(scan_xyz) + 1
+    ox = np.empty((cap, 3)); on = np.empty((cap, 3)); keys = np.empty((cap, 3), dtype=np.int32)
+    m = lib().orc_submap_insert_scan(_p(map_xyz), _p(map_nrm), C.c_size_t(len(map_xyz)), _p(scan_xyz), _p(scan_nrm),
+                                     C.c_size_t(len(scan_xyz)), _p(T), C.c_double(map_voxel), C.byref(c), _p(ox), _p(on), _p(keys))
+    out = (ox[:m].copy(), on[:m].copy())
+    return out + (keys[:m].copy(),) if return_keys else out
+
+
+class DenseMap:
+    """VoxelizedPointCloud restatement (core/src/Voxel.cpp:18-115)."""
+
+    def __init__(self, voxel, max_voxels=1 << 20):
+        self._h = C.c_void_p(lib().orc_dense_create(C.c_double(voxel), C.c_size_t(max_voxels)))
+        self._cap = max_voxels
+
+    def insert(self, xyz, nrm=None):
+        xyz = _f64(xyz).reshape(-1, 3)
+        nrm = None if nrm is None else _f64(nrm).reshape(-1, 3)
+        if lib().orc_dense_insert(self._h, _p(xyz), _p(nrm), C.c_size_t(len(xyz))) != 0:
+            raise RuntimeError("dense map capacity exceeded")
+
+    def to_cloud(self):
+        ox = np.empty((self._cap, 3)); on = np.empty((self._cap, 3)); keys = np.empty((self._cap, 3), dtype=np.int32)
+        m = lib().orc_dense_to_cloud(self._h, _p(ox), _p(on), _p(keys))
+        return ox[:m].copy(), on[:m].copy(), keys[:m].copy()
+
+    def __del__(self):
+        try:
+            lib().orc_dense_destroy(self._h)
+        except Exception:
+            pass
+
+
+def process_scan(raw_xyz, map_builder_cropper: Cropper, scan_matcher_cropper: Cropper, voxel, knn, knn_radius, ratio, seed):
+    raw = _f64(raw_xyz).reshape(-1, 3)
+    n = len(raw)
+    mx = np.empty((n, 3)); mn = np.empty((n, 3)); ax = np.empty((n, 3)); an = np.empty((n, 3))
+    nm = C.c_size_t(); na = C.c_size_t()
+    rc = lib().orc_process_scan(_p(raw), C.c_size_t(n), C.byref(map_builder_cropper), C.byref(scan_matcher_cropper),
+                                C.c_double(voxel), C.c_int(knn), C.c_double(knn_radius), C.c_double(ratio), C.c_uint32(seed),
+                                _p(mx), _p(mn), C.byref(nm), _p(ax), _p(an), C.byref(na))
+    if rc != 0:
+        raise RuntimeError("ScanToMapIcp: cropped size is zero")  # core/src/ScanToMapRegistration.cpp:51-52
+    return (mx[:nm.value].copy(), mn[:nm.value].copy()), (ax[:na.value].copy(), an[:na.value].copy())
+
+
+def kdtree_search_hybrid(pts, q, radius, max_nn):
+    pts = _f64(pts).reshape(-1, 3)
+    t = C.c_void_p(lib().orc_kdtree_build(_p(pts), C.c_int(len(pts))))
+    q = _f64(q).reshape(-1, 3)
+    out = []
+    d2 = np.empty(max_nn); idx = np.empty(max_nn, dtype=np.int32)
+    for qi in q:
+        qi = np.ascontiguousarray(qi)
+        k = lib().orc_kdtree_search_hybrid(t, _p(qi), C.c_double(radius), C.c_int(max_nn), _p(d2), _p(idx))
+        out.append((idx[:k].copy(), d2[:k].copy()))
+    lib().orc_kdtree_free(t)
+    return out
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
