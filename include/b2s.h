@@ -1,0 +1,192 @@
+/*
+ * b2s.h -- C ABI of the B200-native scan-to-map registration and voxel-map fusion engine.
+ *
+ * This is the drop-in boundary behind open3d_slam's CloudRegistration / ScanToMapRegistration /
+ * Submap interfaces.  The reference has NO C/FFI boundary today: its seam is a pair of abstract C++
+ * classes plus factories (paths relative to /root/reference/open3d_slam/open3d_slam/):
+ *     include/open3d_slam/CloudRegistration.hpp:19-27      CloudRegistration::registerClouds,
+ *                                                          estimateNormalsOrCovariancesIfNeeded
+ *     include/open3d_slam/ScanToMapRegistration.hpp:29-38  ScanToMapRegistration::processForScanMatchingAndMerging,
+ *                                                          scanToMapRegistration, prepareInitialMap
+ *     include/open3d_slam/Submap.hpp:38-45                 Submap::insertScan / insertScanDenseMap / getMapPointCloud
+ * Each entry point below names the reference interface (file:line) it replaces.  The C++ subclasses a
+ * maintainer adds on the reference side live in shim/ and are described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C99, no torch / CUDA types in any signature (a CUDA stream crosses as void*).
+ *   - every function returns int32_t status: B2S_OK (0) or a negative B2S_E_* code; the message of the
+ *     last failure on the calling thread is available from b2s_last_error().  No exception crosses.
+ *   - host point data is the reference's own memory layout: array-of-xyz doubles, 24-byte stride
+ *     (std::vector<Eigen::Vector3d>, include/open3d_slam/typedefs.hpp:23), or float32 xyz with an arbitrary
+ *     stride (sensor_msgs/PointCloud2 wire format, open3d_conversions.cpp:61-67).
+ *   - 4x4 transforms are 16 doubles in ROW-MAJOR order (Eigen::Matrix4d is column-major: copy element-wise).
+ *   - all arithmetic on the device is fp64 like the reference (ScanToMap ICP parity target 1e-4, achieved ~1e-12).
+ *   - a handle owns one CUDA stream; calls on one handle are serialised by an internal mutex and are
+ *     asynchronous with respect to the host unless they return data to host memory.  Use one handle per
+ *     host thread for concurrency (the reference calls registerClouds from 3 threads, SlamWrapper.cpp:228-231).
+ *   - the CUDA extension is the only implementation: there is no CPU fallback.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define B2S_OK 0
+#define B2S_E_INVALID (-1)      /* bad argument (reference: assert_* / LogError -> std::runtime_error) */
+#define B2S_E_CUDA (-2)         /* CUDA runtime failure */
+#define B2S_E_EMPTY (-3)        /* empty cloud where the reference asserts non-empty (ScanToMapRegistration.cpp:51-52,60) */
+#define B2S_E_NO_NORMALS (-4)   /* point-to-plane target without normals ([O3D] RegistrationICP LogError) */
+#define B2S_E_CAPACITY (-5)     /* a fixed-capacity device structure would overflow */
+#define B2S_E_UNSUPPORTED (-6)
+
+typedef struct b2s_handle b2s_handle;
+typedef struct b2s_cloud b2s_cloud;     /* device-resident point cloud: xyz (+ normals) fp64 */
+typedef struct b2s_submap b2s_submap;   /* device-resident sparse map cloud (+ optional dense voxel map) */
+
+/* CroppingVolumeEnum / croppingVolumeFactory  (src/croppers.cpp:27-51, include/open3d_slam/croppers.hpp) */
+enum { B2S_CROP_NONE = 0, B2S_CROP_MAX_RADIUS = 1, B2S_CROP_MIN_RADIUS = 2, B2S_CROP_MINMAX_RADIUS = 3, B2S_CROP_CYLINDER = 4 };
+
+/* ScanCroppingParameters (include/open3d_slam/Parameters.hpp:51-57) + the CroppingVolume state
+ * (isInvertVolume_, pose_ translation; src/croppers.cpp:57-67).  Only the translation of the pose is used. */
+typedef struct b2s_cropper {
+  int32_t kind;
+  int32_t invert;
+  double rmin, rmax, zmin, zmax;
+  double center[3];
+} b2s_cropper;
+
+/* CloudRegistrationType (Parameters.hpp:37).  Only point-to-plane is implemented in this round. */
+enum { B2S_REG_POINT_TO_PLANE = 0, B2S_REG_POINT_TO_POINT = 1, B2S_REG_GENERALIZED = 2 };
+
+/* IcpParameters + ICPConvergenceCriteria (Parameters.hpp:66-71; src/CloudRegistration.cpp:58-66; [O3D] defaults
+ * relative_fitness = relative_rmse = 1e-6) */
+typedef struct b2s_icp_params {
+  int32_t reg_type;
+  int32_t max_iter;            /* icp.max_n_iter */
+  double max_corr_dist;        /* icp.max_correspondence_dist */
+  int32_t knn;                 /* icp.knn            (normal estimation) */
+  double knn_radius;           /* icp.max_distance_knn */
+  double rel_fitness, rel_rmse;
+} b2s_icp_params;
+
+/* ScanProcessingParameters + the two croppers ScanToMapIcp holds (Parameters.hpp:59-64, ScanToMapRegistration.cpp:29-33) */
+typedef struct b2s_scan_params {
+  double voxel_size;           /* scan_processing.voxel_size */
+  double downsampling_ratio;   /* scan_processing.downsampling_ratio */
+  uint32_t seed;               /* replaces std::random_device in [O3D] RandomDownSample */
+  b2s_cropper map_builder_cropper;   /* params_.mapBuilder_.cropper_  : applied to the raw scan (preprocess) */
+  b2s_cropper scan_matcher_cropper;  /* params_.scanProcessing_.cropper_ : narrow crop / map patch crop */
+} b2s_scan_params;
+
+typedef struct b2s_config {
+  b2s_icp_params icp;
+  b2s_scan_params scan;
+  double map_voxel_size;       /* map_builder.map_voxel_size (Parameters.hpp:94) */
+  double dense_voxel_size;     /* dense_map_builder.map_voxel_size */
+  double nn_cell_size;         /* 0 = automatic (max_corr_dist / 2) : cell edge of the nearest-neighbour grid */
+} b2s_config;
+
+/* open3d::pipelines::registration::RegistrationResult as read by the callers
+ * (src/Mapper.cpp:151-159, src/Odometry.cpp:51-72, src/PlaceRecognition.cpp:118-149) */
+typedef struct b2s_result {
+  double T[16];                /* transformation_ (row-major) */
+  double fitness;              /* fitness_ */
+  double inlier_rmse;          /* inlier_rmse_ */
+  int32_t n_corr;              /* correspondence_set_.size() */
+  int32_t iters;               /* ICP updates applied */
+} b2s_result;
+
+void b2s_default_config(b2s_config* cfg);   /* Lua defaults, parameter_structure_definitions.lua:52-72,102, PointToPlaneIcp */
+
+/* ---- engine life cycle : cloudRegistrationFactory / scanToMapRegistrationFactory
+ *      (src/CloudRegistration.cpp:85-100, src/ScanToMapRegistration.cpp:91-103) ------------------------------- */
+int32_t b2s_create(const b2s_config* cfg, int32_t device, void* cuda_stream_or_null, b2s_handle** out);
+void b2s_destroy(b2s_handle* h);
+int32_t b2s_set_config(b2s_handle* h, const b2s_config* cfg);    /* ScanToMapIcp::setParameters (ScanToMapRegistration.cpp:24-27) */
+int32_t b2s_synchronize(b2s_handle* h);
+const char* b2s_last_error(void);
+const char* b2s_version(void);
+int32_t b2s_device_count(void);
+/* number of kernels launched by this handle since creation ("gpu_launches" evidence for bench.py) */
+int64_t b2s_launch_count(const b2s_handle* h);
+
+/* ---- clouds (open3d::geometry::PointCloud points_/normals_) ------------------------------------------------ */
+int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out);
+void b2s_cloud_destroy(b2s_cloud* c);
+int32_t b2s_cloud_upload_f64(b2s_handle* h, b2s_cloud* c, const double* xyz, const double* normals_or_null, size_t n);
+int32_t b2s_cloud_upload_f32(b2s_handle* h, b2s_cloud* c, const void* xyz, size_t n, size_t stride_bytes);
+int32_t b2s_cloud_size(b2s_handle* h, const b2s_cloud* c, size_t* n, int32_t* has_normals);   /* synchronises */
+int32_t b2s_cloud_download(b2s_handle* h, const b2s_cloud* c, double* xyz, double* normals_or_null, size_t capacity, size_t* n);
+int32_t b2s_cloud_copy(b2s_handle* h, const b2s_cloud* src, b2s_cloud* dst);
+
+/* ---- stages of the hot path (SURVEY.md section 8a row ids) ---------------------------------------------- */
+/* P1  CroppingVolume::crop                                   src/croppers.cpp:76-106 */
+int32_t b2s_crop(b2s_handle* h, const b2s_cloud* in, const b2s_cropper* cropper, b2s_cloud* out);
+/* P2  o3d_slam::voxelize -> [O3D] VoxelDownSample             src/helpers.cpp:107-113 */
+int32_t b2s_voxel_down_sample(b2s_handle* h, const b2s_cloud* in, double voxel_size, b2s_cloud* out);
+/* P3  estimateNormalsOrCovariancesIfNeeded                    src/CloudRegistration.cpp:49-56 */
+int32_t b2s_estimate_normals(b2s_handle* h, b2s_cloud* cloud, int32_t knn, double radius);
+/* P4  [O3D] RandomDownSample (seeded)                         src/ScanToMapRegistration.cpp:39 */
+int32_t b2s_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed, b2s_cloud* out);
+/* F0  o3d_slam::transform (keeps the near-identity duplication quirk)   src/helpers.cpp:273-305 */
+int32_t b2s_transform(b2s_handle* h, const b2s_cloud* in, const double T[16], b2s_cloud* out);
+/* S1  ScanToMapIcp::processForScanMatchingAndMerging          src/ScanToMapRegistration.cpp:42-54
+ *     raw scan -> merge_ (wide) and match_ (narrow); B2S_E_EMPTY when either is empty (checked lazily) */
+int32_t b2s_process_scan(b2s_handle* h, const b2s_cloud* raw, b2s_cloud* merge, b2s_cloud* match);
+/* R1  CloudRegistration::registerClouds (point-to-plane)      src/CloudRegistration.cpp:44-48 */
+int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double init[16], b2s_result* out);
+/* config 4: n independent registrations in one launch (PlaceRecognition.cpp:71,111 iterates them serially) */
+int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sources, const b2s_cloud* const* targets,
+                           const double* inits /* n x 16 */, b2s_result* out /* n */);
+/* host-pointer convenience form of R1 used by the C++ shim: uploads, registers, returns. */
+int32_t b2s_register_host(b2s_handle* h, const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_normals,
+                          size_t n_tgt, const double init[16], b2s_result* out);
+
+/* ---- submap (Submap::mapCloud_ / denseMap_)   include/open3d_slam/Submap.hpp:38-45 ----------------------- */
+int32_t b2s_submap_create(b2s_handle* h, size_t capacity_points, b2s_submap** out);
+void b2s_submap_destroy(b2s_submap* sm);
+/* F1  Submap::insertScan without carving: transform, append, voxelizeWithinCroppingVolume around the sensor
+ *     src/Submap.cpp:39-75, src/helpers.cpp:115-183 */
+int32_t b2s_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* preprocessed_scan, const double map_to_sensor[16]);
+/* F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert           src/Submap.cpp:77-92, src/Voxel.cpp:66-88 */
+int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
+                                const b2s_cropper* dense_cropper);
+/* Submap::getMapPointCloud (copy-out)                                       src/Submap.cpp:184-191 */
+int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n);
+int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, size_t capacity, size_t* n);
+int32_t b2s_submap_dense_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, int32_t* keys, size_t capacity,
+                                  size_t* n);
+int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* cloud);   /* load / initial map */
+/* S2  ScanToMapIcp::scanToMapRegistration: crop the map patch around the sensor, then R1
+ *     src/ScanToMapRegistration.cpp:55-62 */
+int32_t b2s_register_to_submap(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double map_to_sensor[16],
+                               const double init[16], b2s_result* out);
+
+/* ---- fused device-side chain for throughput runs: S1 -> S2 -> fitness gate -> F1, no host round trip.
+ *      Restates the steady-state branch of Mapper::addRangeMeasurement (src/Mapper.cpp:139-177) with the pose
+ *      prediction supplied by the caller.  The result is written to device memory and fetched with
+ *      b2s_scan_result_fetch after b2s_synchronize. ------------------------------------------------------------ */
+/* the pose state mapToRangeSensor_ lives on the device next to the map (Mapper.hpp mapToRangeSensor_/mapToRangeSensorPrev_) */
+int32_t b2s_submap_set_pose(b2s_handle* h, b2s_submap* sm, const double map_to_sensor[16]);
+int32_t b2s_submap_get_pose(b2s_handle* h, const b2s_submap* sm, double map_to_sensor[16]);
+/* one scan: guess = pose * odometry_motion (Mapper.cpp:130-137); S1; S2 around the pose state; gate
+ * (fitness < min_refinement_fitness rejects unless ignore_min_fitness, Mapper.cpp:151); accepted -> pose = result, F1. */
+int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double odometry_motion[16],
+                              double min_refinement_fitness, int32_t ignore_min_fitness, int32_t slot /* 0..255 */);
+int32_t b2s_scan_result_fetch(b2s_handle* h, int32_t slot, b2s_result* out);   /* synchronises */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI in include/b2s.h (open3d_slam_b200/libb2s.so).
+
+The CUDA library is the only implementation: if it is missing or no GPU is visible the calls fail loudly
+(there is no CPU fallback and nothing here imports oracle/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2s.so")
+
+OK, E_INVALID, E_CUDA, E_EMPTY, E_NO_NORMALS, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+CROP_NONE, CROP_MAX_RADIUS, CROP_MIN_RADIUS, CROP_MINMAX_RADIUS, CROP_CYLINDER = 0, 1, 2, 3, 4
+CROPPER_NAMES = {"None": 0, "MaxRadius": 1, "MinRadius": 2, "MinMaxRadius": 3, "Cylinder": 4}  # croppers.hpp cropperNames
+REG_POINT_TO_PLANE, REG_POINT_TO_POINT, REG_GENERALIZED = 0, 1, 2
+
+
+class Cropper(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("invert", C.c_int32), ("rmin", C.c_double), ("rmax", C.c_double),
+                ("zmin", C.c_double), ("zmax", C.c_double), ("center", C.c_double * 3)]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("reg_type", C.c_int32), ("max_iter", C.c_int32), ("max_corr_dist", C.c_double), ("knn", C.c_int32),
+                ("knn_radius", C.c_double), ("rel_fitness", C.c_double), ("rel_rmse", C.c_double)]
+
+
+class ScanParams(C.Structure):
+    _fields_ = [("voxel_size", C.c_double), ("downsampling_ratio", C.c_double), ("seed", C.c_uint32),
+                ("map_builder_cropper", Cropper), ("scan_matcher_cropper", Cropper)]
+
+
+class Config(C.Structure):
+    _fields_ = [("icp", IcpParams), ("scan", ScanParams), ("map_voxel_size", C.c_double), ("dense_voxel_size", C.c_double),
+                ("nn_cell_size", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("fitness", C.c_double), ("inlier_rmse", C.c_double), ("n_corr", C.c_int32),
+                ("iters", C.c_int32)]
+
+
+# every symbol include/b2s.h declares (checked by tests/test_abi.py without needing a GPU)
+SYMBOLS = [
+    "b2s_default_config", "b2s_create", "b2s_destroy", "b2s_set_config", "b2s_synchronize", "b2s_last_error", "b2s_version",
+    "b2s_device_count", "b2s_launch_count", "b2s_cloud_create", "b2s_cloud_destroy", "b2s_cloud_upload_f64", "b2s_cloud_upload_f32",
+    "b2s_cloud_size", "b2s_cloud_download", "b2s_cloud_copy", "b2s_crop", "b2s_voxel_down_sample", "b2s_estimate_normals",
+    "b2s_random_down_sample", "b2s_transform", "b2s_process_scan", "b2s_register", "b2s_register_batch", "b2s_register_host",
+    "b2s_submap_create", "b2s_submap_destroy", "b2s_submap_insert", "b2s_submap_insert_dense", "b2s_submap_size", "b2s_submap_download",
+    "b2s_submap_dense_download", "b2s_submap_set_cloud", "b2s_register_to_submap", "b2s_submap_set_pose", "b2s_submap_get_pose",
+    "b2s_mapper_step_async", "b2s_scan_result_fetch",
+]
+
+_lib = None
+
+
+class B2SError(RuntimeError):
+    """Mirrors the std::runtime_error the reference throws from assert_* / Open3D LogError."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"b2s error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
+                              "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.b2s_last_error.restype = C.c_char_p
+        L.b2s_version.restype = C.c_char_p
+        L.b2s_launch_count.restype = C.c_int64
+        L.b2s_launch_count.argtypes = [C.c_void_p]
+        L.b2s_destroy.restype = None
+        L.b2s_cloud_destroy.restype = None
+        L.b2s_submap_destroy.restype = None
+        L.b2s_default_config.restype = None
+        L.b2s_destroy.argtypes = [C.c_void_p]
+        L.b2s_cloud_destroy.argtypes = [C.c_void_p]
+        L.b2s_submap_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise B2SError(code, lib().b2s_last_error().decode("utf-8", "replace"))

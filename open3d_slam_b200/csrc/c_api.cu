@@ -1,0 +1,535 @@
+// c_api.cu -- the extern "C" boundary declared in include/b2s.h.  Host-side plumbing only: argument checks mirroring
+// the reference's asserts, device staging, kernel sequencing.  No arithmetic of the hot path runs on the host.
+#include <math.h>
+
+#include <new>
+
+#include "common.cuh"
+
+using namespace b2s;
+
+namespace b2s {
+int32_t pose_to_device(b2s_handle* h, const double* T, double* dst);
+int32_t dense_init(b2s_handle* h, b2s_submap* sm, size_t cap, double voxel);
+int32_t dense_to_cloud(b2s_handle* h, b2s_submap* sm, double* d_xyz, int32_t* d_keys, int32_t* d_out_n);
+
+__global__ void f32_to_f64_kernel(const unsigned char* __restrict__ src, size_t stride, int n, double* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
+    dst[3 * i] = (double)p[0]; dst[3 * i + 1] = (double)p[1]; dst[3 * i + 2] = (double)p[2];
+  }
+}
+
+__global__ void empty_check_kernel(const int32_t* a, const int32_t* b, uint32_t* status) {
+  if (*a <= 0 || *b <= 0) atomicOr(status, ST_EMPTY);
+}
+
+// guess = pose * odom ; (row-major 4x4)
+__global__ void compose_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
+  const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
+  if (threadIdx.x < 16) {
+    double s = 0.0;
+    for (int k = 0; k < 4; k++) s += A[4 * i + k] * B[4 * k + j];
+    C[4 * i + j] = s;
+  }
+}
+
+// Mapper::addRangeMeasurement fitness gate (core/src/Mapper.cpp:151-160): accept -> mapToRangeSensor_ = result
+__global__ void gate_kernel(const b2s_result* __restrict__ res, double min_fitness, int ignore_fitness, double* pose_state, int32_t* gate) {
+  if (threadIdx.x == 0) {
+    const bool ok = ignore_fitness || !(res->fitness < min_fitness);
+    *gate = ok ? 1 : 0;
+    if (ok) for (int i = 0; i < 16; i++) pose_state[i] = res->T[i];
+  }
+}
+
+static double nn_cell(const b2s_handle* h, double max_corr) {
+  if (h->cfg.nn_cell_size > 0.0) return h->cfg.nn_cell_size;
+  return max_corr * 0.5;
+}
+
+static int32_t check_icp_params(const b2s_icp_params& p) {
+  B2S_REQUIRE(p.reg_type == B2S_REG_POINT_TO_PLANE, B2S_E_UNSUPPORTED, "only PointToPlaneIcp is implemented on the device");
+  B2S_REQUIRE(p.max_corr_dist > 0.0, B2S_E_INVALID, "[RegistrationICP] Invalid max_correspondence_distance.");
+  B2S_REQUIRE(p.max_iter >= 0, B2S_E_INVALID, "max_iter must be >= 0");
+  return B2S_OK;
+}
+
+static void fill_problem(b2s_handle* h, IcpProblem* P, const b2s_cloud* src, const GridIndex* g, const double* init_host,
+                         const double* init_dev, double* work, b2s_result* out_dev) {
+  memset(P, 0, sizeof(*P));
+  P->src_xyz = src->xyz.as<double>();
+  P->src_n = src->dn.as<int32_t>();
+  P->ghdr = g->hdr.as<GridHeader>();
+  P->cell_start = grid_starts(g);
+  P->tgt_pts = g->pts.as<double>();
+  P->tgt_nrm = g->nrm.as<double>();
+  P->work_xyz = work;
+  P->init_dev = init_dev;
+  if (init_host) memcpy(P->init, init_host, 128);
+  P->max_corr = h->cfg.icp.max_corr_dist;
+  P->rel_fitness = h->cfg.icp.rel_fitness;
+  P->rel_rmse = h->cfg.icp.rel_rmse;
+  P->max_iter = h->cfg.icp.max_iter;
+  P->src_n_max = (int32_t)src->n_max;
+  P->out = out_dev;
+}
+
+static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud* merge, b2s_cloud* match) {
+  const b2s_scan_params& sp = h->cfg.scan;
+  b2s_cropper c0 = sp.map_builder_cropper;
+  c0.center[0] = c0.center[1] = c0.center[2] = 0.0;   // ScanToMapIcp's own cropper never gets a pose: sensor frame
+  CropDev wide = make_crop(&c0);
+  const bool has_crop = c0.kind != B2S_CROP_NONE || c0.invert;
+  if (sp.voxel_size > 0.0) B2S_TRY(op_voxel_down_sample(h, raw, has_crop ? &wide : nullptr, sp.voxel_size, h->t0));
+  else if (has_crop) B2S_TRY(op_crop(h, raw, wide, h->t0));
+  else B2S_TRY(op_voxel_down_sample(h, raw, nullptr, 0.0, h->t0));
+  B2S_TRY(op_estimate_normals(h, h->t0, h->cfg.icp.knn, h->cfg.icp.knn_radius, sp.voxel_size > 0.0 ? 4.0 * sp.voxel_size : 0.0));
+  B2S_TRY(op_random_down_sample(h, h->t0, sp.downsampling_ratio, sp.seed, merge));
+  b2s_cropper c1 = sp.scan_matcher_cropper;
+  c1.center[0] = c1.center[1] = c1.center[2] = 0.0;   // ScanToMapRegistration.cpp:47 setPose(Identity)
+  B2S_TRY(op_crop(h, merge, make_crop(&c1), match));
+  empty_check_kernel<<<1, 1, 0, h->stream>>>(merge->dn.as<int32_t>(), match->dn.as<int32_t>(), h->status.as<uint32_t>());
+  h->launches++;
+  return B2S_OK;
+}
+
+}  // namespace b2s
+
+#define LOCK(h) std::lock_guard<std::mutex> _lk((h)->mu); cudaSetDevice((h)->device)
+
+extern "C" {
+
+void b2s_default_config(b2s_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->icp.reg_type = B2S_REG_POINT_TO_PLANE;
+  cfg->icp.max_iter = 50; cfg->icp.max_corr_dist = 1.0; cfg->icp.knn = 20; cfg->icp.knn_radius = 3.0;
+  cfg->icp.rel_fitness = 1e-6; cfg->icp.rel_rmse = 1e-6;
+  cfg->scan.voxel_size = 0.1; cfg->scan.downsampling_ratio = 0.3; cfg->scan.seed = 0;
+  b2s_cropper c;
+  memset(&c, 0, sizeof(c));
+  c.kind = B2S_CROP_MINMAX_RADIUS; c.rmin = 2.0; c.rmax = 30.0; c.zmin = -50.0; c.zmax = 50.0;
+  cfg->scan.map_builder_cropper = c;
+  cfg->scan.scan_matcher_cropper = c;
+  cfg->map_voxel_size = 0.1;
+  cfg->dense_voxel_size = 0.05;
+  cfg->nn_cell_size = 0.0;
+}
+
+const char* b2s_last_error(void) { return get_error(); }
+const char* b2s_version(void) { return "b2s 0.1 (sm_100a, fp64)"; }
+int32_t b2s_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int64_t b2s_launch_count(const b2s_handle* h) { return h ? h->launches : 0; }
+
+int32_t b2s_create(const b2s_config* cfg, int32_t device, void* cuda_stream_or_null, b2s_handle** out) {
+  B2S_REQUIRE(out != nullptr, B2S_E_INVALID, "b2s_create: out is null");
+  int ndev = 0;
+  B2S_CUDA(cudaGetDeviceCount(&ndev));
+  B2S_REQUIRE(ndev > 0, B2S_E_CUDA, "no CUDA device visible: the b2s engine has no CPU fallback");
+  B2S_REQUIRE(device >= 0 && device < ndev, B2S_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+  B2S_CUDA(cudaSetDevice(device));
+  b2s_handle* h = new (std::nothrow) b2s_handle();
+  B2S_REQUIRE(h != nullptr, B2S_E_INVALID, "out of host memory");
+  h->device = device;
+  if (cfg) h->cfg = *cfg; else b2s_default_config(&h->cfg);
+  if (cuda_stream_or_null) { h->stream = (cudaStream_t)cuda_stream_or_null; h->own_stream = false; }
+  else { B2S_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+  B2S_TRY(h->status.ensure(64, h->stream));
+  B2S_CUDA(cudaMemsetAsync(h->status.p, 0, 64, h->stream));
+  B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream));
+  B2S_TRY(h->slots.ensure(256 * sizeof(b2s_result), h->stream));
+  B2S_CUDA(cudaMemsetAsync(h->slots.p, 0, 256 * sizeof(b2s_result), h->stream));
+  b2s_cloud** tmp[4] = {&h->t0, &h->t1, &h->t2, &h->t3};
+  for (int i = 0; i < 4; i++) { *tmp[i] = new b2s_cloud(); (*tmp[i])->h = h; B2S_TRY(cloud_reserve(h, *tmp[i], 1, true)); B2S_TRY(cloud_set_count(h, *tmp[i], 0)); }
+  *out = h;
+  return B2S_OK;
+}
+
+void b2s_destroy(b2s_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  b2s_cloud* tmp[4] = {h->t0, h->t1, h->t2, h->t3};
+  for (int i = 0; i < 4; i++) if (tmp[i]) { tmp[i]->xyz.release(); tmp[i]->nrm.release(); tmp[i]->dn.release(); delete tmp[i]; }
+  for (auto* g : h->batch_grids) { g->release(); delete g; }
+  h->grid_a.release(); h->grid_b.release();
+  DevBuf* bufs[] = {&h->status, &h->scan.state, &h->sort.hist, &h->sort.keys_alt, &h->sort.vals_alt, &h->keys, &h->vals, &h->flags, &h->offs,
+                    &h->tmp_i32, &h->tmp_f64, &h->misc, &h->work_xyz, &h->problems, &h->results, &h->slots, &h->poses};
+  for (DevBuf* b : bufs) b->release();
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t b2s_set_config(b2s_handle* h, const b2s_config* cfg) {
+  B2S_REQUIRE(h && cfg, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  h->cfg = *cfg;
+  return B2S_OK;
+}
+
+int32_t b2s_synchronize(b2s_handle* h) {
+  B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
+  LOCK(h);
+  return check_status(h);
+}
+
+// ---- clouds ----------------------------------------------------------------------------------------------------------
+int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out) {
+  B2S_REQUIRE(h && out, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  b2s_cloud* c = new (std::nothrow) b2s_cloud();
+  B2S_REQUIRE(c, B2S_E_INVALID, "out of host memory");
+  c->h = h;
+  B2S_TRY(cloud_reserve(h, c, 1, false));
+  B2S_TRY(cloud_set_count(h, c, 0));
+  *out = c;
+  return B2S_OK;
+}
+
+void b2s_cloud_destroy(b2s_cloud* c) {
+  if (!c) return;
+  if (c->h) { cudaSetDevice(c->h->device); cudaStreamSynchronize(c->h->stream); }
+  c->xyz.release(); c->nrm.release(); c->dn.release();
+  delete c;
+}
+
+int32_t b2s_cloud_upload_f64(b2s_handle* h, b2s_cloud* c, const double* xyz, const double* normals, size_t n) {
+  B2S_REQUIRE(h && c && (xyz || n == 0), B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(n < (size_t)0x7fffffff / 4, B2S_E_INVALID, "cloud too large");
+  LOCK(h);
+  B2S_TRY(cloud_reserve(h, c, n, normals != nullptr));
+  if (n) B2S_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  if (n && normals) B2S_CUDA(cudaMemcpyAsync(c->nrm.p, normals, n * 24, cudaMemcpyHostToDevice, h->stream));
+  c->has_normals = normals != nullptr;
+  return cloud_set_count(h, c, n);
+}
+
+int32_t b2s_cloud_upload_f32(b2s_handle* h, b2s_cloud* c, const void* xyz, size_t n, size_t stride_bytes) {
+  B2S_REQUIRE(h && c && (xyz || n == 0), B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, B2S_E_INVALID, "stride must be a multiple of 4 and >= 12");
+  B2S_REQUIRE(n < (size_t)0x7fffffff / 4, B2S_E_INVALID, "cloud too large");
+  LOCK(h);
+  B2S_TRY(cloud_reserve(h, c, n, false));
+  B2S_TRY(h->tmp_f64.ensure(n * stride_bytes + 16, h->stream));
+  if (n) {
+    B2S_CUDA(cudaMemcpyAsync(h->tmp_f64.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
+    f32_to_f64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->tmp_f64.as<unsigned char>(), stride_bytes, (int)n, c->xyz.as<double>());
+    h->launches++;
+  }
+  c->has_normals = false;
+  return cloud_set_count(h, c, n);
+}
+
+static int32_t cloud_count_sync(b2s_handle* h, const b2s_cloud* c, size_t* n) {
+  if (c->n_known >= 0) { *n = (size_t)c->n_known; return B2S_OK; }
+  int32_t v = 0;
+  B2S_CUDA(cudaMemcpyAsync(&v, c->dn.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  *n = (size_t)v;
+  const_cast<b2s_cloud*>(c)->n_known = v;
+  return B2S_OK;
+}
+
+int32_t b2s_cloud_size(b2s_handle* h, const b2s_cloud* c, size_t* n, int32_t* has_normals) {
+  B2S_REQUIRE(h && c && n, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  B2S_TRY(cloud_count_sync(h, c, n));
+  if (has_normals) *has_normals = c->has_normals ? 1 : 0;
+  return B2S_OK;
+}
+
+int32_t b2s_cloud_download(b2s_handle* h, const b2s_cloud* c, double* xyz, double* normals, size_t capacity, size_t* n_out) {
+  B2S_REQUIRE(h && c, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  size_t n = 0;
+  B2S_TRY(cloud_count_sync(h, c, &n));
+  if (n_out) *n_out = n;
+  B2S_REQUIRE(n <= capacity, B2S_E_CAPACITY, "download buffer too small: %zu points, capacity %zu", n, capacity);
+  if (n && xyz) B2S_CUDA(cudaMemcpyAsync(xyz, c->xyz.p, n * 24, cudaMemcpyDeviceToHost, h->stream));
+  if (n && normals) {
+    B2S_REQUIRE(c->has_normals, B2S_E_NO_NORMALS, "cloud has no normals");
+    B2S_CUDA(cudaMemcpyAsync(normals, c->nrm.p, n * 24, cudaMemcpyDeviceToHost, h->stream));
+  }
+  return check_status(h);
+}
+
+int32_t b2s_cloud_copy(b2s_handle* h, const b2s_cloud* src, b2s_cloud* dst) {
+  B2S_REQUIRE(h && src && dst, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  return op_voxel_down_sample(h, src, nullptr, 0.0, dst);
+}
+
+// ---- stages ----------------------------------------------------------------------------------------------------------
+int32_t b2s_crop(b2s_handle* h, const b2s_cloud* in, const b2s_cropper* cropper, b2s_cloud* out) {
+  B2S_REQUIRE(h && in && cropper && out && in != out, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  return op_crop(h, in, make_crop(cropper), out);
+}
+
+int32_t b2s_voxel_down_sample(b2s_handle* h, const b2s_cloud* in, double voxel_size, b2s_cloud* out) {
+  B2S_REQUIRE(h && in && out && in != out, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  return op_voxel_down_sample(h, in, nullptr, voxel_size, out);
+}
+
+int32_t b2s_estimate_normals(b2s_handle* h, b2s_cloud* cloud, int32_t knn, double radius) {
+  B2S_REQUIRE(h && cloud, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  return op_estimate_normals(h, cloud, knn, radius, h->cfg.scan.voxel_size > 0.0 ? 4.0 * h->cfg.scan.voxel_size : 0.0);
+}
+
+int32_t b2s_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed, b2s_cloud* out) {
+  B2S_REQUIRE(h && in && out && in != out, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  return op_random_down_sample(h, in, ratio, seed, out);
+}
+
+int32_t b2s_transform(b2s_handle* h, const b2s_cloud* in, const double T[16], b2s_cloud* out) {
+  B2S_REQUIRE(h && in && out && T && in != out, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  return op_transform(h, in, T, out);
+}
+
+int32_t b2s_process_scan(b2s_handle* h, const b2s_cloud* raw, b2s_cloud* merge, b2s_cloud* match) {
+  B2S_REQUIRE(h && raw && merge && match && merge != match && raw != merge && raw != match, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  return process_scan_impl(h, raw, merge, match);
+}
+
+int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double init[16], b2s_result* out) {
+  B2S_REQUIRE(h && source && target && init && out, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  B2S_TRY(check_icp_params(h->cfg.icp));
+  B2S_REQUIRE(target->has_normals, B2S_E_NO_NORMALS, "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
+  B2S_TRY(grid_build(h, &h->grid_a, target, nn_cell(h, h->cfg.icp.max_corr_dist), nullptr, true));
+  B2S_TRY(h->work_xyz.ensure((source->n_max + 1) * 24, h->stream));
+  B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
+  B2S_TRY(h->results.ensure(sizeof(b2s_result), h->stream));
+  IcpProblem P;
+  fill_problem(h, &P, source, &h->grid_a, init, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
+  B2S_CUDA(cudaMemcpyAsync(h->problems.p, &P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
+  B2S_TRY(icp_launch(h, h->problems.as<IcpProblem>(), 1, source->n_max));
+  B2S_CUDA(cudaMemcpyAsync(out, h->results.p, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sources, const b2s_cloud* const* targets, const double* inits,
+                           b2s_result* out) {
+  B2S_REQUIRE(h && sources && targets && inits && out && n >= 0, B2S_E_INVALID, "bad argument");
+  if (n == 0) return B2S_OK;
+  LOCK(h);
+  B2S_TRY(check_icp_params(h->cfg.icp));
+  std::vector<IcpProblem> probs((size_t)n);
+  std::vector<const b2s_cloud*> seen;  // targets shared by several pairs are indexed once
+  std::vector<int> grid_of((size_t)n);
+  size_t work_total = 0, max_src = 0;
+  for (int i = 0; i < n; i++) {
+    B2S_REQUIRE(sources[i] && targets[i], B2S_E_INVALID, "null cloud in batch");
+    B2S_REQUIRE(targets[i]->has_normals, B2S_E_NO_NORMALS, "[RegistrationICP] target %d has no normals", i);
+    int gi = -1;
+    for (size_t k = 0; k < seen.size(); k++) if (seen[k] == targets[i]) { gi = (int)k; break; }
+    if (gi < 0) {
+      gi = (int)seen.size();
+      seen.push_back(targets[i]);
+      if (h->batch_grids.size() <= (size_t)gi) h->batch_grids.push_back(new GridIndex());
+      B2S_TRY(grid_build(h, h->batch_grids[gi], targets[i], nn_cell(h, h->cfg.icp.max_corr_dist), nullptr, true));
+    }
+    grid_of[i] = gi;
+    work_total += sources[i]->n_max + 1;
+    if (sources[i]->n_max > max_src) max_src = sources[i]->n_max;
+  }
+  B2S_TRY(h->work_xyz.ensure(work_total * 24, h->stream));
+  B2S_TRY(h->problems.ensure(sizeof(IcpProblem) * (size_t)n, h->stream));
+  B2S_TRY(h->results.ensure(sizeof(b2s_result) * (size_t)n, h->stream));
+  size_t woff = 0;
+  for (int i = 0; i < n; i++) {
+    fill_problem(h, &probs[i], sources[i], h->batch_grids[grid_of[i]], inits + 16 * (size_t)i, nullptr, h->work_xyz.as<double>() + 3 * woff,
+                 h->results.as<b2s_result>() + i);
+    woff += sources[i]->n_max + 1;
+  }
+  B2S_CUDA(cudaMemcpyAsync(h->problems.p, probs.data(), sizeof(IcpProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));  // probs lives on the host stack frame
+  B2S_TRY(icp_launch(h, h->problems.as<IcpProblem>(), n, max_src));
+  B2S_CUDA(cudaMemcpyAsync(out, h->results.p, sizeof(b2s_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int32_t b2s_register_host(b2s_handle* h, const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_normals, size_t n_tgt,
+                          const double init[16], b2s_result* out) {
+  B2S_REQUIRE(h && init && out, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(tgt_normals != nullptr, B2S_E_NO_NORMALS, "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
+  B2S_TRY(b2s_cloud_upload_f64(h, h->t2, src_xyz, nullptr, n_src));
+  B2S_TRY(b2s_cloud_upload_f64(h, h->t3, tgt_xyz, tgt_normals, n_tgt));
+  return b2s_register(h, h->t2, h->t3, init, out);
+}
+
+// ---- submap ----------------------------------------------------------------------------------------------------------
+int32_t b2s_submap_create(b2s_handle* h, size_t capacity_points, b2s_submap** out) {
+  B2S_REQUIRE(h && out && capacity_points > 0, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  b2s_submap* sm = new (std::nothrow) b2s_submap();
+  B2S_REQUIRE(sm, B2S_E_INVALID, "out of host memory");
+  sm->h = h;
+  sm->capacity = capacity_points;
+  for (int i = 0; i < 2; i++) {
+    sm->cloud[i] = new b2s_cloud();
+    sm->cloud[i]->h = h;
+    B2S_TRY(cloud_reserve(h, sm->cloud[i], capacity_points, true));
+    B2S_TRY(cloud_set_count(h, sm->cloud[i], 0));
+    sm->cloud[i]->has_normals = true;
+  }
+  B2S_TRY(sm->pose.ensure(4 * 16 * 8, h->stream));
+  const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  B2S_TRY(pose_to_device(h, I, sm->pose.as<double>()));
+  *out = sm;
+  return B2S_OK;
+}
+
+void b2s_submap_destroy(b2s_submap* sm) {
+  if (!sm) return;
+  if (sm->h) { cudaSetDevice(sm->h->device); cudaStreamSynchronize(sm->h->stream); }
+  for (int i = 0; i < 2; i++) if (sm->cloud[i]) { sm->cloud[i]->xyz.release(); sm->cloud[i]->nrm.release(); sm->cloud[i]->dn.release(); delete sm->cloud[i]; }
+  sm->dense_keys.release(); sm->dense_sum.release(); sm->dense_cnt.release(); sm->dense_used.release(); sm->pose.release();
+  delete sm;
+}
+
+int32_t b2s_submap_set_pose(b2s_handle* h, b2s_submap* sm, const double T[16]) {
+  B2S_REQUIRE(h && sm && T, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  return pose_to_device(h, T, sm->pose.as<double>());
+}
+
+int32_t b2s_submap_get_pose(b2s_handle* h, const b2s_submap* sm, double T[16]) {
+  B2S_REQUIRE(h && sm && T, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  B2S_CUDA(cudaMemcpyAsync(T, sm->pose.p, 128, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int32_t b2s_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double T[16]) {
+  B2S_REQUIRE(h && sm && scan && T, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  double* Td = sm->pose.as<double>() + 16;  // slot 1: pose used by this insertion
+  B2S_TRY(pose_to_device(h, T, Td));
+  return op_submap_insert(h, sm, scan, Td, nullptr);
+}
+
+int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double T[16], const b2s_cropper* crop) {
+  B2S_REQUIRE(h && sm && raw && T, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  if (sm->dense_cap == 0) {
+    B2S_REQUIRE(h->cfg.dense_voxel_size > 0.0, B2S_E_INVALID, "dense_voxel_size must be > 0");
+    B2S_TRY(dense_init(h, sm, (size_t)1 << 22, h->cfg.dense_voxel_size));
+  }
+  return op_dense_insert(h, sm, raw, T, crop);
+}
+
+int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n) {
+  B2S_REQUIRE(h && sm && n, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  sm->cloud[0]->n_known = -1;
+  return cloud_count_sync(h, sm->cloud[0], n);
+}
+
+int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, size_t capacity, size_t* n_out) {
+  B2S_REQUIRE(h && sm, B2S_E_INVALID, "null argument");
+  sm->cloud[0]->n_known = -1;
+  return b2s_cloud_download(h, sm->cloud[0], xyz, normals, capacity, n_out);
+}
+
+int32_t b2s_submap_dense_download(b2s_handle* h, const b2s_submap* sm_c, double* xyz, double* normals, int32_t* keys, size_t capacity,
+                                  size_t* n_out) {
+  B2S_REQUIRE(h && sm_c, B2S_E_INVALID, "null argument");
+  (void)normals;
+  b2s_submap* sm = const_cast<b2s_submap*>(sm_c);
+  LOCK(h);
+  if (sm->dense_cap == 0) { if (n_out) *n_out = 0; return B2S_OK; }
+  B2S_TRY(h->tmp_f64.ensure(sm->dense_cap * 24 + 64, h->stream));
+  B2S_TRY(h->tmp_i32.ensure(sm->dense_cap * 12 + 64, h->stream));
+  int32_t* d_keys = h->tmp_i32.as<int32_t>() + 16;
+  int32_t* d_n = h->tmp_i32.as<int32_t>();
+  B2S_TRY(dense_to_cloud(h, sm, h->tmp_f64.as<double>(), d_keys, d_n));
+  int32_t n = 0;
+  B2S_CUDA(cudaMemcpyAsync(&n, d_n, 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_out) *n_out = (size_t)n;
+  B2S_REQUIRE((size_t)n <= capacity, B2S_E_CAPACITY, "download buffer too small");
+  if (n && xyz) B2S_CUDA(cudaMemcpyAsync(xyz, h->tmp_f64.p, (size_t)n * 24, cudaMemcpyDeviceToHost, h->stream));
+  if (n && keys) B2S_CUDA(cudaMemcpyAsync(keys, d_keys, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* cloud) {
+  B2S_REQUIRE(h && sm && cloud, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(cloud->has_normals, B2S_E_NO_NORMALS, "map cloud needs normals");
+  B2S_REQUIRE(cloud->n_max <= sm->capacity, B2S_E_CAPACITY, "cloud larger than the submap capacity");
+  LOCK(h);
+  b2s_cloud* m = sm->cloud[0];
+  if (cloud->n_max) {
+    B2S_CUDA(cudaMemcpyAsync(m->xyz.p, cloud->xyz.p, cloud->n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(m->nrm.p, cloud->nrm.p, cloud->n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  B2S_CUDA(cudaMemcpyAsync(m->dn.p, cloud->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+  m->n_max = cloud->n_max; m->n_known = cloud->n_known; m->has_normals = true;
+  return B2S_OK;
+}
+
+static int32_t register_to_submap_async(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double* sensor_pose_host,
+                                        const double* sensor_pose_dev, const double* init_host, const double* init_dev, b2s_result* out_dev) {
+  B2S_TRY(check_icp_params(h->cfg.icp));
+  const b2s_cloud* map = sm->cloud[0];
+  b2s_cropper c = h->cfg.scan.scan_matcher_cropper;  // ScanToMapRegistration.cpp:58 setPose(mapToRangeSensor)
+  if (sensor_pose_host) { c.center[0] = sensor_pose_host[3]; c.center[1] = sensor_pose_host[7]; c.center[2] = sensor_pose_host[11]; }
+  CropDev patch = make_crop(&c, sensor_pose_dev);
+  B2S_TRY(grid_build(h, &h->grid_a, map, nn_cell(h, h->cfg.icp.max_corr_dist), &patch, true));
+  B2S_TRY(h->work_xyz.ensure((scan->n_max + 1) * 24, h->stream));
+  B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
+  IcpProblem P;
+  fill_problem(h, &P, scan, &h->grid_a, init_host, init_dev, h->work_xyz.as<double>(), out_dev);
+  B2S_CUDA(cudaMemcpyAsync(h->problems.p, &P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
+  return icp_launch(h, h->problems.as<IcpProblem>(), 1, scan->n_max);
+}
+
+int32_t b2s_register_to_submap(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double map_to_sensor[16],
+                               const double init[16], b2s_result* out) {
+  B2S_REQUIRE(h && scan && sm && map_to_sensor && init && out, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  B2S_TRY(h->results.ensure(sizeof(b2s_result), h->stream));
+  B2S_TRY(register_to_submap_async(h, scan, sm, map_to_sensor, nullptr, init, nullptr, h->results.as<b2s_result>()));
+  B2S_CUDA(cudaMemcpyAsync(out, h->results.p, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
+  GridHeader gh;
+  B2S_CUDA(cudaMemcpyAsync(&gh, h->grid_a.hdr.p, sizeof(gh), cudaMemcpyDeviceToHost, h->stream));
+  B2S_TRY(check_status(h));
+  B2S_REQUIRE(gh.n > 0, B2S_E_EMPTY, "map patch size is zero");  // ScanToMapRegistration.cpp:60
+  return B2S_OK;
+}
+
+int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double odometry_motion[16],
+                              double min_refinement_fitness, int32_t ignore_min_fitness, int32_t slot) {
+  B2S_REQUIRE(h && sm && raw_scan && odometry_motion, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(slot >= 0 && slot < 256, B2S_E_INVALID, "slot out of range");
+  LOCK(h);
+  double* pose_state = sm->pose.as<double>();        // mapToRangeSensor_ (== mapToRangeSensorPrev_ in steady state)
+  double* odom = pose_state + 32;
+  double* guess = pose_state + 48;
+  int32_t* gate = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 4);
+  b2s_result* res = h->slots.as<b2s_result>() + slot;
+  B2S_TRY(process_scan_impl(h, raw_scan, h->t1, h->t2));                      // Mapper.cpp:139
+  B2S_TRY(pose_to_device(h, odometry_motion, odom));
+  compose_kernel<<<1, 32, 0, h->stream>>>(pose_state, odom, guess);           // Mapper.cpp:130-137
+  h->launches++;
+  B2S_TRY(register_to_submap_async(h, h->t2, sm, nullptr, pose_state, nullptr, guess, res));  // Mapper.cpp:140-141
+  gate_kernel<<<1, 32, 0, h->stream>>>(res, min_refinement_fitness, ignore_min_fitness, pose_state, gate);  // Mapper.cpp:151-160
+  h->launches++;
+  return op_submap_insert(h, sm, h->t1, pose_state, gate);                   // Mapper.cpp:174
+}
+
+int32_t b2s_scan_result_fetch(b2s_handle* h, int32_t slot, b2s_result* out) {
+  B2S_REQUIRE(h && out && slot >= 0 && slot < 256, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  B2S_CUDA(cudaMemcpyAsync(out, h->slots.as<b2s_result>() + slot, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+}  // extern "C"

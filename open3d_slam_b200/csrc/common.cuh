@@ -1,0 +1,303 @@
+// common.cuh -- shared device helpers and the host-side runtime types of the b2s engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2s.h"
+
+namespace b2s {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: no exception crosses the C ABI; the message is kept per host thread
+// ------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define B2S_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::b2s::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return B2S_E_CUDA;                                                                          \
+    }                                                                                             \
+  } while (0)
+
+#define B2S_TRY(expr)              \
+  do {                             \
+    int32_t _s = (expr);           \
+    if (_s != B2S_OK) return _s;   \
+  } while (0)
+
+#define B2S_REQUIRE(cond, code, ...)     \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::b2s::set_error(__VA_ARGS__);     \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// grow-only device buffer
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int32_t ensure(size_t bytes, cudaStream_t s, bool preserve = false);
+  void release();
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// device-side status word: kernels OR error bits into it, the host checks it when it synchronises
+enum : uint32_t { ST_KEY_OVERFLOW = 1u, ST_CAPACITY = 2u, ST_EMPTY = 4u, ST_HASH_FULL = 8u };
+
+struct GridHeader {      // one per nearest-neighbour grid, lives in device memory
+  double origin[3];
+  double cell, inv_cell;
+  int32_t dims[3];
+  int32_t ncell;
+  int32_t n;             // points indexed
+  int32_t pad;
+};
+
+// dense-grid nearest-neighbour index over a point set (K-index): points counting-sorted by cell
+struct GridIndex {
+  DevBuf hdr;            // GridHeader
+  DevBuf bbox;           // 6 x uint64 ordered-double min/max
+  DevBuf cell_start;     // int32 [cap_cells + 1]
+  DevBuf rank;           // int32 per point: rank within its cell (-1 = not indexed)
+  DevBuf pts;            // double4 per indexed point: x,y,z, bits(original index)
+  DevBuf nrm;            // double4 per indexed point: nx,ny,nz,0
+  int32_t cap_cells = 0;
+  void release();
+};
+
+struct ScanScratch {     // decoupled look-back scan state
+  DevBuf state;          // uint64 per tile + int32 tile counter
+  int32_t cap_tiles = 0;
+};
+
+struct SortScratch {
+  DevBuf hist;           // 256 x nblocks int32
+  DevBuf keys_alt, vals_alt;
+};
+
+}  // namespace b2s
+
+struct b2s_cloud {
+  b2s_handle* h = nullptr;
+  b2s::DevBuf xyz;       // 3 x f64 per point (the reference's AoS layout)
+  b2s::DevBuf nrm;       // 3 x f64 per point
+  b2s::DevBuf dn;        // int32 device-side point count
+  size_t n_max = 0;      // host-side upper bound of the count (launch sizing)
+  long long n_known = 0; // exact count when the host knows it, -1 otherwise
+  bool has_normals = false;
+};
+
+struct b2s_submap {
+  b2s_handle* h = nullptr;
+  b2s_cloud* cloud[2] = {nullptr, nullptr};  // ping-pong map cloud (mapCloud_)
+  int cur = 0;
+  size_t capacity = 0;
+  // dense map (VoxelizedPointCloud): open-addressing hash of running sums
+  b2s::DevBuf dense_keys;    // uint64 packed key, EMPTY = ~0
+  b2s::DevBuf dense_sum;     // 6 x f64 per slot
+  b2s::DevBuf dense_cnt;     // int32 per slot
+  b2s::DevBuf dense_used;    // int32 occupied-slot counter
+  size_t dense_cap = 0;
+  double dense_voxel = 0.0;
+  bool dense_has_normals = false;
+  b2s::DevBuf pose;          // 4 x (4x4 f64): [0] mapToRangeSensor_ state, [1] insertion pose, [2] odometry motion, [3] initial guess
+};
+
+struct b2s_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::mutex mu;
+  b2s_config cfg;
+  int64_t launches = 0;
+
+  b2s::DevBuf status;                 // uint32 device status word
+  b2s::ScanScratch scan;
+  b2s::SortScratch sort;
+  b2s::GridIndex grid_a, grid_b;      // target index (ICP) / self index (normals)
+  // generic scratch buffers, by role
+  b2s::DevBuf keys, vals, flags, offs, tmp_i32, tmp_f64, misc, work_xyz;
+  b2s::DevBuf problems;               // IcpProblem array (device)
+  b2s::DevBuf results;                // b2s_result array (device)
+  b2s::DevBuf slots;                  // per-slot results for the async mapper step
+  b2s::DevBuf poses;                  // small device-resident transforms
+  void* pinned = nullptr;             // pinned host staging
+  size_t pinned_cap = 0;
+  // temporaries for the fused chains
+  b2s_cloud* t0 = nullptr; b2s_cloud* t1 = nullptr; b2s_cloud* t2 = nullptr; b2s_cloud* t3 = nullptr;
+  std::vector<b2s::GridIndex*> batch_grids;
+};
+
+namespace b2s {
+
+int32_t ensure_pinned(b2s_handle* h, size_t bytes);
+int32_t check_status(b2s_handle* h);     // synchronises and converts device status bits into an error
+
+// ---- primitives (scan.cu / radix_sort.cu / grid_index.cu / ...) : all asynchronous on h->stream ----
+// exclusive scan of in[0..*d_n) into out[0..*d_n]; out[*d_n] and *d_total (optional) receive the total
+int32_t scan_exclusive_i32(b2s_handle* h, const int32_t* in, int32_t* out, const int32_t* d_n, size_t n_max, int32_t* d_total);
+// stable LSD radix sort of (key, value) pairs, key_bits low bits significant; result ends in keys/vals
+// (pointers are swapped so that keys/vals designate the sorted arrays on return, *_alt the scratch)
+int32_t radix_sort_pairs_u32(b2s_handle* h, uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, uint32_t*& vals_alt,
+                             const int32_t* d_n, size_t n_max, int key_bits);
+int32_t radix_sort_pairs_u64(b2s_handle* h, uint64_t*& keys, uint32_t*& vals, uint64_t*& keys_alt, uint32_t*& vals_alt,
+                             const int32_t* d_n, size_t n_max, int key_bits);
+inline const int32_t* grid_starts(const GridIndex* g) { return g->cell_start.as<int32_t>() + g->cap_cells + 2; }
+
+// K-index: build the NN grid over cloud points (optionally only those inside `patch`, centre read from device pose)
+struct CropDev {      // cropper passed by value to kernels; centre may come from a device-resident 4x4 (row-major)
+  int32_t kind, invert;
+  double rmin, rmax, zmin, zmax;
+  double cx, cy, cz;
+  const double* pose_dev;   // if non-null the centre is (pose[3], pose[7], pose[11])
+};
+CropDev make_crop(const b2s_cropper* c, const double* pose_dev = nullptr);
+int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double cell, const CropDev* patch, bool with_normals);
+
+int32_t cloud_reserve(b2s_handle* h, b2s_cloud* c, size_t n, bool normals);
+int32_t cloud_set_count(b2s_handle* h, b2s_cloud* c, size_t n);
+
+// stages
+int32_t op_crop(b2s_handle* h, const b2s_cloud* in, const CropDev& crop, b2s_cloud* out);
+int32_t op_voxel_down_sample(b2s_handle* h, const b2s_cloud* in, const CropDev* crop, double voxel, b2s_cloud* out);
+int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius, double cell_hint);
+int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed, b2s_cloud* out);
+int32_t op_transform(b2s_handle* h, const b2s_cloud* in, const double* T_host, b2s_cloud* out);
+
+struct IcpProblem {
+  const double* src_xyz;
+  const int32_t* src_n;
+  const GridHeader* ghdr;
+  const int32_t* cell_start;
+  const double* tgt_pts;    // double4
+  const double* tgt_nrm;    // double4
+  double* work_xyz;         // global working copy of the source (used when it does not fit in shared memory)
+  const double* init_dev;   // optional device-resident init (overrides init)
+  double init[16];
+  double max_corr;
+  double rel_fitness, rel_rmse;
+  int32_t max_iter;
+  int32_t src_n_max;
+  b2s_result* out;
+};
+int32_t icp_launch(b2s_handle* h, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
+
+int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev);
+int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const b2s_cropper* crop);
+
+inline int grid_for(size_t n, int threads, int max_blocks = 148 * 16) {
+  size_t b = (n + (size_t)threads - 1) / (size_t)threads;
+  if (b < 1) b = 1;
+  if (b > (size_t)max_blocks) b = (size_t)max_blocks;
+  return (int)b;
+}
+
+}  // namespace b2s
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace b2s {
+
+// order-preserving map double -> uint64 so that atomicMin/atomicMax work on doubles
+__host__ __device__ inline unsigned long long ord_encode(double v) {
+  unsigned long long u;
+#ifdef __CUDA_ARCH__
+  u = (unsigned long long)__double_as_longlong(v);
+#else
+  memcpy(&u, &v, 8);
+#endif
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ inline double ord_decode(unsigned long long u) {
+  u = (u & 0x8000000000000000ull) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double v; memcpy(&v, &u, 8); return v;
+#endif
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// squared distance accumulated exactly like nanoflann's L2 adaptor and the oracle: (dx*dx + dy*dy) + dz*dz,
+// with explicit round-to-nearest ops so that nvcc never contracts it into FMAs (keeps argmin / strict radius
+// decisions bit-identical to the CPU oracle)
+__device__ __forceinline__ double dist2_exact(double ax, double ay, double az, double bx, double by, double bz) {
+  double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// reference croppers (core/src/croppers.cpp:121-165); only the translation of the pose is used
+__device__ __forceinline__ bool crop_within(const CropDev& c, double x, double y, double z) {
+  double cx = c.cx, cy = c.cy, cz = c.cz;
+  if (c.pose_dev) { cx = c.pose_dev[3]; cy = c.pose_dev[7]; cz = c.pose_dev[11]; }
+  double dx = __dsub_rn(x, cx), dy = __dsub_rn(y, cy), dz = __dsub_rn(z, cz);
+  bool w = true;
+  switch (c.kind) {
+    case B2S_CROP_MAX_RADIUS: w = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))) <= c.rmax; break;
+    case B2S_CROP_MIN_RADIUS: w = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz))) >= c.rmin; break;
+    case B2S_CROP_MINMAX_RADIUS: {
+      double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+      w = d <= c.rmax && d >= c.rmin;
+      break;
+    }
+    case B2S_CROP_CYLINDER: w = z >= c.zmin && z <= c.zmax && sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) <= c.rmax; break;
+    default: w = true;
+  }
+  return c.invert ? !w : w;
+}
+
+// 3 x 10-bit (u32) and 3 x 21-bit (u64) Morton interleave
+__device__ __forceinline__ uint32_t morton_part10(uint32_t x) {
+  x &= 0x3FFu;
+  x = (x | (x << 16)) & 0x030000FFu;
+  x = (x | (x << 8)) & 0x0300F00Fu;
+  x = (x | (x << 4)) & 0x030C30C3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__device__ __forceinline__ uint64_t morton_part21(uint64_t x) {
+  x &= 0x1FFFFFull;
+  x = (x | (x << 32)) & 0x1F00000000FFFFull;
+  x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+}  // namespace b2s
+#endif

@@ -1,0 +1,357 @@
+// fuse.cu -- K-fuse (F0+F1) and K-dense (F3): the map side of the hot path.
+//
+//   F1  Submap::insertScan (no carving)        core/src/Submap.cpp:39-75
+//         transform(T, scan)                   core/src/helpers.cpp:273-305   (duplication quirk when T ~ identity)
+//         mapCloud_ += scan
+//         voxelizeWithinCroppingVolume(...)    core/src/helpers.cpp:115-183   (+ AccumulatedPoint :30-70)
+//   F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert   core/src/Submap.cpp:77-92, core/src/Voxel.cpp:66-88
+//
+// F1 on the device keeps the reference's semantics exactly: the transformed scan is appended to the map arrays, every
+// point inside the map-builder cropper (centred on the sensor) is keyed by floor(p * (1/v)) on the GLOBAL-origin grid,
+// a stable radix sort groups voxel members in map order, one thread per voxel averages them in that order (an old
+// map point counts as ONE member; normals: mean of non-NaN then normalized()), points outside the cropper pass
+// through untouched.  The result is committed back into the map arrays only when the (device-resident) gate is open,
+// which is how the fitness gate of Mapper::addRangeMeasurement (core/src/Mapper.cpp:151) runs without a host sync.
+// Output order: voxels in Morton order of (key - base), then pass-through points (the reference: pass-through first,
+// then std::unordered_map order -- unspecified, nothing downstream depends on it).
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int FZ_THREADS = 256;
+
+int32_t pose_to_device(b2s_handle* h, const double* T, double* dst);  // voxel.cu
+
+// append (optionally duplicated) transformed scan to the map arrays; writes the total into *d_tot
+__global__ void __launch_bounds__(FZ_THREADS) fuse_append_kernel(double* __restrict__ mxyz, double* __restrict__ mnrm,
+                                                                 const int32_t* __restrict__ d_nmap, const double* __restrict__ sxyz,
+                                                                 const double* __restrict__ snrm, const int32_t* __restrict__ d_nscan,
+                                                                 const double* __restrict__ Tdev, const int32_t* __restrict__ gate,
+                                                                 size_t capacity, int32_t* d_tot, uint32_t* status) {
+  const int nmap = *d_nmap;
+  int ns = *d_nscan;
+  const bool open = (gate == nullptr || *gate != 0) && ns > 0;  // Submap.cpp:41-43: empty scan -> nothing happens
+  if (!open) { if (blockIdx.x == 0 && threadIdx.x == 0) *d_tot = 0; return; }
+  double T[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) T[i] = Tdev[i];
+  double mx = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) mx = fmax(mx, fabs(T[i] - ((i % 5 == 0) ? 1.0 : 0.0)));
+  const bool ident = mx < 1e-4;  // helpers.cpp:275
+  const size_t total = (size_t)nmap + (size_t)(ident ? 2 : 1) * (size_t)ns;
+  if (total > capacity) { if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(status, ST_CAPACITY); *d_tot = 0; } return; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *d_tot = (int32_t)total;
+  const size_t b0 = (size_t)nmap, b1 = b0 + (ident ? (size_t)ns : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+    const double px = sxyz[3 * i], py = sxyz[3 * i + 1], pz = sxyz[3 * i + 2];
+    const double a = snrm[3 * i], b = snrm[3 * i + 1], c = snrm[3 * i + 2];
+    if (ident) {
+      mxyz[3 * (b0 + i)] = px; mxyz[3 * (b0 + i) + 1] = py; mxyz[3 * (b0 + i) + 2] = pz;
+      mnrm[3 * (b0 + i)] = a; mnrm[3 * (b0 + i) + 1] = b; mnrm[3 * (b0 + i) + 2] = c;
+    }
+    const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
+    const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], px), __dmul_rn(T[5], py)), __dmul_rn(T[6], pz)), T[7]);
+    const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], px), __dmul_rn(T[9], py)), __dmul_rn(T[10], pz)), T[11]);
+    const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[12], px), __dmul_rn(T[13], py)), __dmul_rn(T[14], pz)), T[15]);
+    const size_t o = b1 + i;
+    mxyz[3 * o] = __ddiv_rn(x, w); mxyz[3 * o + 1] = __ddiv_rn(y, w); mxyz[3 * o + 2] = __ddiv_rn(z, w);
+    mnrm[3 * o] = __dadd_rn(__dadd_rn(__dmul_rn(T[0], a), __dmul_rn(T[1], b)), __dmul_rn(T[2], c));
+    mnrm[3 * o + 1] = __dadd_rn(__dadd_rn(__dmul_rn(T[4], a), __dmul_rn(T[5], b)), __dmul_rn(T[6], c));
+    mnrm[3 * o + 2] = __dadd_rn(__dadd_rn(__dmul_rn(T[8], a), __dmul_rn(T[9], b)), __dmul_rn(T[10], c));
+  }
+}
+
+template <typename K>
+__device__ __forceinline__ K morton3f(uint32_t x, uint32_t y, uint32_t z);
+template <>
+__device__ __forceinline__ uint32_t morton3f<uint32_t>(uint32_t x, uint32_t y, uint32_t z) {
+  return morton_part10(x) | (morton_part10(y) << 1) | (morton_part10(z) << 2);
+}
+template <>
+__device__ __forceinline__ uint64_t morton3f<uint64_t>(uint32_t x, uint32_t y, uint32_t z) {
+  return morton_part21(x) | (morton_part21(y) << 1) | (morton_part21(z) << 2);
+}
+
+// key = Morton(floor(p * inv) - base) for points inside the cropper, sentinel otherwise.
+// base: bounded cropper -> floor((centre - rmax) * inv) - 1 per axis; unbounded -> -2^20 (21-bit keys).
+template <typename K>
+__global__ void __launch_bounds__(FZ_THREADS) fuse_keys_kernel(const double* __restrict__ mxyz, const int32_t* __restrict__ d_tot,
+                                                               CropDev crop, double inv, int bits, int bounded,
+                                                               K* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* status) {
+  const int n = *d_tot;
+  const K invalid = (K)1 << (3 * bits);
+  double bx, by, bz;
+  if (bounded) {
+    double cx = crop.cx, cy = crop.cy, cz = crop.cz;
+    if (crop.pose_dev) { cx = crop.pose_dev[3]; cy = crop.pose_dev[7]; cz = crop.pose_dev[11]; }
+    bx = floor((cx - crop.rmax) * inv) - 1.0; by = floor((cy - crop.rmax) * inv) - 1.0; bz = floor((cz - crop.rmax) * inv) - 1.0;
+  } else { bx = by = bz = -1048576.0; }
+  const double lim = (double)(1u << bits);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double x = mxyz[3 * i], y = mxyz[3 * i + 1], z = mxyz[3 * i + 2];
+    K key = invalid;
+    if (crop_within(crop, x, y, z)) {
+      // getVoxelIdx(p, invVoxelSize): int(floor(p * invSize))   VoxelHashMap.hpp:47-50
+      const double fx = floor(__dmul_rn(x, inv)) - bx, fy = floor(__dmul_rn(y, inv)) - by, fz = floor(__dmul_rn(z, inv)) - bz;
+      if (fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < lim && fy < lim && fz < lim) key = morton3f<K>((uint32_t)fx, (uint32_t)fy, (uint32_t)fz);
+      else atomicOr(status, ST_KEY_OVERFLOW);
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(FZ_THREADS) fuse_head_kernel(const K* __restrict__ keys, const int32_t* __restrict__ d_tot, int bits,
+                                                               int32_t* __restrict__ head) {
+  const int n = *d_tot;
+  const K invalid = (K)1 << (3 * bits);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const K k = keys[j];
+    head[j] = (k >= invalid) ? 1 : ((j == 0 || keys[j - 1] != k) ? 1 : 0);  // pass-through points are singleton segments
+  }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(FZ_THREADS) fuse_mean_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                               const int32_t* __restrict__ d_tot, int bits,
+                                                               const int32_t* __restrict__ head, const int32_t* __restrict__ offs,
+                                                               const double* __restrict__ mxyz, const double* __restrict__ mnrm,
+                                                               double* __restrict__ oxyz, double* __restrict__ onrm, int32_t* d_out_n) {
+  const int n = *d_tot;
+  const K invalid = (K)1 << (3 * bits);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *d_out_n = n > 0 ? offs[n] : 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    if (!head[j]) continue;
+    const K k = keys[j];
+    const int o = offs[j];
+    if (k >= invalid) {  // outside the cropper: copied through unchanged (helpers.cpp:156-166)
+      const uint32_t i = vals[j];
+      oxyz[3 * o] = mxyz[3 * i]; oxyz[3 * o + 1] = mxyz[3 * i + 1]; oxyz[3 * o + 2] = mxyz[3 * i + 2];
+      onrm[3 * o] = mnrm[3 * i]; onrm[3 * o + 1] = mnrm[3 * i + 1]; onrm[3 * o + 2] = mnrm[3 * i + 2];
+      continue;
+    }
+    double sx = 0, sy = 0, sz = 0, nx = 0, ny = 0, nz = 0;
+    int cnt = 0;
+    for (int t = j; t < n && keys[t] == k; ++t) {
+      const uint32_t i = vals[t];
+      sx = __dadd_rn(sx, mxyz[3 * i]); sy = __dadd_rn(sy, mxyz[3 * i + 1]); sz = __dadd_rn(sz, mxyz[3 * i + 2]);
+      const double a = mnrm[3 * i], b = mnrm[3 * i + 1], c = mnrm[3 * i + 2];
+      if (a == a && b == b && c == c) { nx = __dadd_rn(nx, a); ny = __dadd_rn(ny, b); nz = __dadd_rn(nz, c); }
+      cnt++;
+    }
+    const double c = (double)cnt;
+    oxyz[3 * o] = __ddiv_rn(sx, c); oxyz[3 * o + 1] = __ddiv_rn(sy, c); oxyz[3 * o + 2] = __ddiv_rn(sz, c);
+    double a0 = __ddiv_rn(nx, c), a1 = __ddiv_rn(ny, c), a2 = __ddiv_rn(nz, c);
+    const double zz = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+    if (zz > 0.0) { const double sn = sqrt(zz); a0 = __ddiv_rn(a0, sn); a1 = __ddiv_rn(a1, sn); a2 = __ddiv_rn(a2, sn); }  // .normalized()
+    onrm[3 * o] = a0; onrm[3 * o + 1] = a1; onrm[3 * o + 2] = a2;
+  }
+}
+
+__global__ void __launch_bounds__(FZ_THREADS) fuse_commit_kernel(const double* __restrict__ oxyz, const double* __restrict__ onrm,
+                                                                 const int32_t* __restrict__ d_out_n, const int32_t* __restrict__ d_tot,
+                                                                 double* __restrict__ mxyz, double* __restrict__ mnrm, int32_t* d_nmap) {
+  if (*d_tot <= 0) return;  // gate closed, empty scan or capacity error: the map stays as it was
+  const int n = *d_out_n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *d_nmap = n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += gridDim.x * blockDim.x) { mxyz[i] = oxyz[i]; mnrm[i] = onrm[i]; }
+}
+
+static int bits_for_range(double cells) {
+  int b = 1;
+  while ((double)(1u << b) < cells && b < 22) b++;
+  return b;
+}
+
+template <typename K>
+static int32_t fuse_impl(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev,
+                         const CropDev& crop, double inv, int bits, int bounded, size_t tot_max) {
+  b2s_cloud* map = sm->cloud[0];
+  b2s_cloud* tmp = sm->cloud[1];
+  B2S_TRY(h->keys.ensure(tot_max * sizeof(K) * 2, h->stream));
+  B2S_TRY(h->vals.ensure(tot_max * 4 * 2, h->stream));
+  B2S_TRY(h->flags.ensure((tot_max + 1) * 4, h->stream));
+  B2S_TRY(h->offs.ensure((tot_max + 2) * 4, h->stream));
+  B2S_TRY(h->tmp_i32.ensure(64, h->stream));
+  int32_t* d_tot = h->tmp_i32.as<int32_t>();
+  int32_t* d_out_n = d_tot + 1;
+  K* keys = h->keys.as<K>(); K* keys_alt = keys + tot_max;
+  uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + tot_max;
+  const int sblocks = grid_for(scan->n_max > 0 ? scan->n_max : 1, FZ_THREADS);
+  const int blocks = grid_for(tot_max, FZ_THREADS);
+  fuse_append_kernel<<<sblocks, FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>(),
+                                                            scan->xyz.as<double>(), scan->nrm.as<double>(), scan->dn.as<int32_t>(), T_dev,
+                                                            gate_dev, sm->capacity, d_tot, h->status.as<uint32_t>());
+  fuse_keys_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), d_tot, crop, inv, bits, bounded, keys, vals,
+                                                            h->status.as<uint32_t>());
+  h->launches += 2;
+  if constexpr (sizeof(K) == 4) {
+    B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, d_tot, tot_max, 3 * bits + 1));
+  } else {
+    B2S_TRY(radix_sort_pairs_u64(h, keys, vals, keys_alt, vals_alt, d_tot, tot_max, 3 * bits + 1));
+  }
+  fuse_head_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(keys, d_tot, bits, h->flags.as<int32_t>());
+  h->launches++;
+  B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_tot, tot_max, nullptr));
+  fuse_mean_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(keys, vals, d_tot, bits, h->flags.as<int32_t>(), h->offs.as<int32_t>(),
+                                                            map->xyz.as<double>(), map->nrm.as<double>(), tmp->xyz.as<double>(),
+                                                            tmp->nrm.as<double>(), d_out_n);
+  fuse_commit_kernel<<<blocks, FZ_THREADS, 0, h->stream>>>(tmp->xyz.as<double>(), tmp->nrm.as<double>(), d_out_n, d_tot,
+                                                           map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>());
+  h->launches += 2;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev) {
+  B2S_REQUIRE(scan->has_normals, B2S_E_NO_NORMALS, "Submap::insertScan: the pre-processed scan must carry normals");
+  b2s_cloud* map = sm->cloud[0];
+  const double v = h->cfg.map_voxel_size;
+  B2S_REQUIRE(v > 0.0, B2S_E_UNSUPPORTED, "map_voxel_size <= 0 (no voxelisation) is not supported on the device path");
+  // host-side upper bound of the map size; refreshed from the device when it would exceed the capacity
+  size_t tot_max = map->n_max + 2 * scan->n_max;
+  if (tot_max > sm->capacity) {
+    int32_t n = 0;
+    B2S_CUDA(cudaMemcpyAsync(&n, map->dn.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    map->n_max = (size_t)n; map->n_known = n;
+    tot_max = map->n_max + 2 * scan->n_max;
+    B2S_REQUIRE(tot_max <= sm->capacity, B2S_E_CAPACITY, "submap capacity %zu too small for %zu points", sm->capacity, tot_max);
+  }
+  CropDev crop = make_crop(&h->cfg.scan.map_builder_cropper, T_dev);  // Submap.cpp:71 setPose(mapToRangeSensor)
+  const double inv = 1.0 / v;
+  const int bounded = (!crop.invert && (crop.kind == B2S_CROP_MAX_RADIUS || crop.kind == B2S_CROP_MINMAX_RADIUS)) ? 1 : 0;
+  const int bits = bounded ? bits_for_range(floor(2.0 * crop.rmax * inv) + 4.0) : 21;
+  B2S_REQUIRE(bits <= 21, B2S_E_INVALID, "map voxel size too small for the cropper radius");
+  int32_t rc = (bits <= 10) ? fuse_impl<uint32_t>(h, sm, scan, T_dev, gate_dev, crop, inv, bits, bounded, tot_max)
+                            : fuse_impl<uint64_t>(h, sm, scan, T_dev, gate_dev, crop, inv, bits, bounded, tot_max);
+  map->n_max = tot_max;   // upper bound only; the exact count lives on the device
+  map->n_known = -1;
+  map->has_normals = true;
+  return rc;
+}
+
+// =====================================================================================================================
+//  F3 dense map: open-addressing hash (64-bit packed key) of running position / normal sums and counts
+// =====================================================================================================================
+constexpr unsigned long long DENSE_EMPTY = ~0ull;
+
+__device__ __forceinline__ unsigned long long dense_pack(int x, int y, int z) {
+  return ((unsigned long long)(unsigned)(x + 1048576) << 42) | ((unsigned long long)(unsigned)(y + 1048576) << 21) |
+         (unsigned long long)(unsigned)(z + 1048576);
+}
+__device__ __forceinline__ unsigned long long dense_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+
+__global__ void __launch_bounds__(FZ_THREADS) dense_insert_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
+                                                                  const double* __restrict__ Tdev, CropDev crop, double inv,
+                                                                  unsigned long long* __restrict__ keys, double* __restrict__ sums,
+                                                                  int32_t* __restrict__ cnts, size_t cap, int32_t* used, uint32_t* status) {
+  const int n = *d_n;
+  double T[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) T[i] = Tdev[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    if (!(px == px && py == py && pz == pz)) continue;
+    if (!crop_within(crop, px, py, pz)) continue;  // denseMapCropper_ at identity, applied in the sensor frame (Submap.cpp:78-79)
+    const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
+    const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], px), __dmul_rn(T[5], py)), __dmul_rn(T[6], pz)), T[7]);
+    const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], px), __dmul_rn(T[9], py)), __dmul_rn(T[10], pz)), T[11]);
+    const double fx = floor(__dmul_rn(x, inv)), fy = floor(__dmul_rn(y, inv)), fz = floor(__dmul_rn(z, inv));
+    if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) { atomicOr(status, ST_KEY_OVERFLOW); continue; }
+    const unsigned long long key = dense_pack((int)fx, (int)fy, (int)fz);
+    size_t slot = (size_t)(dense_hash(key) % cap);
+    for (size_t probe = 0; probe < cap; ++probe) {
+      unsigned long long prev = atomicCAS(&keys[slot], DENSE_EMPTY, key);
+      if (prev == DENSE_EMPTY) {
+        if ((size_t)atomicAdd(used, 1) + 1 > cap - cap / 8) atomicOr(status, ST_HASH_FULL);
+        prev = key;
+      }
+      if (prev == key) {
+        atomicAdd(&sums[6 * slot], x); atomicAdd(&sums[6 * slot + 1], y); atomicAdd(&sums[6 * slot + 2], z);
+        atomicAdd(&cnts[slot], 1);
+        break;
+      }
+      slot = slot + 1 == cap ? 0 : slot + 1;
+    }
+  }
+}
+
+__global__ void dense_init_kernel(unsigned long long* keys, double* sums, int32_t* cnts, size_t cap, int32_t* used) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    keys[i] = DENSE_EMPTY; cnts[i] = 0;
+    for (int k = 0; k < 6; k++) sums[6 * i + k] = 0.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *used = 0;
+}
+
+int32_t dense_init(b2s_handle* h, b2s_submap* sm, size_t cap, double voxel) {
+  B2S_TRY(sm->dense_keys.ensure(cap * 8, h->stream));
+  B2S_TRY(sm->dense_sum.ensure(cap * 48, h->stream));
+  B2S_TRY(sm->dense_cnt.ensure(cap * 4, h->stream));
+  B2S_TRY(sm->dense_used.ensure(16, h->stream));
+  sm->dense_cap = cap; sm->dense_voxel = voxel;
+  dense_init_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
+                                                    sm->dense_cnt.as<int32_t>(), cap, sm->dense_used.as<int32_t>());
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const b2s_cropper* crop) {
+  B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
+  B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream, true));
+  double* Td = h->poses.as<double>() + 16 * 62;
+  B2S_TRY(pose_to_device(h, T_host, Td));
+  b2s_cropper c0;
+  memset(&c0, 0, sizeof(c0));
+  if (crop) c0 = *crop;
+  c0.center[0] = c0.center[1] = c0.center[2] = 0.0;  // Submap.cpp:78 setPose(Identity)
+  dense_insert_kernel<<<grid_for(raw->n_max > 0 ? raw->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+      raw->xyz.as<double>(), raw->dn.as<int32_t>(), Td, make_crop(&c0), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(),
+      sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, sm->dense_used.as<int32_t>(), h->status.as<uint32_t>());
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+// VoxelizedPointCloud::toPointCloud (Voxel.cpp:90-115): flags -> scan -> gather of sum / count
+__global__ void dense_flags_kernel(const int32_t* __restrict__ cnts, size_t cap, int32_t* __restrict__ flags) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) flags[i] = cnts[i] > 0 ? 1 : 0;
+}
+__global__ void dense_gather_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sums,
+                                    const int32_t* __restrict__ cnts, size_t cap, const int32_t* __restrict__ flags,
+                                    const int32_t* __restrict__ offs, double* __restrict__ oxyz, int32_t* __restrict__ okeys, int32_t* out_n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = offs[cap];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    if (!flags[i]) continue;
+    const int o = offs[i];
+    const double c = (double)cnts[i];
+    oxyz[3 * o] = sums[6 * i] / c; oxyz[3 * o + 1] = sums[6 * i + 1] / c; oxyz[3 * o + 2] = sums[6 * i + 2] / c;
+    const unsigned long long k = keys[i];
+    okeys[3 * o] = (int)((k >> 42) & 0x1FFFFF) - 1048576; okeys[3 * o + 1] = (int)((k >> 21) & 0x1FFFFF) - 1048576;
+    okeys[3 * o + 2] = (int)(k & 0x1FFFFF) - 1048576;
+  }
+}
+
+int32_t dense_to_cloud(b2s_handle* h, b2s_submap* sm, double* d_xyz, int32_t* d_keys, int32_t* d_out_n) {
+  const size_t cap = sm->dense_cap;
+  B2S_TRY(h->flags.ensure((cap + 1) * 4, h->stream));
+  B2S_TRY(h->offs.ensure((cap + 2) * 4, h->stream));
+  dense_flags_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_cnt.as<int32_t>(), cap, h->flags.as<int32_t>());
+  h->launches++;
+  B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), nullptr, cap, nullptr));
+  dense_gather_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
+                                                      sm->dense_cnt.as<int32_t>(), cap, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_xyz,
+                                                      d_keys, d_out_n);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+}  // namespace b2s

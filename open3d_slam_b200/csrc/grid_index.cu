@@ -1,0 +1,171 @@
+// grid_index.cu -- K-index: the spatial index that replaces the KD-tree the reference rebuilds inside every
+// [O3D] RegistrationICP / EstimateNormals call (KDTreeFlann::SetGeometry).
+//
+// Layout (HBM): a dense grid of cells over the (optionally cropped) point set; points are counting-sorted by
+// linear cell id (x fastest) into a packed double4 array {x,y,z,bits(original index)}; normals likewise.
+// cell_start[c] .. cell_start[c+1] is the slot range of cell c.  Because x is the fastest axis, a run of
+// neighbouring cells along x is ONE contiguous slot range, so a 3x3x3 neighbourhood is 9 ranges.
+// Points outside the grid box are clamped into the border cells, which the search treats as semi-infinite.
+//
+// Build = bbox reduce -> header (1 thread) -> count (atomics, keeps the rank) -> look-back scan -> scatter.
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int GB_THREADS = 256;
+
+__global__ void grid_bbox_init_kernel(unsigned long long* bbox) {
+  int t = threadIdx.x;
+  if (t < 3) bbox[t] = ord_encode(INFINITY);
+  else if (t < 6) bbox[t] = ord_encode(-INFINITY);
+}
+
+__global__ void __launch_bounds__(GB_THREADS) grid_bbox_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
+                                                               CropDev crop, int use_crop, unsigned long long* bbox) {
+  const int n = *d_n;
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    if (use_crop && !crop_within(crop, x, y, z)) continue;
+    if (!(x == x && y == y && z == z)) continue;
+    mn[0] = fmin(mn[0], x); mn[1] = fmin(mn[1], y); mn[2] = fmin(mn[2], z);
+    mx[0] = fmax(mx[0], x); mx[1] = fmax(mx[1], y); mx[2] = fmax(mx[2], z);
+  }
+  __shared__ double s[6][GB_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < 3; d++) { mn[d] = warp_min(mn[d]); mx[d] = warp_max(mx[d]); }
+  if (lane == 0) { for (int d = 0; d < 3; d++) { s[d][warp] = mn[d]; s[3 + d][warp] = mx[d]; } }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    int d = threadIdx.x;
+    double v = s[d][0];
+    for (int w = 1; w < GB_THREADS / 32; w++) v = d < 3 ? fmin(v, s[d][w]) : fmax(v, s[d][w]);
+    if (d < 3) atomicMin(&bbox[d], ord_encode(v)); else atomicMax(&bbox[d], ord_encode(v));
+  }
+}
+
+__global__ void grid_header_kernel(const unsigned long long* bbox, double cell, int cap_cells, GridHeader* hdr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mn[3], mx[3];
+  for (int d = 0; d < 3; d++) { mn[d] = ord_decode(bbox[d]); mx[d] = ord_decode(bbox[3 + d]); }
+  if (!(mn[0] <= mx[0])) { for (int d = 0; d < 3; d++) { mn[d] = 0.0; mx[d] = 0.0; } }  // empty set
+  int dims[3];
+  for (;;) {
+    double total = 1.0;
+    for (int d = 0; d < 3; d++) {
+      double e = floor((mx[d] - mn[d]) / cell) + 1.0;
+      if (e > 2.0e9) e = 2.0e9;
+      dims[d] = (int)e;
+      total *= e;
+    }
+    if (total <= (double)cap_cells) break;
+    cell *= 2.0;  // coarser cells only cost speed, never exactness
+  }
+  for (int d = 0; d < 3; d++) { hdr->origin[d] = mn[d]; hdr->dims[d] = dims[d]; }
+  hdr->cell = cell;
+  hdr->inv_cell = 1.0 / cell;
+  hdr->ncell = dims[0] * dims[1] * dims[2];
+  hdr->n = 0;
+}
+
+__device__ __forceinline__ int grid_cell_of(const GridHeader& g, double x, double y, double z) {
+  double fx = floor((x - g.origin[0]) * g.inv_cell), fy = floor((y - g.origin[1]) * g.inv_cell), fz = floor((z - g.origin[2]) * g.inv_cell);
+  int cx = (int)fmin(fmax(fx, 0.0), (double)(g.dims[0] - 1));
+  int cy = (int)fmin(fmax(fy, 0.0), (double)(g.dims[1] - 1));
+  int cz = (int)fmin(fmax(fz, 0.0), (double)(g.dims[2] - 1));
+  return (cz * g.dims[1] + cy) * g.dims[0] + cx;
+}
+
+__global__ void grid_zero_kernel(const GridHeader* hdr, int32_t* counts) {
+  const int nc = hdr->ncell + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) counts[i] = 0;
+}
+
+__global__ void __launch_bounds__(GB_THREADS) grid_count_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
+                                                                CropDev crop, int use_crop, const GridHeader* __restrict__ hdr,
+                                                                int32_t* counts, int32_t* __restrict__ rank) {
+  const int n = *d_n;
+  __shared__ GridHeader g;
+  if (threadIdx.x == 0) g = *hdr;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    int r = -1;
+    if ((x == x && y == y && z == z) && (!use_crop || crop_within(crop, x, y, z))) r = atomicAdd(&counts[grid_cell_of(g, x, y, z)], 1);
+    rank[i] = r;
+  }
+}
+
+__global__ void __launch_bounds__(GB_THREADS) grid_scatter_kernel(const double* __restrict__ xyz, const double* __restrict__ nrm,
+                                                                  const int32_t* __restrict__ d_n, GridHeader* hdr,
+                                                                  const int32_t* __restrict__ cell_start,
+                                                                  const int32_t* __restrict__ rank, double4* __restrict__ pts,
+                                                                  double4* __restrict__ onrm) {
+  const int n = *d_n;
+  __shared__ GridHeader g;
+  if (threadIdx.x == 0) g = *hdr;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) hdr->n = cell_start[g.ncell];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int r = rank[i];
+    if (r < 0) continue;
+    double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    int slot = cell_start[grid_cell_of(g, x, y, z)] + r;
+    pts[slot] = make_double4(x, y, z, __longlong_as_double((long long)i));
+    if (nrm) onrm[slot] = make_double4(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2], 0.0);
+  }
+}
+
+CropDev make_crop(const b2s_cropper* c, const double* pose_dev) {
+  CropDev d;
+  memset(&d, 0, sizeof(d));
+  if (c) {
+    d.kind = c->kind; d.invert = c->invert; d.rmin = c->rmin; d.rmax = c->rmax; d.zmin = c->zmin; d.zmax = c->zmax;
+    d.cx = c->center[0]; d.cy = c->center[1]; d.cz = c->center[2];
+  }
+  d.pose_dev = pose_dev;
+  return d;
+}
+
+int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double cell, const CropDev* patch, bool with_normals) {
+  B2S_REQUIRE(cell > 0.0, B2S_E_INVALID, "grid_build: cell size must be > 0");
+  const size_t n_max = cloud->n_max > 0 ? cloud->n_max : 1;
+  // cell budget: enough for a 64 m x 64 m x 32 m box at 0.25 m, bounded by 16 cells per point + slack
+  size_t want = n_max * 16 + 4096;
+  if (want > (size_t)1 << 25) want = (size_t)1 << 25;
+  if (want < (size_t)1 << 16) want = (size_t)1 << 16;
+  if ((size_t)g->cap_cells < want) {
+    B2S_TRY(g->cell_start.ensure((want + 2) * 4 * 2, h->stream));  // counts + starts
+    g->cap_cells = (int32_t)want;
+  }
+  B2S_TRY(g->hdr.ensure(sizeof(GridHeader), h->stream));
+  B2S_TRY(g->bbox.ensure(64, h->stream));
+  B2S_TRY(g->rank.ensure(n_max * 4, h->stream));
+  B2S_TRY(g->pts.ensure(n_max * 32, h->stream));
+  if (with_normals) B2S_TRY(g->nrm.ensure(n_max * 32, h->stream));
+  CropDev cd = patch ? *patch : make_crop(nullptr);
+  const int use_crop = patch ? 1 : 0;
+  const int blocks = grid_for(n_max, GB_THREADS);
+  int32_t* counts = g->cell_start.as<int32_t>();
+  int32_t* starts = counts + g->cap_cells + 2;
+  const int32_t* d_n = cloud->dn.as<int32_t>();
+  GridHeader* hdr = g->hdr.as<GridHeader>();
+  grid_bbox_init_kernel<<<1, 32, 0, h->stream>>>(g->bbox.as<unsigned long long>());
+  grid_bbox_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(), d_n, cd, use_crop, g->bbox.as<unsigned long long>());
+  grid_header_kernel<<<1, 32, 0, h->stream>>>(g->bbox.as<unsigned long long>(), cell, g->cap_cells, hdr);
+  grid_zero_kernel<<<148 * 4, 256, 0, h->stream>>>(hdr, counts);
+  grid_count_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(), d_n, cd, use_crop, hdr, counts, g->rank.as<int32_t>());
+  h->launches += 5;
+  // scan over ncell (device-known) counts; launch sized for the capacity
+  B2S_TRY(scan_exclusive_i32(h, counts, starts, &hdr->ncell, (size_t)g->cap_cells, nullptr));
+  grid_scatter_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(),
+                                                            (with_normals && cloud->has_normals) ? cloud->nrm.as<double>() : nullptr, d_n,
+                                                            hdr, starts, g->rank.as<int32_t>(), g->pts.as<double4>(),
+                                                            with_normals ? g->nrm.as<double4>() : nullptr);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+}  // namespace b2s

@@ -1,0 +1,272 @@
+// normals.cu -- K-normals (P3): RegistrationIcpPointToPlane::estimateNormalsOrCovariancesIfNeeded
+// (core/src/CloudRegistration.cpp:49-56) = [O3D] EstimateNormals(KDTreeSearchParamHybrid(radius, knn)) +
+// NormalizeNormals + OrientNormalsTowardsCameraLocation(0,0,0).
+//
+// One WARP per query point.  The warp walks the dense grid (grid_index.cu) ring by ring; each 32-candidate chunk of a
+// cell row is one coalesced 128-bit load per lane; the current k best (k <= 32) are kept as a sorted list with ONE
+// entry per lane, and a qualifying candidate is inserted with a single shuffle-up step.  Search stops as soon as the
+// k-th distance is below the distance to the unvisited shell (exact k-NN), or the shell is beyond the radius.
+// The covariance is then accumulated in the neighbour order the reference uses (ascending distance, nanoflann's
+// result order) with the reference's single-pass cumulant formula in explicitly rounded fp64, the neighbour
+// coordinates being broadcast across the warp by shuffles; lane 0 runs the analytic 3x3 eigen-solver
+// ([O3D] FastEigen3x3, geometrictools RobustEigenSymmetric3x3) and writes the oriented unit normal.
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int NK_THREADS = 256;
+
+__device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
+
+__device__ __forceinline__ double slab_gap_n(double q, double o, double cell, int i, int n, double eps) {
+  double g = 0.0;
+  if (i > 0) { double lo = o + (double)i * cell; if (q < lo) g = lo - q; }
+  if (i < n - 1) { double hi = o + (double)(i + 1) * cell; if (q > hi) g = q - hi; }
+  g -= eps;
+  return g > 0.0 ? g : 0.0;
+}
+
+__device__ __forceinline__ void cross3d(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3d(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ void eigvec0_dev(const double* A, double eval0, double* out) {
+  double row0[3] = {A[0] - eval0, A[1], A[2]}, row1[3] = {A[1], A[4] - eval0, A[5]}, row2[3] = {A[2], A[5], A[8] - eval0};
+  double r01[3], r02[3], r12[3];
+  cross3d(row0, row1, r01); cross3d(row0, row2, r02); cross3d(row1, row2, r12);
+  const double d0 = dot3d(r01, r01), d1 = dot3d(r02, r02), d2 = dot3d(r12, r12);
+  double dmax = d0; int imax = 0;
+  if (d1 > dmax) { dmax = d1; imax = 1; }
+  if (d2 > dmax) { imax = 2; }
+  const double* v = imax == 0 ? r01 : (imax == 1 ? r02 : r12);
+  const double s = sqrt(imax == 0 ? d0 : (imax == 1 ? d1 : d2));
+  out[0] = v[0] / s; out[1] = v[1] / s; out[2] = v[2] / s;
+}
+
+__device__ void eigvec1_dev(const double* A, const double* e0, double eval1, double* out) {
+  double U[3], V[3];
+  if (fabs(e0[0]) > fabs(e0[1])) {
+    const double inv = 1 / sqrt(e0[0] * e0[0] + e0[2] * e0[2]);
+    U[0] = -e0[2] * inv; U[1] = 0; U[2] = e0[0] * inv;
+  } else {
+    const double inv = 1 / sqrt(e0[1] * e0[1] + e0[2] * e0[2]);
+    U[0] = 0; U[1] = e0[2] * inv; U[2] = -e0[1] * inv;
+  }
+  cross3d(e0, U, V);
+  const double AU[3] = {A[0] * U[0] + A[1] * U[1] + A[2] * U[2], A[1] * U[0] + A[4] * U[1] + A[5] * U[2], A[2] * U[0] + A[5] * U[1] + A[8] * U[2]};
+  const double AV[3] = {A[0] * V[0] + A[1] * V[1] + A[2] * V[2], A[1] * V[0] + A[4] * V[1] + A[5] * V[2], A[2] * V[0] + A[5] * V[1] + A[8] * V[2]};
+  double m00 = dot3d(U, AU) - eval1, m01 = dot3d(U, AV), m11 = dot3d(V, AV) - eval1;
+  const double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+  if (a00 >= a11) {
+    const double mx = a00 > a01 ? a00 : a01;
+    if (mx > 0) {
+      if (a00 >= a01) { m01 /= m00; m00 = 1 / sqrt(1 + m01 * m01); m01 *= m00; }
+      else { m00 /= m01; m01 = 1 / sqrt(1 + m00 * m00); m00 *= m01; }
+      for (int d = 0; d < 3; d++) out[d] = m01 * U[d] - m00 * V[d];
+    } else { out[0] = U[0]; out[1] = U[1]; out[2] = U[2]; }
+  } else {
+    const double mx = a11 > a01 ? a11 : a01;
+    if (mx > 0) {
+      if (a11 >= a01) { m01 /= m11; m11 = 1 / sqrt(1 + m01 * m01); m01 *= m11; }
+      else { m11 /= m01; m01 = 1 / sqrt(1 + m11 * m11); m11 *= m01; }
+      for (int d = 0; d < 3; d++) out[d] = m11 * U[d] - m01 * V[d];
+    } else { out[0] = U[0]; out[1] = U[1]; out[2] = U[2]; }
+  }
+}
+
+// eigenvector of the smallest eigenvalue of a symmetric 3x3 (row-major, full)
+__device__ void fast_eigen3x3_dev(const double* cov, double* out) {
+  double A[9];
+  for (int i = 0; i < 9; i++) A[i] = cov[i];
+  double mc = A[0];
+  for (int i = 1; i < 9; i++) if (A[i] > mc) mc = A[i];
+  if (mc == 0) { out[0] = out[1] = out[2] = 0; return; }
+  for (int i = 0; i < 9; i++) A[i] /= mc;
+  const double norm = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+  if (norm > 0) {
+    double eval[3], e0[3], e1[3], e2[3];
+    const double q = (A[0] + A[4] + A[8]) / 3;
+    const double b00 = A[0] - q, b11 = A[4] - q, b22 = A[8] - q;
+    const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2) / 6);
+    const double c00 = b11 * b22 - A[5] * A[5];
+    const double c01 = A[1] * b22 - A[5] * A[2];
+    const double c02 = A[1] * A[5] - b11 * A[2];
+    const double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
+    double half_det = det * 0.5;
+    half_det = fmin(fmax(half_det, -1.0), 1.0);
+    const double angle = acos(half_det) / 3.0;
+    const double two_thirds_pi = 2.09439510239319549;
+    const double beta2 = cos(angle) * 2;
+    const double beta0 = cos(angle + two_thirds_pi) * 2;
+    const double beta1 = -(beta0 + beta2);
+    eval[0] = q + p * beta0; eval[1] = q + p * beta1; eval[2] = q + p * beta2;
+    if (half_det >= 0) {
+      eigvec0_dev(A, eval[2], e2);
+      if (eval[2] < eval[0] && eval[2] < eval[1]) { out[0] = e2[0]; out[1] = e2[1]; out[2] = e2[2]; return; }
+      eigvec1_dev(A, e2, eval[1], e1);
+      if (eval[1] < eval[0] && eval[1] < eval[2]) { out[0] = e1[0]; out[1] = e1[1]; out[2] = e1[2]; return; }
+      cross3d(e1, e2, e0);
+      out[0] = e0[0]; out[1] = e0[1]; out[2] = e0[2];
+    } else {
+      eigvec0_dev(A, eval[0], e0);
+      if (eval[0] < eval[1] && eval[0] < eval[2]) { out[0] = e0[0]; out[1] = e0[1]; out[2] = e0[2]; return; }
+      eigvec1_dev(A, e0, eval[1], e1);
+      if (eval[1] < eval[0] && eval[1] < eval[2]) { out[0] = e1[0]; out[1] = e1[1]; out[2] = e1[2]; return; }
+      cross3d(e0, e1, e2);
+      out[0] = e2[0]; out[1] = e2[1]; out[2] = e2[2];
+    }
+  } else {
+    const double a0 = A[0] * mc, a1 = A[4] * mc, a2 = A[8] * mc;
+    if (a0 < a1 && a0 < a2) { out[0] = 1; out[1] = 0; out[2] = 0; }
+    else if (a1 < a0 && a1 < a2) { out[0] = 0; out[1] = 1; out[2] = 0; }
+    else { out[0] = 0; out[1] = 0; out[2] = 1; }
+  }
+}
+
+__global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
+                                                             const double4* __restrict__ pts, int knn, double radius,
+                                                             double* __restrict__ out_nrm, double* __restrict__ out_cov) {
+  __shared__ GridHeader g;
+  if (threadIdx.x == 0) g = *hdr;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (NK_THREADS / 32);
+  const int n = g.n;
+  const double r2 = radius * radius;
+  const double eps = 1e-9 * g.cell;
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  for (int s = blockIdx.x * (NK_THREADS / 32) + (threadIdx.x >> 5); s < n; s += warps_total) {
+    const double4 qp = pts[s];
+    const double qx = qp.x, qy = qp.y, qz = qp.z;
+    const int qi = (int)__double_as_longlong(qp.w);
+    const int cx = (int)fmin(fmax(floor((qx - g.origin[0]) * g.inv_cell), 0.0), (double)(nx - 1));
+    const int cy = (int)fmin(fmax(floor((qy - g.origin[1]) * g.inv_cell), 0.0), (double)(ny - 1));
+    const int cz = (int)fmin(fmax(floor((qz - g.origin[2]) * g.inv_cell), 0.0), (double)(nz - 1));
+    double ed = INFINITY; int ei = 0x7fffffff; int es = -1;  // this lane's entry of the sorted k-best list
+    double kd = INFINITY; int ki = 0x7fffffff;               // current k-th best (lane knn-1)
+    for (int R = 0;; ++R) {
+      const int z0 = max(cz - R, 0), z1 = min(cz + R, nz - 1);
+      const int y0 = max(cy - R, 0), y1 = min(cy + R, ny - 1);
+      const int x0 = max(cx - R, 0), x1 = min(cx + R, nx - 1);
+      for (int z = z0; z <= z1; ++z) {
+        const double gz = slab_gap_n(qz, g.origin[2], g.cell, z, nz, eps);
+        const double gz2 = gz * gz;
+        if (gz2 > fmin(kd, r2)) continue;
+        const bool zface = (z == cz - R) || (z == cz + R);
+        for (int y = y0; y <= y1; ++y) {
+          const double gy = slab_gap_n(qy, g.origin[1], g.cell, y, ny, eps);
+          if (gz2 + gy * gy > fmin(kd, r2)) continue;
+          const int row = (z * ny + y) * nx;
+          const bool shell = zface || y == cy - R || y == cy + R;
+          // up to two x-ranges: the whole row on the shell, otherwise the two end cells
+          for (int part = 0; part < 2; ++part) {
+            int a, b;
+            if (shell) { if (part == 1) break; a = cs[row + x0]; b = cs[row + x1 + 1]; }
+            else if (part == 0) { if (cx - R < 0) continue; a = cs[row + cx - R]; b = cs[row + cx - R + 1]; }
+            else { if (cx + R > nx - 1) continue; a = cs[row + cx + R]; b = cs[row + cx + R + 1]; }
+            for (int j0 = a; j0 < b; j0 += 32) {
+              const int j = j0 + lane;
+              double d = INFINITY; int idx = 0x7fffffff;
+              if (j < b) {
+                const double4 p = pts[j];
+                d = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+                idx = (int)__double_as_longlong(p.w);
+              }
+              unsigned mask = __ballot_sync(0xffffffffu, j < b && d < r2 && lex_less(d, idx, kd, ki));
+              while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double cd = __shfl_sync(0xffffffffu, d, src);
+                const int ci = __shfl_sync(0xffffffffu, idx, src);
+                const int cslot = j0 + src;
+                const double pd = __shfl_up_sync(0xffffffffu, ed, 1);
+                const int pi = __shfl_up_sync(0xffffffffu, ei, 1);
+                const int ps = __shfl_up_sync(0xffffffffu, es, 1);
+                if (lex_less(cd, ci, ed, ei)) {
+                  if (lane > 0 && lex_less(cd, ci, pd, pi)) { ed = pd; ei = pi; es = ps; }
+                  else { ed = cd; ei = ci; es = cslot; }
+                }
+                kd = __shfl_sync(0xffffffffu, ed, knn - 1);
+                ki = __shfl_sync(0xffffffffu, ei, knn - 1);
+              }
+            }
+          }
+        }
+      }
+      double bound = INFINITY;
+      if (cx - R > 0) bound = fmin(bound, qx - (g.origin[0] + (double)(cx - R) * g.cell));
+      if (cx + R < nx - 1) bound = fmin(bound, (g.origin[0] + (double)(cx + R + 1) * g.cell) - qx);
+      if (cy - R > 0) bound = fmin(bound, qy - (g.origin[1] + (double)(cy - R) * g.cell));
+      if (cy + R < ny - 1) bound = fmin(bound, (g.origin[1] + (double)(cy + R + 1) * g.cell) - qy);
+      if (cz - R > 0) bound = fmin(bound, qz - (g.origin[2] + (double)(cz - R) * g.cell));
+      if (cz + R < nz - 1) bound = fmin(bound, (g.origin[2] + (double)(cz + R + 1) * g.cell) - qz);
+      bound -= eps;
+      if (bound < 0.0) bound = 0.0;
+      if (bound == INFINITY || bound * bound > fmin(kd, r2)) break;
+    }
+    // ---- covariance in the reference's neighbour order (ascending (d2, index)), single-pass cumulants ----
+    const int kk = __popc(__ballot_sync(0xffffffffu, lane < knn && es >= 0));
+    double nx_ = 0.0, ny_ = 0.0, nz_ = 0.0;
+    double4 np = make_double4(0, 0, 0, 0);
+    if (lane < kk) np = pts[es];
+    double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // [O3D] fewer than 3 neighbours -> identity covariance
+    if (kk >= 3) {
+      double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int t = 0; t < kk; ++t) {
+        const double x = __shfl_sync(0xffffffffu, np.x, t), y = __shfl_sync(0xffffffffu, np.y, t), z = __shfl_sync(0xffffffffu, np.z, t);
+        c[0] = __dadd_rn(c[0], x); c[1] = __dadd_rn(c[1], y); c[2] = __dadd_rn(c[2], z);
+        c[3] = __dadd_rn(c[3], __dmul_rn(x, x)); c[4] = __dadd_rn(c[4], __dmul_rn(x, y)); c[5] = __dadd_rn(c[5], __dmul_rn(x, z));
+        c[6] = __dadd_rn(c[6], __dmul_rn(y, y)); c[7] = __dadd_rn(c[7], __dmul_rn(y, z)); c[8] = __dadd_rn(c[8], __dmul_rn(z, z));
+      }
+      const double kf = (double)kk;
+#pragma unroll
+      for (int t = 0; t < 9; t++) c[t] = __ddiv_rn(c[t], kf);
+      cov[0] = __dsub_rn(c[3], __dmul_rn(c[0], c[0]));
+      cov[4] = __dsub_rn(c[6], __dmul_rn(c[1], c[1]));
+      cov[8] = __dsub_rn(c[8], __dmul_rn(c[2], c[2]));
+      cov[1] = cov[3] = __dsub_rn(c[4], __dmul_rn(c[0], c[1]));
+      cov[2] = cov[6] = __dsub_rn(c[5], __dmul_rn(c[0], c[2]));
+      cov[5] = cov[7] = __dsub_rn(c[7], __dmul_rn(c[1], c[2]));
+    }
+    if (lane == 0) {
+      double nr[3];
+      fast_eigen3x3_dev(cov, nr);
+      if (sqrt(dot3d(nr, nr)) == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+      const double zz = dot3d(nr, nr);  // NormalizeNormals
+      if (zz > 0) { const double sn = sqrt(zz); nr[0] /= sn; nr[1] /= sn; nr[2] /= sn; }
+      if (nr[0] != nr[0]) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+      const double ref[3] = {-qx, -qy, -qz};  // OrientNormalsTowardsCameraLocation(0,0,0)
+      if (sqrt(dot3d(nr, nr)) == 0.0) {
+        const double rn = sqrt(dot3d(ref, ref));
+        if (rn == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+        else { nr[0] = ref[0] / rn; nr[1] = ref[1] / rn; nr[2] = ref[2] / rn; }
+      } else if (dot3d(nr, ref) < 0.0) { nr[0] *= -1.0; nr[1] *= -1.0; nr[2] *= -1.0; }
+      nx_ = nr[0]; ny_ = nr[1]; nz_ = nr[2];
+      out_nrm[3 * (size_t)qi] = nx_; out_nrm[3 * (size_t)qi + 1] = ny_; out_nrm[3 * (size_t)qi + 2] = nz_;
+      if (out_cov) for (int t = 0; t < 9; t++) out_cov[9 * (size_t)qi + t] = cov[t];
+    }
+  }
+}
+
+int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius, double cell_hint) {
+  B2S_REQUIRE(radius > 0.0, B2S_E_INVALID, "maxRadiusNormalEstimation_ must be > 0");  // CloudRegistration.cpp:50
+  B2S_REQUIRE(knn > 0, B2S_E_INVALID, "knnNormalEstimation_ must be > 0");            // CloudRegistration.cpp:51
+  B2S_REQUIRE(knn <= 32, B2S_E_UNSUPPORTED, "knn > 32 is not supported by the warp k-best list yet");
+  double cell = cell_hint > 0.0 ? cell_hint : radius / 4.0;
+  if (cell < radius / 16.0) cell = radius / 16.0;  // bound the ring count of the worst case
+  B2S_TRY(grid_build(h, &h->grid_b, c, cell, nullptr, false));
+  const size_t n_max = c->n_max > 0 ? c->n_max : 1;
+  B2S_TRY(c->nrm.ensure(n_max * 24, h->stream));
+  int blocks = (int)((n_max + (NK_THREADS / 32) - 1) / (NK_THREADS / 32));
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  normals_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(h->grid_b.hdr.as<GridHeader>(), grid_starts(&h->grid_b), h->grid_b.pts.as<double4>(),
+                                                       knn, radius, c->nrm.as<double>(), nullptr);
+  h->launches++;
+  c->has_normals = true;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+}  // namespace b2s

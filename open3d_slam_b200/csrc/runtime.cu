@@ -1,0 +1,299 @@
+// runtime.cu -- host runtime (errors, buffers) and the two device-wide primitives everything else is built
+// from: a single-pass decoupled-look-back exclusive scan and a stable LSD radix sort (8-bit digits,
+// match_any warp ranking).  Hand-written for sm_100a; no CUB/Thrust on the product path.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b2s {
+
+static thread_local char g_err[1024] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int32_t DevBuf::ensure(size_t bytes, cudaStream_t s, bool preserve) {
+  if (bytes <= cap && p) return B2S_OK;
+  size_t ncap = cap + cap / 2;
+  if (ncap < bytes) ncap = bytes;
+  ncap = (ncap + 255) & ~(size_t)255;
+  if (ncap < 256) ncap = 256;
+  void* np = nullptr;
+  B2S_CUDA(cudaMalloc(&np, ncap));
+  if (p) {
+    if (preserve) B2S_CUDA(cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, s));
+    B2S_CUDA(cudaStreamSynchronize(s));  // earlier kernels may still read the old allocation
+    B2S_CUDA(cudaFree(p));
+  }
+  p = np;
+  cap = ncap;
+  return B2S_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+void GridIndex::release() {
+  hdr.release(); bbox.release(); cell_start.release(); rank.release(); pts.release(); nrm.release();
+  cap_cells = 0;
+}
+
+int32_t ensure_pinned(b2s_handle* h, size_t bytes) {
+  if (bytes <= h->pinned_cap) return B2S_OK;
+  if (h->pinned) {
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFreeHost(h->pinned);
+    h->pinned = nullptr; h->pinned_cap = 0;
+  }
+  size_t cap = (bytes + 4095) & ~(size_t)4095;
+  B2S_CUDA(cudaMallocHost(&h->pinned, cap));
+  h->pinned_cap = cap;
+  return B2S_OK;
+}
+
+int32_t check_status(b2s_handle* h) {
+  uint32_t st = 0;
+  B2S_CUDA(cudaMemcpyAsync(&st, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  if (st == 0) return B2S_OK;
+  B2S_CUDA(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
+  if (st & ST_CAPACITY) { set_error("device structure capacity exceeded (status 0x%x)", st); return B2S_E_CAPACITY; }
+  if (st & ST_HASH_FULL) { set_error("dense voxel hash is full (status 0x%x)", st); return B2S_E_CAPACITY; }
+  if (st & ST_KEY_OVERFLOW) { set_error("voxel key out of range for the chosen key width (status 0x%x)", st); return B2S_E_INVALID; }
+  if (st & ST_EMPTY) { set_error("cloud is empty where the reference asserts a non-empty cloud (status 0x%x)", st); return B2S_E_EMPTY; }
+  set_error("unknown device status 0x%x", st);
+  return B2S_E_INVALID;
+}
+
+// =================================================================================================
+//  exclusive scan, single pass, decoupled look-back
+// =================================================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+#define FLAG_AGG (1ull << 62)
+#define FLAG_PREFIX (2ull << 62)
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                                     const int32_t* __restrict__ d_n, int32_t n_host,
+                                                                     unsigned long long* state, int32_t* tile_counter,
+                                                                     int32_t* d_total) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[SCAN_THREADS / 32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  const int n = d_n ? *d_n : n_host;
+  const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (tile >= ntiles) {
+    if (tile == 0 && threadIdx.x == 0) { out[0] = 0; if (d_total) *d_total = 0; }
+    return;
+  }
+  const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n) {
+    const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS / 4; k++) { int4 q = p[k]; v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = (base + k < n) ? in[base + k] : 0;
+  }
+  int tsum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) tsum += v[k];
+  // block exclusive scan of the per-thread sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int woff = 0, agg = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; w++) { int t = s_warp[w]; if (w < warp) woff += t; agg += t; }
+  int texcl = woff + inc - tsum;
+  // decoupled look-back (warp 0)
+  if (warp == 0) {
+    volatile unsigned long long* vs = state;
+    if (tile == 0) {
+      if (lane == 0) { vs[0] = FLAG_PREFIX | (unsigned long long)(unsigned)agg; s_prefix = 0; }
+    } else {
+      if (lane == 0) vs[tile] = FLAG_AGG | (unsigned long long)(unsigned)agg;
+      int look = tile - 1, excl = 0;
+      while (true) {
+        int idx = look - lane;
+        unsigned long long s = (idx >= 0) ? vs[idx] : FLAG_PREFIX;
+        unsigned flag = (unsigned)(s >> 62);
+        if (__any_sync(0xffffffffu, flag == 0)) continue;
+        unsigned pmask = __ballot_sync(0xffffffffu, flag == 2);
+        int val = (int)(unsigned)(s & 0xffffffffull);
+        if (pmask) {
+          int first = __ffs(pmask) - 1;
+          excl += warp_sum_i(lane <= first ? val : 0);
+          excl = __shfl_sync(0xffffffffu, excl, 0);
+          break;
+        }
+        excl += warp_sum_i(val);
+        excl = __shfl_sync(0xffffffffu, excl, 0);
+        look -= 32;
+      }
+      if (lane == 0) { vs[tile] = FLAG_PREFIX | (unsigned long long)(unsigned)(excl + agg); s_prefix = excl; }
+    }
+  }
+  __syncthreads();
+  int run = s_prefix + texcl;
+  if (base + SCAN_ITEMS <= n) {
+    int o[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { o[k] = run; run += v[k]; }
+    int4* p = reinterpret_cast<int4*>(out + base);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS / 4; k++) p[k] = make_int4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+  }
+  if (tile == ntiles - 1 && threadIdx.x == SCAN_THREADS - 1) {
+    out[n] = s_prefix + agg;
+    if (d_total) *d_total = s_prefix + agg;
+  }
+}
+
+static int32_t scan_impl(b2s_handle* h, const int32_t* in, int32_t* out, const int32_t* d_n, int32_t n_host, size_t n_max,
+                         int32_t* d_total) {
+  int ntiles = (int)((n_max + SCAN_TILE - 1) / SCAN_TILE);
+  if (ntiles < 1) ntiles = 1;
+  B2S_TRY(h->scan.state.ensure((size_t)ntiles * 8 + 64, h->stream));
+  B2S_CUDA(cudaMemsetAsync(h->scan.state.p, 0, (size_t)ntiles * 8 + 64, h->stream));
+  unsigned long long* st = h->scan.state.as<unsigned long long>();
+  int32_t* counter = reinterpret_cast<int32_t*>(st + ntiles);
+  scan_lookback_kernel<<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, out, d_n, n_host, st, counter, d_total);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t scan_exclusive_i32(b2s_handle* h, const int32_t* in, int32_t* out, const int32_t* d_n, size_t n_max, int32_t* d_total) {
+  return scan_impl(h, in, out, d_n, (int32_t)n_max, n_max, d_total);
+}
+
+// =================================================================================================
+//  stable LSD radix sort, 8-bit digits: per pass  histogram -> scan -> ranked scatter
+// =================================================================================================
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K* __restrict__ keys, const int32_t* __restrict__ d_n, int shift,
+                                                             int32_t* __restrict__ hist, int nblocks) {
+  __shared__ int s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const int n = *d_n;
+  const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    int i = base + k * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&s_h[(int)((keys[i] >> shift) & 0xFF)], 1);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                const int32_t* __restrict__ d_n, int shift,
+                                                                const int32_t* __restrict__ offs, int nblocks) {
+  __shared__ int s_cnt[RS_WARPS][256];
+  __shared__ int s_base[256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int n = *d_n;
+  // warp w owns the contiguous slice [base + w*32*ITEMS, +32*ITEMS) processed in ITEMS rounds of 32 keys:
+  // the (round, lane) order equals the input order, which makes the pass stable
+  const int wbase = blockIdx.x * RS_TILE + warp * 32 * RS_ITEMS;
+  K key[RS_ITEMS];
+  int lrank[RS_ITEMS];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    int i = wbase + k * 32 + lane;
+    bool valid = i < n;
+    key[k] = valid ? keys_in[i] : (K)0;
+    int d = valid ? (int)((key[k] >> shift) & 0xFF) : 256 + lane;  // invalid lanes match nobody
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int prior = valid ? s_cnt[warp][d] : 0;
+    __syncwarp();
+    lrank[k] = prior + __popc(peers & ((1u << lane) - 1u));
+    if (valid && (peers & ((1u << lane) - 1u)) == 0) s_cnt[warp][d] = prior + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per digit: exclusive scan over the warps, add the global base of this (digit, block)
+    const int d = threadIdx.x;
+    int run = offs[d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) { int c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    int i = wbase + k * 32 + lane;
+    if (i < n) {
+      int d = (int)((key[k] >> shift) & 0xFF);
+      int pos = s_cnt[warp][d] + lrank[k];
+      keys_out[pos] = key[k];
+      vals_out[pos] = vals_in[i];
+    }
+  }
+  (void)s_base;
+}
+
+// returns 0 when the result is in (keys, vals), 1 when it is in (keys_alt, vals_alt) -- callers get the
+// pointers swapped so that (keys, vals) always designate the sorted arrays afterwards
+template <typename K>
+static int32_t radix_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& keys_alt, uint32_t*& vals_alt, const int32_t* d_n,
+                               size_t n_max, int key_bits) {
+  int nblocks = (int)((n_max + RS_TILE - 1) / RS_TILE);
+  if (nblocks < 1) nblocks = 1;
+  size_t hist_n = (size_t)256 * nblocks;
+  B2S_TRY(h->sort.hist.ensure((hist_n + 1) * 4 * 2, h->stream));
+  int32_t* hist = h->sort.hist.as<int32_t>();
+  int32_t* offs = hist + hist_n + 1;
+  int passes = (key_bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  for (int p = 0; p < passes; p++) {
+    int shift = 8 * p;
+    rs_hist_kernel<K><<<nblocks, RS_THREADS, 0, h->stream>>>(keys, d_n, shift, hist, nblocks);
+    h->launches++;
+    B2S_TRY(scan_impl(h, hist, offs, nullptr, (int32_t)hist_n, hist_n, nullptr));
+    rs_scatter_kernel<K><<<nblocks, RS_THREADS, 0, h->stream>>>(keys, vals, keys_alt, vals_alt, d_n, shift, offs, nblocks);
+    h->launches++;
+    K* tk = keys; keys = keys_alt; keys_alt = tk;
+    uint32_t* tv = vals; vals = vals_alt; vals_alt = tv;
+  }
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t radix_sort_pairs_u32(b2s_handle* h, uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, uint32_t*& vals_alt,
+                             const int32_t* d_n, size_t n_max, int key_bits) {
+  return radix_sort_impl<uint32_t>(h, keys, vals, keys_alt, vals_alt, d_n, n_max, key_bits);
+}
+int32_t radix_sort_pairs_u64(b2s_handle* h, uint64_t*& keys, uint32_t*& vals, uint64_t*& keys_alt, uint32_t*& vals_alt,
+                             const int32_t* d_n, size_t n_max, int key_bits) {
+  return radix_sort_impl<uint64_t>(h, keys, vals, keys_alt, vals_alt, d_n, n_max, key_bits);
+}
+
+}  // namespace b2s

@@ -1,0 +1,501 @@
+"""Host-side mirror of the reference's operator interface for the hot path, on top of the C ABI (include/b2s.h).
+
+Names, argument meaning and error behaviour follow open3d_slam (paths relative to
+/root/reference/open3d_slam/open3d_slam/):
+    CloudRegistration / RegistrationIcpPointToPlane / cloudRegistrationFactory   include/open3d_slam/CloudRegistration.hpp:19-73
+    ScanToMapRegistration / ScanToMapIcp / scanToMapRegistrationFactory          include/open3d_slam/ScanToMapRegistration.hpp:24-61
+    Submap.insertScan / getMapPointCloud                                         include/open3d_slam/Submap.hpp:38-45
+    Mapper.addRangeMeasurement (host control flow only)                          src/Mapper.cpp:101-181
+The reference itself is C++; its C++ subclasses live in shim/.  This Python mirror exists so that tests/ and
+bench.py read like tests of the reference interface.  All arithmetic happens in libb2s.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+
+# --------------------------------------------------------------------------------------------------------------------
+# parameters (include/open3d_slam/Parameters.hpp:51-98); defaults = the Lua defaults
+# (ros/open3d_slam_ros/param/default/parameter_structure_definitions.lua:52-72,102) with PointToPlaneIcp
+# --------------------------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class ScanCroppingParameters:
+    cropperName: str = "MinMaxRadius"
+    croppingMinRadius: float = 2.0
+    croppingMaxRadius: float = 30.0
+    croppingMinZ: float = -50.0
+    croppingMaxZ: float = 50.0
+
+    def to_c(self, center=(0.0, 0.0, 0.0), invert=False) -> L.Cropper:
+        c = L.Cropper()
+        c.kind = L.CROPPER_NAMES[self.cropperName]
+        c.invert = int(invert)
+        c.rmin, c.rmax, c.zmin, c.zmax = self.croppingMinRadius, self.croppingMaxRadius, self.croppingMinZ, self.croppingMaxZ
+        c.center[0], c.center[1], c.center[2] = (float(v) for v in center)
+        return c
+
+
+@dataclass
+class IcpParameters:
+    maxNumIter: int = 50
+    maxCorrespondenceDistance: float = 1.0
+    knn: int = 20
+    maxDistanceKnn: float = 3.0
+
+
+@dataclass
+class ScanProcessingParameters:
+    voxelSize: float = 0.1
+    downSamplingRatio: float = 0.3
+    cropper: ScanCroppingParameters = field(default_factory=ScanCroppingParameters)
+
+
+@dataclass
+class MapBuilderParameters:
+    mapVoxelSize: float = 0.1
+    cropper: ScanCroppingParameters = field(default_factory=ScanCroppingParameters)
+
+
+@dataclass
+class CloudRegistrationParameters:
+    regType: str = "PointToPlaneIcp"
+    icp: IcpParameters = field(default_factory=IcpParameters)
+
+
+@dataclass
+class MapperParameters:
+    scanToMapRegType: str = "PointToPlaneIcp"
+    minRefinementFitness: float = 0.7
+    icp: IcpParameters = field(default_factory=IcpParameters)
+    scanProcessing: ScanProcessingParameters = field(default_factory=ScanProcessingParameters)
+    mapBuilder: MapBuilderParameters = field(default_factory=MapBuilderParameters)
+    denseMapVoxelSize: float = 0.05
+    isIgnoreMinRefinementFitness: bool = False
+    minMovementBetweenMappingSteps: float = 0.0
+    seed: int = 0            # replaces std::random_device of [O3D] RandomDownSample
+    nnCellSize: float = 0.0  # engine knob: NN grid cell (0 = maxCorrespondenceDistance / 2)
+
+    def to_config(self) -> L.Config:
+        if self.scanToMapRegType != "PointToPlaneIcp":
+            raise L.B2SError(L.E_UNSUPPORTED, f"registration type {self.scanToMapRegType} is not implemented on the device")
+        cfg = L.Config()
+        L.lib().b2s_default_config(C.byref(cfg))
+        cfg.icp.reg_type = L.REG_POINT_TO_PLANE
+        cfg.icp.max_iter = int(self.icp.maxNumIter)
+        cfg.icp.max_corr_dist = float(self.icp.maxCorrespondenceDistance)
+        cfg.icp.knn = int(self.icp.knn)
+        cfg.icp.knn_radius = float(self.icp.maxDistanceKnn)
+        cfg.icp.rel_fitness = 1e-6
+        cfg.icp.rel_rmse = 1e-6
+        cfg.scan.voxel_size = float(self.scanProcessing.voxelSize)
+        cfg.scan.downsampling_ratio = float(self.scanProcessing.downSamplingRatio)
+        cfg.scan.seed = int(self.seed)
+        cfg.scan.map_builder_cropper = self.mapBuilder.cropper.to_c()
+        cfg.scan.scan_matcher_cropper = self.scanProcessing.cropper.to_c()
+        cfg.map_voxel_size = float(self.mapBuilder.mapVoxelSize)
+        cfg.dense_voxel_size = float(self.denseMapVoxelSize)
+        cfg.nn_cell_size = float(self.nnCellSize)
+        return cfg
+
+
+@dataclass
+class RegistrationResult:
+    """open3d::pipelines::registration::RegistrationResult as read by the callers."""
+    transformation_: np.ndarray
+    fitness_: float
+    inlier_rmse_: float
+    n_corr: int = 0
+    iters: int = 0
+
+
+def _res(r: L.Result) -> RegistrationResult:
+    return RegistrationResult(np.array(r.T, dtype=np.float64).reshape(4, 4), float(r.fitness), float(r.inlier_rmse), int(r.n_corr),
+                              int(r.iters))
+
+
+def _mat(T) -> np.ndarray:
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float64).reshape(4, 4))
+    return T
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# engine handle and device clouds
+# --------------------------------------------------------------------------------------------------------------------
+
+
+class Engine:
+    """One b2s_handle (one CUDA stream).  Use one per host thread."""
+
+    def __init__(self, params: MapperParameters | None = None, device: int = 0, cuda_stream: int | None = None):
+        self.params = params or MapperParameters()
+        self._h = C.c_void_p()
+        cfg = self.params.to_config()
+        L.check(L.lib().b2s_create(C.byref(cfg), C.c_int32(device), C.c_void_p(cuda_stream or 0), C.byref(self._h)))
+        self.device = device
+
+    def set_parameters(self, params: MapperParameters):
+        self.params = params
+        cfg = params.to_config()
+        L.check(L.lib().b2s_set_config(self._h, C.byref(cfg)))
+
+    def synchronize(self):
+        L.check(L.lib().b2s_synchronize(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(L.lib().b2s_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            L.lib().b2s_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- clouds
+    def cloud(self, xyz=None, normals=None) -> "Cloud":
+        c = Cloud(self)
+        if xyz is not None:
+            c.upload(xyz, normals)
+        return c
+
+
+class Cloud:
+    """Device-resident open3d::geometry::PointCloud (points_ + normals_)."""
+
+    def __init__(self, eng: Engine):
+        self.eng = eng
+        self._c = C.c_void_p()
+        L.check(L.lib().b2s_cloud_create(eng._h, C.byref(self._c)))
+
+    def upload(self, xyz, normals=None):
+        xyz = np.asarray(xyz)
+        if xyz.dtype == np.float32 and normals is None:
+            xyz = np.ascontiguousarray(xyz.reshape(-1, 3))
+            L.check(L.lib().b2s_cloud_upload_f32(self.eng._h, self._c, xyz.ctypes.data_as(C.c_void_p), C.c_size_t(len(xyz)),
+                                                 C.c_size_t(12)))
+            return self
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        n = len(xyz)
+        nptr = None
+        if normals is not None:
+            normals = np.ascontiguousarray(normals, dtype=np.float64).reshape(-1, 3)
+            assert len(normals) == n
+            nptr = _pd(normals)
+        L.check(L.lib().b2s_cloud_upload_f64(self.eng._h, self._c, _pd(xyz), nptr, C.c_size_t(n)))
+        return self
+
+    def upload_pinned_f32(self, ptr: int, n: int, stride: int = 12):
+        L.check(L.lib().b2s_cloud_upload_f32(self.eng._h, self._c, C.c_void_p(ptr), C.c_size_t(n), C.c_size_t(stride)))
+        return self
+
+    def size(self):
+        n = C.c_size_t(); hn = C.c_int32()
+        L.check(L.lib().b2s_cloud_size(self.eng._h, self._c, C.byref(n), C.byref(hn)))
+        return int(n.value), bool(hn.value)
+
+    def __len__(self):
+        return self.size()[0]
+
+    def HasNormals(self):
+        return self.size()[1]
+
+    def download(self):
+        n, hn = self.size()
+        xyz = np.empty((n, 3)); nrm = np.empty((n, 3)) if hn else None
+        m = C.c_size_t()
+        L.check(L.lib().b2s_cloud_download(self.eng._h, self._c, _pd(xyz), _pd(nrm) if hn else None, C.c_size_t(n), C.byref(m)))
+        return xyz, nrm
+
+    def free(self):
+        if self._c:
+            L.lib().b2s_cloud_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# stage-level operators
+# --------------------------------------------------------------------------------------------------------------------
+
+
+def crop(eng: Engine, cloud: Cloud, cropper: L.Cropper) -> Cloud:
+    out = Cloud(eng)
+    L.check(L.lib().b2s_crop(eng._h, cloud._c, C.byref(cropper), out._c))
+    return out
+
+
+def voxelize(eng: Engine, cloud: Cloud, voxel_size: float) -> Cloud:
+    """o3d_slam::voxelize (src/helpers.cpp:107-113)."""
+    out = Cloud(eng)
+    L.check(L.lib().b2s_voxel_down_sample(eng._h, cloud._c, C.c_double(voxel_size), out._c))
+    return out
+
+
+def random_down_sample(eng: Engine, cloud: Cloud, ratio: float, seed: int) -> Cloud:
+    out = Cloud(eng)
+    L.check(L.lib().b2s_random_down_sample(eng._h, cloud._c, C.c_double(ratio), C.c_uint32(seed), out._c))
+    return out
+
+
+def transform(eng: Engine, T, cloud: Cloud) -> Cloud:
+    """o3d_slam::transform (src/helpers.cpp:273-305)."""
+    out = Cloud(eng)
+    T = _mat(T)
+    L.check(L.lib().b2s_transform(eng._h, cloud._c, _pd(T), out._c))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CloudRegistration (include/open3d_slam/CloudRegistration.hpp)
+# --------------------------------------------------------------------------------------------------------------------
+
+
+class CloudRegistration:
+    def registerClouds(self, source: Cloud, target: Cloud, init) -> RegistrationResult:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def estimateNormalsOrCovariancesIfNeeded(self, cloud: Cloud) -> None:
+        return None
+
+
+class RegistrationIcpPointToPlane(CloudRegistration):
+    """src/CloudRegistration.cpp:44-66"""
+
+    def __init__(self, eng: Engine, p: CloudRegistrationParameters | None = None):
+        self.eng = eng
+        p = p or CloudRegistrationParameters(icp=eng.params.icp)
+        self.maxCorrespondenceDistance_ = p.icp.maxCorrespondenceDistance
+        self.knnNormalEstimation_ = p.icp.knn
+        self.maxRadiusNormalEstimation_ = p.icp.maxDistanceKnn
+        self.max_iteration_ = p.icp.maxNumIter
+
+    def _apply(self):
+        mp = self.eng.params
+        if (mp.icp.maxCorrespondenceDistance, mp.icp.maxNumIter) != (self.maxCorrespondenceDistance_, self.max_iteration_):
+            import copy
+            mp = copy.deepcopy(mp)
+            mp.icp.maxCorrespondenceDistance = self.maxCorrespondenceDistance_
+            mp.icp.maxNumIter = self.max_iteration_
+            self.eng.set_parameters(mp)
+
+    def registerClouds(self, source: Cloud, target: Cloud, init) -> RegistrationResult:
+        self._apply()
+        T = _mat(init)
+        r = L.Result()
+        L.check(L.lib().b2s_register(self.eng._h, source._c, target._c, _pd(T), C.byref(r)))
+        return _res(r)
+
+    def registerCloudsBatch(self, sources, targets, inits):
+        """n independent registrations in one launch (the loop of src/PlaceRecognition.cpp:71,111)."""
+        self._apply()
+        n = len(sources)
+        S = (C.c_void_p * n)(*[s._c for s in sources]); Tg = (C.c_void_p * n)(*[t._c for t in targets])
+        I = np.ascontiguousarray(np.asarray(inits, dtype=np.float64).reshape(n, 16))
+        R = (L.Result * n)()
+        L.check(L.lib().b2s_register_batch(self.eng._h, C.c_int32(n), S, Tg, _pd(I), R))
+        return [_res(r) for r in R]
+
+    def estimateNormalsOrCovariancesIfNeeded(self, cloud: Cloud) -> None:
+        L.check(L.lib().b2s_estimate_normals(self.eng._h, cloud._c, C.c_int32(self.knnNormalEstimation_),
+                                             C.c_double(self.maxRadiusNormalEstimation_)))
+
+
+def cloudRegistrationFactory(eng: Engine, p: CloudRegistrationParameters) -> CloudRegistration:
+    """src/CloudRegistration.cpp:85-100"""
+    if p.regType == "PointToPlaneIcp":
+        return RegistrationIcpPointToPlane(eng, p)
+    if p.regType in ("PointToPointIcp", "GeneralizedIcp"):
+        raise L.B2SError(L.E_UNSUPPORTED, f"{p.regType} is not implemented on the device (SURVEY.md 8f rank 3)")
+    raise RuntimeError("cloud: unknown type of cloud registration")
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Submap (map side) and ScanToMapIcp
+# --------------------------------------------------------------------------------------------------------------------
+
+
+class Submap:
+    """Device-resident Submap::mapCloud_ (+ dense map).  src/Submap.cpp:39-92,184-191"""
+
+    def __init__(self, eng: Engine, capacity_points: int = 2_000_000):
+        self.eng = eng
+        self._s = C.c_void_p()
+        L.check(L.lib().b2s_submap_create(eng._h, C.c_size_t(capacity_points), C.byref(self._s)))
+        self.capacity = capacity_points
+        self.nScansInsertedMap_ = 0
+
+    def isEmpty(self) -> bool:
+        return self.size() == 0
+
+    def size(self) -> int:
+        n = C.c_size_t()
+        L.check(L.lib().b2s_submap_size(self.eng._h, self._s, C.byref(n)))
+        return int(n.value)
+
+    def insertScan(self, rawScan, preProcessedScan: Cloud, mapToRangeSensor, time=None, isPerformCarving=False) -> bool:
+        if isPerformCarving:
+            raise L.B2SError(L.E_UNSUPPORTED, "space carving is not implemented yet (SURVEY.md 8f rank 1)")
+        T = _mat(mapToRangeSensor)
+        L.check(L.lib().b2s_submap_insert(self.eng._h, self._s, preProcessedScan._c, _pd(T)))
+        self.nScansInsertedMap_ += 1
+        return True
+
+    def insertScanDenseMap(self, rawScan: Cloud, mapToRangeSensor, denseCropper: L.Cropper | None = None) -> bool:
+        T = _mat(mapToRangeSensor)
+        L.check(L.lib().b2s_submap_insert_dense(self.eng._h, self._s, rawScan._c, _pd(T), C.byref(denseCropper) if denseCropper else None))
+        return True
+
+    def getMapPointCloud(self):
+        n = self.size()
+        xyz = np.empty((n, 3)); nrm = np.empty((n, 3)); m = C.c_size_t()
+        L.check(L.lib().b2s_submap_download(self.eng._h, self._s, _pd(xyz), _pd(nrm), C.c_size_t(n), C.byref(m)))
+        return xyz[:m.value], nrm[:m.value]
+
+    def getDenseMap(self, capacity=1 << 22):
+        xyz = np.empty((capacity, 3)); keys = np.empty((capacity, 3), dtype=np.int32); m = C.c_size_t()
+        L.check(L.lib().b2s_submap_dense_download(self.eng._h, self._s, _pd(xyz), None, keys.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                  C.c_size_t(capacity), C.byref(m)))
+        return xyz[:m.value].copy(), keys[:m.value].copy()
+
+    def setMapPointCloud(self, cloud: Cloud):
+        L.check(L.lib().b2s_submap_set_cloud(self.eng._h, self._s, cloud._c))
+
+    def setPose(self, T):
+        T = _mat(T)
+        L.check(L.lib().b2s_submap_set_pose(self.eng._h, self._s, _pd(T)))
+
+    def getPose(self):
+        T = np.empty((4, 4))
+        L.check(L.lib().b2s_submap_get_pose(self.eng._h, self._s, _pd(T)))
+        return T
+
+    def free(self):
+        if self._s:
+            L.lib().b2s_submap_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class ProcessedScans:
+    merge_: Cloud
+    match_: Cloud
+
+
+class ScanToMapRegistration:
+    pass
+
+
+class ScanToMapIcp(ScanToMapRegistration):
+    """src/ScanToMapRegistration.cpp:19-89"""
+
+    def __init__(self, eng: Engine):
+        self.eng = eng
+        self.params_ = eng.params
+
+    def setParameters(self, p: MapperParameters):
+        self.params_ = p
+        self.eng.set_parameters(p)
+
+    def processForScanMatchingAndMerging(self, rawScan: Cloud, mapToRangeSensor=None) -> ProcessedScans:
+        merge, match = Cloud(self.eng), Cloud(self.eng)
+        L.check(L.lib().b2s_process_scan(self.eng._h, rawScan._c, merge._c, match._c))
+        # assert_gt(narrowCropped / wideCropped size, 0)   ScanToMapRegistration.cpp:51-52
+        self.eng.synchronize()
+        return ProcessedScans(merge, match)
+
+    def scanToMapRegistration(self, scan: Cloud, activeSubmap: Submap, mapToRangeSensor, initialGuess) -> RegistrationResult:
+        T0 = _mat(mapToRangeSensor); T1 = _mat(initialGuess)
+        r = L.Result()
+        L.check(L.lib().b2s_register_to_submap(self.eng._h, scan._c, activeSubmap._s, _pd(T0), _pd(T1), C.byref(r)))
+        return _res(r)
+
+    def isMergeScanValid(self, cloud: Cloud) -> bool:
+        return cloud.HasNormals()
+
+    def prepareInitialMap(self, mapCloud: Cloud) -> None:
+        ic = self.params_.icp
+        L.check(L.lib().b2s_estimate_normals(self.eng._h, mapCloud._c, C.c_int32(ic.knn), C.c_double(ic.maxDistanceKnn)))
+
+
+def scanToMapRegistrationFactory(eng: Engine, p: MapperParameters) -> ScanToMapRegistration:
+    """src/ScanToMapRegistration.cpp:91-103"""
+    if p.scanToMapRegType in ("PointToPlaneIcp",):
+        s = ScanToMapIcp(eng)
+        s.setParameters(p)
+        return s
+    if p.scanToMapRegType in ("GeneralizedIcp", "PointToPointIcp"):
+        raise L.B2SError(L.E_UNSUPPORTED, f"{p.scanToMapRegType} is not implemented on the device")
+    raise RuntimeError("scanToMapRegistrationFactory: unknown type of registration scan to map")
+
+
+class Mapper:
+    """Host control flow of Mapper::addRangeMeasurement (src/Mapper.cpp:101-181), single active submap, no carving.
+    The odometry prediction is supplied per call as `odometryMotion` (odomToRangeSensorPrev^-1 * odomToRangeSensor)."""
+
+    def __init__(self, eng: Engine, submap_capacity: int = 2_000_000):
+        self.eng = eng
+        self.params_ = eng.params
+        self.scan2MapReg_ = scanToMapRegistrationFactory(eng, eng.params)
+        self.submap = Submap(eng, submap_capacity)
+        self.mapToRangeSensor_ = np.eye(4)
+        self.mapToRangeSensorPrev_ = np.eye(4)
+        self.mapToRangeSensorLastScanInsertion_ = np.eye(4)
+        self._first = True
+        self.lastResult = None
+
+    def addRangeMeasurement(self, rawScan: Cloud, odometryMotion=None) -> bool:
+        if self._first:  # Mapper.cpp:105-114
+            processed = self.scan2MapReg_.processForScanMatchingAndMerging(rawScan, self.mapToRangeSensor_)
+            self.submap.insertScan(rawScan, processed.merge_, np.eye(4))
+            self._first = False
+            return True
+        estimate = self.mapToRangeSensorPrev_ if odometryMotion is None else self.mapToRangeSensorPrev_ @ _mat(odometryMotion)
+        processed = self.scan2MapReg_.processForScanMatchingAndMerging(rawScan, self.mapToRangeSensor_)
+        result = self.scan2MapReg_.scanToMapRegistration(processed.match_, self.submap, self.mapToRangeSensor_, estimate)
+        self.lastResult = result
+        if (not self.params_.isIgnoreMinRefinementFitness) and result.fitness_ < self.params_.minRefinementFitness:
+            return False  # Mapper.cpp:151-156
+        self.mapToRangeSensor_ = result.transformation_.copy()
+        motion = np.linalg.inv(self.mapToRangeSensorLastScanInsertion_) @ self.mapToRangeSensor_
+        if not (np.linalg.norm(motion[:3, 3]) < self.params_.minMovementBetweenMappingSteps):
+            self.submap.insertScan(rawScan, processed.merge_, self.mapToRangeSensor_)
+            self.mapToRangeSensorLastScanInsertion_ = self.mapToRangeSensor_.copy()
+        self.mapToRangeSensorPrev_ = self.mapToRangeSensor_.copy()
+        return True
+
+    # ---- asynchronous device-resident chain (no host round trip per scan) ---------------------------------------------
+    def addRangeMeasurementAsync(self, rawScan: Cloud, odometryMotion, slot: int = 0):
+        M = _mat(odometryMotion)
+        L.check(L.lib().b2s_mapper_step_async(self.eng._h, self.submap._s, rawScan._c, _pd(M), C.c_double(self.params_.minRefinementFitness),
+                                              C.c_int32(int(self.params_.isIgnoreMinRefinementFitness)), C.c_int32(slot)))
+
+    def fetchResult(self, slot: int = 0) -> RegistrationResult:
+        r = L.Result()
+        L.check(L.lib().b2s_scan_result_fetch(self.eng._h, C.c_int32(slot), C.byref(r)))
+        return _res(r)
