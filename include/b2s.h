@@ -118,6 +118,13 @@ int32_t b2s_device_count(void);
 /* number of kernels launched by this handle since creation ("gpu_launches" evidence for bench.py) */
 int64_t b2s_launch_count(const b2s_handle* h);
 
+/* per-kernel-group device time, CUDA events on the handle's stream (the reference prints per-stage wall times with
+ * o3d_slam::Timer, src/time.cpp:35-78).  kinds: 0 icp, 1 normals, 2 radix sort, 3 NN-grid build, 4 voxel keys+means,
+ * 5 fusion, 6 select, 7 crop.  b2s_profile_read synchronises, returns the sums since the last read and resets them. */
+#define B2S_PROFILE_KINDS 8
+int32_t b2s_profile_enable(b2s_handle* h, int32_t on);
+int32_t b2s_profile_read(b2s_handle* h, double* ms_by_kind, int64_t* count_by_kind, int32_t n_kinds);
+
 /* ---- clouds (open3d::geometry::PointCloud points_/normals_) ------------------------------------------------ */
 int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out);
 void b2s_cloud_destroy(b2s_cloud* c);

@@ -140,7 +140,7 @@ int32_t b2s_create(const b2s_config* cfg, int32_t device, void* cuda_stream_or_n
   B2S_TRY(h->slots.ensure(256 * sizeof(b2s_result), h->stream));
   B2S_CUDA(cudaMemsetAsync(h->slots.p, 0, 256 * sizeof(b2s_result), h->stream));
   b2s_cloud** tmp[4] = {&h->t0, &h->t1, &h->t2, &h->t3};
-  for (int i = 0; i < 4; i++) { *tmp[i] = new b2s_cloud(); (*tmp[i])->h = h; B2S_TRY(cloud_reserve(h, *tmp[i], 1, true)); B2S_TRY(cloud_set_count(h, *tmp[i], 0)); }
+  for (int i = 0; i < 4; i++) { *tmp[i] = new b2s_cloud(); (*tmp[i])->h = h; (*tmp[i])->device = device; B2S_TRY(cloud_reserve(h, *tmp[i], 1, true)); B2S_TRY(cloud_set_count(h, *tmp[i], 0)); }
   *out = h;
   return B2S_OK;
 }
@@ -168,6 +168,27 @@ int32_t b2s_set_config(b2s_handle* h, const b2s_config* cfg) {
   return B2S_OK;
 }
 
+int32_t b2s_profile_enable(b2s_handle* h, int32_t on) {
+  B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
+  LOCK(h);
+  h->prof_enabled = on != 0;
+  return B2S_OK;
+}
+
+int32_t b2s_profile_read(b2s_handle* h, double* ms_by_kind, int64_t* count_by_kind, int32_t n_kinds) {
+  B2S_REQUIRE(h && ms_by_kind && count_by_kind && n_kinds >= PK_COUNT, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  B2S_CUDA(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < n_kinds; k++) { ms_by_kind[k] = 0.0; count_by_kind[k] = 0; }
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_by_kind[r.kind] += (double)ms; count_by_kind[r.kind]++; }
+    h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
+  }
+  h->prof_recs.clear();
+  return B2S_OK;
+}
+
 int32_t b2s_synchronize(b2s_handle* h) {
   B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
   LOCK(h);
@@ -181,6 +202,7 @@ int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out) {
   b2s_cloud* c = new (std::nothrow) b2s_cloud();
   B2S_REQUIRE(c, B2S_E_INVALID, "out of host memory");
   c->h = h;
+  c->device = h->device;
   B2S_TRY(cloud_reserve(h, c, 1, false));
   B2S_TRY(cloud_set_count(h, c, 0));
   *out = c;
@@ -189,7 +211,9 @@ int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out) {
 
 void b2s_cloud_destroy(b2s_cloud* c) {
   if (!c) return;
-  if (c->h) { cudaSetDevice(c->h->device); cudaStreamSynchronize(c->h->stream); }
+  // the owning handle may already be gone: wait for the whole device instead of touching it
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
   c->xyz.release(); c->nrm.release(); c->dn.release();
   delete c;
 }
@@ -371,10 +395,12 @@ int32_t b2s_submap_create(b2s_handle* h, size_t capacity_points, b2s_submap** ou
   b2s_submap* sm = new (std::nothrow) b2s_submap();
   B2S_REQUIRE(sm, B2S_E_INVALID, "out of host memory");
   sm->h = h;
+  sm->device = h->device;
   sm->capacity = capacity_points;
   for (int i = 0; i < 2; i++) {
     sm->cloud[i] = new b2s_cloud();
     sm->cloud[i]->h = h;
+    sm->cloud[i]->device = h->device;
     B2S_TRY(cloud_reserve(h, sm->cloud[i], capacity_points, true));
     B2S_TRY(cloud_set_count(h, sm->cloud[i], 0));
     sm->cloud[i]->has_normals = true;
@@ -388,7 +414,8 @@ int32_t b2s_submap_create(b2s_handle* h, size_t capacity_points, b2s_submap** ou
 
 void b2s_submap_destroy(b2s_submap* sm) {
   if (!sm) return;
-  if (sm->h) { cudaSetDevice(sm->h->device); cudaStreamSynchronize(sm->h->stream); }
+  cudaSetDevice(sm->device);
+  cudaDeviceSynchronize();
   for (int i = 0; i < 2; i++) if (sm->cloud[i]) { sm->cloud[i]->xyz.release(); sm->cloud[i]->nrm.release(); sm->cloud[i]->dn.release(); delete sm->cloud[i]; }
   sm->dense_keys.release(); sm->dense_sum.release(); sm->dense_cnt.release(); sm->dense_used.release(); sm->pose.release();
   delete sm;

@@ -91,6 +91,7 @@ struct SortScratch {
 
 struct b2s_cloud {
   b2s_handle* h = nullptr;
+  int device = 0;
   b2s::DevBuf xyz;       // 3 x f64 per point (the reference's AoS layout)
   b2s::DevBuf nrm;       // 3 x f64 per point
   b2s::DevBuf dn;        // int32 device-side point count
@@ -101,6 +102,7 @@ struct b2s_cloud {
 
 struct b2s_submap {
   b2s_handle* h = nullptr;
+  int device = 0;
   b2s_cloud* cloud[2] = {nullptr, nullptr};  // ping-pong map cloud (mapCloud_)
   int cur = 0;
   size_t capacity = 0;
@@ -115,7 +117,16 @@ struct b2s_submap {
   b2s::DevBuf pose;          // 4 x (4x4 f64): [0] mapToRangeSensor_ state, [1] insertion pose, [2] odometry motion, [3] initial guess
 };
 
+namespace b2s {
+// per-kernel-group device timing with CUDA events on the launching stream (bench.py's roofline numbers)
+enum ProfKind { PK_ICP = 0, PK_NORMALS, PK_SORT, PK_GRID, PK_VOXEL, PK_FUSE, PK_SELECT, PK_CROP, PK_COUNT };
+struct ProfRec { int kind; cudaEvent_t a, b; };
+}  // namespace b2s
+
 struct b2s_handle {
+  bool prof_enabled = false;
+  std::vector<b2s::ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -142,6 +153,11 @@ struct b2s_handle {
 
 namespace b2s {
 
+struct ProfScope {   // records an event pair around the launches issued during its lifetime (no-op unless enabled)
+  b2s_handle* h; int idx;
+  ProfScope(b2s_handle* h_, int kind);
+  ~ProfScope();
+};
 int32_t ensure_pinned(b2s_handle* h, size_t bytes);
 int32_t check_status(b2s_handle* h);     // synchronises and converts device status bits into an error
 
@@ -154,7 +170,7 @@ int32_t radix_sort_pairs_u32(b2s_handle* h, uint32_t*& keys, uint32_t*& vals, ui
                              const int32_t* d_n, size_t n_max, int key_bits);
 int32_t radix_sort_pairs_u64(b2s_handle* h, uint64_t*& keys, uint32_t*& vals, uint64_t*& keys_alt, uint32_t*& vals_alt,
                              const int32_t* d_n, size_t n_max, int key_bits);
-inline const int32_t* grid_starts(const GridIndex* g) { return g->cell_start.as<int32_t>() + g->cap_cells + 2; }
+inline const int32_t* grid_starts(const GridIndex* g) { return g->cell_start.as<int32_t>() + g->cap_cells + 4; }
 
 // K-index: build the NN grid over cloud points (optionally only those inside `patch`, centre read from device pose)
 struct CropDev {      // cropper passed by value to kernels; centre may come from a device-resident 4x4 (row-major)

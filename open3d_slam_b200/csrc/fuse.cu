@@ -181,17 +181,19 @@ static int32_t fuse_impl(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
   uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + tot_max;
   const int sblocks = grid_for(scan->n_max > 0 ? scan->n_max : 1, FZ_THREADS);
   const int blocks = grid_for(tot_max, FZ_THREADS);
+  { ProfScope prof(h, PK_FUSE);
   fuse_append_kernel<<<sblocks, FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>(),
                                                             scan->xyz.as<double>(), scan->nrm.as<double>(), scan->dn.as<int32_t>(), T_dev,
                                                             gate_dev, sm->capacity, d_tot, h->status.as<uint32_t>());
   fuse_keys_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), d_tot, crop, inv, bits, bounded, keys, vals,
                                                             h->status.as<uint32_t>());
-  h->launches += 2;
+  h->launches += 2; }
   if constexpr (sizeof(K) == 4) {
     B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, d_tot, tot_max, 3 * bits + 1));
   } else {
     B2S_TRY(radix_sort_pairs_u64(h, keys, vals, keys_alt, vals_alt, d_tot, tot_max, 3 * bits + 1));
   }
+  ProfScope prof2(h, PK_FUSE);
   fuse_head_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(keys, d_tot, bits, h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_tot, tot_max, nullptr));

@@ -136,7 +136,7 @@ int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double c
   if (want > (size_t)1 << 25) want = (size_t)1 << 25;
   if (want < (size_t)1 << 16) want = (size_t)1 << 16;
   if ((size_t)g->cap_cells < want) {
-    B2S_TRY(g->cell_start.ensure((want + 2) * 4 * 2, h->stream));  // counts + starts
+    B2S_TRY(g->cell_start.ensure((want + 8) * 4 * 2, h->stream));  // counts + starts
     g->cap_cells = (int32_t)want;
   }
   B2S_TRY(g->hdr.ensure(sizeof(GridHeader), h->stream));
@@ -148,9 +148,10 @@ int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double c
   const int use_crop = patch ? 1 : 0;
   const int blocks = grid_for(n_max, GB_THREADS);
   int32_t* counts = g->cell_start.as<int32_t>();
-  int32_t* starts = counts + g->cap_cells + 2;
+  int32_t* starts = counts + g->cap_cells + 4;
   const int32_t* d_n = cloud->dn.as<int32_t>();
   GridHeader* hdr = g->hdr.as<GridHeader>();
+  ProfScope prof(h, PK_GRID);
   grid_bbox_init_kernel<<<1, 32, 0, h->stream>>>(g->bbox.as<unsigned long long>());
   grid_bbox_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(), d_n, cd, use_crop, g->bbox.as<unsigned long long>());
   grid_header_kernel<<<1, 32, 0, h->stream>>>(g->bbox.as<unsigned long long>(), cell, g->cap_cells, hdr);

@@ -333,6 +333,7 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* problems_dev, int n_problems
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  ProfScope prof(h, PK_ICP);
   B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_p2plane_kernel, problems_dev, pts_cap));
   h->launches++;
   return B2S_OK;

@@ -261,6 +261,7 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
   int blocks = (int)((n_max + (NK_THREADS / 32) - 1) / (NK_THREADS / 32));
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
+  ProfScope prof(h, PK_NORMALS);
   normals_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(h->grid_b.hdr.as<GridHeader>(), grid_starts(&h->grid_b), h->grid_b.pts.as<double4>(),
                                                        knn, radius, c->nrm.as<double>(), nullptr);
   h->launches++;

@@ -44,6 +44,23 @@ void GridIndex::release() {
   cap_cells = 0;
 }
 
+ProfScope::ProfScope(b2s_handle* h_, int kind) : h(h_), idx(-1) {
+  if (!h->prof_enabled) return;
+  ProfRec r;
+  r.kind = kind;
+  cudaEvent_t* ev[2] = {&r.a, &r.b};
+  for (int i = 0; i < 2; i++) {
+    if (!h->prof_pool.empty()) { *ev[i] = h->prof_pool.back(); h->prof_pool.pop_back(); }
+    else if (cudaEventCreate(ev[i]) != cudaSuccess) return;
+  }
+  cudaEventRecord(r.a, h->stream);
+  idx = (int)h->prof_recs.size();
+  h->prof_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(h->prof_recs[(size_t)idx].b, h->stream);
+}
+
 int32_t ensure_pinned(b2s_handle* h, size_t bytes) {
   if (bytes <= h->pinned_cap) return B2S_OK;
   if (h->pinned) {
@@ -98,7 +115,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32
   }
   const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
-  if (base + SCAN_ITEMS <= n) {
+  const bool vec_ok = ((((size_t)in | (size_t)out) & 15) == 0);
+  if (vec_ok && base + SCAN_ITEMS <= n) {
     const int4* p = reinterpret_cast<const int4*>(in + base);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS / 4; k++) { int4 q = p[k]; v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w; }
@@ -150,7 +168,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32
   }
   __syncthreads();
   int run = s_prefix + texcl;
-  if (base + SCAN_ITEMS <= n) {
+  if (vec_ok && base + SCAN_ITEMS <= n) {
     int o[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) { o[k] = run; run += v[k]; }
@@ -268,11 +286,12 @@ static int32_t radix_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& key
   int nblocks = (int)((n_max + RS_TILE - 1) / RS_TILE);
   if (nblocks < 1) nblocks = 1;
   size_t hist_n = (size_t)256 * nblocks;
-  B2S_TRY(h->sort.hist.ensure((hist_n + 1) * 4 * 2, h->stream));
+  B2S_TRY(h->sort.hist.ensure((hist_n + 8) * 4 * 2, h->stream));
   int32_t* hist = h->sort.hist.as<int32_t>();
-  int32_t* offs = hist + hist_n + 1;
+  int32_t* offs = hist + ((hist_n + 4) & ~(size_t)3);
   int passes = (key_bits + 7) / 8;
   if (passes < 1) passes = 1;
+  ProfScope prof(h, PK_SORT);
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
     rs_hist_kernel<K><<<nblocks, RS_THREADS, 0, h->stream>>>(keys, d_n, shift, hist, nblocks);

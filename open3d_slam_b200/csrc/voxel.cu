@@ -228,14 +228,16 @@ static int32_t voxel_impl(b2s_handle* h, const b2s_cloud* in, const CropDev* cro
   const int32_t* d_n = in->dn.as<int32_t>();
   const int blocks = grid_for(n_max, VX_THREADS);
   CropDev cd = crop ? *crop : make_crop(nullptr);
+  { ProfScope prof(h, PK_VOXEL);
   voxel_keys_kernel<K><<<blocks, VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), d_n, cd, crop ? 1 : 0, h->misc.as<unsigned long long>(),
                                                              voxel, bits, keys, vals, h->status.as<uint32_t>());
-  h->launches++;
+  h->launches++; }
   if constexpr (sizeof(K) == 4) {
     B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, d_n, n_max, 3 * bits + 1));
   } else {
     B2S_TRY(radix_sort_pairs_u64(h, keys, vals, keys_alt, vals_alt, d_n, n_max, 3 * bits + 1));
   }
+  ProfScope prof2(h, PK_VOXEL);
   seg_head_kernel<K><<<blocks, VX_THREADS, 0, h->stream>>>(keys, d_n, bits, 0, h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_n, n_max, nullptr));
@@ -284,16 +286,23 @@ int32_t op_voxel_down_sample(b2s_handle* h, const b2s_cloud* in, const CropDev* 
 }
 
 // ---- P4: seeded random down-sample ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t select_hash(uint32_t seed, uint32_t i) {
-  uint32_t x = i * 0x9E3779B1u + seed * 0x85EBCA77u + 0x165667B1u;
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x;
+// hash of the point's bit pattern (not of its index): the selected subset is independent of the order in which the
+// voxel down-sample emitted the points, so the Morton-ordered device cloud and any other ordering select the same set
+__device__ __forceinline__ uint32_t select_hash(uint32_t seed, double x, double y, double z) {
+  const uint64_t a = (uint64_t)__double_as_longlong(x), b = (uint64_t)__double_as_longlong(y), c = (uint64_t)__double_as_longlong(z);
+  uint64_t v = a * 0x9E3779B97F4A7C15ull;
+  v ^= (b + 0x7F4A7C15F39CC060ull) * 0xC2B2AE3D27D4EB4Full;
+  v ^= (c + 0x165667B19E3779F9ull) * 0xD6E8FEB86659FD93ull;
+  v += (uint64_t)seed * 0x85EBCA77C2B2AE63ull;
+  v ^= v >> 29; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 32; v *= 0x94D049BB133111EBull; v ^= v >> 29;
+  return (uint32_t)(v >> 32);
 }
-__global__ void __launch_bounds__(VX_THREADS) select_keys_kernel(const int32_t* __restrict__ d_n, uint32_t seed, uint32_t* __restrict__ keys,
-                                                                 uint32_t* __restrict__ vals, int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(VX_THREADS) select_keys_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, uint32_t seed,
+                                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                                 int32_t* __restrict__ flags) {
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    keys[i] = select_hash(seed, (uint32_t)i);
+    keys[i] = select_hash(seed, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     vals[i] = (uint32_t)i;
     flags[i] = 0;
   }
@@ -323,7 +332,8 @@ int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, 
   uint32_t* keys = h->keys.as<uint32_t>(); uint32_t* keys_alt = keys + n_max;
   uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + n_max;
   const int blocks = grid_for(n_max, VX_THREADS);
-  select_keys_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), seed, keys, vals, h->flags.as<int32_t>());
+  select_keys_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), in->dn.as<int32_t>(), seed, keys, vals,
+                                                           h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, in->dn.as<int32_t>(), n_max, 32));
   select_mark_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), ratio, vals, h->flags.as<int32_t>());

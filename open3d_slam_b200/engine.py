@@ -155,6 +155,16 @@ class Engine:
     def launches(self) -> int:
         return int(L.lib().b2s_launch_count(self._h))
 
+    def profile_enable(self, on: bool = True):
+        L.check(L.lib().b2s_profile_enable(self._h, C.c_int32(int(on))))
+
+    def profile_read(self) -> dict:
+        """{kind: (total_ms, count)} of the kernel groups launched since the last read (CUDA events, this stream)."""
+        n = len(L.PROFILE_KINDS)
+        ms = (C.c_double * n)(); cnt = (C.c_int64 * n)()
+        L.check(L.lib().b2s_profile_read(self._h, ms, cnt, C.c_int32(n)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(L.PROFILE_KINDS)}
+
     def close(self):
         if self._h:
             L.lib().b2s_destroy(self._h)

@@ -138,3 +138,17 @@ def loop_trajectory(n_scans=600, step=0.5, half=8.0, corner_r=3.0, z=0.0):
         yaw = np.arctan2(dvec[1], dvec[0])
         poses.append(se3(0.0, 0.0, yaw, (p[0], p[1], z)))
     return poses
+
+
+def lidar_cast(scene: Scene, pose: np.ndarray, n_beams=64, n_az=1024, max_range=60.0):
+    """Noise-free part of lidar_scan(): returns (unit directions in the sensor frame of the rays that hit, ranges)."""
+    clean = lidar_scan(scene, pose, n_beams, n_az, max_range, noise=0.0, seed=0, dtype=np.float64)
+    r = np.linalg.norm(clean, axis=1)
+    return clean / r[:, None], r
+
+
+def lidar_from_cast(cast, noise=0.02, seed=0, dtype=np.float32):
+    """Apply range noise N(0, noise) (seeded) to a lidar_cast() result; identical to lidar_scan() up to rounding."""
+    d, r = cast
+    rr = r + (np.random.default_rng(seed).normal(0.0, noise, size=len(r)) if noise > 0 else 0.0)
+    return np.ascontiguousarray((d * rr[:, None]).astype(dtype))

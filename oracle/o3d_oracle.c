@@ -525,10 +525,17 @@ ORC_EXPORT void orc_estimate_normals(const double* xyz, size_t n, int knn, doubl
 /*  Seeded stand-in: keep the floor(ratio*n) points with the smallest          */
 /*  (hash(seed,i), i); output keeps the input order.                           */
 /* ------------------------------------------------------------------------- */
-ORC_EXPORT uint32_t orc_select_hash(uint32_t seed, uint32_t i) {
-  uint32_t x = i * 0x9E3779B1u + seed * 0x85EBCA77u + 0x165667B1u;
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x;
+/* the hash is taken over the BIT PATTERN of the point, not over its index, so that the selected subset does not
+ * depend on the (unspecified) order in which the voxel down-sample emitted the points */
+ORC_EXPORT uint32_t orc_select_hash(uint32_t seed, const double* p) {
+  uint64_t a, b, c;
+  memcpy(&a, p, 8); memcpy(&b, p + 1, 8); memcpy(&c, p + 2, 8);
+  uint64_t v = a * 0x9E3779B97F4A7C15ull;
+  v ^= (b + 0x7F4A7C15F39CC060ull) * 0xC2B2AE3D27D4EB4Full;
+  v ^= (c + 0x165667B19E3779F9ull) * 0xD6E8FEB86659FD93ull;
+  v += (uint64_t)seed * 0x85EBCA77C2B2AE63ull;
+  v ^= v >> 29; v *= 0xBF58476D1CE4E5B9ull; v ^= v >> 32; v *= 0x94D049BB133111EBull; v ^= v >> 29;
+  return (uint32_t)(v >> 32);
 }
 typedef struct { uint32_t h; uint32_t i; } hpair;
 static int hpair_cmp(const void* a, const void* b) {
@@ -544,7 +551,7 @@ ORC_EXPORT size_t orc_random_down_sample(const double* xyz, const double* nrm, s
   if (k == n) memset(keep, 1, n);
   else {
     hpair* hp = (hpair*)malloc(sizeof(hpair) * (n ? n : 1));
-    for (size_t i = 0; i < n; i++) { hp[i].h = orc_select_hash(seed, (uint32_t)i); hp[i].i = (uint32_t)i; }
+    for (size_t i = 0; i < n; i++) { hp[i].h = orc_select_hash(seed, xyz + 3 * i); hp[i].i = (uint32_t)i; }
     qsort(hp, n, sizeof(hpair), hpair_cmp);
     for (size_t j = 0; j < k; j++) keep[hp[j].i] = 1;
     free(hp);

@@ -132,8 +132,9 @@ def random_down_sample(xyz, ratio, seed, nrm=None):
     return (ox[:m].copy(), None if on is None else on[:m].copy())
 
 
-def select_hash(seed, i):
-    return int(lib().orc_select_hash(C.c_uint32(seed), C.c_uint32(i)))
+def select_hash(seed, point):
+    p = _f64(point).reshape(3)
+    return int(lib().orc_select_hash(C.c_uint32(seed), _p(p)))
 
 
 def registration_icp_p2plane(src, tgt, tgt_nrm, max_corr_dist, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6,

@@ -335,11 +335,15 @@ def test_mapper_async_chain_matches_sync(engine_factory):
             continue
         m2.addRangeMeasurementAsync(e2.cloud(raw), delta, slot=k)
         r2 = m2.fetchResult(k)
-        assert np.array_equal(r2.transformation_, m1.lastResult.transformation_)
+        # the initial guess is composed on the host (numpy) in one path and on the device in the other: last-bit
+        # differences in the guess are allowed, the converged results must agree far below the 1e-4 target
+        assert np.abs(r2.transformation_ - m1.lastResult.transformation_).max() < 1e-10
         assert r2.n_corr == m1.lastResult.n_corr and r2.iters == m1.lastResult.iters
-    assert np.array_equal(m2.submap.getPose(), m1.mapToRangeSensor_)
+    assert np.abs(m2.submap.getPose() - m1.mapToRangeSensor_).max() < 1e-10
     a = m1.submap.getMapPointCloud()[0]; b = m2.submap.getMapPointCloud()[0]
-    assert np.array_equal(a, b)
+    assert a.shape == b.shape
+    ka, kb = _keyed(a, a, 0.1)[0], _keyed(b, b, 0.1)[0]
+    assert np.abs(ka - kb).max() < 1e-9
 
 
 def test_dense_map_running_sums(engine_factory):
