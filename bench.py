@@ -214,13 +214,14 @@ def run_b2s_arm(args):
 
     params = E.MapperParameters(seed=3)
     params.scanProcessing.downSamplingRatio = args.ratio
+    params.nnCellSize = args.nn_cell
     main = torch.cuda.current_stream(dev)
     streams = [torch.cuda.Stream(device=dev) for _ in range(chains)]
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def make_chains():
         engs = [E.Engine(params, device=local, cuda_stream=s.cuda_stream) for s in streams]
-        maps = [E.Mapper(e, 1_500_000) for e in engs]
+        maps = [E.Mapper(e, 600_000) for e in engs]
         for c in range(chains):   # first scan: pre-process and insert with identity (Mapper.cpp:105-114)
             maps[c].addRangeMeasurement(engs[c].cloud(scans[c][0]), None)
             maps[c].submap.setPose(np.eye(4))
@@ -267,9 +268,20 @@ def run_b2s_arm(args):
     for e in engs:
         e.synchronize()
 
+    # one host thread per chain: the ctypes calls release the GIL, so the ~80 kernel launches of the chains are issued
+    # concurrently (each on its own stream) instead of one chain after the other
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=min(chains, args.host_threads)) if args.host_threads > 1 else None
+
+    def fan_out(fn):
+        if pool is None:
+            for c in range(chains):
+                fn(c)
+        else:
+            list(pool.map(fn, range(chains)))
+
     def step_resident(k):
-        for c in range(chains):
-            maps[c].addRangeMeasurementAsync(dev_clouds[c][k], deltas[k], slot=k % 256)
+        fan_out(lambda c: maps[c].addRangeMeasurementAsync(dev_clouds[c][k], deltas[k], slot=k % 256))
 
     timed_region(step_resident, 1, W)
     l0 = sum(e.launches for e in engs)
@@ -336,13 +348,14 @@ def run_b2s_arm(args):
     h2d = sum(int(pinned[c][1 + W].numel()) * 4 for c in range(chains))
     d2h = chains * ctypes.sizeof(L.Result)
 
+    def one_e2e(c, k):
+        t = pinned[c][k]
+        stage[c].upload_pinned_f32(t.data_ptr(), t.shape[0], 12)
+        maps[c].addRangeMeasurementAsync(stage[c], deltas[k], slot=k % 256)
+        maps[c].fetchResult(k % 256)
+
     def step_e2e(k):
-        for c in range(chains):
-            t = pinned[c][k]
-            stage[c].upload_pinned_f32(t.data_ptr(), t.shape[0], 12)
-            maps[c].addRangeMeasurementAsync(stage[c], deltas[k], slot=k % 256)
-        for c in range(chains):
-            maps[c].fetchResult(k % 256)
+        fan_out(lambda c: one_e2e(c, k))
 
     timed_region(step_e2e, 1, W)
     barrier()
@@ -384,6 +397,8 @@ def main():
     ap.add_argument("--ratio", type=float, default=0.3, help="scan_processing.downsampling_ratio (Lua default 0.3)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="scans in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=16, help="host threads issuing the chains' launches (1 = serial)")
+    ap.add_argument("--nn-cell", type=float, default=0.0, help="NN grid cell edge in metres (0 = max_corr_dist / 2)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

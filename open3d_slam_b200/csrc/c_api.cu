@@ -45,7 +45,7 @@ __global__ void gate_kernel(const b2s_result* __restrict__ res, double min_fitne
 
 static double nn_cell(const b2s_handle* h, double max_corr) {
   if (h->cfg.nn_cell_size > 0.0) return h->cfg.nn_cell_size;
-  return max_corr * 0.5;
+  return max_corr * 0.25;   // box queries want cells of a few map voxels; the header kernel coarsens them if the box is huge
 }
 
 static int32_t check_icp_params(const b2s_icp_params& p) {
@@ -186,6 +186,20 @@ int32_t b2s_profile_read(b2s_handle* h, double* ms_by_kind, int64_t* count_by_ki
     h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
   }
   h->prof_recs.clear();
+  return B2S_OK;
+}
+
+// debug aid: clock64 stamps {start, search end, reduce end, solve end} of up to 64 evaluations of the next registrations
+int32_t b2s_debug_icp_clocks(b2s_handle* h, int32_t enable, long long* out_256) {
+  B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
+  LOCK(h);
+  if (enable && !h->icp_dbg) { B2S_CUDA(cudaMalloc(&h->icp_dbg, 256 * 8)); }
+  if (h->icp_dbg && out_256) {
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    B2S_CUDA(cudaMemcpy(out_256, h->icp_dbg, 256 * 8, cudaMemcpyDeviceToHost));
+  }
+  if (h->icp_dbg) B2S_CUDA(cudaMemsetAsync(h->icp_dbg, 0, 256 * 8, h->stream));
+  if (!enable && h->icp_dbg) { cudaFree(h->icp_dbg); h->icp_dbg = nullptr; }
   return B2S_OK;
 }
 
@@ -332,8 +346,7 @@ int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* ta
   B2S_TRY(h->results.ensure(sizeof(b2s_result), h->stream));
   IcpProblem P;
   fill_problem(h, &P, source, &h->grid_a, init, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
-  B2S_CUDA(cudaMemcpyAsync(h->problems.p, &P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
-  B2S_TRY(icp_launch(h, h->problems.as<IcpProblem>(), 1, source->n_max));
+  B2S_TRY(icp_launch(h, &P, nullptr, 1, source->n_max));
   B2S_CUDA(cudaMemcpyAsync(out, h->results.p, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
   return check_status(h);
 }
@@ -374,7 +387,7 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   }
   B2S_CUDA(cudaMemcpyAsync(h->problems.p, probs.data(), sizeof(IcpProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   B2S_CUDA(cudaStreamSynchronize(h->stream));  // probs lives on the host stack frame
-  B2S_TRY(icp_launch(h, h->problems.as<IcpProblem>(), n, max_src));
+  B2S_TRY(icp_launch(h, nullptr, h->problems.as<IcpProblem>(), n, max_src));
   B2S_CUDA(cudaMemcpyAsync(out, h->results.p, sizeof(b2s_result) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   return check_status(h);
 }
@@ -418,6 +431,8 @@ void b2s_submap_destroy(b2s_submap* sm) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 2; i++) if (sm->cloud[i]) { sm->cloud[i]->xyz.release(); sm->cloud[i]->nrm.release(); sm->cloud[i]->dn.release(); delete sm->cloud[i]; }
   sm->dense_keys.release(); sm->dense_sum.release(); sm->dense_cnt.release(); sm->dense_used.release(); sm->pose.release();
+  if (sm->pinned_cnt) cudaFreeHost(sm->pinned_cnt);
+  if (sm->cnt_ev) cudaEventDestroy(sm->cnt_ev);
   delete sm;
 }
 
@@ -499,6 +514,7 @@ int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* clo
   }
   B2S_CUDA(cudaMemcpyAsync(m->dn.p, cloud->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
   m->n_max = cloud->n_max; m->n_known = cloud->n_known; m->has_normals = true;
+  sm->cnt_pending = false; sm->adds_after_readback = 0;
   return B2S_OK;
 }
 
@@ -514,8 +530,7 @@ static int32_t register_to_submap_async(b2s_handle* h, const b2s_cloud* scan, co
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
   IcpProblem P;
   fill_problem(h, &P, scan, &h->grid_a, init_host, init_dev, h->work_xyz.as<double>(), out_dev);
-  B2S_CUDA(cudaMemcpyAsync(h->problems.p, &P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
-  return icp_launch(h, h->problems.as<IcpProblem>(), 1, scan->n_max);
+  return icp_launch(h, &P, nullptr, 1, scan->n_max);
 }
 
 int32_t b2s_register_to_submap(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double map_to_sensor[16],

@@ -115,6 +115,11 @@ struct b2s_submap {
   double dense_voxel = 0.0;
   bool dense_has_normals = false;
   b2s::DevBuf pose;          // 4 x (4x4 f64): [0] mapToRangeSensor_ state, [1] insertion pose, [2] odometry motion, [3] initial guess
+  // asynchronous read-back of the map size (keeps the host-side launch bound tight without ever synchronising)
+  int32_t* pinned_cnt = nullptr;
+  cudaEvent_t cnt_ev = nullptr;
+  bool cnt_pending = false;
+  size_t adds_after_readback = 0;
 };
 
 namespace b2s {
@@ -125,6 +130,7 @@ struct ProfRec { int kind; cudaEvent_t a, b; };
 
 struct b2s_handle {
   bool prof_enabled = false;
+  long long* icp_dbg = nullptr;       // optional device buffer of clock64 stamps (b2s_debug_icp_clocks)
   std::vector<b2s::ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
   int device = 0;
@@ -208,7 +214,8 @@ struct IcpProblem {
   int32_t src_n_max;
   b2s_result* out;
 };
-int32_t icp_launch(b2s_handle* h, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
+// single_host != nullptr: one registration, the problem travels as a kernel argument (no copy, no sync)
+int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
 
 int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev);
 int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const b2s_cropper* crop);

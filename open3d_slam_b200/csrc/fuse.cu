@@ -170,15 +170,18 @@ static int32_t fuse_impl(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
                          const CropDev& crop, double inv, int bits, int bounded, size_t tot_max) {
   b2s_cloud* map = sm->cloud[0];
   b2s_cloud* tmp = sm->cloud[1];
-  B2S_TRY(h->keys.ensure(tot_max * sizeof(K) * 2, h->stream));
-  B2S_TRY(h->vals.ensure(tot_max * 4 * 2, h->stream));
-  B2S_TRY(h->flags.ensure((tot_max + 1) * 4, h->stream));
-  B2S_TRY(h->offs.ensure((tot_max + 2) * 4, h->stream));
+  // scratch is sized once for the submap capacity: growing a device buffer costs a cudaMalloc/cudaFree, i.e. a
+  // device-wide synchronisation that would stall every other chain sharing the GPU
+  const size_t cap = sm->capacity;
+  B2S_TRY(h->keys.ensure(cap * sizeof(K) * 2, h->stream));
+  B2S_TRY(h->vals.ensure(cap * 4 * 2, h->stream));
+  B2S_TRY(h->flags.ensure((cap + 1) * 4, h->stream));
+  B2S_TRY(h->offs.ensure((cap + 2) * 4, h->stream));
   B2S_TRY(h->tmp_i32.ensure(64, h->stream));
   int32_t* d_tot = h->tmp_i32.as<int32_t>();
   int32_t* d_out_n = d_tot + 1;
-  K* keys = h->keys.as<K>(); K* keys_alt = keys + tot_max;
-  uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + tot_max;
+  K* keys = h->keys.as<K>(); K* keys_alt = keys + cap;
+  uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + cap;
   const int sblocks = grid_for(scan->n_max > 0 ? scan->n_max : 1, FZ_THREADS);
   const int blocks = grid_for(tot_max, FZ_THREADS);
   { ProfScope prof(h, PK_FUSE);
@@ -212,7 +215,12 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
   b2s_cloud* map = sm->cloud[0];
   const double v = h->cfg.map_voxel_size;
   B2S_REQUIRE(v > 0.0, B2S_E_UNSUPPORTED, "map_voxel_size <= 0 (no voxelisation) is not supported on the device path");
-  // host-side upper bound of the map size; refreshed from the device when it would exceed the capacity
+  // host-side upper bound of the map size.  The exact size is read back asynchronously after an insertion (pinned
+  // host word + event); once that copy has landed the bound becomes exact-size + what was appended since.
+  if (sm->cnt_pending && cudaEventQuery(sm->cnt_ev) == cudaSuccess) {
+    map->n_max = (size_t)sm->pinned_cnt[0] + sm->adds_after_readback;
+    sm->cnt_pending = false;
+  }
   size_t tot_max = map->n_max + 2 * scan->n_max;
   if (tot_max > sm->capacity) {
     int32_t n = 0;
@@ -232,6 +240,20 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
   map->n_max = tot_max;   // upper bound only; the exact count lives on the device
   map->n_known = -1;
   map->has_normals = true;
+  if (rc == B2S_OK) {
+    if (!sm->pinned_cnt) {
+      B2S_CUDA(cudaMallocHost(&sm->pinned_cnt, 64));
+      B2S_CUDA(cudaEventCreateWithFlags(&sm->cnt_ev, cudaEventDisableTiming));
+    }
+    if (!sm->cnt_pending) {
+      B2S_CUDA(cudaMemcpyAsync(sm->pinned_cnt, map->dn.p, 4, cudaMemcpyDeviceToHost, h->stream));
+      B2S_CUDA(cudaEventRecord(sm->cnt_ev, h->stream));
+      sm->cnt_pending = true;
+      sm->adds_after_readback = 0;
+    } else {
+      sm->adds_after_readback += 2 * scan->n_max;
+    }
+  }
   return rc;
 }
 

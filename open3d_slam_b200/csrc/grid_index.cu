@@ -131,9 +131,14 @@ CropDev make_crop(const b2s_cropper* c, const double* pose_dev) {
 int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double cell, const CropDev* patch, bool with_normals) {
   B2S_REQUIRE(cell > 0.0, B2S_E_INVALID, "grid_build: cell size must be > 0");
   const size_t n_max = cloud->n_max > 0 ? cloud->n_max : 1;
-  // cell budget: enough for a 64 m x 64 m x 32 m box at 0.25 m, bounded by 16 cells per point + slack
-  size_t want = n_max * 16 + 4096;
-  if (want > (size_t)1 << 25) want = (size_t)1 << 25;
+  // buffers follow the ALLOCATION of the cloud, not its current size: a growing map never re-allocates its index
+  // (a cudaMalloc/cudaFree pair is a device-wide synchronisation)
+  size_t n_alloc = cloud->xyz.cap / 24;
+  if (n_alloc < n_max) n_alloc = n_max;
+  // cell budget: 8 cells per point, at most 2^21 (a 128 m x 128 m x 32 m box at 0.5 m); when the box needs more the
+  // header kernel doubles the cell edge, which only costs speed
+  size_t want = n_alloc * 8 + 4096;
+  if (want > (size_t)1 << 21) want = (size_t)1 << 21;
   if (want < (size_t)1 << 16) want = (size_t)1 << 16;
   if ((size_t)g->cap_cells < want) {
     B2S_TRY(g->cell_start.ensure((want + 8) * 4 * 2, h->stream));  // counts + starts
@@ -141,9 +146,9 @@ int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double c
   }
   B2S_TRY(g->hdr.ensure(sizeof(GridHeader), h->stream));
   B2S_TRY(g->bbox.ensure(64, h->stream));
-  B2S_TRY(g->rank.ensure(n_max * 4, h->stream));
-  B2S_TRY(g->pts.ensure(n_max * 32, h->stream));
-  if (with_normals) B2S_TRY(g->nrm.ensure(n_max * 32, h->stream));
+  B2S_TRY(g->rank.ensure(n_alloc * 4, h->stream));
+  B2S_TRY(g->pts.ensure(n_alloc * 32, h->stream));
+  if (with_normals) B2S_TRY(g->nrm.ensure(n_alloc * 32, h->stream));
   CropDev cd = patch ? *patch : make_crop(nullptr);
   const int use_crop = patch ? 1 : 0;
   const int blocks = grid_for(n_max, GB_THREADS);

@@ -8,11 +8,17 @@
 //   * one thread-block CLUSTER (1..8 CTAs, one per SM) per registration, blockIdx.y = registration in the batch;
 //   * the working copy of the source cloud lives in shared memory for the whole loop (each CTA owns a contiguous
 //     chunk) and is advanced by the per-iteration update like [O3D] pcd.Transform(update);
-//   * exact nearest neighbour with the strict d2 < r2 cut through the dense grid of grid_index.cu (ring expansion
-//     with box-distance pruning; ties -> lower target index) -- gathers hit the L2-resident target;
+//   * exact nearest neighbour with the strict d2 < r2 cut through the dense grid of grid_index.cu, in two phases:
+//       phase 1, one thread per point: rings 0..1 around the query cell, seeded by the previous iteration's
+//                neighbour (the seed only tightens the pruning radius) -- resolves almost every point;
+//       phase 2, one WARP per unresolved point (outliers / empty neighbourhoods, queued in shared memory):
+//                the rows of ring R are spread over the 32 lanes, followed by a warp lexicographic-min reduce.
+//     Without phase 2 a handful of outliers scanning hundreds of cells serially set the iteration time.
+//     Ties -> lower target index.  Gathers hit the L2-resident target.
 //   * per-thread fp64 accumulation of the 21 + 6 + 2 sums, warp-shuffle tree, CTA tree, then a DSMEM exchange:
 //     every CTA reads all cluster partials in rank order and redundantly solves the 6x6 system (LDLT with
-//     diagonal pivoting), so one cluster barrier per iteration is enough and no host round trip ever happens;
+//     diagonal pivoting, fully unrolled into registers), so one cluster barrier per iteration is enough and no
+//     host round trip ever happens;
 //   * all arithmetic fp64; distances and the point transform use explicitly rounded ops (no FMA contraction) so
 //     that correspondences are bit-identical to the CPU oracle.
 #include <cooperative_groups.h>
@@ -26,6 +32,7 @@ namespace b2s {
 constexpr int ICP_THREADS = 512;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
+constexpr int ICP_R1 = -1;  // phase 1 is a box query, not a ring walk: phase 2 starts its ring walk at ring 0
 
 struct GridView {
   double ox, oy, oz, cell, inv, eps;
@@ -33,6 +40,11 @@ struct GridView {
   const int32_t* __restrict__ cs;
   const double4* __restrict__ pts;
   const double4* __restrict__ nrm;
+};
+
+struct NNState {
+  double best;
+  int bidx, bslot;
 };
 
 __device__ __forceinline__ double slab_gap(double q, double o, double cell, int i, int n, double eps) {
@@ -43,112 +55,188 @@ __device__ __forceinline__ double slab_gap(double q, double o, double cell, int 
   return g > 0.0 ? g : 0.0;
 }
 
-__device__ __forceinline__ void nn_scan_range(const double4* __restrict__ pts, int s, int e, double qx, double qy, double qz,
-                                              double& best, int& bidx, int& bslot) {
+__device__ __forceinline__ void nn_scan_range(const double4* __restrict__ pts, int s, int e, double qx, double qy, double qz, NNState& st) {
+#pragma unroll 4
   for (int j = s; j < e; ++j) {
     const double4 p = pts[j];
     const double d = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
     const int idx = (int)__double_as_longlong(p.w);
-    if (d < best || (d == best && bslot >= 0 && idx < bidx)) { best = d; bidx = idx; bslot = j; }
+    if (d < st.best || (d == st.best && st.bslot >= 0 && idx < st.bidx)) { st.best = d; st.bidx = idx; st.bslot = j; }
   }
 }
 
-// exact nearest neighbour of q among the indexed points with d2 < r2 (strict). returns slot or -1.
-__device__ __forceinline__ int nn_search(const GridView& g, double qx, double qy, double qz, double r2, double& d2_out) {
-  if (!(qx == qx && qy == qy && qz == qz)) return -1;
-  const int cx = (int)fmin(fmax(floor((qx - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
-  const int cy = (int)fmin(fmax(floor((qy - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
-  const int cz = (int)fmin(fmax(floor((qz - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
-  double best = r2;
-  int bidx = 0x7fffffff, bslot = -1;
-  for (int R = 0;; ++R) {
-    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
-    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+// one (y, z) row of ring R around cell (cx, cy, cz): the whole (clipped) x-run on the shell, else the two end cells
+__device__ __forceinline__ void nn_scan_row(const GridView& g, double qx, double qy, double qz, int cx, int cy, int cz, int R, int y, int z,
+                                            NNState& st) {
+  const double gz = slab_gap(qz, g.oz, g.cell, z, g.nz, g.eps);
+  const double gy = slab_gap(qy, g.oy, g.cell, y, g.ny, g.eps);
+  const double g2 = gz * gz + gy * gy;
+  if (g2 > st.best) return;
+  const int row = (z * g.ny + y) * g.nx;
+  if (z == cz - R || z == cz + R || y == cy - R || y == cy + R) {
     const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
-    for (int z = z0; z <= z1; ++z) {
-      const double gz = slab_gap(qz, g.oz, g.cell, z, g.nz, g.eps);
-      const double gz2 = gz * gz;
-      if (gz2 > best) continue;
-      const bool zface = (z == cz - R) || (z == cz + R);
-      for (int y = y0; y <= y1; ++y) {
-        const double gy = slab_gap(qy, g.oy, g.cell, y, g.ny, g.eps);
-        if (gz2 + gy * gy > best) continue;
-        const int row = (z * g.ny + y) * g.nx;
-        if (zface || y == cy - R || y == cy + R) {
-          nn_scan_range(g.pts, g.cs[row + x0], g.cs[row + x1 + 1], qx, qy, qz, best, bidx, bslot);
-        } else {
-          if (cx - R >= 0) nn_scan_range(g.pts, g.cs[row + cx - R], g.cs[row + cx - R + 1], qx, qy, qz, best, bidx, bslot);
-          if (cx + R <= g.nx - 1) nn_scan_range(g.pts, g.cs[row + cx + R], g.cs[row + cx + R + 1], qx, qy, qz, best, bidx, bslot);
-        }
-      }
-    }
-    // every unvisited point lies beyond the faces of the (2R+1)^3 block that still have cells behind them
-    double bound = INFINITY;
-    if (cx - R > 0) bound = fmin(bound, qx - (g.ox + (double)(cx - R) * g.cell));
-    if (cx + R < g.nx - 1) bound = fmin(bound, (g.ox + (double)(cx + R + 1) * g.cell) - qx);
-    if (cy - R > 0) bound = fmin(bound, qy - (g.oy + (double)(cy - R) * g.cell));
-    if (cy + R < g.ny - 1) bound = fmin(bound, (g.oy + (double)(cy + R + 1) * g.cell) - qy);
-    if (cz - R > 0) bound = fmin(bound, qz - (g.oz + (double)(cz - R) * g.cell));
-    if (cz + R < g.nz - 1) bound = fmin(bound, (g.oz + (double)(cz + R + 1) * g.cell) - qz);
-    bound -= g.eps;
-    if (bound < 0.0) bound = 0.0;
-    if (bound == INFINITY || bound * bound > best) break;
+    // clip the run to the cells the current best sphere can reach along x
+    const double xr = sqrt(fmax(st.best - g2, 0.0)) + g.eps;
+    const int xa = max(x0, (int)fmin(fmax(floor((qx - xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1)));
+    const int xb = min(x1, (int)fmin(fmax(floor((qx + xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1)));
+    if (xa <= xb) nn_scan_range(g.pts, g.cs[row + xa], g.cs[row + xb + 1], qx, qy, qz, st);
+  } else {
+    if (cx - R >= 0) nn_scan_range(g.pts, g.cs[row + cx - R], g.cs[row + cx - R + 1], qx, qy, qz, st);
+    if (cx + R <= g.nx - 1) nn_scan_range(g.pts, g.cs[row + cx + R], g.cs[row + cx + R + 1], qx, qy, qz, st);
   }
-  d2_out = best;
-  return bslot;
 }
 
-// ---- small fp64 linear algebra on one thread ----------------------------------------------------------------------
-__device__ void ldlt6_solve_dev(const double* A_in, const double* b_in, double* x) {
-  double A[36];
-  for (int i = 0; i < 36; i++) A[i] = A_in[i];
-  int perm[6] = {0, 1, 2, 3, 4, 5};
-  for (int k = 0; k < 6; k++) {
-    int piv = k;
-    double best = fabs(A[7 * k]);
-    for (int i = k + 1; i < 6; i++) if (fabs(A[7 * i]) > best) { best = fabs(A[7 * i]); piv = i; }
-    if (piv != k) {
-      for (int j = 0; j < 6; j++) { double t = A[6 * k + j]; A[6 * k + j] = A[6 * piv + j]; A[6 * piv + j] = t; }
-      for (int j = 0; j < 6; j++) { double t = A[6 * j + k]; A[6 * j + k] = A[6 * j + piv]; A[6 * j + piv] = t; }
-      int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+// distance below which every unvisited point must lie after the (2R+1)^3 block has been scanned (inf: grid exhausted)
+__device__ __forceinline__ double ring_bound(const GridView& g, double qx, double qy, double qz, int cx, int cy, int cz, int R) {
+  double bound = INFINITY;
+  if (cx - R > 0) bound = fmin(bound, qx - (g.ox + (double)(cx - R) * g.cell));
+  if (cx + R < g.nx - 1) bound = fmin(bound, (g.ox + (double)(cx + R + 1) * g.cell) - qx);
+  if (cy - R > 0) bound = fmin(bound, qy - (g.oy + (double)(cy - R) * g.cell));
+  if (cy + R < g.ny - 1) bound = fmin(bound, (g.oy + (double)(cy + R + 1) * g.cell) - qy);
+  if (cz - R > 0) bound = fmin(bound, qz - (g.oz + (double)(cz - R) * g.cell));
+  if (cz + R < g.nz - 1) bound = fmin(bound, (g.oz + (double)(cz + R + 1) * g.cell) - qz);
+  if (bound == INFINITY) return bound;
+  bound -= g.eps;
+  return bound > 0.0 ? bound : 0.0;
+}
+
+__device__ __forceinline__ void cell_of(const GridView& g, double qx, double qy, double qz, int& cx, int& cy, int& cz) {
+  cx = (int)fmin(fmax(floor((qx - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+  cy = (int)fmin(fmax(floor((qy - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  cz = (int)fmin(fmax(floor((qz - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+}
+
+// phase 1 (one thread): BOX QUERY.  The previous iteration's neighbour (`hint`, -1 = none) is almost always still the
+// nearest or next to it, so the exact answer lies within its distance d_h of the query: scan exactly the cells that
+// overlap the box [q - d_h, q + d_h] (one contiguous slot range per (y, z) row) -- a handful of candidates, no ring
+// walk, no per-row bounds.  Without a usable hint the box half-width is one cell edge; a hit inside that radius is
+// exact as well.  Anything else (no point within the box radius, or a box wider than 2 cells) is left to phase 2.
+// Cell indices use the same floor((v - o) * inv) expression as the index build, which is monotone in v, so no point
+// inside the box can sit in a cell outside the index range.  Returns true when st holds the exact answer.
+__device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double qy, double qz, double r2, int hint, NNState& st) {
+  st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1;
+  if (!(qx == qx && qy == qy && qz == qz)) return true;
+  double rad2 = fmin(r2, g.cell * g.cell);
+  bool seeded = false;
+  if (hint >= 0) {
+    const double4 p = g.pts[hint];
+    const double d = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+    if (d < r2) { st.best = d; st.bidx = (int)__double_as_longlong(p.w); st.bslot = hint; rad2 = d; seeded = true; }
+  }
+  const double radm = sqrt(rad2) * (1.0 + 1e-12) + 1e-300;
+  if (radm > 2.0 * g.cell) return false;
+  const int ix0 = (int)fmin(fmax(floor((qx - radm - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+  const int ix1 = (int)fmin(fmax(floor((qx + radm - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+  const int iy0 = (int)fmin(fmax(floor((qy - radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  const int iy1 = (int)fmin(fmax(floor((qy + radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  const int iz0 = (int)fmin(fmax(floor((qz - radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+  const int iz1 = (int)fmin(fmax(floor((qz + radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+  for (int z = iz0; z <= iz1; ++z)
+    for (int y = iy0; y <= iy1; ++y) {
+      const int row = (z * g.ny + y) * g.nx;
+      nn_scan_range(g.pts, g.cs[row + ix0], g.cs[row + ix1 + 1], qx, qy, qz, st);
     }
-    const double d = A[7 * k];
+  // seeded: every point at distance <= d_h was scanned.  unseeded: exact iff the best lies within the box radius.
+  return seeded || (st.bslot >= 0 && st.best <= rad2);
+}
+
+// phase 2 (one warp, all lanes with the same query): continues from ring ICP_R1 + 1 with the rows of each ring spread
+// over the lanes.  st must hold the phase-1 state; on return every lane holds the exact answer.
+__device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, double qy, double qz, NNState& st) {
+  const int lane = threadIdx.x & 31;
+  int cx, cy, cz;
+  cell_of(g, qx, qy, qz, cx, cy, cz);
+  for (int R = ICP_R1 + 1;; ++R) {
+    const int side = 2 * R + 1;
+    for (int t = lane; t < side * side; t += 32) {
+      const int z = cz - R + t / side, y = cy - R + t % side;
+      if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+      nn_scan_row(g, qx, qy, qz, cx, cy, cz, R, y, z, st);
+    }
+    // lexicographic (d2, index) minimum over the lanes; a lane without a hit carries slot -1
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, st.best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, st.bidx, o);
+      const int os = __shfl_xor_sync(0xffffffffu, st.bslot, o);
+      const bool take = os >= 0 && (st.bslot < 0 || od < st.best || (od == st.best && oi < st.bidx));
+      if (take) { st.best = od; st.bidx = oi; st.bslot = os; }
+    }
+    const double bound = ring_bound(g, qx, qy, qz, cx, cy, cz, R);
+    if (bound == INFINITY || bound * bound > st.best) break;
+  }
+}
+
+// ---- small fp64 linear algebra on one thread, registers only -----------------------------------------------------
+#define B2S_SWAP(u, v) { const double _t = (u); (u) = (v); (v) = _t; }
+
+// A x = b, A symmetric 6x6 (full storage a[6][6]).  LDL^T with symmetric pivoting on the largest |diagonal|, the
+// scheme Eigen's LDLT uses for [O3D] SolveLinearSystemPSD (no determinant / PSD check on this call path).  Every loop
+// is fully unrolled and every index static: pivot swaps are predicated register moves, nothing goes to local memory.
+__device__ __forceinline__ void ldlt6_solve_reg(double (&a)[6][6], double (&b)[6], double (&x)[6]) {
+  int piv[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    int p = k;
+    double best = fabs(a[k][k]);
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) { const double v = fabs(a[i][i]); if (v > best) { best = v; p = i; } }
+    piv[k] = p;
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {
+      // data-flow selects, not branches: a branchy "if (p == i) swap" chain gets re-rolled by the compiler into
+      // dynamically indexed (local-memory) accesses
+      const bool sw = (p == i);
+#pragma unroll
+      for (int j = 0; j < 6; j++) { const double u = a[k][j], v = a[i][j]; a[k][j] = sw ? v : u; a[i][j] = sw ? u : v; }
+#pragma unroll
+      for (int j = 0; j < 6; j++) { const double u = a[j][k], v = a[j][i]; a[j][k] = sw ? v : u; a[j][i] = sw ? u : v; }
+      { const double u = b[k], v = b[i]; b[k] = sw ? v : u; b[i] = sw ? u : v; }
+    }
+    const double d = a[k][k];
     if (d != 0.0) {
-      for (int i = k + 1; i < 6; i++) A[6 * i + k] /= d;
+#pragma unroll
+      for (int i = k + 1; i < 6; i++) a[i][k] /= d;
+#pragma unroll
       for (int i = k + 1; i < 6; i++)
+#pragma unroll
         for (int j = k + 1; j <= i; j++) {
-          A[6 * i + j] -= A[6 * i + k] * d * A[6 * j + k];
-          A[6 * j + i] = A[6 * i + j];
+          a[i][j] -= a[i][k] * d * a[j][k];
+          a[j][i] = a[i][j];
         }
     }
   }
   double y[6];
-  for (int i = 0; i < 6; i++) y[i] = b_in[perm[i]];
-  for (int i = 0; i < 6; i++) for (int j = 0; j < i; j++) y[i] -= A[6 * i + j] * y[j];
-  for (int i = 0; i < 6; i++) { const double d = A[7 * i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
-  for (int i = 5; i >= 0; i--) for (int j = i + 1; j < 6; j++) y[i] -= A[6 * j + i] * y[j];
-  for (int i = 0; i < 6; i++) x[perm[i]] = y[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) y[i] = b[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < i; j++) y[i] -= a[i][j] * y[j];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { const double d = a[i][i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
+#pragma unroll
+  for (int i = 5; i >= 0; i--)
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) y[i] -= a[j][i] * y[j];
+  // undo the permutation: apply the recorded transpositions in reverse order
+#pragma unroll
+  for (int k = 5; k >= 0; k--) {
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) { const bool sw = (piv[k] == i); const double u = y[k], v = y[i]; y[k] = sw ? v : u; y[i] = sw ? u : v; }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) x[i] = y[i];
 }
 
 // [O3D] TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x[3..5]
-__device__ void vec6_to_mat4_dev(const double* x, double* T) {
+__device__ __forceinline__ void vec6_to_mat4_dev(const double (&x)[6], double* T) {
   double sa, ca, sb, cb, sg, cgm;
   sincos(x[0], &sa, &ca); sincos(x[1], &sb, &cb); sincos(x[2], &sg, &cgm);
   T[0] = cgm * cb; T[1] = cgm * sb * sa - sg * ca; T[2] = cgm * sb * ca + sg * sa; T[3] = x[3];
   T[4] = sg * cb;  T[5] = sg * sb * sa + cgm * ca; T[6] = sg * sb * ca - cgm * sa; T[7] = x[4];
   T[8] = -sb;      T[9] = cb * sa;                 T[10] = cb * ca;                T[11] = x[5];
   T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
-}
-
-__device__ void mat4_mul_dev(const double* A, const double* B, double* C) {
-  double t[16];
-  for (int i = 0; i < 4; i++)
-    for (int j = 0; j < 4; j++) {
-      double s = 0;
-      for (int k = 0; k < 4; k++) s += A[4 * i + k] * B[4 * k + j];
-      t[4 * i + j] = s;
-    }
-  for (int i = 0; i < 16; i++) C[i] = t[i];
 }
 
 __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-12)
@@ -163,12 +251,37 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
 }
 
 constexpr int ICP_FIXED_SMEM_DOUBLES = ICP_WARPS * NACC + 2 * NACC + NACC + 16 + 16 + 8;
+constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4;  // working point, previous-neighbour slot, phase-2 queue entry
 
-__global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpProblem* __restrict__ problems, int smem_pts_cap) {
+__device__ __forceinline__ void icp_accumulate(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz) {
+  const double4 q = g.pts[slot];
+  const double4 nn = g.nrm[slot];
+  const double r = (px - q.x) * nn.x + (py - q.y) * nn.y + (pz - q.z) * nn.z;
+  double J[6];
+  J[0] = py * nn.z - pz * nn.y; J[1] = pz * nn.x - px * nn.z; J[2] = px * nn.y - py * nn.x;
+  J[3] = nn.x; J[4] = nn.y; J[5] = nn.z;
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) acc[k++] += J[a] * J[b];
+#pragma unroll
+  for (int a = 0; a < 6; a++) acc[21 + a] += J[a] * r;
+  acc[27] += d2;
+  acc[28] += 1.0;
+}
+
+// `single` carries the problem by value (kernel parameter space) for the one-registration calls, so that no
+// host->device copy -- and no implicit stream synchronisation of a pageable copy -- sits in front of the launch;
+// batches pass an array.  dbg (optional): clock64 stamps of problem 0 / CTA 0 per evaluation {start, search, reduce, solve}.
+__global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __grid_constant__ IcpProblem single,
+                                                                     const IcpProblem* __restrict__ problems, int smem_pts_cap,
+                                                                     long long* dbg) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const unsigned csize = cluster.num_blocks();
-  const IcpProblem& P = problems[blockIdx.y];
+  const IcpProblem& P = problems ? problems[blockIdx.y] : single;
+  const bool dbg_on = dbg != nullptr && blockIdx.y == 0 && crank == 0 && threadIdx.x == 0;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_red = reinterpret_cast<double*>(smem_raw);  // [ICP_WARPS][NACC]
@@ -178,14 +291,18 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
   double* s_T = s_U + 16;                               // [16] accumulated transformation
   double* s_misc = s_T + 16;                            // [0] prev fitness [1] prev rmse [2] done [3] apply
   GridHeader* s_g = reinterpret_cast<GridHeader*>(s_misc + 8);
-  double* s_pts = reinterpret_cast<double*>(s_g + 1);
+  int* s_qn = reinterpret_cast<int*>(s_g + 1);          // phase-2 queue length (16 bytes reserved)
+  double* s_pts = reinterpret_cast<double*>(s_qn + 4);
+  int* s_prev = reinterpret_cast<int*>(s_pts + 3 * (size_t)smem_pts_cap);  // previous neighbour slot per point (warm start)
+  int* s_queue = s_prev + smem_pts_cap;                                    // local indices of points left to phase 2
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *P.src_n;
   const int chunk = (n + (int)csize - 1) / (int)csize;
   const int lo = min((int)crank * chunk, n), hi = min(lo + chunk, n);
   const int cnt = hi - lo;
-  double* work = (cnt <= smem_pts_cap) ? s_pts : (P.work_xyz + 3 * (size_t)lo);
+  const bool in_smem = cnt <= smem_pts_cap;
+  double* work = in_smem ? s_pts : (P.work_xyz + 3 * (size_t)lo);
 
   if (tid == 0) {
     *s_g = *P.ghdr;
@@ -193,10 +310,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
     for (int i = 0; i < 16; i++) { s_T[i] = init[i]; s_U[i] = init[i]; }
     s_misc[0] = 0.0; s_misc[1] = 0.0; s_misc[2] = 0.0;
     s_misc[3] = mat4_is_identity_dev(init) ? 0.0 : 1.0;  // [O3D]: if (!init.isIdentity()) pcd.Transform(init)
+    *s_qn = 0;
   }
   {  // stage this CTA's chunk of the source cloud
     const double* src = P.src_xyz + 3 * (size_t)lo;
     for (int i = tid; i < 3 * cnt; i += ICP_THREADS) work[i] = src[i];
+    if (in_smem) for (int i = tid; i < cnt; i += ICP_THREADS) s_prev[i] = -1;
   }
   __syncthreads();
 
@@ -211,6 +330,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
   const int max_iter = P.max_iter;
 
   for (int e = 0;; ++e) {
+    if (dbg_on && e < 64) dbg[4 * e] = clock64();
     const bool apply = s_misc[3] != 0.0;
     double U[12];
 #pragma unroll
@@ -220,6 +340,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
 #pragma unroll
     for (int i = 0; i < NACC; i++) acc[i] = 0.0;
 
+    // ---- phase 1: one thread per point ----
     for (int i = tid; i < cnt; i += ICP_THREADS) {
       double px = work[3 * i], py = work[3 * i + 1], pz = work[3 * i + 2];
       if (apply) {  // [O3D] TransformPoints with w == 1 exactly for a rigid update; same association as Eigen's product
@@ -229,26 +350,49 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
         px = x; py = y; pz = z;
         work[3 * i] = px; work[3 * i + 1] = py; work[3 * i + 2] = pz;
       }
-      double d2;
-      const int slot = nn_search(g, px, py, pz, r2, d2);
-      if (slot >= 0) {
-        const double4 q = g.pts[slot];
-        const double4 nn = g.nrm[slot];
-        const double r = (px - q.x) * nn.x + (py - q.y) * nn.y + (pz - q.z) * nn.z;
-        double J[6];
-        J[0] = py * nn.z - pz * nn.y; J[1] = pz * nn.x - px * nn.z; J[2] = px * nn.y - py * nn.x;
-        J[3] = nn.x; J[4] = nn.y; J[5] = nn.z;
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int b = a; b < 6; b++) acc[k++] += J[a] * J[b];
-#pragma unroll
-        for (int a = 0; a < 6; a++) acc[21 + a] += J[a] * r;
-        acc[27] += d2;
-        acc[28] += 1.0;
+      NNState st;
+      bool done = nn_phase1(g, px, py, pz, r2, in_smem ? s_prev[i] : -1, st);
+      if (!done && !in_smem) {  // no queue for clouds that overflow shared memory: finish serially
+        int cx, cy, cz;
+        cell_of(g, px, py, pz, cx, cy, cz);
+        for (int R = ICP_R1 + 1;; ++R) {
+          const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1), y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+          for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y) nn_scan_row(g, px, py, pz, cx, cy, cz, R, y, z, st);
+          const double bound = ring_bound(g, px, py, pz, cx, cy, cz, R);
+          if (bound == INFINITY || bound * bound > st.best) break;
+        }
+        done = true;
+      }
+      if (in_smem) s_prev[i] = st.bslot;
+      if (done) {
+        if (st.bslot >= 0) icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+      } else {
+        s_queue[atomicAdd(s_qn, 1)] = i;
       }
     }
+    __syncthreads();
+    // ---- phase 2: one warp per point that needs rings beyond ICP_R1 ----
+    {
+      const int qn = *s_qn;
+      for (int qi = warp; qi < qn; qi += ICP_WARPS) {
+        const int i = s_queue[qi];
+        const double px = work[3 * i], py = work[3 * i + 1], pz = work[3 * i + 2];
+        NNState st;
+        st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1;
+        const int hs = s_prev[i];  // best of rings 0..ICP_R1 (or the seed), -1 when nothing was in range
+        if (hs >= 0) {
+          const double4 p = g.pts[hs];
+          st.best = dist2_exact(px, py, pz, p.x, p.y, p.z); st.bidx = (int)__double_as_longlong(p.w); st.bslot = hs;
+        }
+        nn_phase2_warp(g, px, py, pz, st);
+        if (lane == 0) {
+          s_prev[i] = st.bslot;
+          if (st.bslot >= 0) icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+        }
+      }
+    }
+    if (dbg_on && e < 64) dbg[4 * e + 1] = clock64();
     // warp tree -> CTA tree (fixed order => run-to-run deterministic)
 #pragma unroll
     for (int i = 0; i < NACC; i++) {
@@ -262,6 +406,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
       for (int w = 0; w < ICP_WARPS; w++) v += s_red[w * NACC + tid];
       s_part[buf * NACC + tid] = v;
     }
+    if (tid == 0) *s_qn = 0;
     cluster.sync();
     if (tid < NACC) {
       double v = 0.0;
@@ -272,6 +417,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
       s_tot[tid] = v;
     }
     __syncthreads();
+    if (dbg_on && e < 64) dbg[4 * e + 2] = clock64();
     if (tid == 0) {
       const double c = s_tot[28];
       const double fit = (c > 0.0 && n > 0) ? c / (double)n : 0.0;
@@ -282,17 +428,34 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
       if (!done) {
         double Upd[16];
         if (c > 0.0) {
-          double A[36], b[6], x[6];
-          int k = 0;
-          for (int a = 0; a < 6; a++) for (int bb = a; bb < 6; bb++) { A[6 * a + bb] = s_tot[k]; A[6 * bb + a] = s_tot[k]; k++; }
+          double A[6][6], b[6], x[6];
+          {
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+              for (int bb = a; bb < 6; bb++) { A[a][bb] = s_tot[k]; A[bb][a] = s_tot[k]; k++; }
+          }
+#pragma unroll
           for (int a = 0; a < 6; a++) b[a] = -s_tot[21 + a];
-          ldlt6_solve_dev(A, b, x);
+          ldlt6_solve_reg(A, b, x);
           vec6_to_mat4_dev(x, Upd);
         } else {  // [O3D] ComputeTransformation: corres.empty() -> Identity
+#pragma unroll
           for (int i = 0; i < 16; i++) Upd[i] = (i % 5 == 0) ? 1.0 : 0.0;
         }
-        mat4_mul_dev(Upd, s_T, s_T);
-        for (int i = 0; i < 16; i++) s_U[i] = Upd[i];
+        double Tn[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) s += Upd[4 * i + k] * s_T[4 * k + j];
+            Tn[4 * i + j] = s;
+          }
+#pragma unroll
+        for (int i = 0; i < 16; i++) { s_T[i] = Tn[i]; s_U[i] = Upd[i]; }
         s_misc[0] = fit; s_misc[1] = rmse; s_misc[3] = 1.0;
       } else {
         s_misc[2] = 1.0;
@@ -303,6 +466,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
         }
       }
     }
+    if (dbg_on && e < 64) dbg[4 * e + 3] = clock64();
     __syncthreads();
     if (s_misc[2] != 0.0) break;
   }
@@ -312,21 +476,32 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const IcpPr
 static bool g_icp_attr_set = false;
 constexpr int ICP_DYN_SMEM = 200 * 1024;
 
-int32_t icp_launch(b2s_handle* h, const IcpProblem* problems_dev, int n_problems, size_t max_src_points) {
+int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points) {
   if (n_problems <= 0) return B2S_OK;
+  IcpProblem single;
+  memset(&single, 0, sizeof(single));
+  if (single_host) { single = *single_host; problems_dev = nullptr; n_problems = 1; }
   if (!g_icp_attr_set) {
     B2S_CUDA(cudaFuncSetAttribute(icp_p2plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
     g_icp_attr_set = true;
   }
   int csize = 1;
   while (csize < 8 && (size_t)csize * ICP_THREADS * 2 < max_src_points) csize *= 2;
-  const int fixed = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16;
-  const int pts_cap = (ICP_DYN_SMEM - fixed) / 24;
+  const int fixed = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16 + 16;
+  // shared memory is sized for THIS launch's chunk only: whatever is not claimed stays L1, and the candidate gathers of
+  // neighbouring queries hit the same lines (4 target points per 128-byte line)
+  int pts_cap = (ICP_DYN_SMEM - fixed) / ICP_BYTES_PER_POINT;
+  {
+    const size_t chunk = (max_src_points + (size_t)csize - 1) / (size_t)csize;
+    const size_t want = ((chunk + 63) / 64) * 64 + 64;
+    if (want < (size_t)pts_cap) pts_cap = (int)want;
+  }
+  const int dyn_smem = fixed + pts_cap * ICP_BYTES_PER_POINT;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(csize, n_problems, 1);
   cfg.blockDim = dim3(ICP_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = ICP_DYN_SMEM;
+  cfg.dynamicSmemBytes = (size_t)dyn_smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -334,7 +509,7 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* problems_dev, int n_problems
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(h, PK_ICP);
-  B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_p2plane_kernel, problems_dev, pts_cap));
+  B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_p2plane_kernel, single, problems_dev, pts_cap, h->icp_dbg));
   h->launches++;
   return B2S_OK;
 }

@@ -14,7 +14,7 @@
 
 namespace b2s {
 
-constexpr int NK_THREADS = 256;
+constexpr int NK_THREADS = 128;
 
 __device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
 
@@ -124,27 +124,70 @@ __device__ void fast_eigen3x3_dev(const double* cov, double* out) {
   }
 }
 
+
+// Post-search part shared by all KMAX: covariance in the reference's neighbour order (ascending (d2, index)) with
+// the reference's single-pass cumulant formula in explicitly rounded fp64, analytic eigen-solver, normalise, orient.
+__device__ __forceinline__ void finish_normal(const double c_in[9], int kk, double qx, double qy, double qz, double* nr) {
+  double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // [O3D] fewer than 3 neighbours -> identity covariance
+  if (kk >= 3) {
+    double c[9];
+    const double kf = (double)kk;
+#pragma unroll
+    for (int t = 0; t < 9; t++) c[t] = __ddiv_rn(c_in[t], kf);
+    cov[0] = __dsub_rn(c[3], __dmul_rn(c[0], c[0]));
+    cov[4] = __dsub_rn(c[6], __dmul_rn(c[1], c[1]));
+    cov[8] = __dsub_rn(c[8], __dmul_rn(c[2], c[2]));
+    cov[1] = cov[3] = __dsub_rn(c[4], __dmul_rn(c[0], c[1]));
+    cov[2] = cov[6] = __dsub_rn(c[5], __dmul_rn(c[0], c[2]));
+    cov[5] = cov[7] = __dsub_rn(c[7], __dmul_rn(c[1], c[2]));
+  }
+  fast_eigen3x3_dev(cov, nr);
+  if (sqrt(dot3d(nr, nr)) == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+  const double zz = dot3d(nr, nr);  // NormalizeNormals
+  if (zz > 0) { const double sn = sqrt(zz); nr[0] /= sn; nr[1] /= sn; nr[2] /= sn; }
+  if (nr[0] != nr[0]) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+  const double ref[3] = {-qx, -qy, -qz};  // OrientNormalsTowardsCameraLocation(0,0,0)
+  if (sqrt(dot3d(nr, nr)) == 0.0) {
+    const double rn = sqrt(dot3d(ref, ref));
+    if (rn == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
+    else { nr[0] = ref[0] / rn; nr[1] = ref[1] / rn; nr[2] = ref[2] / rn; }
+  } else if (dot3d(nr, ref) < 0.0) { nr[0] *= -1.0; nr[1] *= -1.0; nr[2] *= -1.0; }
+}
+
+// One THREAD per query point, queries taken in grid-slot order so that the 32 lanes of a warp sit in the same or
+// in adjacent cells and walk (nearly) the same candidate ranges: the candidate loads are warp-broadcasts out of L1.
+// The k best are a sorted list held entirely in REGISTERS (KMAX compile-time, insertion fully unrolled into
+// predicated moves; no local memory).  Exact k-NN: ring expansion stops when the k-th distance is below the distance
+// to the unvisited shell or the shell is beyond the radius; ties are broken towards the lower original index.
+// Queries that still need rings beyond `ring_limit` (sparse far-range areas, isolated points) are NOT finished here:
+// their slot is pushed to `queue` and normals_phase2_kernel finishes them with one warp each.  Without that split a
+// few threads walking hundreds of empty cells serially set the duration of the whole kernel.
+template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
-                                                             const double4* __restrict__ pts, int knn, double radius,
-                                                             double* __restrict__ out_nrm, double* __restrict__ out_cov) {
+                                                             const double4* __restrict__ pts, int knn, double radius, int ring_limit,
+                                                             int32_t* __restrict__ queue, int32_t* queue_n,
+                                                             double* __restrict__ out_nrm) {
   __shared__ GridHeader g;
   if (threadIdx.x == 0) g = *hdr;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (NK_THREADS / 32);
   const int n = g.n;
   const double r2 = radius * radius;
   const double eps = 1e-9 * g.cell;
   const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
-  for (int s = blockIdx.x * (NK_THREADS / 32) + (threadIdx.x >> 5); s < n; s += warps_total) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     const double4 qp = pts[s];
     const double qx = qp.x, qy = qp.y, qz = qp.z;
     const int qi = (int)__double_as_longlong(qp.w);
     const int cx = (int)fmin(fmax(floor((qx - g.origin[0]) * g.inv_cell), 0.0), (double)(nx - 1));
     const int cy = (int)fmin(fmax(floor((qy - g.origin[1]) * g.inv_cell), 0.0), (double)(ny - 1));
     const int cz = (int)fmin(fmax(floor((qz - g.origin[2]) * g.inv_cell), 0.0), (double)(nz - 1));
-    double ed = INFINITY; int ei = 0x7fffffff; int es = -1;  // this lane's entry of the sorted k-best list
-    double kd = INFINITY; int ki = 0x7fffffff;               // current k-th best (lane knn-1)
+    double bd[KMAX];
+    int bs[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; j++) { bd[j] = INFINITY; bs[j] = -1; }
+    double kd = INFINITY;   // current k-th best distance (entry knn-1); +inf until k neighbours are known
+    int kslot = -1;
+    bool unresolved = false;
     for (int R = 0;; ++R) {
       const int z0 = max(cz - R, 0), z1 = min(cz + R, nz - 1);
       const int y0 = max(cy - R, 0), y1 = min(cy + R, ny - 1);
@@ -159,12 +202,130 @@ __global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* _
           if (gz2 + gy * gy > fmin(kd, r2)) continue;
           const int row = (z * ny + y) * nx;
           const bool shell = zface || y == cy - R || y == cy + R;
-          // up to two x-ranges: the whole row on the shell, otherwise the two end cells
           for (int part = 0; part < 2; ++part) {
             int a, b;
             if (shell) { if (part == 1) break; a = cs[row + x0]; b = cs[row + x1 + 1]; }
             else if (part == 0) { if (cx - R < 0) continue; a = cs[row + cx - R]; b = cs[row + cx - R + 1]; }
             else { if (cx + R > nx - 1) continue; a = cs[row + cx + R]; b = cs[row + cx + R + 1]; }
+            for (int j = a; j < b; ++j) {
+              const double4 p = pts[j];
+              const double d = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+              if (!(d < r2)) continue;
+              if (d > kd) continue;
+              if (d == kd) {  // exact tie with the current k-th: lower original index wins (rare path)
+                const int ik = (int)__double_as_longlong(pts[kslot].w), ic = (int)__double_as_longlong(p.w);
+                if (!(ic < ik)) continue;
+              }
+              // sorted insertion, fully unrolled (registers only).  Equal distances: order by original index.
+              const int ic = (int)__double_as_longlong(p.w);
+#pragma unroll
+              for (int t = KMAX - 1; t >= 1; --t) {
+                bool before_prev = d < bd[t - 1];
+                if (d == bd[t - 1]) before_prev = ic < (int)__double_as_longlong(pts[bs[t - 1]].w);
+                bool before_cur = d < bd[t];
+                if (d == bd[t] && bs[t] >= 0) before_cur = ic < (int)__double_as_longlong(pts[bs[t]].w);
+                if (before_prev) { bd[t] = bd[t - 1]; bs[t] = bs[t - 1]; }
+                else if (before_cur) { bd[t] = d; bs[t] = j; }
+              }
+              {
+                bool before0 = d < bd[0];
+                if (d == bd[0] && bs[0] >= 0) before0 = ic < (int)__double_as_longlong(pts[bs[0]].w);
+                if (before0) { bd[0] = d; bs[0] = j; }
+              }
+              if (EXACT) { kd = bd[KMAX - 1]; kslot = bs[KMAX - 1]; }   // knn == KMAX: static index, the list stays in registers
+              else { kd = bd[knn - 1]; kslot = bs[knn - 1]; }          // generic knn: dynamic index (list lives in local memory)
+            }
+          }
+        }
+      }
+      double bound = INFINITY;
+      if (cx - R > 0) bound = fmin(bound, qx - (g.origin[0] + (double)(cx - R) * g.cell));
+      if (cx + R < nx - 1) bound = fmin(bound, (g.origin[0] + (double)(cx + R + 1) * g.cell) - qx);
+      if (cy - R > 0) bound = fmin(bound, qy - (g.origin[1] + (double)(cy - R) * g.cell));
+      if (cy + R < ny - 1) bound = fmin(bound, (g.origin[1] + (double)(cy + R + 1) * g.cell) - qy);
+      if (cz - R > 0) bound = fmin(bound, qz - (g.origin[2] + (double)(cz - R) * g.cell));
+      if (cz + R < nz - 1) bound = fmin(bound, (g.origin[2] + (double)(cz + R + 1) * g.cell) - qz);
+      bound -= eps;
+      if (bound < 0.0) bound = 0.0;
+      if (bound == INFINITY || bound * bound > fmin(kd, r2)) break;
+      if (R >= ring_limit) { unresolved = true; break; }
+    }
+    if (unresolved) { queue[atomicAdd(queue_n, 1)] = s; continue; }
+    // cumulants over the kk <= knn neighbours in ascending (d2, index) order
+    double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int kk = 0;
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) {
+      if (t < knn && bs[t] >= 0) {
+        const double4 p = pts[bs[t]];
+        c[0] = __dadd_rn(c[0], p.x); c[1] = __dadd_rn(c[1], p.y); c[2] = __dadd_rn(c[2], p.z);
+        c[3] = __dadd_rn(c[3], __dmul_rn(p.x, p.x)); c[4] = __dadd_rn(c[4], __dmul_rn(p.x, p.y)); c[5] = __dadd_rn(c[5], __dmul_rn(p.x, p.z));
+        c[6] = __dadd_rn(c[6], __dmul_rn(p.y, p.y)); c[7] = __dadd_rn(c[7], __dmul_rn(p.y, p.z)); c[8] = __dadd_rn(c[8], __dmul_rn(p.z, p.z));
+        kk++;
+      }
+    }
+    double nr[3];
+    finish_normal(c, kk, qx, qy, qz, nr);
+    out_nrm[3 * (size_t)qi] = nr[0]; out_nrm[3 * (size_t)qi + 1] = nr[1]; out_nrm[3 * (size_t)qi + 2] = nr[2];
+  }
+}
+
+// Phase 2: one WARP per queued query, restarted from ring 0.  Per ring, each lane first resolves ONE (y, z) row --
+// pruning test and the two dependent cell_start loads, the latency that dominates in empty space -- then the warp
+// walks the non-empty rows together: 32 candidates per step, the k best kept as a sorted list with one entry per lane
+// (k <= 32), a qualifying candidate inserted with a single shuffle-up step.
+__global__ void __launch_bounds__(NK_THREADS) normals_phase2_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
+                                                                    const double4* __restrict__ pts, int knn, double radius,
+                                                                    const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_n,
+                                                                    double* __restrict__ out_nrm) {
+  __shared__ GridHeader g;
+  if (threadIdx.x == 0) g = *hdr;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (NK_THREADS / 32);
+  const int nq = *queue_n;
+  const double r2 = radius * radius;
+  const double eps = 1e-9 * g.cell;
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  for (int w = blockIdx.x * (NK_THREADS / 32) + (threadIdx.x >> 5); w < nq; w += warps_total) {
+    const int s = queue[w];
+    const double4 qp = pts[s];
+    const double qx = qp.x, qy = qp.y, qz = qp.z;
+    const int qi = (int)__double_as_longlong(qp.w);
+    const int cx = (int)fmin(fmax(floor((qx - g.origin[0]) * g.inv_cell), 0.0), (double)(nx - 1));
+    const int cy = (int)fmin(fmax(floor((qy - g.origin[1]) * g.inv_cell), 0.0), (double)(ny - 1));
+    const int cz = (int)fmin(fmax(floor((qz - g.origin[2]) * g.inv_cell), 0.0), (double)(nz - 1));
+    double ed = INFINITY; int ei = 0x7fffffff; int es = -1;  // this lane's entry of the sorted k-best list
+    double kd = INFINITY; int ki = 0x7fffffff;               // current k-th best (lane knn-1)
+    for (int R = 0;; ++R) {
+      const int side = 2 * R + 1;
+      const int x0 = max(cx - R, 0), x1 = min(cx + R, nx - 1);
+      for (int t0 = 0; t0 < side * side; t0 += 32) {
+        // each lane resolves one row: up to two candidate ranges [a0,b0) and [a1,b1)
+        int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+        const int t = t0 + lane;
+        if (t < side * side) {
+          const int z = cz - R + t / side, y = cy - R + t % side;
+          if (z >= 0 && z < nz && y >= 0 && y < ny) {
+            const double gz = slab_gap_n(qz, g.origin[2], g.cell, z, nz, eps);
+            const double gy = slab_gap_n(qy, g.origin[1], g.cell, y, ny, eps);
+            if (gz * gz + gy * gy <= fmin(kd, r2)) {
+              const int row = (z * ny + y) * nx;
+              if (z == cz - R || z == cz + R || y == cy - R || y == cy + R) { a0 = cs[row + x0]; b0 = cs[row + x1 + 1]; }
+              else {
+                if (cx - R >= 0) { a0 = cs[row + cx - R]; b0 = cs[row + cx - R + 1]; }
+                if (cx + R <= nx - 1) { a1 = cs[row + cx + R]; b1 = cs[row + cx + R + 1]; }
+              }
+            }
+          }
+        }
+        for (int part = 0; part < 2; ++part) {
+          unsigned rows = __ballot_sync(0xffffffffu, part == 0 ? (b0 > a0) : (b1 > a1));
+          while (rows) {
+            const int src_lane = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int a = __shfl_sync(0xffffffffu, part == 0 ? a0 : a1, src_lane);
+            const int b = __shfl_sync(0xffffffffu, part == 0 ? b0 : b1, src_lane);
             for (int j0 = a; j0 < b; j0 += 32) {
               const int j = j0 + lane;
               double d = INFINITY; int idx = 0x7fffffff;
@@ -205,66 +366,59 @@ __global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* _
       if (bound < 0.0) bound = 0.0;
       if (bound == INFINITY || bound * bound > fmin(kd, r2)) break;
     }
-    // ---- covariance in the reference's neighbour order (ascending (d2, index)), single-pass cumulants ----
+    // cumulants in ascending (d2, index) order: lane t holds the t-th neighbour, broadcast by shuffles
     const int kk = __popc(__ballot_sync(0xffffffffu, lane < knn && es >= 0));
-    double nx_ = 0.0, ny_ = 0.0, nz_ = 0.0;
     double4 np = make_double4(0, 0, 0, 0);
     if (lane < kk) np = pts[es];
-    double cov[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // [O3D] fewer than 3 neighbours -> identity covariance
-    if (kk >= 3) {
-      double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int t = 0; t < kk; ++t) {
-        const double x = __shfl_sync(0xffffffffu, np.x, t), y = __shfl_sync(0xffffffffu, np.y, t), z = __shfl_sync(0xffffffffu, np.z, t);
-        c[0] = __dadd_rn(c[0], x); c[1] = __dadd_rn(c[1], y); c[2] = __dadd_rn(c[2], z);
-        c[3] = __dadd_rn(c[3], __dmul_rn(x, x)); c[4] = __dadd_rn(c[4], __dmul_rn(x, y)); c[5] = __dadd_rn(c[5], __dmul_rn(x, z));
-        c[6] = __dadd_rn(c[6], __dmul_rn(y, y)); c[7] = __dadd_rn(c[7], __dmul_rn(y, z)); c[8] = __dadd_rn(c[8], __dmul_rn(z, z));
-      }
-      const double kf = (double)kk;
-#pragma unroll
-      for (int t = 0; t < 9; t++) c[t] = __ddiv_rn(c[t], kf);
-      cov[0] = __dsub_rn(c[3], __dmul_rn(c[0], c[0]));
-      cov[4] = __dsub_rn(c[6], __dmul_rn(c[1], c[1]));
-      cov[8] = __dsub_rn(c[8], __dmul_rn(c[2], c[2]));
-      cov[1] = cov[3] = __dsub_rn(c[4], __dmul_rn(c[0], c[1]));
-      cov[2] = cov[6] = __dsub_rn(c[5], __dmul_rn(c[0], c[2]));
-      cov[5] = cov[7] = __dsub_rn(c[7], __dmul_rn(c[1], c[2]));
+    double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < kk; ++t) {
+      const double x = __shfl_sync(0xffffffffu, np.x, t), y = __shfl_sync(0xffffffffu, np.y, t), z = __shfl_sync(0xffffffffu, np.z, t);
+      c[0] = __dadd_rn(c[0], x); c[1] = __dadd_rn(c[1], y); c[2] = __dadd_rn(c[2], z);
+      c[3] = __dadd_rn(c[3], __dmul_rn(x, x)); c[4] = __dadd_rn(c[4], __dmul_rn(x, y)); c[5] = __dadd_rn(c[5], __dmul_rn(x, z));
+      c[6] = __dadd_rn(c[6], __dmul_rn(y, y)); c[7] = __dadd_rn(c[7], __dmul_rn(y, z)); c[8] = __dadd_rn(c[8], __dmul_rn(z, z));
     }
     if (lane == 0) {
       double nr[3];
-      fast_eigen3x3_dev(cov, nr);
-      if (sqrt(dot3d(nr, nr)) == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
-      const double zz = dot3d(nr, nr);  // NormalizeNormals
-      if (zz > 0) { const double sn = sqrt(zz); nr[0] /= sn; nr[1] /= sn; nr[2] /= sn; }
-      if (nr[0] != nr[0]) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
-      const double ref[3] = {-qx, -qy, -qz};  // OrientNormalsTowardsCameraLocation(0,0,0)
-      if (sqrt(dot3d(nr, nr)) == 0.0) {
-        const double rn = sqrt(dot3d(ref, ref));
-        if (rn == 0.0) { nr[0] = 0; nr[1] = 0; nr[2] = 1; }
-        else { nr[0] = ref[0] / rn; nr[1] = ref[1] / rn; nr[2] = ref[2] / rn; }
-      } else if (dot3d(nr, ref) < 0.0) { nr[0] *= -1.0; nr[1] *= -1.0; nr[2] *= -1.0; }
-      nx_ = nr[0]; ny_ = nr[1]; nz_ = nr[2];
-      out_nrm[3 * (size_t)qi] = nx_; out_nrm[3 * (size_t)qi + 1] = ny_; out_nrm[3 * (size_t)qi + 2] = nz_;
-      if (out_cov) for (int t = 0; t < 9; t++) out_cov[9 * (size_t)qi + t] = cov[t];
+      finish_normal(c, kk, qx, qy, qz, nr);
+      out_nrm[3 * (size_t)qi] = nr[0]; out_nrm[3 * (size_t)qi + 1] = nr[1]; out_nrm[3 * (size_t)qi + 2] = nr[2];
     }
   }
 }
 
+__global__ void zero_i32_kernel(int32_t* p) { *p = 0; }
+
 int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius, double cell_hint) {
   B2S_REQUIRE(radius > 0.0, B2S_E_INVALID, "maxRadiusNormalEstimation_ must be > 0");  // CloudRegistration.cpp:50
   B2S_REQUIRE(knn > 0, B2S_E_INVALID, "knnNormalEstimation_ must be > 0");            // CloudRegistration.cpp:51
-  B2S_REQUIRE(knn <= 32, B2S_E_UNSUPPORTED, "knn > 32 is not supported by the warp k-best list yet");
+  B2S_REQUIRE(knn <= 32, B2S_E_UNSUPPORTED, "knn > 32 is not supported by the register-resident k-best list yet");
   double cell = cell_hint > 0.0 ? cell_hint : radius / 4.0;
   if (cell < radius / 16.0) cell = radius / 16.0;  // bound the ring count of the worst case
   B2S_TRY(grid_build(h, &h->grid_b, c, cell, nullptr, false));
   const size_t n_max = c->n_max > 0 ? c->n_max : 1;
   B2S_TRY(c->nrm.ensure(n_max * 24, h->stream));
-  int blocks = (int)((n_max + (NK_THREADS / 32) - 1) / (NK_THREADS / 32));
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  int blocks = (int)((n_max + NK_THREADS - 1) / NK_THREADS);
+  if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
+  // phase-2 queue: counter + one slot per point
+  B2S_TRY(h->tmp_i32.ensure((n_max + 64) * 4, h->stream));
+  int32_t* qn = h->tmp_i32.as<int32_t>() + 8;
+  int32_t* queue = h->tmp_i32.as<int32_t>() + 16;
+  const int ring_limit = 2;
   ProfScope prof(h, PK_NORMALS);
-  normals_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(h->grid_b.hdr.as<GridHeader>(), grid_starts(&h->grid_b), h->grid_b.pts.as<double4>(),
-                                                       knn, radius, c->nrm.as<double>(), nullptr);
-  h->launches++;
+  const GridHeader* hdr = h->grid_b.hdr.as<GridHeader>();
+  const int32_t* cs = grid_starts(&h->grid_b);
+  const double4* pts = h->grid_b.pts.as<double4>();
+  double* out = c->nrm.as<double>();
+  zero_i32_kernel<<<1, 1, 0, h->stream>>>(qn);
+  // exact instantiations for the knn values the reference's presets use (Lua default 20, C++ struct default 5,
+  // place-recognition normals 10); any other knn <= 32 takes the generic variants
+  if (knn == 20) normals_kernel<20, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
+  else if (knn == 10) normals_kernel<10, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
+  else if (knn == 5) normals_kernel<5, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
+  else if (knn <= 16) normals_kernel<16, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
+  else normals_kernel<32, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
+  normals_phase2_kernel<<<148 * 4, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, queue, qn, out);
+  h->launches += 3;
   c->has_normals = true;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;

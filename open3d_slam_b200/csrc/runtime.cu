@@ -19,8 +19,11 @@ const char* get_error() { return g_err; }
 
 int32_t DevBuf::ensure(size_t bytes, cudaStream_t s, bool preserve) {
   if (bytes <= cap && p) return B2S_OK;
+  // 25 % headroom on every (re)allocation: scan sizes jitter by a few percent from scan to scan and a re-allocation
+  // is a device-wide synchronisation (cudaMalloc / cudaFree), so steady state must never re-allocate
   size_t ncap = cap + cap / 2;
-  if (ncap < bytes) ncap = bytes;
+  const size_t want = bytes > 4096 ? bytes + bytes / 4 : bytes;
+  if (ncap < want) ncap = want;
   ncap = (ncap + 255) & ~(size_t)255;
   if (ncap < 256) ncap = 256;
   void* np = nullptr;

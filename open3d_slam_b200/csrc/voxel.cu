@@ -338,7 +338,11 @@ int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, 
   B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, in->dn.as<int32_t>(), n_max, 32));
   select_mark_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), ratio, vals, h->flags.as<int32_t>());
   h->launches++;
-  return compact_cloud(h, in, h->flags.as<int32_t>(), out);
+  B2S_TRY(compact_cloud(h, in, h->flags.as<int32_t>(), out));
+  // floor(ratio * n) <= ratio * n_max: keeps the launch bounds of everything downstream (ICP shared memory!) tight
+  const size_t bound = (size_t)((double)in->n_max * ratio) + 1;
+  if (bound < out->n_max) out->n_max = bound;
+  return B2S_OK;
 }
 
 // ---- F0: transform (with the reference's near-identity duplication quirk) --------------------------------------------
