@@ -1,0 +1,165 @@
+// b2s_open3d_slam.cpp -- see b2s_open3d_slam.hpp.  Everything here is marshalling: AoS fp64 host vectors <-> the C ABI.
+#include "b2s_open3d_slam.hpp"
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace o3d_slam {
+
+namespace {
+void toRowMajor(const Eigen::Matrix4d& m, double out[16]) {
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) out[4 * r + c] = m(r, c);   // Eigen is column-major: copy element-wise
+}
+RegistrationResult toResult(const b2s_result& r) {
+  RegistrationResult out;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out.transformation_(i, j) = r.T[4 * i + j];
+  out.fitness_ = r.fitness;
+  out.inlier_rmse_ = r.inlier_rmse;
+  return out;
+}
+int32_t cropperKind(const std::string& name) {   // croppers.hpp cropperNames
+  if (name == "Cylinder") return B2S_CROP_CYLINDER;
+  if (name == "MinRadius") return B2S_CROP_MIN_RADIUS;
+  if (name == "MaxRadius") return B2S_CROP_MAX_RADIUS;
+  if (name == "MinMaxRadius") return B2S_CROP_MINMAX_RADIUS;
+  throw std::runtime_error("Unknown cropper type");
+}
+b2s_cropper toCropper(const ScanCroppingParameters& p) {
+  b2s_cropper c;
+  std::memset(&c, 0, sizeof(c));
+  c.kind = cropperKind(p.cropperName_);
+  c.rmin = p.croppingMinRadius_; c.rmax = p.croppingMaxRadius_; c.zmin = p.croppingMinZ_; c.zmax = p.croppingMaxZ_;
+  return c;
+}
+struct DeviceCloud {   // RAII wrapper of a b2s_cloud uploaded from a reference PointCloud
+  b2s_handle* h; b2s_cloud* c = nullptr;
+  DeviceCloud(b2s_handle* h_, const PointCloud& pc, bool withNormals) : h(h_) {
+    int32_t rc = b2s_cloud_create(h, &c);
+    if (rc != B2S_OK) b2sThrow(rc);
+    const double* xyz = pc.points_.empty() ? nullptr : pc.points_.front().data();
+    const double* nrm = (withNormals && pc.HasNormals()) ? pc.normals_.front().data() : nullptr;
+    rc = b2s_cloud_upload_f64(h, c, xyz, nrm, pc.points_.size());
+    if (rc != B2S_OK) { b2s_cloud_destroy(c); b2sThrow(rc); }
+  }
+  explicit DeviceCloud(b2s_handle* h_) : h(h_) { int32_t rc = b2s_cloud_create(h, &c); if (rc != B2S_OK) b2sThrow(rc); }
+  ~DeviceCloud() { b2s_cloud_destroy(c); }
+  PointCloudPtr download() const {
+    size_t n = 0; int32_t hasN = 0;
+    int32_t rc = b2s_cloud_size(h, c, &n, &hasN);
+    if (rc != B2S_OK) b2sThrow(rc);
+    auto out = std::make_shared<PointCloud>();
+    out->points_.resize(n);
+    if (hasN) out->normals_.resize(n);
+    rc = b2s_cloud_download(h, c, n ? out->points_.front().data() : nullptr, (hasN && n) ? out->normals_.front().data() : nullptr, n, &n);
+    if (rc != B2S_OK) b2sThrow(rc);
+    return out;
+  }
+};
+}  // namespace
+
+void b2sThrow(int32_t code) { throw std::runtime_error(std::string("b2s error ") + std::to_string(code) + ": " + b2s_last_error()); }
+
+b2s_config b2sConfigFrom(const IcpParameters& icp, const ScanProcessingParameters* scan, const MapBuilderParameters* mapBuilder) {
+  b2s_config cfg;
+  b2s_default_config(&cfg);
+  cfg.icp.reg_type = B2S_REG_POINT_TO_PLANE;
+  cfg.icp.max_iter = icp.maxNumIter_;                       // src/CloudRegistration.cpp:63
+  cfg.icp.max_corr_dist = icp.maxCorrespondenceDistance_;   // :60
+  cfg.icp.knn = icp.knn_;                                   // :61
+  cfg.icp.knn_radius = icp.maxDistanceKnn_;                 // :62
+  if (scan) {
+    cfg.scan.voxel_size = scan->voxelSize_;
+    cfg.scan.downsampling_ratio = scan->downSamplingRatio_;
+    cfg.scan.scan_matcher_cropper = toCropper(scan->cropper_);   // src/ScanToMapRegistration.cpp:31
+  }
+  if (mapBuilder) {
+    cfg.map_voxel_size = mapBuilder->mapVoxelSize_;
+    cfg.scan.map_builder_cropper = toCropper(mapBuilder->cropper_);   // src/ScanToMapRegistration.cpp:30
+  }
+  return cfg;
+}
+
+b2s_handle* b2sThreadHandle(const b2s_config& cfg) {
+  struct Holder { b2s_handle* h = nullptr; ~Holder() { b2s_destroy(h); } };
+  thread_local Holder holder;
+  if (!holder.h) {
+    int32_t rc = b2s_create(&cfg, 0, nullptr, &holder.h);
+    if (rc != B2S_OK) b2sThrow(rc);
+  } else {
+    int32_t rc = b2s_set_config(holder.h, &cfg);
+    if (rc != B2S_OK) b2sThrow(rc);
+  }
+  return holder.h;
+}
+
+RegistrationIcpPointToPlaneB200::RegistrationIcpPointToPlaneB200(const CloudRegistrationParameters& p) : cfg_(b2sConfigFrom(p.icp_, nullptr, nullptr)) {}
+
+RegistrationResult RegistrationIcpPointToPlaneB200::registerClouds(const PointCloud& source, const PointCloud& target, const Transform& init) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  double T0[16];
+  toRowMajor(init.matrix(), T0);
+  b2s_result r;
+  const double* tn = target.HasNormals() ? target.normals_.front().data() : nullptr;   // nullptr -> B2S_E_NO_NORMALS, like [O3D] LogError
+  int32_t rc = b2s_register_host(h, source.points_.empty() ? nullptr : source.points_.front().data(), source.points_.size(),
+                                 target.points_.empty() ? nullptr : target.points_.front().data(), tn, target.points_.size(), T0, &r);
+  if (rc != B2S_OK) b2sThrow(rc);
+  return toResult(r);
+}
+
+void RegistrationIcpPointToPlaneB200::estimateNormalsOrCovariancesIfNeeded(PointCloud* cloud) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  DeviceCloud d(h, *cloud, false);
+  int32_t rc = b2s_estimate_normals(h, d.c, cfg_.icp.knn, cfg_.icp.knn_radius);   // asserts radius > 0, knn > 0 like :50-51
+  if (rc != B2S_OK) b2sThrow(rc);
+  cloud->normals_ = d.download()->normals_;
+}
+
+ScanToMapIcpB200::ScanToMapIcpB200(const MapperParameters& p) : cfg_(b2sConfigFrom(p.scanMatcher_.icp_, &p.scanProcessing_, &p.mapBuilder_)) {}
+
+ProcessedScans ScanToMapIcpB200::processForScanMatchingAndMerging(const PointCloud& in, const Transform&) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  DeviceCloud raw(h, in, false), merge(h), match(h);
+  int32_t rc = b2s_process_scan(h, raw.c, merge.c, match.c);
+  if (rc == B2S_OK) rc = b2s_synchronize(h);     // B2S_E_EMPTY here == the reference's assert_gt on the cropped sizes (:51-52)
+  if (rc != B2S_OK) b2sThrow(rc);
+  ProcessedScans out;
+  out.merge_ = merge.download();
+  out.match_ = match.download();
+  return out;
+}
+
+RegistrationResult ScanToMapIcpB200::scanToMapRegistration(const PointCloud& scan, const Submap& activeSubmap, const Transform& mapToRangeSensor,
+                                                           const Transform& initialGuess) const {
+  // Host-resident submap variant: the map cloud is uploaded per call.  With the device-resident b2s_submap
+  // (b2s_submap_insert / b2s_register_to_submap) the upload disappears; that needs Submap to own a b2s_submap* (INTEGRATION.md).
+  b2s_handle* h = b2sThreadHandle(cfg_);
+#ifdef B2S_SHIM_STANDALONE_CHECK
+  const PointCloud& map = getMapPointCloudOf(activeSubmap);
+#else
+  const PointCloud& map = activeSubmap.getMapPointCloud();
+#endif
+  DeviceCloud dscan(h, scan, false), dmap(h, map, true);
+  b2s_submap* sm = nullptr;
+  int32_t rc = b2s_submap_create(h, map.points_.size() + 1, &sm);
+  if (rc != B2S_OK) b2sThrow(rc);
+  rc = b2s_submap_set_cloud(h, sm, dmap.c);
+  double Ts[16], Tg[16];
+  toRowMajor(mapToRangeSensor.matrix(), Ts);
+  toRowMajor(initialGuess.matrix(), Tg);
+  b2s_result r;
+  if (rc == B2S_OK) rc = b2s_register_to_submap(h, dscan.c, sm, Ts, Tg, &r);   // B2S_E_EMPTY == "map patch size is zero" (:60)
+  b2s_submap_destroy(sm);
+  if (rc != B2S_OK) b2sThrow(rc);
+  return toResult(r);
+}
+
+void ScanToMapIcpB200::prepareInitialMap(PointCloud* map) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  DeviceCloud d(h, *map, false);
+  int32_t rc = b2s_estimate_normals(h, d.c, cfg_.icp.knn, cfg_.icp.knn_radius);
+  if (rc != B2S_OK) b2sThrow(rc);
+  map->normals_ = d.download()->normals_;
+}
+
+}  // namespace o3d_slam

@@ -1,0 +1,50 @@
+// b2s_open3d_slam.hpp -- the C++ subclasses a maintainer adds to open3d_slam to run the hot path on a B200 through the
+// C ABI of include/b2s.h.  They implement the reference's own abstract interfaces
+//     o3d_slam::CloudRegistration        (include/open3d_slam/CloudRegistration.hpp:19-27)
+//     o3d_slam::ScanToMapRegistration    (include/open3d_slam/ScanToMapRegistration.hpp:29-38)
+// and are selected from the reference's factories (src/CloudRegistration.cpp:85-100, src/ScanToMapRegistration.cpp:91-103)
+// by one extra enum value each.  Host data stays in the reference's own layout
+// (std::vector<Eigen::Vector3d>, 24-byte stride), which is exactly what the ABI takes.
+#pragma once
+#ifdef B2S_SHIM_STANDALONE_CHECK
+#include "open3d_slam/interfaces.hpp"   // stand-in declarations (shim/stubs), type-check only
+#else
+#include "open3d_slam/CloudRegistration.hpp"
+#include "open3d_slam/ScanToMapRegistration.hpp"
+#include "open3d_slam/Submap.hpp"
+#endif
+#include <memory>
+#include <mutex>
+#include "b2s.h"
+
+namespace o3d_slam {
+
+// one engine handle per host thread (the reference calls registerClouds from up to three threads, SlamWrapper.cpp:228-231)
+b2s_handle* b2sThreadHandle(const b2s_config& cfg);
+b2s_config b2sConfigFrom(const IcpParameters& icp, const ScanProcessingParameters* scan, const MapBuilderParameters* mapBuilder);
+[[noreturn]] void b2sThrow(int32_t code);   // status -> std::runtime_error, the reference's failure mode (assert.hpp:12-63)
+
+class RegistrationIcpPointToPlaneB200 : public CloudRegistration {
+ public:
+  explicit RegistrationIcpPointToPlaneB200(const CloudRegistrationParameters& p);
+  RegistrationResult registerClouds(const PointCloud& source, const PointCloud& target, const Transform& init) const final;
+  void estimateNormalsOrCovariancesIfNeeded(PointCloud* cloud) const final;
+
+ private:
+  b2s_config cfg_;
+};
+
+class ScanToMapIcpB200 : public ScanToMapRegistration {
+ public:
+  explicit ScanToMapIcpB200(const MapperParameters& p);
+  ProcessedScans processForScanMatchingAndMerging(const PointCloud& in, const Transform& mapToRangeSensor) const final;
+  RegistrationResult scanToMapRegistration(const PointCloud& scan, const Submap& activeSubmap, const Transform& mapToRangeSensor,
+                                           const Transform& initialGuess) const final;
+  bool isMergeScanValid(const PointCloud& in) const final { return in.HasNormals(); }
+  void prepareInitialMap(PointCloud* map) const final;
+
+ private:
+  b2s_config cfg_;
+};
+
+}  // namespace o3d_slam

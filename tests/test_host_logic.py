@@ -73,3 +73,11 @@ def test_bench_reference_arm_smoke():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
         assert k in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_reference_side_shim_type_checks():
+    """shim/b2s_open3d_slam.cpp (the C++ subclasses of CloudRegistration / ScanToMapRegistration) compiles against the
+    C header and stand-in Open3D/Eigen declarations."""
+    import subprocess
+    out = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "shim"), "check"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
