@@ -84,8 +84,18 @@ static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud*
   if (sp.voxel_size > 0.0) B2S_TRY(op_voxel_down_sample(h, raw, has_crop ? &wide : nullptr, sp.voxel_size, h->t0));
   else if (has_crop) B2S_TRY(op_crop(h, raw, wide, h->t0));
   else B2S_TRY(op_voxel_down_sample(h, raw, nullptr, 0.0, h->t0));
-  B2S_TRY(op_estimate_normals(h, h->t0, h->cfg.icp.knn, h->cfg.icp.knn_radius, sp.voxel_size > 0.0 ? 4.0 * sp.voxel_size : 0.0));
-  B2S_TRY(op_random_down_sample(h, h->t0, sp.downsampling_ratio, sp.seed, merge));
+  const double cell_hint = sp.voxel_size > 0.0 ? 4.0 * sp.voxel_size : 0.0;
+  if (sp.downsampling_ratio < 1.0) {
+    // reference order: normals for every voxel point, then RandomDownSample.  The selection only depends on the point
+    // positions, so select first and estimate normals for the survivors only (neighbours still from the full cloud).
+    B2S_REQUIRE(sp.downsampling_ratio >= 0.0, B2S_E_INVALID, "[RandomDownSample] sampling_ratio must be in [0, 1]");
+    B2S_TRY(select_flags(h, h->t0, sp.downsampling_ratio, sp.seed));
+    B2S_TRY(op_estimate_normals(h, h->t0, h->cfg.icp.knn, h->cfg.icp.knn_radius, cell_hint, h->flags.as<int32_t>()));
+    B2S_TRY(select_compact(h, h->t0, sp.downsampling_ratio, merge));
+  } else {
+    B2S_TRY(op_estimate_normals(h, h->t0, h->cfg.icp.knn, h->cfg.icp.knn_radius, cell_hint));
+    B2S_TRY(op_random_down_sample(h, h->t0, sp.downsampling_ratio, sp.seed, merge));
+  }
   b2s_cropper c1 = sp.scan_matcher_cropper;
   c1.center[0] = c1.center[1] = c1.center[2] = 0.0;   // ScanToMapRegistration.cpp:47 setPose(Identity)
   B2S_TRY(op_crop(h, merge, make_crop(&c1), match));
@@ -193,12 +203,12 @@ int32_t b2s_profile_read(b2s_handle* h, double* ms_by_kind, int64_t* count_by_ki
 int32_t b2s_debug_icp_clocks(b2s_handle* h, int32_t enable, long long* out_256) {
   B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
   LOCK(h);
-  if (enable && !h->icp_dbg) { B2S_CUDA(cudaMalloc(&h->icp_dbg, 256 * 8)); }
+  if (enable && !h->icp_dbg) { B2S_CUDA(cudaMalloc(&h->icp_dbg, 512 * 8)); }
   if (h->icp_dbg && out_256) {
     B2S_CUDA(cudaStreamSynchronize(h->stream));
-    B2S_CUDA(cudaMemcpy(out_256, h->icp_dbg, 256 * 8, cudaMemcpyDeviceToHost));
+    B2S_CUDA(cudaMemcpy(out_256, h->icp_dbg, 512 * 8, cudaMemcpyDeviceToHost));
   }
-  if (h->icp_dbg) B2S_CUDA(cudaMemsetAsync(h->icp_dbg, 0, 256 * 8, h->stream));
+  if (h->icp_dbg) B2S_CUDA(cudaMemsetAsync(h->icp_dbg, 0, 512 * 8, h->stream));
   if (!enable && h->icp_dbg) { cudaFree(h->icp_dbg); h->icp_dbg = nullptr; }
   return B2S_OK;
 }

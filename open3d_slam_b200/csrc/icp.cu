@@ -143,27 +143,36 @@ __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double q
 // phase 2 (one warp, all lanes with the same query): continues from ring ICP_R1 + 1 with the rows of each ring spread
 // over the lanes.  st must hold the phase-1 state; on return every lane holds the exact answer.
 __device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, double qy, double qz, NNState& st) {
+  // One pass over the box that encloses the sphere of the seed distance (or of the correspondence radius when there is
+  // no seed): the (y, z) rows of the box are independent, so they are spread over the lanes and every lane clips its
+  // row's x-run to the sphere.  No ring-by-ring termination tests, one warp reduction at the end.
   const int lane = threadIdx.x & 31;
-  int cx, cy, cz;
-  cell_of(g, qx, qy, qz, cx, cy, cz);
-  for (int R = ICP_R1 + 1;; ++R) {
-    const int side = 2 * R + 1;
-    for (int t = lane; t < side * side; t += 32) {
-      const int z = cz - R + t / side, y = cy - R + t % side;
-      if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
-      nn_scan_row(g, qx, qy, qz, cx, cy, cz, R, y, z, st);
-    }
-    // lexicographic (d2, index) minimum over the lanes; a lane without a hit carries slot -1
+  const double radm = sqrt(st.best) * (1.0 + 1e-12) + 1e-300;   // st.best = seed distance^2, or r^2 when unseeded
+  const int iy0 = (int)fmin(fmax(floor((qy - radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  const int iy1 = (int)fmin(fmax(floor((qy + radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  const int iz0 = (int)fmin(fmax(floor((qz - radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+  const int iz1 = (int)fmin(fmax(floor((qz + radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+  const int ny_ = iy1 - iy0 + 1, nrows = ny_ * (iz1 - iz0 + 1);
+  for (int t = lane; t < nrows; t += 32) {
+    const int y = iy0 + t % ny_, z = iz0 + t / ny_;
+    const double gz = slab_gap(qz, g.oz, g.cell, z, g.nz, g.eps);
+    const double gy = slab_gap(qy, g.oy, g.cell, y, g.ny, g.eps);
+    const double g2 = gz * gz + gy * gy;
+    if (g2 > st.best) continue;
+    const double xr = sqrt(fmax(st.best - g2, 0.0)) * (1.0 + 1e-12) + g.eps;
+    const int xa = (int)fmin(fmax(floor((qx - xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+    const int xb = (int)fmin(fmax(floor((qx + xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+    const int row = (z * g.ny + y) * g.nx;
+    nn_scan_range(g.pts, g.cs[row + xa], g.cs[row + xb + 1], qx, qy, qz, st);
+  }
+  // lexicographic (d2, index) minimum over the lanes; a lane without a hit carries slot -1
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double od = __shfl_xor_sync(0xffffffffu, st.best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, st.bidx, o);
-      const int os = __shfl_xor_sync(0xffffffffu, st.bslot, o);
-      const bool take = os >= 0 && (st.bslot < 0 || od < st.best || (od == st.best && oi < st.bidx));
-      if (take) { st.best = od; st.bidx = oi; st.bslot = os; }
-    }
-    const double bound = ring_bound(g, qx, qy, qz, cx, cy, cz, R);
-    if (bound == INFINITY || bound * bound > st.best) break;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, st.best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, st.bidx, o);
+    const int os = __shfl_xor_sync(0xffffffffu, st.bslot, o);
+    const bool take = os >= 0 && (st.bslot < 0 || od < st.best || (od == st.best && oi < st.bidx));
+    if (take) { st.best = od; st.bidx = oi; st.bslot = os; }
   }
 }
 
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
   const int chunk = (n + (int)csize - 1) / (int)csize;
   const int lo = min((int)crank * chunk, n), hi = min(lo + chunk, n);
   const int cnt = hi - lo;
-  const bool in_smem = cnt <= smem_pts_cap;
+  const bool in_smem = chunk <= smem_pts_cap;   // uniform over the cluster (phase 2 shares work across CTAs)
   double* work = in_smem ? s_pts : (P.work_xyz + 3 * (size_t)lo);
 
   if (tid == 0) {
@@ -331,6 +340,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
 
   for (int e = 0;; ++e) {
     if (dbg_on && e < 64) dbg[4 * e] = clock64();
+    const bool bal_on = dbg != nullptr && blockIdx.y == 0 && tid == 0 && e < 8;
+    long long t_start = 0;
+    if (bal_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const bool apply = s_misc[3] != 0.0;
     double U[12];
 #pragma unroll
@@ -372,27 +384,52 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       }
     }
     __syncthreads();
+    long long t_p1 = 0;
+    if (bal_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_p1));
     // ---- phase 2: one warp per point that needs rings beyond ICP_R1 ----
-    {
-      const int qn = *s_qn;
-      for (int qi = warp; qi < qn; qi += ICP_WARPS) {
-        const int i = s_queue[qi];
-        const double px = work[3 * i], py = work[3 * i + 1], pz = work[3 * i + 2];
+    // The unresolved points cluster spatially (map frontier), i.e. in one or two CTAs of the Morton-ordered source:
+    // the queues of ALL CTAs are therefore drained by ALL warps of the cluster, through distributed shared memory.
+    // The sums are cluster totals anyway, so a point may be accumulated by any CTA.
+    if (in_smem) {
+      cluster.sync();  // every queue is complete
+      int qoff[9];
+      qoff[0] = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) qoff[r + 1] = qoff[r] + ((unsigned)r < csize ? *cluster.map_shared_rank(s_qn, r) : 0);
+      for (int gi = (int)crank * ICP_WARPS + warp; gi < qoff[8]; gi += (int)csize * ICP_WARPS) {
+        int r = 0;
+#pragma unroll
+        for (int k = 1; k < 8; k++) if (gi >= qoff[k]) r = k;
+        const int li = gi - qoff[r];
+        const int i = cluster.map_shared_rank(s_queue, r)[li];
+        const double* rw = cluster.map_shared_rank(s_pts, r);
+        int* rp = cluster.map_shared_rank(s_prev, r);
+        const double px = rw[3 * i], py = rw[3 * i + 1], pz = rw[3 * i + 2];
         NNState st;
         st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1;
-        const int hs = s_prev[i];  // best of rings 0..ICP_R1 (or the seed), -1 when nothing was in range
+        const int hs = rp[i];  // best of the box query (or the seed), -1 when nothing was in range
         if (hs >= 0) {
           const double4 p = g.pts[hs];
           st.best = dist2_exact(px, py, pz, p.x, p.y, p.z); st.bidx = (int)__double_as_longlong(p.w); st.bslot = hs;
+          if (!(st.best < r2)) { st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; }
         }
         nn_phase2_warp(g, px, py, pz, st);
         if (lane == 0) {
-          s_prev[i] = st.bslot;
+          rp[i] = st.bslot;
           if (st.bslot >= 0) icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
         }
       }
     }
     if (dbg_on && e < 64) dbg[4 * e + 1] = clock64();
+    if (dbg != nullptr && blockIdx.y == 0 && e < 8) {   // per-CTA balance: {phase-1 end, phase-2 end (all warps), queue length, points}
+      __syncthreads();
+      if (tid == 0) {
+        long long t_p2;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_p2));
+        long long* d = dbg + 256 + (e * 8 + (int)crank) * 4;
+        d[0] = t_p1 - t_start; d[1] = t_p2 - t_p1; d[2] = *s_qn; d[3] = cnt;   // ns, ns, queue length, points
+      }
+    }
     // warp tree -> CTA tree (fixed order => run-to-run deterministic)
 #pragma unroll
     for (int i = 0; i < NACC; i++) {
@@ -406,8 +443,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       for (int w = 0; w < ICP_WARPS; w++) v += s_red[w * NACC + tid];
       s_part[buf * NACC + tid] = v;
     }
-    if (tid == 0) *s_qn = 0;
     cluster.sync();
+    if (tid == 0) *s_qn = 0;   // only after the barrier: peers read this queue during their phase 2
     if (tid < NACC) {
       double v = 0.0;
       for (unsigned r = 0; r < csize; r++) {

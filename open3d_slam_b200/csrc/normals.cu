@@ -166,6 +166,7 @@ template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
                                                              const double4* __restrict__ pts, int knn, double radius, int ring_limit,
                                                              int32_t* __restrict__ queue, int32_t* queue_n,
+                                                             const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
                                                              double* __restrict__ out_nrm) {
   __shared__ GridHeader g;
   if (threadIdx.x == 0) g = *hdr;
@@ -174,7 +175,10 @@ __global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* _
   const double r2 = radius * radius;
   const double eps = 1e-9 * g.cell;
   const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+  const int nq = qlist ? *qcount : n;   // optional query list: only these slots get a normal (fused down-sample)
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nq; t += gridDim.x * blockDim.x) {
+    const int s = qlist ? qlist[t] : t;
+    if (ring_limit < 0) { queue[atomicAdd(queue_n, 1)] = s; continue; }   // everything to the warp-cooperative kernel
     const double4 qp = pts[s];
     const double qx = qp.x, qy = qp.y, qz = qp.z;
     const int qi = (int)__double_as_longlong(qp.w);
@@ -385,9 +389,385 @@ __global__ void __launch_bounds__(NK_THREADS) normals_phase2_kernel(const GridHe
   }
 }
 
-__global__ void zero_i32_kernel(int32_t* p) { *p = 0; }
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path: one warp per query, GATHER the candidates of the 3x3x3 cell block once, SELECT the k nearest by counting,
+// reduce the covariance with warp shuffles.
+//   1. lanes 0..8 resolve the nine (y, z) rows of the block (one contiguous slot range each);
+//   2. the candidates (at most NS_CHUNKS*32) are dealt round-robin to the lanes: distance + index live in registers;
+//   3. the k-th smallest (d2, index) is found WITHOUT sorting: a 32-bin histogram over d2 (neighbours on a surface are
+//      ~uniform in d2) built with shared-memory atomics, a warp prefix sum to locate the bin that holds the k-th, and a
+//      few warp arg-min rounds inside that bin;
+//   4. every lane accumulates the cumulants of its own selected candidates, a butterfly of shuffles sums them
+//      (the covariance is therefore summed in a different order than the reference's ascending-distance order: the
+//      difference is O(1e-16) relative);
+//   5. the query is exact iff the k-th distance lies inside the scanned block (or the block already covers the radius);
+//      anything else -- sparse neighbourhoods, more than NS_CHUNKS*32 candidates -- is queued for normals_phase2_kernel.
+// A warp handles 32 consecutive queries and only then runs the eigen-solver, one query per lane.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NS_CHUNKS = 8;
 
-int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius, double cell_hint) {
+__global__ void __launch_bounds__(NK_THREADS) normals_select_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
+                                                                    const double4* __restrict__ pts, int knn, double radius,
+                                                                    const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
+                                                                    int32_t* __restrict__ queue, int32_t* queue_n,
+                                                                    double* __restrict__ cum) {
+  __shared__ GridHeader g;
+  __shared__ int s_hist[NK_THREADS / 32][32];
+  if (threadIdx.x == 0) g = *hdr;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n = g.n;
+  const int nq = qlist ? *qcount : n;
+  const double r2 = radius * radius;
+  const double eps = 1e-9 * g.cell;
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int warps_total = gridDim.x * (NK_THREADS / 32);
+  {
+    for (int tq = blockIdx.x * (NK_THREADS / 32) + wib; tq < nq; tq += warps_total) {
+      const int s = qlist ? qlist[tq] : tq;
+      const double4 qp = pts[s];
+      const double qx = qp.x, qy = qp.y, qz = qp.z;
+      const int cx = (int)fmin(fmax(floor((qx - g.origin[0]) * g.inv_cell), 0.0), (double)(nx - 1));
+      const int cy = (int)fmin(fmax(floor((qy - g.origin[1]) * g.inv_cell), 0.0), (double)(ny - 1));
+      const int cz = (int)fmin(fmax(floor((qz - g.origin[2]) * g.inv_cell), 0.0), (double)(nz - 1));
+      // 1. rows of the 3x3x3 block
+      int a = 0, cnt = 0;
+      if (lane < 9) {
+        const int y = cy - 1 + lane % 3, z = cz - 1 + lane / 3;
+        if (y >= 0 && y < ny && z >= 0 && z < nz) {
+          const int row = (z * ny + y) * nx;
+          a = cs[row + max(cx - 1, 0)];
+          cnt = cs[row + min(cx + 1, nx - 1) + 1] - a;
+        }
+      }
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      const int ntot = __shfl_sync(0xffffffffu, inc, 8);
+      const int delta_l = a - (inc - cnt);   // slot = t + delta for candidate number t of this row
+      int offs[9], delta[9];
+#pragma unroll
+      for (int r = 0; r < 9; r++) { offs[r] = __shfl_sync(0xffffffffu, inc - cnt, r); delta[r] = __shfl_sync(0xffffffffu, delta_l, r); }
+      bool fallback = ntot > NS_CHUNKS * 32;
+      if (fallback && lane == 0) atomicAdd(queue_n + 2, 1);   // debug counter: block holds too many candidates
+      // 2. candidates -> registers
+      double d[NS_CHUNKS]; int idx[NS_CHUNKS], sl[NS_CHUNKS];
+      int nvalid = 0;
+      double dmax = 0.0;
+      if (!fallback) {
+#pragma unroll
+        for (int c = 0; c < NS_CHUNKS; c++) {
+          const int t = c * 32 + lane;
+          int dl = delta[0];
+#pragma unroll
+          for (int r = 1; r < 9; r++) if (t >= offs[r]) dl = delta[r];
+          d[c] = INFINITY; idx[c] = 0x7fffffff; sl[c] = -1;
+          if (t < ntot) {
+            const int slot = t + dl;
+            const double4 p = pts[slot];
+            const double dd = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+            if (dd < r2) { d[c] = dd; idx[c] = (int)__double_as_longlong(p.w); sl[c] = slot; dmax = fmax(dmax, dd); }
+          }
+          nvalid += __popc(__ballot_sync(0xffffffffu, sl[c] >= 0));
+        }
+      }
+      // 3. threshold (td, ti): the `need`-th smallest (d2, index)
+      const int need = min(knn, nvalid);
+      double td = INFINITY; int ti = 0x7fffffff;   // nvalid <= knn: everything valid is selected
+      if (!fallback && nvalid > knn) {
+        dmax = warp_max(dmax);
+        const double scale = dmax > 0.0 ? 32.0 / dmax : 0.0;
+        s_hist[wib][lane] = 0;
+        __syncwarp();
+        int bin[NS_CHUNKS];
+#pragma unroll
+        for (int c = 0; c < NS_CHUNKS; c++) {
+          bin[c] = 32;
+          if (sl[c] >= 0) { bin[c] = min(31, (int)(d[c] * scale)); atomicAdd(&s_hist[wib][bin[c]], 1); }
+        }
+        __syncwarp();
+        int cum = s_hist[wib][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cum, o); if (lane >= o) cum += t; }
+        const int B = __ffs(__ballot_sync(0xffffffffu, cum >= need)) - 1;
+        const int below = B > 0 ? __shfl_sync(0xffffffffu, cum, B - 1) : 0;
+        const int m = need - below;    // how many of bin B belong to the k nearest (>= 1)
+        double ld = -1.0; int li = -1; // last extracted (d2, index), lexicographic lower bound
+        for (int round = 0; round < m; ++round) {
+          double bd = INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+          for (int c = 0; c < NS_CHUNKS; c++) {
+            const bool in_bin = bin[c] == B;
+            const bool after = d[c] > ld || (d[c] == ld && idx[c] > li);
+            const bool better = d[c] < bd || (d[c] == bd && idx[c] < bi);
+            if (in_bin && after && better) { bd = d[c]; bi = idx[c]; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+          }
+          ld = bd; li = bi;
+        }
+        td = ld; ti = li;
+        // everything in a lower bin is selected, bin B up to (td, ti): express both with one lexicographic threshold
+#pragma unroll
+        for (int c = 0; c < NS_CHUNKS; c++) if (bin[c] > B) sl[c] = -1;   // beyond the k-th
+#pragma unroll
+        for (int c = 0; c < NS_CHUNKS; c++) if (bin[c] == B && (d[c] > td || (d[c] == td && idx[c] > ti))) sl[c] = -1;
+      }
+      // 5. exact?  the k-th distance must lie inside the scanned block, or the block must cover the whole radius
+      double bound = INFINITY;
+      if (cx - 1 > 0) bound = fmin(bound, qx - (g.origin[0] + (double)(cx - 1) * g.cell));
+      if (cx + 1 < nx - 1) bound = fmin(bound, (g.origin[0] + (double)(cx + 2) * g.cell) - qx);
+      if (cy - 1 > 0) bound = fmin(bound, qy - (g.origin[1] + (double)(cy - 1) * g.cell));
+      if (cy + 1 < ny - 1) bound = fmin(bound, (g.origin[1] + (double)(cy + 2) * g.cell) - qy);
+      if (cz - 1 > 0) bound = fmin(bound, qz - (g.origin[2] + (double)(cz - 1) * g.cell));
+      if (cz + 1 < nz - 1) bound = fmin(bound, (g.origin[2] + (double)(cz + 2) * g.cell) - qz);
+      if (bound != INFINITY) { bound -= eps; if (bound < 0.0) bound = 0.0; }
+      const double b2 = bound == INFINITY ? INFINITY : bound * bound;
+      const double kth = nvalid >= knn ? td : INFINITY;   // fewer than k found: only exact if the block covers the radius
+      if (!fallback && !(b2 > fmin(kth, r2))) { fallback = true; if (lane == 0) atomicAdd(queue_n + (nvalid >= knn ? 3 : 4), 1); }  // debug counters: k-th outside the block / fewer than k in the block
+      if (fallback) {
+        if (lane == 0) { queue[atomicAdd(queue_n, 1)] = s; cum[10 * (size_t)tq + 9] = -1.0; }
+        continue;
+      }
+      // 4. cumulants of the selected candidates, butterfly sum
+      double c9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < NS_CHUNKS; c++) {
+        if (sl[c] >= 0) {
+          const double4 p = pts[sl[c]];
+          c9[0] += p.x; c9[1] += p.y; c9[2] += p.z;
+          c9[3] += p.x * p.x; c9[4] += p.x * p.y; c9[5] += p.x * p.z;
+          c9[6] += p.y * p.y; c9[7] += p.y * p.z; c9[8] += p.z * p.z;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c9[t] += __shfl_xor_sync(0xffffffffu, c9[t], o);
+      }
+      {
+        double v = (double)need;   // lane 9 writes the neighbour count, lanes 0..8 one cumulant each (all lanes hold the sums)
+#pragma unroll
+        for (int t = 0; t < 9; t++) if (lane == t) v = c9[t];
+        if (lane < 10) cum[10 * (size_t)tq + lane] = v;
+      }
+    }
+  }
+}
+
+// Second-generation fast path: same GATHER -> SELECT-BY-COUNTING -> BUTTERFLY pipeline as normals_select_kernel, but the
+// gathered candidates go through a per-warp shared-memory buffer, which lets the block radius R grow (1, 2, 3 cells)
+// until the k-th neighbour provably lies inside the block: dense areas finish at R = 1, sparse far-range areas at
+// R = 2 or 3, and only what is still unresolved (or holds more than NS2_CAP candidates) goes to normals_phase2_kernel.
+constexpr int NS2_CAP = 256;
+constexpr int NS2_CHUNKS = NS2_CAP / 32;
+constexpr int NS2_RMAX = 3;
+
+__global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
+                                                                     const double4* __restrict__ pts, int knn, double radius,
+                                                                     const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
+                                                                     int32_t* __restrict__ queue, int32_t* queue_n,
+                                                                     double* __restrict__ cum) {
+  __shared__ GridHeader g;
+  __shared__ double s_d[NK_THREADS / 32][NS2_CAP];
+  __shared__ int s_i[NK_THREADS / 32][NS2_CAP];
+  __shared__ int s_s[NK_THREADS / 32][NS2_CAP];
+  __shared__ int s_hist[NK_THREADS / 32][32];
+  if (threadIdx.x == 0) g = *hdr;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int n = g.n;
+  const int nq = qlist ? *qcount : n;
+  const double r2 = radius * radius;
+  const double eps = 1e-9 * g.cell;
+  const int nx = g.dims[0], ny = g.dims[1], nz = g.dims[2];
+  const int warps_total = gridDim.x * (NK_THREADS / 32);
+  for (int tq = blockIdx.x * (NK_THREADS / 32) + wib; tq < nq; tq += warps_total) {
+    const int s = qlist ? qlist[tq] : tq;
+    const double4 qp = pts[s];
+    const double qx = qp.x, qy = qp.y, qz = qp.z;
+    const int cx = (int)fmin(fmax(floor((qx - g.origin[0]) * g.inv_cell), 0.0), (double)(nx - 1));
+    const int cy = (int)fmin(fmax(floor((qy - g.origin[1]) * g.inv_cell), 0.0), (double)(ny - 1));
+    const int cz = (int)fmin(fmax(floor((qz - g.origin[2]) * g.inv_cell), 0.0), (double)(nz - 1));
+    bool resolved = false;
+    int need = 0;
+    double c9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int R = 1; R <= NS2_RMAX && !resolved; ++R) {
+      // ---- gather the (2R+1)^3 block into shared memory (valid = inside the radius), rows resolved by the lanes ----
+      const int side = 2 * R + 1;
+      const int x0 = max(cx - R, 0), x1 = min(cx + R, nx - 1);
+      int nc = 0;
+      for (int t0 = 0; t0 < side * side; t0 += 32) {
+        int a = 0, b = 0;
+        const int t = t0 + lane;
+        if (t < side * side) {
+          const int z = cz - R + t / side, y = cy - R + t % side;
+          if (z >= 0 && z < nz && y >= 0 && y < ny) { const int row = (z * ny + y) * nx; a = cs[row + x0]; b = cs[row + x1 + 1]; }
+        }
+        unsigned rows = __ballot_sync(0xffffffffu, b > a);
+        while (rows) {
+          const int src_lane = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const int ra = __shfl_sync(0xffffffffu, a, src_lane), rb = __shfl_sync(0xffffffffu, b, src_lane);
+          for (int j0 = ra; j0 < rb; j0 += 32) {
+            const int j = j0 + lane;
+            double dd = INFINITY; int ii = 0x7fffffff;
+            if (j < rb) {
+              const double4 p = pts[j];
+              dd = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+              ii = (int)__double_as_longlong(p.w);
+            }
+            const bool ok = j < rb && dd < r2;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int pos = nc + __popc(m & lt_mask);
+            if (ok && pos < NS2_CAP) { s_d[wib][pos] = dd; s_i[wib][pos] = ii; s_s[wib][pos] = j; }
+            nc += __popc(m);
+          }
+        }
+      }
+      __syncwarp();
+      if (nc > NS2_CAP) break;   // too dense for the buffer: general kernel
+      // ---- candidates -> registers (round-robin), statistics ----
+      double d[NS2_CHUNKS]; int idx[NS2_CHUNKS], sl[NS2_CHUNKS];
+      double dmax = 0.0;
+#pragma unroll
+      for (int c = 0; c < NS2_CHUNKS; c++) {
+        const int t = c * 32 + lane;
+        d[c] = INFINITY; idx[c] = 0x7fffffff; sl[c] = -1;
+        if (t < nc) { d[c] = s_d[wib][t]; idx[c] = s_i[wib][t]; sl[c] = s_s[wib][t]; dmax = fmax(dmax, d[c]); }
+      }
+      __syncwarp();
+      need = min(knn, nc);
+      double td = INFINITY; int ti = 0x7fffffff;
+      if (nc > knn) {   // k-th smallest (d2, index) by counting: 32-bin histogram over d2, then arg-min rounds in one bin
+        dmax = warp_max(dmax);
+        const double scale = dmax > 0.0 ? 32.0 / dmax : 0.0;
+        s_hist[wib][lane] = 0;
+        __syncwarp();
+        int bin[NS2_CHUNKS];
+#pragma unroll
+        for (int c = 0; c < NS2_CHUNKS; c++) {
+          bin[c] = 32;
+          if (sl[c] >= 0) { bin[c] = min(31, (int)(d[c] * scale)); atomicAdd(&s_hist[wib][bin[c]], 1); }
+        }
+        __syncwarp();
+        int cumh = s_hist[wib][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cumh, o); if (lane >= o) cumh += t; }
+        const int B = __ffs(__ballot_sync(0xffffffffu, cumh >= need)) - 1;
+        const int below = B > 0 ? __shfl_sync(0xffffffffu, cumh, B - 1) : 0;
+        const int m = need - below;
+        double ld = -1.0; int li = -1;
+        for (int round = 0; round < m; ++round) {
+          double bd = INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+          for (int c = 0; c < NS2_CHUNKS; c++) {
+            const bool in_bin = bin[c] == B;
+            const bool after = d[c] > ld || (d[c] == ld && idx[c] > li);
+            const bool better = d[c] < bd || (d[c] == bd && idx[c] < bi);
+            if (in_bin && after && better) { bd = d[c]; bi = idx[c]; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+          }
+          ld = bd; li = bi;
+        }
+        td = ld; ti = li;
+#pragma unroll
+        for (int c = 0; c < NS2_CHUNKS; c++)
+          if (bin[c] > B || (bin[c] == B && (d[c] > td || (d[c] == td && idx[c] > ti)))) sl[c] = -1;
+      }
+      // ---- exact?  k-th inside the scanned block, or the block covers the whole radius ----
+      double bound = INFINITY;
+      if (cx - R > 0) bound = fmin(bound, qx - (g.origin[0] + (double)(cx - R) * g.cell));
+      if (cx + R < nx - 1) bound = fmin(bound, (g.origin[0] + (double)(cx + R + 1) * g.cell) - qx);
+      if (cy - R > 0) bound = fmin(bound, qy - (g.origin[1] + (double)(cy - R) * g.cell));
+      if (cy + R < ny - 1) bound = fmin(bound, (g.origin[1] + (double)(cy + R + 1) * g.cell) - qy);
+      if (cz - R > 0) bound = fmin(bound, qz - (g.origin[2] + (double)(cz - R) * g.cell));
+      if (cz + R < nz - 1) bound = fmin(bound, (g.origin[2] + (double)(cz + R + 1) * g.cell) - qz);
+      if (bound != INFINITY) { bound -= eps; if (bound < 0.0) bound = 0.0; }
+      const double b2 = bound == INFINITY ? INFINITY : bound * bound;
+      const double kth = nc > knn ? td : INFINITY;   // k or fewer inside the radius so far: exact only if the block covers the radius
+      if (!(b2 > fmin(kth, r2))) continue;           // grow the block
+      // ---- cumulants of the selected candidates, butterfly sum over the warp ----
+#pragma unroll
+      for (int c = 0; c < NS2_CHUNKS; c++) {
+        if (sl[c] >= 0) {
+          const double4 p = pts[sl[c]];
+          c9[0] += p.x; c9[1] += p.y; c9[2] += p.z;
+          c9[3] += p.x * p.x; c9[4] += p.x * p.y; c9[5] += p.x * p.z;
+          c9[6] += p.y * p.y; c9[7] += p.y * p.z; c9[8] += p.z * p.z;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c9[t] += __shfl_xor_sync(0xffffffffu, c9[t], o);
+      }
+      resolved = true;
+    }
+    if (!resolved) {
+      if (lane == 0) { queue[atomicAdd(queue_n, 1)] = s; cum[10 * (size_t)tq + 9] = -1.0; }
+      continue;
+    }
+    {
+      double v = (double)need;   // lane 9 writes the neighbour count, lanes 0..8 one cumulant each (all lanes hold the sums)
+#pragma unroll
+      for (int t = 0; t < 9; t++) if (lane == t) v = c9[t];
+      if (lane < 10) cum[10 * (size_t)tq + lane] = v;
+    }
+  }
+}
+
+// eigen-solver + normalise + orient for the queries the select kernel resolved: one THREAD per query
+__global__ void __launch_bounds__(NK_THREADS) normals_finish_kernel(const GridHeader* __restrict__ hdr, const double4* __restrict__ pts,
+                                                                    const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
+                                                                    const double* __restrict__ cum, double* __restrict__ out_nrm) {
+  const int nq = qlist ? *qcount : hdr->n;
+  for (int tq = blockIdx.x * blockDim.x + threadIdx.x; tq < nq; tq += gridDim.x * blockDim.x) {
+    const double kkd = cum[10 * (size_t)tq + 9];
+    if (kkd < 0.0) continue;   // left to normals_phase2_kernel
+    double c9[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) c9[t] = cum[10 * (size_t)tq + t];
+    const double4 qp = pts[qlist ? qlist[tq] : tq];
+    double nr[3];
+    finish_normal(c9, (int)kkd, qp.x, qp.y, qp.z, nr);
+    const size_t qi = (size_t)(int)__double_as_longlong(qp.w);
+    out_nrm[3 * qi] = nr[0]; out_nrm[3 * qi + 1] = nr[1]; out_nrm[3 * qi + 2] = nr[2];
+  }
+}
+
+
+__global__ void zero_i32_kernel(int32_t* p) { for (int i = 0; i < 6; i++) p[i] = 0; }
+
+// query list = grid slots whose original point is flagged; warp-aggregated append keeps neighbouring slots together
+__global__ void __launch_bounds__(NK_THREADS) normals_qlist_kernel(const GridHeader* __restrict__ hdr, const double4* __restrict__ pts,
+                                                                   const int32_t* __restrict__ flags, int32_t* __restrict__ qlist,
+                                                                   int32_t* qcount) {
+  const int n = hdr->n;
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n + 31) & ~31;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_round; s += gridDim.x * blockDim.x) {
+    bool take = false;
+    if (s < n) take = flags[(int)__double_as_longlong(pts[s].w)] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(qcount, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) qlist[base + __popc(m & ((1u << lane) - 1u))] = s;
+  }
+}
+
+int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius, double cell_hint, const int32_t* flags) {
   B2S_REQUIRE(radius > 0.0, B2S_E_INVALID, "maxRadiusNormalEstimation_ must be > 0");  // CloudRegistration.cpp:50
   B2S_REQUIRE(knn > 0, B2S_E_INVALID, "knnNormalEstimation_ must be > 0");            // CloudRegistration.cpp:51
   B2S_REQUIRE(knn <= 32, B2S_E_UNSUPPORTED, "knn > 32 is not supported by the register-resident k-best list yet");
@@ -400,23 +780,55 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   // phase-2 queue: counter + one slot per point
-  B2S_TRY(h->tmp_i32.ensure((n_max + 64) * 4, h->stream));
-  int32_t* qn = h->tmp_i32.as<int32_t>() + 8;
+  B2S_TRY(h->tmp_i32.ensure((2 * n_max + 64) * 4, h->stream));
+  int32_t* qn = h->tmp_i32.as<int32_t>() + 8;        // [0] phase-2 queue length, [1] query-list length
   int32_t* queue = h->tmp_i32.as<int32_t>() + 16;
-  const int ring_limit = 2;
+  int32_t* qlist = flags ? queue + n_max : nullptr;
+  const int32_t* qcount = flags ? qn + 1 : nullptr;
+  // rings the thread-per-query kernel may walk before handing a query to the warp-cooperative kernel
+  // (B2S_NORMALS_RING_LIMIT: tuning knob; -1 = every query goes to the warp-cooperative kernel)
+  // measured on B200 (config 2, 11 k queries): all-warp 0.13 ms, thread kernel + warp stragglers 0.35 ms -> default -1
+  static const int ring_limit_env = getenv("B2S_NORMALS_RING_LIMIT") ? atoi(getenv("B2S_NORMALS_RING_LIMIT")) : -1;
+  const int ring_limit = ring_limit_env;
   ProfScope prof(h, PK_NORMALS);
   const GridHeader* hdr = h->grid_b.hdr.as<GridHeader>();
   const int32_t* cs = grid_starts(&h->grid_b);
   const double4* pts = h->grid_b.pts.as<double4>();
   double* out = c->nrm.as<double>();
   zero_i32_kernel<<<1, 1, 0, h->stream>>>(qn);
+  if (flags) {
+    normals_qlist_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(hdr, pts, flags, qlist, qn + 1);
+    h->launches++;
+  }
   // exact instantiations for the knn values the reference's presets use (Lua default 20, C++ struct default 5,
   // place-recognition normals 10); any other knn <= 32 takes the generic variants
-  if (knn == 20) normals_kernel<20, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
-  else if (knn == 10) normals_kernel<10, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
-  else if (knn == 5) normals_kernel<5, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
-  else if (knn <= 16) normals_kernel<16, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
-  else normals_kernel<32, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, out);
+  if (ring_limit == -1) {   // default: gather + select (one warp per query), stragglers to the general warp kernel
+    int wblocks = (int)((n_max + (NK_THREADS / 32) - 1) / (NK_THREADS / 32));
+    if (wblocks > 148 * 16) wblocks = 148 * 16;
+    if (wblocks < 1) wblocks = 1;
+    B2S_TRY(h->tmp_f64.ensure((n_max + 1) * 80, h->stream));
+    double* cum = h->tmp_f64.as<double>();
+    static const bool use_v1 = getenv("B2S_NORMALS_SELECT_V1") != nullptr;   // A/B knob: fixed 3x3x3 block, register gather
+    if (use_v1) normals_select_kernel<<<wblocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, qlist, qcount, queue, qn, cum);
+    else normals_select2_kernel<<<wblocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, qlist, qcount, queue, qn, cum);
+    normals_finish_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(hdr, pts, qlist, qcount, cum, out);
+    h->launches++;
+  } else if (knn == 20) normals_kernel<20, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else if (knn == 10) normals_kernel<10, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else if (knn == 5) normals_kernel<5, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else if (knn <= 16) normals_kernel<16, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else normals_kernel<32, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  static const bool dbg_counts = getenv("B2S_DEBUG_NORMALS") != nullptr;
+  if (dbg_counts) {   // debug aid: how many queries the fast path left to the general kernel
+    int32_t hq[6] = {0, 0, 0, 0, 0, 0};
+    GridHeader gh;
+    cudaMemcpyAsync(hq, qn, 24, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&gh, hdr, sizeof(gh), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    fprintf(stderr, "[b2s normals] too-many %d kth-outside %d fewer-than-k %d\n", hq[2], hq[3], hq[4]);
+    fprintf(stderr, "[b2s normals] indexed %d queries %d fallback %d cell %.3f dims %dx%dx%d\n", gh.n, flags ? hq[1] : gh.n, hq[0], gh.cell,
+            gh.dims[0], gh.dims[1], gh.dims[2]);
+  }
   normals_phase2_kernel<<<148 * 4, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, queue, qn, out);
   h->launches += 3;
   c->has_normals = true;

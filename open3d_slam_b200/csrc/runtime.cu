@@ -1,7 +1,9 @@
 // runtime.cu -- host runtime (errors, buffers) and the two device-wide primitives everything else is built
 // from: a single-pass decoupled-look-back exclusive scan and a stable LSD radix sort (8-bit digits,
 // match_any warp ranking).  Hand-written for sm_100a; no CUB/Thrust on the product path.
+#include <cooperative_groups.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -281,11 +283,151 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restr
   (void)s_base;
 }
 
+// =================================================================================================
+//  single-launch radix sort: one thread-block cluster does ALL passes
+// =================================================================================================
+// The multi-kernel sort above costs 3 launches + a memset per pass (12-24 launches per sort, three sorts per scan); at
+// the sizes of this workload (5e4 .. 4e5 keys) every one of them is launch-latency bound.  Here one cluster of CS_CTAS
+// CTAs owns the whole sort: per pass each CTA histograms its contiguous chunk in shared memory, a cluster barrier
+// publishes the histograms, every CTA derives its per-digit base offsets from ALL histograms through distributed shared
+// memory, scatters its chunk tile by tile with the same stable warp ranking as rs_scatter_kernel, and a second cluster
+// barrier (release/acquire at cluster scope) makes the scattered keys visible to the peers before the next pass.
+constexpr int CS_CTAS = 8;
+constexpr int CS_THREADS = 1024;
+constexpr int CS_WARPS = CS_THREADS / 32;
+constexpr int CS_ITEMS = 8;
+constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
+
+template <typename K>
+__global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS, 1)
+    cluster_sort_kernel(K* __restrict__ keys_a, uint32_t* __restrict__ vals_a, K* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
+                        const int32_t* __restrict__ d_n, int passes) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ int cs_smem[];
+  int* s_hist = cs_smem;                 // [256]   this CTA's digit counts (read by the peers)
+  int* s_base = s_hist + 256;            // [256]   running global offset per digit for this CTA
+  int* s_scan = s_base + 256;            // [CS_WARPS] scratch of the 256-wide block scan
+  int* s_cnt = s_scan + CS_WARPS;        // [CS_WARPS][256] per-warp digit counters of the current tile
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = *d_n;
+  // contiguous chunk per CTA, tile-aligned so that the (CTA, tile, warp, round, lane) order is the input order
+  const int tiles_total = (n + CS_TILE - 1) / CS_TILE;
+  const int tiles_per = (tiles_total + CS_CTAS - 1) / CS_CTAS;
+  const int lo = min(rank * tiles_per * CS_TILE, n), hi = min(lo + tiles_per * CS_TILE, n);
+  for (int p = 0; p < passes; ++p) {
+    const K* kin = (p & 1) ? keys_b : keys_a;
+    const uint32_t* vin = (p & 1) ? vals_b : vals_a;
+    K* kout = (p & 1) ? keys_a : keys_b;
+    uint32_t* vout = (p & 1) ? vals_a : vals_b;
+    const int shift = 8 * p;
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    for (int i = lo + tid; i < hi; i += CS_THREADS) atomicAdd(&s_hist[(int)((kin[i] >> shift) & 0xFF)], 1);
+    cluster.sync();
+    {  // base[d] = (keys with a smaller digit, all CTAs) + (keys with digit d in lower-ranked CTAs)
+      int tot = 0, mine = 0;
+      if (tid < 256) {
+        for (int r = 0; r < CS_CTAS; ++r) {
+          const int c = cluster.map_shared_rank(s_hist, r)[tid];
+          if (r < rank) mine += c;
+          tot += c;
+        }
+      }
+      int inc = tot;   // inclusive scan over the 256 digits (threads 0..255 = warps 0..7)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31 && warp < 8) s_scan[warp] = inc;
+      __syncthreads();
+      if (tid < 256) {
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_scan[w];
+        s_base[tid] = woff + inc - tot + mine;
+      }
+    }
+    __syncthreads();
+    for (int t0 = lo; t0 < hi; t0 += CS_TILE) {
+      for (int i = tid; i < CS_WARPS * 256; i += CS_THREADS) s_cnt[i] = 0;
+      __syncthreads();
+      const int wbase = t0 + warp * 32 * CS_ITEMS;
+      K key[CS_ITEMS];
+      int lrank[CS_ITEMS];
+#pragma unroll
+      for (int k = 0; k < CS_ITEMS; k++) {   // all loads first: the ranking rounds below are separated by warp barriers
+        const int i = wbase + k * 32 + lane;
+        key[k] = (i < hi) ? kin[i] : (K)0;
+      }
+#pragma unroll
+      for (int k = 0; k < CS_ITEMS; k++) {
+        const int i = wbase + k * 32 + lane;
+        const bool valid = i < hi;
+        const int d = valid ? (int)((key[k] >> shift) & 0xFF) : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int prior = valid ? s_cnt[warp * 256 + d] : 0;
+        __syncwarp();
+        lrank[k] = prior + __popc(peers & ((1u << lane) - 1u));
+        if (valid && (peers & ((1u << lane) - 1u)) == 0) s_cnt[warp * 256 + d] = prior + __popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      if (tid < 256) {  // exclusive scan over the warps, seeded with the running base of this digit
+        int run = s_base[tid];
+        for (int w = 0; w < CS_WARPS; w++) { const int c = s_cnt[w * 256 + tid]; s_cnt[w * 256 + tid] = run; run += c; }
+        s_base[tid] = run;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CS_ITEMS; k++) {
+        const int i = wbase + k * 32 + lane;
+        if (i < hi) {
+          const int d = (int)((key[k] >> shift) & 0xFF);
+          const int pos = s_cnt[warp * 256 + d] + lrank[k];
+          kout[pos] = key[k];
+          vout[pos] = vin[i];
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    cluster.sync();
+  }
+}
+
+static bool g_cs_attr32 = false, g_cs_attr64 = false;
+
+template <typename K>
+static int32_t cluster_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& keys_alt, uint32_t*& vals_alt, const int32_t* d_n, int key_bits) {
+  int passes = (key_bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  const size_t smem = (size_t)(256 + 256 + CS_WARPS + CS_WARPS * 256) * sizeof(int);
+  bool& attr = sizeof(K) == 4 ? g_cs_attr32 : g_cs_attr64;
+  if (!attr) {
+    B2S_CUDA(cudaFuncSetAttribute(cluster_sort_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  ProfScope prof(h, PK_SORT);
+  cluster_sort_kernel<K><<<CS_CTAS, CS_THREADS, smem, h->stream>>>(keys, vals, keys_alt, vals_alt, d_n, passes);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  if (passes & 1) {
+    K* tk = keys; keys = keys_alt; keys_alt = tk;
+    uint32_t* tv = vals; vals = vals_alt; vals_alt = tv;
+  }
+  return B2S_OK;
+}
+
+static bool use_multi_kernel_sort() {
+  static const bool v = getenv("B2S_SORT") && strcmp(getenv("B2S_SORT"), "multi") == 0;
+  return v;
+}
+
 // returns 0 when the result is in (keys, vals), 1 when it is in (keys_alt, vals_alt) -- callers get the
 // pointers swapped so that (keys, vals) always designate the sorted arrays afterwards
 template <typename K>
 static int32_t radix_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& keys_alt, uint32_t*& vals_alt, const int32_t* d_n,
                                size_t n_max, int key_bits) {
+  if (!use_multi_kernel_sort()) return cluster_sort_impl<K>(h, keys, vals, keys_alt, vals_alt, d_n, key_bits);
   int nblocks = (int)((n_max + RS_TILE - 1) / RS_TILE);
   if (nblocks < 1) nblocks = 1;
   size_t hist_n = (size_t)256 * nblocks;

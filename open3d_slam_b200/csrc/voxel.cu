@@ -315,17 +315,13 @@ __global__ void __launch_bounds__(VX_THREADS) select_mark_kernel(const int32_t* 
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < (int)k; j += gridDim.x * blockDim.x) flags[vals[j]] = 1;
 }
 
-int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed, b2s_cloud* out) {
-  B2S_REQUIRE(ratio >= 0.0, B2S_E_INVALID, "[RandomDownSample] sampling_ratio must be in [0, 1]");
+// Selection flags of the seeded down-sample, one int per point of `in`, left in h->flags (ratio < 1 only).
+// The hash depends on the point POSITION only, so the flags can be computed before the normals exist: the fused
+// pre-processing chain estimates normals for the selected points only (their neighbours still come from the full
+// voxelised cloud, so the result is identical to the reference's normals-then-select order).
+int32_t select_flags(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed) {
+  B2S_REQUIRE(ratio >= 0.0 && ratio < 1.0, B2S_E_INVALID, "[RandomDownSample] sampling_ratio must be in [0, 1]");
   const size_t n_max = in->n_max > 0 ? in->n_max : 1;
-  if (ratio >= 1.0) {  // the reference only shuffles in this case; the order carries no meaning downstream
-    B2S_TRY(cloud_reserve(h, out, n_max, in->has_normals));
-    B2S_CUDA(cudaMemcpyAsync(out->xyz.p, in->xyz.p, n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
-    if (in->has_normals) B2S_CUDA(cudaMemcpyAsync(out->nrm.p, in->nrm.p, n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
-    B2S_CUDA(cudaMemcpyAsync(out->dn.p, in->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
-    out->has_normals = in->has_normals; out->n_max = in->n_max; out->n_known = in->n_known;
-    return B2S_OK;
-  }
   B2S_TRY(h->keys.ensure(n_max * 4 * 2, h->stream));
   B2S_TRY(h->vals.ensure(n_max * 4 * 2, h->stream));
   B2S_TRY(h->flags.ensure((n_max + 1) * 4, h->stream));
@@ -338,11 +334,32 @@ int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, 
   B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, in->dn.as<int32_t>(), n_max, 32));
   select_mark_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), ratio, vals, h->flags.as<int32_t>());
   h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+// compaction of `in` by h->flags (as left by select_flags) into `out`
+int32_t select_compact(b2s_handle* h, const b2s_cloud* in, double ratio, b2s_cloud* out) {
   B2S_TRY(compact_cloud(h, in, h->flags.as<int32_t>(), out));
   // floor(ratio * n) <= ratio * n_max: keeps the launch bounds of everything downstream (ICP shared memory!) tight
   const size_t bound = (size_t)((double)in->n_max * ratio) + 1;
   if (bound < out->n_max) out->n_max = bound;
   return B2S_OK;
+}
+
+int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed, b2s_cloud* out) {
+  B2S_REQUIRE(ratio >= 0.0, B2S_E_INVALID, "[RandomDownSample] sampling_ratio must be in [0, 1]");
+  const size_t n_max = in->n_max > 0 ? in->n_max : 1;
+  if (ratio >= 1.0) {  // the reference only shuffles in this case; the order carries no meaning downstream
+    B2S_TRY(cloud_reserve(h, out, n_max, in->has_normals));
+    B2S_CUDA(cudaMemcpyAsync(out->xyz.p, in->xyz.p, n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
+    if (in->has_normals) B2S_CUDA(cudaMemcpyAsync(out->nrm.p, in->nrm.p, n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
+    B2S_CUDA(cudaMemcpyAsync(out->dn.p, in->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+    out->has_normals = in->has_normals; out->n_max = in->n_max; out->n_known = in->n_known;
+    return B2S_OK;
+  }
+  B2S_TRY(select_flags(h, in, ratio, seed));
+  return select_compact(h, in, ratio, out);
 }
 
 // ---- F0: transform (with the reference's near-identity duplication quirk) --------------------------------------------

@@ -9,17 +9,20 @@ p.nnCellSize = float(sys.argv[1]) if len(sys.argv) > 1 else 0.0
 eng = E.Engine(p)
 sc = synth.Scene(); poses = synth.loop_trajectory(8)
 m = E.Mapper(eng, 800_000)
-buf = (C.c_longlong * 256)()
+buf = (C.c_longlong * 512)()
 for k in range(6):
     raw = synth.lidar_scan(sc, poses[k], seed=k)
     if k == 5:
         L.check(L.lib().b2s_debug_icp_clocks(eng._h, 1, None))
     m.addRangeMeasurement(eng.cloud(raw), np.eye(4) if k == 0 else np.linalg.inv(poses[k - 1]) @ poses[k])
 L.check(L.lib().b2s_debug_icp_clocks(eng._h, 1, buf))
-a = np.array(buf[:]).reshape(64, 4)
+a = np.array(buf[:256]).reshape(64, 4)
+bal = np.array(buf[256:]).reshape(8, 8, 4)
 r = m.lastResult
 print("iters", r.iters, "n_corr", r.n_corr, "fitness", r.fitness_)
 for e in range(r.iters + 1):
     t = a[e]
     nxt = a[e + 1][0] if e < r.iters else t[3]
     print(f"eval {e}: search {t[1]-t[0]:8d}  reduce+cluster {t[2]-t[1]:8d}  solve {t[3]-t[2]:8d} cycles")
+for e in range(min(r.iters + 1, 8)):
+    print(f"eval {e} per-CTA phase1 ns {bal[e,:,0].tolist()} phase2 ns {bal[e,:,1].tolist()} queue {bal[e,:,2].tolist()} pts {bal[e,:,3].tolist()}")
