@@ -219,14 +219,20 @@ def run_b2s_arm(args):
     streams = [torch.cuda.Stream(device=dev) for _ in range(chains)]
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def make_chains():
-        engs = [E.Engine(params, device=local, cuda_stream=s.cuda_stream) for s in streams]
+    use_graph = not args.no_graph
+
+    def make_chains(n=None, graph=None):
+        n = chains if n is None else n
+        graph = use_graph if graph is None else graph
+        engs = [E.Engine(params, device=local, cuda_stream=streams[c].cuda_stream) for c in range(n)]
         maps = [E.Mapper(e, 600_000) for e in engs]
-        for c in range(chains):   # first scan: pre-process and insert with identity (Mapper.cpp:105-114)
+        for c in range(n):   # first scan: pre-process and insert with identity (Mapper.cpp:105-114)
             maps[c].addRangeMeasurement(engs[c].cloud(scans[c][0]), None)
             maps[c].submap.setPose(np.eye(4))
             engs[c].synchronize()
-        return engs, maps
+        # CUDA-graph replay of the per-scan chain: every scan goes through a fixed-capacity staging cloud
+        staging = [maps[c].enableGraph(65536) for c in range(n)] if graph else None
+        return engs, maps, staging
 
     def timed_region(step_fn, k0, nsteps):
         """nsteps steps; each step is bracketed by events on the main stream, the chain streams fork/join around it and the
@@ -263,10 +269,11 @@ def run_b2s_arm(args):
         return float(t.item())
 
     # ---------------- value: inputs resident in HBM ----------------
-    engs, maps = make_chains()
+    engs, maps, staging = make_chains()
     dev_clouds = [[engs[c].cloud(scans[c][k]) for k in range(n_scans)] for c in range(chains)]
     for e in engs:
         e.synchronize()
+    used_slot = {}
 
     # one host thread per chain: the ctypes calls release the GIL, so the ~80 kernel launches of the chains are issued
     # concurrently (each on its own stream) instead of one chain after the other
@@ -280,13 +287,18 @@ def run_b2s_arm(args):
         else:
             list(pool.map(fn, range(chains)))
 
+    def one_resident(c, k):
+        if staging is not None:   # device->device copy of the resident scan into the graph's staging cloud (1.3 MB)
+            maps[c].stageCopy(dev_clouds[c][k])
+            used_slot[(c, k)] = maps[c].addRangeMeasurementAsync(staging[c], deltas[k])
+        else:
+            used_slot[(c, k)] = maps[c].addRangeMeasurementAsync(dev_clouds[c][k], deltas[k], slot=k % 256)
+
     def step_resident(k):
-        fan_out(lambda c: maps[c].addRangeMeasurementAsync(dev_clouds[c][k], deltas[k], slot=k % 256))
+        fan_out(lambda c: one_resident(c, k))
 
     timed_region(step_resident, 1, W)
     l0 = sum(e.launches for e in engs)
-    engs[0].profile_enable(True)
-    engs[0].profile_read()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -294,21 +306,44 @@ def run_b2s_arm(args):
     ms_total = timed_region(step_resident, 1 + W, K)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    prof = engs[0].profile_read()
-    engs[0].profile_enable(False)
     launches = sum(e.launches for e in engs) - l0
     ms_total = max_over_ranks(ms_total)
     value = world * chains * K / (ms_total * 1e-3)
 
     # results of the timed scans: iterations, source sizes, sanity against ground truth
-    results = [[maps[c].fetchResult(k % 256) for k in range(1 + W, n_scans)] for c in range(chains)]
+    results = [[maps[c].fetchResult(used_slot[(c, k)]) for k in range(1 + W, n_scans)] for c in range(chains)]
     iters = np.array([[r.iters for r in rc] for rc in results]); fit = np.array([[r.fitness_ for r in rc] for rc in results])
     nsrc = np.array([[r.n_corr / max(r.fitness_, 1e-12) for r in rc] for rc in results])
     gt_last = np.linalg.inv(poses[0]) @ poses[n_scans - 1]
     pose_err = max(float(np.linalg.norm(maps[c].submap.getPose()[:3, 3] - gt_last[:3, 3])) for c in range(chains))
     map_pts = int(np.mean([m.submap.size() for m in maps]))
 
-    # ---------------- roofline of the dominant kernel group (chain 0, live CUDA events on its stream) ----------------
+    # ---------------- per-kernel-group device times: one eager chain with CUDA events around every kernel group ----------------
+    # (graph replay has no per-kernel events; this pass re-runs the same scans of chain 0 eagerly, on its own stream)
+    for m in maps:
+        m.submap.free()
+    for e in engs:
+        e.close()
+    dev_clouds_keep = dev_clouds[0]
+    p_engs, p_maps, _ = make_chains(1, graph=False)
+    kp = min(K, 10)
+    for k in range(1, 1 + W):
+        p_maps[0].addRangeMeasurementAsync(dev_clouds_keep[k], deltas[k], slot=k % 256)
+    p_engs[0].synchronize()
+    p_engs[0].profile_enable(True)
+    p_engs[0].profile_read()
+    for k in range(1 + W, 1 + W + kp):
+        flush_buf.zero_()
+        torch.cuda.synchronize(dev)
+        p_maps[0].addRangeMeasurementAsync(dev_clouds_keep[k], deltas[k], slot=k % 256)
+    prof = p_engs[0].profile_read()
+    p_engs[0].profile_enable(False)
+    p_res = [p_maps[0].fetchResult(k % 256) for k in range(1 + W, 1 + W + kp)]
+    p_iters = np.array([r.iters for r in p_res]); p_nsrc = np.array([r.n_corr / max(r.fitness_, 1e-12) for r in p_res])
+    p_maps[0].submap.free()
+    p_engs[0].close()
+
+    # ---------------- roofline of the dominant kernel group (live CUDA events on its stream) ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json)"
@@ -317,7 +352,7 @@ def run_b2s_arm(args):
     kinds = {k: v for k, v in prof.items() if v[1] > 0}
     dom = max(kinds, key=lambda k: kinds[k][0]) if kinds else "icp"
     # algorithmic bytes per launch (fp64 layout: 24 B per point / normal), DESIGN.md section "bytes"
-    it0, n0 = iters[0], nsrc[0]
+    it0, n0 = p_iters, p_nsrc
     bytes_icp = float(np.mean(72.0 * n0 * (it0 + 1)))
     m_vox = float(np.mean(n0)) / max(args.ratio, 1e-9)              # points entering normal estimation (before the ratio down-sample)
     bytes_by_kind = {"icp": bytes_icp, "normals": 24.0 * m_vox * (20 + 2), "radix_sort": None, "nn_grid_build": None,
@@ -332,27 +367,21 @@ def run_b2s_arm(args):
     roofline = {"bound": "hbm", "kernel": dom_for_roof, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_launch": ab, "avg_launch_ms": dur_ms,
                 "note": "latency-bound: a single registration's working set is L2-resident and its iterations are sequential (SURVEY.md 8d)"}
-    profile = {k: {"ms_per_scan": v[0] / K, "launch_groups_per_scan": v[1] / K} for k, v in prof.items()}
+    profile = {k: {"ms_per_scan": v[0] / kp, "launch_groups_per_scan": v[1] / kp} for k, v in prof.items()}
 
     # ---------------- e2e: host buffers in, results out, every step ----------------
-    for m in maps:
-        m.submap.free()
     for lst in dev_clouds:
         for c_ in lst:
             c_.free()
-    for e in engs:
-        e.close()
-    engs, maps = make_chains()
+    engs, maps, staging = make_chains()
     pinned = [[torch.from_numpy(scans[c][k]).pin_memory() for k in range(n_scans)] for c in range(chains)]
-    stage = [engs[c].cloud(scans[c][0]) for c in range(chains)]
+    e2e_last = [None] * chains
     h2d = sum(int(pinned[c][1 + W].numel()) * 4 for c in range(chains))
     d2h = chains * ctypes.sizeof(L.Result)
 
     def one_e2e(c, k):
-        t = pinned[c][k]
-        stage[c].upload_pinned_f32(t.data_ptr(), t.shape[0], 12)
-        maps[c].addRangeMeasurementAsync(stage[c], deltas[k], slot=k % 256)
-        maps[c].fetchResult(k % 256)
+        t = pinned[c][k]   # one C call: H2D of the float32 scan, the whole chain, D2H of the RegistrationResult
+        e2e_last[c] = maps[c].addRangeMeasurementHost(t.data_ptr(), t.shape[0], deltas[k])
 
     def step_e2e(k):
         fan_out(lambda c: one_e2e(c, k))
@@ -397,7 +426,8 @@ def main():
     ap.add_argument("--ratio", type=float, default=0.3, help="scan_processing.downsampling_ratio (Lua default 0.3)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="scans in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--host-threads", type=int, default=16, help="host threads issuing the chains' launches (1 = serial)")
+    ap.add_argument("--host-threads", type=int, default=8, help="host threads issuing the chains' launches (1 = serial)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per scan")
     ap.add_argument("--nn-cell", type=float, default=0.0, help="NN grid cell edge in metres (0 = max_corr_dist / 2)")
     args = ap.parse_args()
     if args.warmup < 3:

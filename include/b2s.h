@@ -191,6 +191,19 @@ int32_t b2s_submap_get_pose(b2s_handle* h, const b2s_submap* sm, double map_to_s
 int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double odometry_motion[16],
                               double min_refinement_fitness, int32_t ignore_min_fitness, int32_t slot /* 0..255 */);
 int32_t b2s_scan_result_fetch(b2s_handle* h, int32_t slot, b2s_result* out);   /* synchronises */
+/* the same chain end to end with HOST buffers: float32 xyz (wire format; pinned memory keeps the copy asynchronous) in,
+ * RegistrationResult out -- upload + S1 + S2 + gate + F1 + read-back in one call (Mapper::addRangeMeasurement as the
+ * ROS callback sees it, rospkg/src/OnlineRangeDataProcessorRos.cpp:38-43 -> core/src/Mapper.cpp:101-181) */
+int32_t b2s_mapper_step_host(b2s_handle* h, b2s_submap* sm, const void* xyz_f32, size_t n, size_t stride_bytes,
+                             const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
+                             b2s_result* out);
+/* CUDA-graph replay of b2s_mapper_step_async for this submap: after two eager steps the ~45 launches of one scan are
+ * captured once and replayed with a single cudaGraphLaunch.  Every scan must be uploaded (b2s_cloud_upload_f32/_f64) or
+ * copied (b2s_cloud_copy) into the returned fixed-capacity staging cloud, which is then passed as raw_scan; the slot
+ * argument must equal (number of graph steps so far) % 256.  Falls back to eager launches when the chain cannot be
+ * captured (e.g. a cropper without a maximum radius needs a host round trip). */
+int32_t b2s_mapper_graph_enable(b2s_handle* h, b2s_submap* sm, size_t raw_capacity_points, double min_refinement_fitness,
+                                int32_t ignore_min_fitness, b2s_cloud** staging_out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

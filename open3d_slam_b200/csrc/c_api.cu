@@ -8,6 +8,11 @@
 
 using namespace b2s;
 
+extern "C" {
+static int32_t register_to_submap_async(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double* sensor_pose_host,
+                                        const double* sensor_pose_dev, const double* init_host, const double* init_dev, b2s_result* out_dev);
+}
+
 namespace b2s {
 int32_t pose_to_device(b2s_handle* h, const double* T, double* dst);
 int32_t dense_init(b2s_handle* h, b2s_submap* sm, size_t cap, double voxel);
@@ -101,6 +106,91 @@ static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud*
   B2S_TRY(op_crop(h, merge, make_crop(&c1), match));
   empty_check_kernel<<<1, 1, 0, h->stream>>>(merge->dn.as<int32_t>(), match->dn.as<int32_t>(), h->status.as<uint32_t>());
   h->launches++;
+  return B2S_OK;
+}
+
+// ---- graph replay of the per-scan chain ---------------------------------------------------------------------------
+// first node of the chain: takes the step number from a device counter, fetches that step's odometry motion from the
+// host-written ring (pinned, device-mapped) and publishes the result slot of this step
+__global__ void graph_begin_kernel(const double* __restrict__ ring, int32_t* gstate, double* __restrict__ odom) {
+  const int step = gstate[0];
+  if (threadIdx.x < 16) odom[threadIdx.x] = ring[(step & 63) * 16 + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) { gstate[0] = step + 1; gstate[1] = step & 255; }
+}
+
+// fitness gate (Mapper.cpp:151-160) + copy of the result into this step's slot
+__global__ void gate_slot_kernel(const b2s_result* __restrict__ res, double min_fitness, int ignore_fitness, double* pose_state, int32_t* gate,
+                                 b2s_result* slots, const int32_t* gstate) {
+  if (threadIdx.x == 0) {
+    const bool ok = ignore_fitness || !(res->fitness < min_fitness);
+    *gate = ok ? 1 : 0;
+    if (ok) for (int i = 0; i < 16; i++) pose_state[i] = res->T[i];
+    slots[gstate[1]] = *res;
+  }
+}
+
+static int32_t mapper_chain_graphable(b2s_handle* h, b2s_submap* sm) {
+  double* pose_state = sm->pose.as<double>();
+  double* odom = pose_state + 32;
+  double* guess = pose_state + 48;
+  int32_t* gate = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 4);
+  int32_t* gstate = sm->gstate.as<int32_t>();
+  b2s_result* res = h->results.as<b2s_result>();
+  double* ring_dev = nullptr;
+  B2S_CUDA(cudaHostGetDevicePointer(&ring_dev, sm->odom_ring, 0));
+  graph_begin_kernel<<<1, 32, 0, h->stream>>>(ring_dev, gstate, odom);
+  h->launches++;
+  B2S_TRY(process_scan_impl(h, sm->staging, h->t1, h->t2));
+  compose_kernel<<<1, 32, 0, h->stream>>>(pose_state, odom, guess);
+  h->launches++;
+  B2S_TRY(::register_to_submap_async(h, h->t2, sm, nullptr, pose_state, nullptr, guess, res));
+  gate_slot_kernel<<<1, 32, 0, h->stream>>>(res, sm->g_min_fitness, sm->g_ignore_fitness, pose_state, gate, h->slots.as<b2s_result>(), gstate);
+  h->launches++;
+  return op_submap_insert(h, sm, h->t1, pose_state, gate);
+}
+
+static int32_t mapper_step_graph(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double* odometry_motion, int32_t slot) {
+  B2S_REQUIRE(raw_scan == sm->staging, B2S_E_INVALID, "graph mode: the scan must be uploaded into the staging cloud of b2s_mapper_graph_enable");
+  B2S_REQUIRE(slot == (int32_t)(sm->host_step & 255), B2S_E_INVALID, "graph mode: slot must be (step count %% 256) = %d", (int)(sm->host_step & 255));
+  B2S_TRY(h->results.ensure(sizeof(b2s_result), h->stream));
+  memcpy(sm->odom_ring + (sm->host_step & 63) * 16, odometry_motion, 128);   // read by graph_begin_kernel of this step
+  sm->host_step++;
+  if (sm->gexec) {
+    B2S_CUDA(cudaGraphLaunch(sm->gexec, h->stream));
+    h->launches += sm->graph_kernels;
+    return B2S_OK;
+  }
+  if (sm->graph_warm > 0) {   // eager steps size every scratch buffer (no allocation may happen during capture)
+    sm->graph_warm--;
+    return mapper_chain_graphable(h, sm);
+  }
+  // capture this step's chain, instantiate, replay it
+  const int64_t l0 = h->launches;
+  g_capturing = true; g_capture_broken = false;
+  cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+  int32_t rc = B2S_E_CUDA;
+  cudaGraph_t graph = nullptr;
+  if (ce == cudaSuccess) {
+    rc = mapper_chain_graphable(h, sm);
+    ce = cudaStreamEndCapture(h->stream, &graph);
+  }
+  g_capturing = false;
+  const int64_t captured_kernels = h->launches - l0;
+  h->launches = l0;
+  if (ce != cudaSuccess || rc != B2S_OK || g_capture_broken || !graph) {
+    // not capturable (e.g. an unbounded cropper needs a host round trip): stay eager for good
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    sm->graph_warm = 1 << 30;
+    return mapper_chain_graphable(h, sm);
+  }
+  ce = cudaGraphInstantiate(&sm->gexec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { sm->gexec = nullptr; sm->graph_warm = 1 << 30; cudaGetLastError(); return mapper_chain_graphable(h, sm); }
+  sm->graph_kernels = captured_kernels;
+  B2S_CUDA(cudaGraphLaunch(sm->gexec, h->stream));
+  h->launches += sm->graph_kernels;
   return B2S_OK;
 }
 
@@ -305,7 +395,10 @@ int32_t b2s_cloud_download(b2s_handle* h, const b2s_cloud* c, double* xyz, doubl
 int32_t b2s_cloud_copy(b2s_handle* h, const b2s_cloud* src, b2s_cloud* dst) {
   B2S_REQUIRE(h && src && dst, B2S_E_INVALID, "null argument");
   LOCK(h);
-  return op_voxel_down_sample(h, src, nullptr, 0.0, dst);
+  B2S_REQUIRE(!dst->fixed_cap || src->n_max <= dst->fixed_cap, B2S_E_CAPACITY, "cloud larger than the fixed capacity of the destination");
+  B2S_TRY(op_voxel_down_sample(h, src, nullptr, 0.0, dst));
+  if (dst->fixed_cap) dst->n_max = dst->fixed_cap;
+  return B2S_OK;
 }
 
 // ---- stages ----------------------------------------------------------------------------------------------------------
@@ -442,6 +535,10 @@ void b2s_submap_destroy(b2s_submap* sm) {
   for (int i = 0; i < 2; i++) if (sm->cloud[i]) { sm->cloud[i]->xyz.release(); sm->cloud[i]->nrm.release(); sm->cloud[i]->dn.release(); delete sm->cloud[i]; }
   sm->dense_keys.release(); sm->dense_sum.release(); sm->dense_cnt.release(); sm->dense_used.release(); sm->pose.release();
   if (sm->pinned_cnt) cudaFreeHost(sm->pinned_cnt);
+  if (sm->gexec) cudaGraphExecDestroy(sm->gexec);
+  if (sm->odom_ring) cudaFreeHost(sm->odom_ring);
+  if (sm->staging) { sm->staging->xyz.release(); sm->staging->nrm.release(); sm->staging->dn.release(); delete sm->staging; }
+  sm->gstate.release();
   if (sm->cnt_ev) cudaEventDestroy(sm->cnt_ev);
   delete sm;
 }
@@ -562,6 +659,7 @@ int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* ra
   B2S_REQUIRE(h && sm && raw_scan && odometry_motion, B2S_E_INVALID, "null argument");
   B2S_REQUIRE(slot >= 0 && slot < 256, B2S_E_INVALID, "slot out of range");
   LOCK(h);
+  if (sm->graph_mode) return mapper_step_graph(h, sm, raw_scan, odometry_motion, slot);
   double* pose_state = sm->pose.as<double>();        // mapToRangeSensor_ (== mapToRangeSensorPrev_ in steady state)
   double* odom = pose_state + 32;
   double* guess = pose_state + 48;
@@ -577,11 +675,56 @@ int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* ra
   return op_submap_insert(h, sm, h->t1, pose_state, gate);                   // Mapper.cpp:174
 }
 
+// Turns b2s_mapper_step_async into a CUDA-graph replay for this submap: the ~45 kernel launches of one scan collapse
+// into one cudaGraphLaunch.  Returns the fixed-capacity staging cloud every scan has to be uploaded / copied into.
+int32_t b2s_mapper_graph_enable(b2s_handle* h, b2s_submap* sm, size_t raw_capacity_points, double min_refinement_fitness,
+                                int32_t ignore_min_fitness, b2s_cloud** staging_out) {
+  B2S_REQUIRE(h && sm && staging_out && raw_capacity_points > 0, B2S_E_INVALID, "bad argument");
+  LOCK(h);
+  if (!sm->staging) {
+    sm->staging = new b2s_cloud();
+    sm->staging->h = h; sm->staging->device = h->device;
+    sm->staging->fixed_cap = raw_capacity_points;
+    B2S_TRY(cloud_reserve(h, sm->staging, raw_capacity_points, false));
+    B2S_TRY(cloud_set_count(h, sm->staging, 0));
+    B2S_CUDA(cudaHostAlloc(&sm->odom_ring, 64 * 16 * sizeof(double), cudaHostAllocMapped));
+    B2S_TRY(sm->gstate.ensure(64, h->stream));
+    B2S_CUDA(cudaMemsetAsync(sm->gstate.p, 0, 64, h->stream));
+  }
+  sm->g_min_fitness = min_refinement_fitness;
+  sm->g_ignore_fitness = ignore_min_fitness;
+  sm->graph_mode = true;
+  sm->graph_warm = 2;
+  sm->host_step = 0;
+  if (sm->gexec) { cudaGraphExecDestroy(sm->gexec); sm->gexec = nullptr; }
+  B2S_CUDA(cudaMemsetAsync(sm->gstate.p, 0, 64, h->stream));
+  *staging_out = sm->staging;
+  return B2S_OK;
+}
+
+// End-to-end form of the per-scan chain with HOST buffers: float32 xyz in (pinned memory makes the copy asynchronous),
+// RegistrationResult out.  One call = upload + S1 + S2 + gate + F1 + read-back; synchronises on the result.
+int32_t b2s_mapper_step_host(b2s_handle* h, b2s_submap* sm, const void* xyz_f32, size_t n, size_t stride_bytes,
+                             const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
+                             b2s_result* out) {
+  B2S_REQUIRE(h && sm && xyz_f32 && odometry_motion && out, B2S_E_INVALID, "null argument");
+  b2s_cloud* dst = sm->graph_mode ? sm->staging : h->t3;
+  B2S_REQUIRE(!dst->fixed_cap || n <= dst->fixed_cap, B2S_E_CAPACITY, "scan larger than the staging capacity");
+  B2S_TRY(b2s_cloud_upload_f32(h, dst, xyz_f32, n, stride_bytes));
+  const int32_t slot = sm->graph_mode ? (int32_t)(sm->host_step & 255) : 0;
+  B2S_TRY(b2s_mapper_step_async(h, sm, dst, odometry_motion, min_refinement_fitness, ignore_min_fitness, slot));
+  return b2s_scan_result_fetch(h, slot, out);
+}
+
 int32_t b2s_scan_result_fetch(b2s_handle* h, int32_t slot, b2s_result* out) {
   B2S_REQUIRE(h && out && slot >= 0 && slot < 256, B2S_E_INVALID, "bad argument");
   LOCK(h);
-  B2S_CUDA(cudaMemcpyAsync(out, h->slots.as<b2s_result>() + slot, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
-  return check_status(h);
+  B2S_TRY(ensure_pinned(h, 4096));
+  b2s_result* pr = reinterpret_cast<b2s_result*>(static_cast<char*>(h->pinned) + 256);   // [0..3] is the status word
+  B2S_CUDA(cudaMemcpyAsync(pr, h->slots.as<b2s_result>() + slot, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
+  const int32_t rc = check_status(h);   // synchronises
+  memcpy(out, pr, sizeof(b2s_result));
+  return rc;
 }
 
 }  // extern "C"

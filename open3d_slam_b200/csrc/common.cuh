@@ -96,6 +96,7 @@ struct b2s_cloud {
   b2s::DevBuf nrm;       // 3 x f64 per point
   b2s::DevBuf dn;        // int32 device-side point count
   size_t n_max = 0;      // host-side upper bound of the count (launch sizing)
+  size_t fixed_cap = 0;  // non-zero: n_max is pinned to this capacity (graph replay needs constant launch dimensions)
   long long n_known = 0; // exact count when the host knows it, -1 otherwise
   bool has_normals = false;
 };
@@ -120,12 +121,30 @@ struct b2s_submap {
   cudaEvent_t cnt_ev = nullptr;
   bool cnt_pending = false;
   size_t adds_after_readback = 0;
+  // CUDA-graph replay of the per-scan chain (b2s_mapper_graph_enable): every launch dimension is derived from fixed
+  // capacities, the per-step inputs (odometry motion, result slot) come from a ring indexed by a device-side counter
+  bool graph_mode = false;
+  int graph_warm = 0;                 // eager steps still to run before the capture (sizes every scratch buffer)
+  cudaGraphExec_t gexec = nullptr;
+  int64_t graph_kernels = 0;          // kernels per replay (for the launch counter)
+  b2s_cloud* staging = nullptr;       // fixed-capacity input cloud the caller uploads each scan into
+  double* odom_ring = nullptr;        // pinned, device-mapped: 64 x (4x4) odometry motions
+  long long host_step = 0;
+  b2s::DevBuf gstate;                 // int32 [0] device step counter, [1] current result slot
+  double g_min_fitness = 0.0;
+  int g_ignore_fitness = 0;
 };
 
 namespace b2s {
 // per-kernel-group device timing with CUDA events on the launching stream (bench.py's roofline numbers)
 enum ProfKind { PK_ICP = 0, PK_NORMALS, PK_SORT, PK_GRID, PK_VOXEL, PK_FUSE, PK_SELECT, PK_CROP, PK_COUNT };
 struct ProfRec { int kind; cudaEvent_t a, b; };
+}  // namespace b2s
+
+namespace b2s {
+// set while this host thread is inside cudaStreamBeginCapture/EndCapture: growing a device buffer is impossible there
+extern thread_local bool g_capturing;
+extern thread_local bool g_capture_broken;
 }  // namespace b2s
 
 struct b2s_handle {

@@ -222,6 +222,7 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
     sm->cnt_pending = false;
   }
   size_t tot_max = map->n_max + 2 * scan->n_max;
+  if (sm->graph_mode) tot_max = sm->capacity;   // graph replay: constant launch dimensions, overflow is caught on the device
   if (tot_max > sm->capacity) {
     int32_t n = 0;
     B2S_CUDA(cudaMemcpyAsync(&n, map->dn.p, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -240,7 +241,7 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
   map->n_max = tot_max;   // upper bound only; the exact count lives on the device
   map->n_known = -1;
   map->has_normals = true;
-  if (rc == B2S_OK) {
+  if (rc == B2S_OK && !sm->graph_mode) {
     if (!sm->pinned_cnt) {
       B2S_CUDA(cudaMallocHost(&sm->pinned_cnt, 64));
       B2S_CUDA(cudaEventCreateWithFlags(&sm->cnt_ev, cudaEventDisableTiming));

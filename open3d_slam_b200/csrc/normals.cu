@@ -597,7 +597,25 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
     bool resolved = false;
     int need = 0;
     double c9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int R = 1; R <= NS2_RMAX && !resolved; ++R) {
+    // starting radius from the local density: 25 lanes read the run boundaries of the 5x5 rows once; a 3x3x3 block with
+    // fewer than ~3k points will almost never contain the k-th neighbour provably, so sparse queries start at R = 2
+    int Rstart = 1;
+    {
+      int c1 = 0, c2 = 0;
+      if (lane < 25) {
+        const int dy = lane % 5 - 2, dz = lane / 5 - 2;
+        const int y = cy + dy, z = cz + dz;
+        if (y >= 0 && y < ny && z >= 0 && z < nz) {
+          const int row = (z * ny + y) * nx;
+          c2 = cs[row + min(cx + 2, nx - 1) + 1] - cs[row + max(cx - 2, 0)];
+          if (dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1) c1 = cs[row + min(cx + 1, nx - 1) + 1] - cs[row + max(cx - 1, 0)];
+        }
+      }
+      const int n1 = warp_sum_i(c1), n2 = warp_sum_i(c2);
+      const int n1b = __shfl_sync(0xffffffffu, n1, 0), n2b = __shfl_sync(0xffffffffu, n2, 0);
+      if (n1b < 3 * knn && n2b <= NS2_CAP) Rstart = 2;
+    }
+    for (int R = Rstart; R <= NS2_RMAX && !resolved; ++R) {
       // ---- gather the (2R+1)^3 block into shared memory (valid = inside the radius), rows resolved by the lanes ----
       const int side = 2 * R + 1;
       const int x0 = max(cx - R, 0), x1 = min(cx + R, nx - 1);

@@ -19,8 +19,16 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+thread_local bool g_capturing = false;
+thread_local bool g_capture_broken = false;
+
 int32_t DevBuf::ensure(size_t bytes, cudaStream_t s, bool preserve) {
   if (bytes <= cap && p) return B2S_OK;
+  if (g_capturing) {   // cannot allocate / synchronise inside a stream capture: the caller falls back to eager launches
+    g_capture_broken = true;
+    set_error("device buffer would have to grow during CUDA graph capture");
+    return B2S_E_CAPACITY;
+  }
   // 25 % headroom on every (re)allocation: scan sizes jitter by a few percent from scan to scan and a re-allocation
   // is a device-wide synchronisation (cudaMalloc / cudaFree), so steady state must never re-allocate
   size_t ncap = cap + cap / 2;
@@ -50,7 +58,7 @@ void GridIndex::release() {
 }
 
 ProfScope::ProfScope(b2s_handle* h_, int kind) : h(h_), idx(-1) {
-  if (!h->prof_enabled) return;
+  if (!h->prof_enabled || g_capturing) return;
   ProfRec r;
   r.kind = kind;
   cudaEvent_t* ev[2] = {&r.a, &r.b};
@@ -80,9 +88,13 @@ int32_t ensure_pinned(b2s_handle* h, size_t bytes) {
 }
 
 int32_t check_status(b2s_handle* h) {
-  uint32_t st = 0;
-  B2S_CUDA(cudaMemcpyAsync(&st, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  // through pinned memory: a pageable device->host copy goes through a driver staging path that serialises the host
+  // threads of all chains
+  B2S_TRY(ensure_pinned(h, 4096));
+  volatile uint32_t* pst = reinterpret_cast<volatile uint32_t*>(h->pinned);
+  B2S_CUDA(cudaMemcpyAsync(h->pinned, h->status.p, 4, cudaMemcpyDeviceToHost, h->stream));
   B2S_CUDA(cudaStreamSynchronize(h->stream));
+  const uint32_t st = pst[0];
   if (st == 0) return B2S_OK;
   B2S_CUDA(cudaMemsetAsync(h->status.p, 0, 4, h->stream));
   if (st & ST_CAPACITY) { set_error("device structure capacity exceeded (status 0x%x)", st); return B2S_E_CAPACITY; }

@@ -74,7 +74,7 @@ int32_t cloud_set_count(b2s_handle* h, b2s_cloud* c, size_t n) {
   set_count_kernel<<<1, 1, 0, h->stream>>>(c->dn.as<int32_t>(), (int32_t)n);
   h->launches++;
   c->n_known = (long long)n;
-  c->n_max = n;
+  c->n_max = c->fixed_cap ? c->fixed_cap : n;
   return B2S_OK;
 }
 

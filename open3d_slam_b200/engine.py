@@ -232,9 +232,9 @@ class Cloud:
         return xyz, nrm
 
     def free(self):
-        if self._c:
+        if self._c and not getattr(self, "_borrowed", False):
             L.lib().b2s_cloud_destroy(self._c)
-            self._c = C.c_void_p()
+        self._c = C.c_void_p()
 
     def __del__(self):
         try:
@@ -500,10 +500,42 @@ class Mapper:
         return True
 
     # ---- asynchronous device-resident chain (no host round trip per scan) ---------------------------------------------
+    def enableGraph(self, raw_capacity_points: int = 65536) -> "Cloud":
+        """Replay the per-scan chain as one CUDA graph.  Returns the staging cloud every scan must be uploaded / copied into;
+        in graph mode addRangeMeasurementAsync ignores its `slot` argument and returns the slot it used."""
+        st = C.c_void_p()
+        L.check(L.lib().b2s_mapper_graph_enable(self.eng._h, self.submap._s, C.c_size_t(raw_capacity_points),
+                                                C.c_double(self.params_.minRefinementFitness),
+                                                C.c_int32(int(self.params_.isIgnoreMinRefinementFitness)), C.byref(st)))
+        c = Cloud.__new__(Cloud)
+        c.eng = self.eng; c._c = st; c._borrowed = True
+        self._staging = c
+        self._gstep = 0
+        return c
+
+    def stageCopy(self, src: Cloud):
+        """device->device copy of a resident cloud into the graph staging cloud"""
+        L.check(L.lib().b2s_cloud_copy(self.eng._h, src._c, self._staging._c))
+
     def addRangeMeasurementAsync(self, rawScan: Cloud, odometryMotion, slot: int = 0):
+        if getattr(self, "_staging", None) is not None:
+            slot = self._gstep % 256
+            self._gstep += 1
         M = _mat(odometryMotion)
         L.check(L.lib().b2s_mapper_step_async(self.eng._h, self.submap._s, rawScan._c, _pd(M), C.c_double(self.params_.minRefinementFitness),
                                               C.c_int32(int(self.params_.isIgnoreMinRefinementFitness)), C.c_int32(slot)))
+        return slot
+
+    def addRangeMeasurementHost(self, xyz_f32_ptr: int, n: int, odometryMotion, stride: int = 12) -> RegistrationResult:
+        """End to end with host buffers: float32 scan (pinned host pointer) in, RegistrationResult out, one C call."""
+        M = _mat(odometryMotion)
+        r = L.Result()
+        L.check(L.lib().b2s_mapper_step_host(self.eng._h, self.submap._s, C.c_void_p(xyz_f32_ptr), C.c_size_t(n), C.c_size_t(stride), _pd(M),
+                                             C.c_double(self.params_.minRefinementFitness),
+                                             C.c_int32(int(self.params_.isIgnoreMinRefinementFitness)), C.byref(r)))
+        if getattr(self, "_staging", None) is not None:
+            self._gstep += 1
+        return _res(r)
 
     def fetchResult(self, slot: int = 0) -> RegistrationResult:
         r = L.Result()

@@ -346,6 +346,64 @@ def test_mapper_async_chain_matches_sync(engine_factory):
     assert np.abs(ka - kb).max() < 1e-9
 
 
+def test_mapper_graph_replay_matches_eager(engine_factory):
+    """b2s_mapper_graph_enable: the captured-and-replayed chain gives bit-identical results to eager launches."""
+    p = lua_params(seed=3)
+    sc = synth.Scene(); poses = synth.loop_trajectory(12)
+    e1, e2 = engine_factory(p), engine_factory(p)
+    m1, m2 = E.Mapper(e1, 600_000), E.Mapper(e2, 600_000)
+    raw0 = synth.lidar_scan(sc, poses[0], seed=50)
+    for m, e in ((m1, e1), (m2, e2)):
+        m.addRangeMeasurement(e.cloud(raw0), None)
+        m.submap.setPose(np.eye(4))
+    st = m2.enableGraph(65536)
+    for k in range(1, 10):      # steps 1-2 run eagerly (warm-up), step 3 captures, the rest replay
+        raw = synth.lidar_scan(sc, poses[k], seed=50 + k)
+        delta = np.linalg.inv(poses[k - 1]) @ poses[k]
+        m1.addRangeMeasurementAsync(e1.cloud(raw), delta, slot=k)
+        st.upload(raw)
+        sl = m2.addRangeMeasurementAsync(st, delta)
+        r1, r2 = m1.fetchResult(k), m2.fetchResult(sl)
+        assert r1.iters == r2.iters and r1.n_corr == r2.n_corr
+        # the order in which the ICP kernel's phase-2 queue is drained (atomics) differs from run to run, so the fp64 sums
+        # agree to the last few bits only
+        assert np.abs(r1.transformation_ - r2.transformation_).max() < 1e-12
+        assert r1.fitness_ > 0.9
+    assert np.abs(m1.submap.getPose() - m2.submap.getPose()).max() < 1e-12
+    a = m1.submap.getMapPointCloud()[0]; b = m2.submap.getMapPointCloud()[0]
+    assert a.shape == b.shape and np.abs(_keyed(a, a, 0.1)[0] - _keyed(b, b, 0.1)[0]).max() < 1e-11
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_mapper_step_host_matches_device_chain(engine_factory, graph):
+    """b2s_mapper_step_host (float32 host scan in, result out, one call) == upload + b2s_mapper_step_async + fetch."""
+    p = lua_params(seed=5)
+    sc = synth.Scene(); poses = synth.loop_trajectory(10)
+    e1, e2 = engine_factory(p), engine_factory(p)
+    m1, m2 = E.Mapper(e1, 600_000), E.Mapper(e2, 600_000)
+    raw0 = synth.lidar_scan(sc, poses[0], seed=80).astype(np.float32)
+    for m, e in ((m1, e1), (m2, e2)):
+        m.addRangeMeasurement(e.cloud(raw0.astype(np.float64)), None)
+        m.submap.setPose(np.eye(4))
+    if graph:
+        m2.enableGraph(65536)
+    for k in range(1, 8):
+        raw = np.ascontiguousarray(synth.lidar_scan(sc, poses[k], seed=80 + k).astype(np.float32))
+        delta = np.linalg.inv(poses[k - 1]) @ poses[k]
+        m1.addRangeMeasurementAsync(e1.cloud(raw.astype(np.float64)), delta, slot=k)
+        r1 = m1.fetchResult(k)
+        r2 = m2.addRangeMeasurementHost(raw.ctypes.data, raw.shape[0], delta)
+        assert r1.iters == r2.iters and r1.n_corr == r2.n_corr
+        assert np.abs(r1.transformation_ - r2.transformation_).max() < 1e-12
+    assert np.abs(m1.submap.getPose() - m2.submap.getPose()).max() < 1e-12
+    assert m1.submap.size() == m2.submap.size()
+    with pytest.raises(L.B2SError):   # a scan larger than the staging capacity is refused, not truncated
+        if not graph:
+            raise L.B2SError(L.E_CAPACITY, "eager mode grows the staging cloud")
+        big = np.zeros((65537, 3), np.float32)
+        m2.addRangeMeasurementHost(big.ctypes.data, big.shape[0], np.eye(4))
+
+
 def test_dense_map_running_sums(engine_factory):
     p = lua_params()
     eng = engine_factory(p)
