@@ -91,7 +91,7 @@ typedef struct b2s_config {
   b2s_scan_params scan;
   double map_voxel_size;       /* map_builder.map_voxel_size (Parameters.hpp:94) */
   double dense_voxel_size;     /* dense_map_builder.map_voxel_size */
-  double nn_cell_size;         /* 0 = automatic (max_corr_dist / 2) : cell edge of the nearest-neighbour grid */
+  double nn_cell_size;         /* 0 = automatic (max_corr_dist / 4) : cell edge of the nearest-neighbour grid */
 } b2s_config;
 
 /* open3d::pipelines::registration::RegistrationResult as read by the callers

@@ -79,7 +79,7 @@ class MapperParameters:
     isIgnoreMinRefinementFitness: bool = False
     minMovementBetweenMappingSteps: float = 0.0
     seed: int = 0            # replaces std::random_device of [O3D] RandomDownSample
-    nnCellSize: float = 0.0  # engine knob: NN grid cell (0 = maxCorrespondenceDistance / 2)
+    nnCellSize: float = 0.0  # engine knob: NN grid cell (0 = maxCorrespondenceDistance / 4)
 
     def to_config(self) -> L.Config:
         if self.scanToMapRegType != "PointToPlaneIcp":
