@@ -473,12 +473,13 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
       gi = (int)seen.size();
       seen.push_back(targets[i]);
       if (h->batch_grids.size() <= (size_t)gi) h->batch_grids.push_back(new GridIndex());
-      B2S_TRY(grid_build(h, h->batch_grids[gi], targets[i], nn_cell(h, h->cfg.icp.max_corr_dist), nullptr, true));
     }
     grid_of[i] = gi;
     work_total += sources[i]->n_max + 1;
     if (sources[i]->n_max > max_src) max_src = sources[i]->n_max;
   }
+  // R2 for every distinct target in one set of launches (blockIdx.y = target)
+  B2S_TRY(grid_build_batch(h, h->batch_grids.data(), seen.data(), (int)seen.size(), nn_cell(h, h->cfg.icp.max_corr_dist), true));
   B2S_TRY(h->work_xyz.ensure(work_total * 24, h->stream));
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem) * (size_t)n, h->stream));
   B2S_TRY(h->results.ensure(sizeof(b2s_result) * (size_t)n, h->stream));

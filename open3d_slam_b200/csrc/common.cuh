@@ -82,6 +82,10 @@ struct ScanScratch {     // decoupled look-back scan state
   int32_t cap_tiles = 0;
 };
 
+struct ScanJob {         // one array of a batched scan (scan_exclusive_i32_batch)
+  const int32_t* in; int32_t* out; const int32_t* d_n; unsigned long long* state; int32_t* counter;
+};
+
 struct SortScratch {
   DevBuf hist;           // 256 x nblocks int32
   DevBuf keys_alt, vals_alt;
@@ -174,6 +178,8 @@ struct b2s_handle {
   // temporaries for the fused chains
   b2s_cloud* t0 = nullptr; b2s_cloud* t1 = nullptr; b2s_cloud* t2 = nullptr; b2s_cloud* t3 = nullptr;
   std::vector<b2s::GridIndex*> batch_grids;
+  b2s::DevBuf batch_jobs;             // GridJob + ScanJob tables and the scan tile states of a batched index build
+  std::vector<unsigned char> batch_jobs_host;
 };
 
 namespace b2s {
@@ -189,6 +195,9 @@ int32_t check_status(b2s_handle* h);     // synchronises and converts device sta
 // ---- primitives (scan.cu / radix_sort.cu / grid_index.cu / ...) : all asynchronous on h->stream ----
 // exclusive scan of in[0..*d_n) into out[0..*d_n]; out[*d_n] and *d_total (optional) receive the total
 int32_t scan_exclusive_i32(b2s_handle* h, const int32_t* in, int32_t* out, const int32_t* d_n, size_t n_max, int32_t* d_total);
+// njobs independent scans in one launch; every job's tile state (scan_state_bytes(n_max), zeroed) is supplied by the caller
+size_t scan_state_bytes(size_t n_max);
+int32_t scan_exclusive_i32_batch(b2s_handle* h, const ScanJob* jobs_dev, int njobs, size_t n_max);
 // stable LSD radix sort of (key, value) pairs, key_bits low bits significant; result ends in keys/vals
 // (pointers are swapped so that keys/vals designate the sorted arrays on return, *_alt the scratch)
 int32_t radix_sort_pairs_u32(b2s_handle* h, uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, uint32_t*& vals_alt,
@@ -206,6 +215,8 @@ struct CropDev {      // cropper passed by value to kernels; centre may come fro
 };
 CropDev make_crop(const b2s_cropper* c, const double* pose_dev = nullptr);
 int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double cell, const CropDev* patch, bool with_normals);
+// the same for n clouds at once (batched registration: every pair brings its own target), blockIdx.y = cloud
+int32_t grid_build_batch(b2s_handle* h, GridIndex* const* g, const b2s_cloud* const* clouds, int n, double cell, bool with_normals);
 
 int32_t cloud_reserve(b2s_handle* h, b2s_cloud* c, size_t n, bool normals);
 int32_t cloud_set_count(b2s_handle* h, b2s_cloud* c, size_t n);

@@ -20,8 +20,8 @@ __global__ void grid_bbox_init_kernel(unsigned long long* bbox) {
   else if (t < 6) bbox[t] = ord_encode(-INFINITY);
 }
 
-__global__ void __launch_bounds__(GB_THREADS) grid_bbox_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
-                                                               CropDev crop, int use_crop, unsigned long long* bbox) {
+__device__ __forceinline__ void grid_bbox_body(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, const CropDev& crop,
+                                               int use_crop, unsigned long long* bbox) {
   const int n = *d_n;
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -45,8 +45,12 @@ __global__ void __launch_bounds__(GB_THREADS) grid_bbox_kernel(const double* __r
   }
 }
 
-__global__ void grid_header_kernel(const unsigned long long* bbox, double cell, int cap_cells, GridHeader* hdr) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(GB_THREADS) grid_bbox_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
+                                                               CropDev crop, int use_crop, unsigned long long* bbox) {
+  grid_bbox_body(xyz, d_n, crop, use_crop, bbox);
+}
+
+__device__ void grid_header_body(const unsigned long long* bbox, double cell, int cap_cells, GridHeader* hdr) {
   double mn[3], mx[3];
   for (int d = 0; d < 3; d++) { mn[d] = ord_decode(bbox[d]); mx[d] = ord_decode(bbox[3 + d]); }
   if (!(mn[0] <= mx[0])) { for (int d = 0; d < 3; d++) { mn[d] = 0.0; mx[d] = 0.0; } }  // empty set
@@ -69,6 +73,11 @@ __global__ void grid_header_kernel(const unsigned long long* bbox, double cell, 
   hdr->n = 0;
 }
 
+__global__ void grid_header_kernel(const unsigned long long* bbox, double cell, int cap_cells, GridHeader* hdr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  grid_header_body(bbox, cell, cap_cells, hdr);
+}
+
 __device__ __forceinline__ int grid_cell_of(const GridHeader& g, double x, double y, double z) {
   double fx = floor((x - g.origin[0]) * g.inv_cell), fy = floor((y - g.origin[1]) * g.inv_cell), fz = floor((z - g.origin[2]) * g.inv_cell);
   int cx = (int)fmin(fmax(fx, 0.0), (double)(g.dims[0] - 1));
@@ -82,9 +91,9 @@ __global__ void grid_zero_kernel(const GridHeader* hdr, int32_t* counts) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) counts[i] = 0;
 }
 
-__global__ void __launch_bounds__(GB_THREADS) grid_count_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
-                                                                CropDev crop, int use_crop, const GridHeader* __restrict__ hdr,
-                                                                int32_t* counts, int32_t* __restrict__ rank) {
+__device__ __forceinline__ void grid_count_body(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, const CropDev& crop,
+                                                int use_crop, const GridHeader* __restrict__ hdr, int32_t* counts,
+                                                int32_t* __restrict__ rank) {
   const int n = *d_n;
   __shared__ GridHeader g;
   if (threadIdx.x == 0) g = *hdr;
@@ -97,11 +106,16 @@ __global__ void __launch_bounds__(GB_THREADS) grid_count_kernel(const double* __
   }
 }
 
-__global__ void __launch_bounds__(GB_THREADS) grid_scatter_kernel(const double* __restrict__ xyz, const double* __restrict__ nrm,
-                                                                  const int32_t* __restrict__ d_n, GridHeader* hdr,
-                                                                  const int32_t* __restrict__ cell_start,
-                                                                  const int32_t* __restrict__ rank, double4* __restrict__ pts,
-                                                                  double4* __restrict__ onrm) {
+__global__ void __launch_bounds__(GB_THREADS) grid_count_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
+                                                                CropDev crop, int use_crop, const GridHeader* __restrict__ hdr,
+                                                                int32_t* counts, int32_t* __restrict__ rank) {
+  grid_count_body(xyz, d_n, crop, use_crop, hdr, counts, rank);
+}
+
+__device__ __forceinline__ void grid_scatter_body(const double* __restrict__ xyz, const double* __restrict__ nrm,
+                                                  const int32_t* __restrict__ d_n, GridHeader* hdr,
+                                                  const int32_t* __restrict__ cell_start, const int32_t* __restrict__ rank,
+                                                  double4* __restrict__ pts, double4* __restrict__ onrm) {
   const int n = *d_n;
   __shared__ GridHeader g;
   if (threadIdx.x == 0) g = *hdr;
@@ -115,6 +129,51 @@ __global__ void __launch_bounds__(GB_THREADS) grid_scatter_kernel(const double* 
     pts[slot] = make_double4(x, y, z, __longlong_as_double((long long)i));
     if (nrm) onrm[slot] = make_double4(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2], 0.0);
   }
+}
+
+__global__ void __launch_bounds__(GB_THREADS) grid_scatter_kernel(const double* __restrict__ xyz, const double* __restrict__ nrm,
+                                                                  const int32_t* __restrict__ d_n, GridHeader* hdr,
+                                                                  const int32_t* __restrict__ cell_start,
+                                                                  const int32_t* __restrict__ rank, double4* __restrict__ pts,
+                                                                  double4* __restrict__ onrm) {
+  grid_scatter_body(xyz, nrm, d_n, hdr, cell_start, rank, pts, onrm);
+}
+
+// ---- batched build: blockIdx.y = job -------------------------------------------------------------------------------
+struct GridJob {
+  const double* xyz; const double* nrm; const int32_t* d_n;
+  unsigned long long* bbox; GridHeader* hdr; int32_t* counts; int32_t* starts; int32_t* rank; double4* pts; double4* onrm;
+  int32_t cap_cells; int32_t pad;
+};
+
+__global__ void gridb_init_kernel(const GridJob* __restrict__ jobs, int njobs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs * 6) return;
+  const int t = j % 6;
+  jobs[j / 6].bbox[t] = t < 3 ? ord_encode(INFINITY) : ord_encode(-INFINITY);
+}
+__global__ void __launch_bounds__(GB_THREADS) gridb_bbox_kernel(const GridJob* __restrict__ jobs) {
+  const GridJob j = jobs[blockIdx.y];
+  CropDev none; none.kind = 0; none.invert = 0; none.pose_dev = nullptr;
+  grid_bbox_body(j.xyz, j.d_n, none, 0, j.bbox);
+}
+__global__ void gridb_header_kernel(const GridJob* __restrict__ jobs, int njobs, double cell) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < njobs) grid_header_body(jobs[j].bbox, cell, jobs[j].cap_cells, jobs[j].hdr);
+}
+__global__ void gridb_zero_kernel(const GridJob* __restrict__ jobs) {
+  const GridJob j = jobs[blockIdx.y];
+  const int nc = j.hdr->ncell + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) j.counts[i] = 0;
+}
+__global__ void __launch_bounds__(GB_THREADS) gridb_count_kernel(const GridJob* __restrict__ jobs) {
+  const GridJob j = jobs[blockIdx.y];
+  CropDev none; none.kind = 0; none.invert = 0; none.pose_dev = nullptr;
+  grid_count_body(j.xyz, j.d_n, none, 0, j.hdr, j.counts, j.rank);
+}
+__global__ void __launch_bounds__(GB_THREADS) gridb_scatter_kernel(const GridJob* __restrict__ jobs) {
+  const GridJob j = jobs[blockIdx.y];
+  grid_scatter_body(j.xyz, j.nrm, j.d_n, j.hdr, j.starts, j.rank, j.pts, j.onrm);
 }
 
 CropDev make_crop(const b2s_cropper* c, const double* pose_dev) {
@@ -169,6 +228,83 @@ int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double c
                                                             (with_normals && cloud->has_normals) ? cloud->nrm.as<double>() : nullptr, d_n,
                                                             hdr, starts, g->rank.as<int32_t>(), g->pts.as<double4>(),
                                                             with_normals ? g->nrm.as<double4>() : nullptr);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+
+static int32_t grid_reserve(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, bool with_normals, size_t* n_alloc_out) {
+  const size_t n_max = cloud->n_max > 0 ? cloud->n_max : 1;
+  size_t n_alloc = cloud->xyz.cap / 24;
+  if (n_alloc < n_max) n_alloc = n_max;
+  size_t want = n_alloc * 8 + 4096;
+  if (want > (size_t)1 << 21) want = (size_t)1 << 21;
+  if (want < (size_t)1 << 16) want = (size_t)1 << 16;
+  if ((size_t)g->cap_cells < want) {
+    B2S_TRY(g->cell_start.ensure((want + 8) * 4 * 2, h->stream));  // counts + starts
+    g->cap_cells = (int32_t)want;
+  }
+  B2S_TRY(g->hdr.ensure(sizeof(GridHeader), h->stream));
+  B2S_TRY(g->bbox.ensure(64, h->stream));
+  B2S_TRY(g->rank.ensure(n_alloc * 4, h->stream));
+  B2S_TRY(g->pts.ensure(n_alloc * 32, h->stream));
+  if (with_normals) B2S_TRY(g->nrm.ensure(n_alloc * 32, h->stream));
+  *n_alloc_out = n_alloc;
+  return B2S_OK;
+}
+
+int32_t grid_build_batch(b2s_handle* h, GridIndex* const* g, const b2s_cloud* const* clouds, int n, double cell, bool with_normals) {
+  B2S_REQUIRE(cell > 0.0, B2S_E_INVALID, "grid_build: cell size must be > 0");
+  if (n <= 0) return B2S_OK;
+  size_t max_pts = 1, max_cells = 1;
+  for (int i = 0; i < n; i++) {
+    size_t n_alloc;
+    B2S_TRY(grid_reserve(h, g[i], clouds[i], with_normals, &n_alloc));
+    if (clouds[i]->n_max > max_pts) max_pts = clouds[i]->n_max;
+    if ((size_t)g[i]->cap_cells > max_cells) max_cells = (size_t)g[i]->cap_cells;
+  }
+  // device tables: GridJob[n] | ScanJob[n] | scan tile states (zeroed)
+  const size_t st_bytes = (scan_state_bytes(max_cells) + 15) & ~(size_t)15;
+  const size_t off_scan = ((size_t)n * sizeof(GridJob) + 15) & ~(size_t)15;
+  const size_t off_state = (off_scan + (size_t)n * sizeof(ScanJob) + 15) & ~(size_t)15;
+  const size_t total = off_state + st_bytes * (size_t)n;
+  B2S_TRY(h->batch_jobs.ensure(total, h->stream));
+  h->batch_jobs_host.assign(off_state, 0);
+  GridJob* gj = reinterpret_cast<GridJob*>(h->batch_jobs_host.data());
+  ScanJob* sj = reinterpret_cast<ScanJob*>(h->batch_jobs_host.data() + off_scan);
+  unsigned char* dev = h->batch_jobs.as<unsigned char>();
+  const size_t ntiles = (scan_state_bytes(max_cells) - 64) / 8;
+  for (int i = 0; i < n; i++) {
+    int32_t* counts = g[i]->cell_start.as<int32_t>();
+    int32_t* starts = counts + g[i]->cap_cells + 4;
+    GridHeader* hdr = g[i]->hdr.as<GridHeader>();
+    gj[i].xyz = clouds[i]->xyz.as<double>();
+    gj[i].nrm = (with_normals && clouds[i]->has_normals) ? clouds[i]->nrm.as<double>() : nullptr;
+    gj[i].d_n = clouds[i]->dn.as<int32_t>();
+    gj[i].bbox = g[i]->bbox.as<unsigned long long>();
+    gj[i].hdr = hdr; gj[i].counts = counts; gj[i].starts = starts; gj[i].rank = g[i]->rank.as<int32_t>();
+    gj[i].pts = g[i]->pts.as<double4>();
+    gj[i].onrm = with_normals ? g[i]->nrm.as<double4>() : nullptr;
+    gj[i].cap_cells = g[i]->cap_cells;
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(dev + off_state + st_bytes * (size_t)i);
+    sj[i].in = counts; sj[i].out = starts; sj[i].d_n = &hdr->ncell; sj[i].state = st; sj[i].counter = reinterpret_cast<int32_t*>(st + ntiles);
+  }
+  B2S_CUDA(cudaMemcpyAsync(dev, h->batch_jobs_host.data(), off_state, cudaMemcpyHostToDevice, h->stream));
+  B2S_CUDA(cudaMemsetAsync(dev + off_state, 0, st_bytes * (size_t)n, h->stream));
+  const GridJob* dj = reinterpret_cast<const GridJob*>(dev);
+  const ScanJob* ds = reinterpret_cast<const ScanJob*>(dev + off_scan);
+  int bx = grid_for(max_pts, GB_THREADS, 148 * 2);   // x blocks per job; y = job
+  const dim3 gpts((unsigned)bx, (unsigned)n);
+  ProfScope prof(h, PK_GRID);
+  gridb_init_kernel<<<(n * 6 + 127) / 128, 128, 0, h->stream>>>(dj, n);
+  gridb_bbox_kernel<<<gpts, GB_THREADS, 0, h->stream>>>(dj);
+  gridb_header_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(dj, n, cell);
+  gridb_zero_kernel<<<dim3(148, (unsigned)n), 256, 0, h->stream>>>(dj);
+  gridb_count_kernel<<<gpts, GB_THREADS, 0, h->stream>>>(dj);
+  h->launches += 5;
+  B2S_TRY(scan_exclusive_i32_batch(h, ds, n, max_cells));
+  gridb_scatter_kernel<<<gpts, GB_THREADS, 0, h->stream>>>(dj);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;

@@ -525,6 +525,14 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   int csize = 1;
   while (csize < 8 && (size_t)csize * ICP_THREADS * 2 < max_src_points) csize *= 2;
   const int fixed = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16 + 16;
+  {
+    // a batch that already fills the GPU is served better by small clusters (one CTA per SM is resident either way, and
+    // every evaluation pays its barriers and reduction once per cluster): shrink while the chunk still fits shared memory
+    const size_t smem_pts = (size_t)((ICP_DYN_SMEM - fixed) / ICP_BYTES_PER_POINT) - 64;
+    static const int forced = getenv("B2S_ICP_BATCH_CSIZE") ? atoi(getenv("B2S_ICP_BATCH_CSIZE")) : 0;
+    if (n_problems > 1 && forced > 0) csize = forced;
+    else while (csize > 1 && (size_t)n_problems * (size_t)csize > 148 * 2 && (max_src_points + csize / 2 - 1) / (csize / 2) <= smem_pts) csize /= 2;
+  }
   // shared memory is sized for THIS launch's chunk only: whatever is not claimed stays L1, and the candidate gathers of
   // neighbouring queries hit the same lines (4 target points per 128-byte line)
   int pts_cap = (ICP_DYN_SMEM - fixed) / ICP_BYTES_PER_POINT;

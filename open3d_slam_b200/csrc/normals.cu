@@ -619,6 +619,16 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       // ---- gather the (2R+1)^3 block into shared memory (valid = inside the radius), rows resolved by the lanes ----
       const int side = 2 * R + 1;
       const int x0 = max(cx - R, 0), x1 = min(cx + R, nx - 1);
+      double bound = INFINITY;   // distance from the query to the nearest face of the block that has cells beyond it
+      if (cx - R > 0) bound = fmin(bound, qx - (g.origin[0] + (double)(cx - R) * g.cell));
+      if (cx + R < nx - 1) bound = fmin(bound, (g.origin[0] + (double)(cx + R + 1) * g.cell) - qx);
+      if (cy - R > 0) bound = fmin(bound, qy - (g.origin[1] + (double)(cy - R) * g.cell));
+      if (cy + R < ny - 1) bound = fmin(bound, (g.origin[1] + (double)(cy + R + 1) * g.cell) - qy);
+      if (cz - R > 0) bound = fmin(bound, qz - (g.origin[2] + (double)(cz - R) * g.cell));
+      if (cz + R < nz - 1) bound = fmin(bound, (g.origin[2] + (double)(cz + R + 1) * g.cell) - qz);
+      if (bound != INFINITY) { bound -= eps; if (bound < 0.0) bound = 0.0; }
+      const double b2 = bound == INFINITY ? INFINITY : bound * bound;
+      const double lim2 = fmin(r2, b2);   // candidates beyond the guaranteed ball cannot be certified at this R: drop them
       int nc = 0;
       for (int t0 = 0; t0 < side * side; t0 += 32) {
         int a = 0, b = 0;
@@ -640,7 +650,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
               dd = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
               ii = (int)__double_as_longlong(p.w);
             }
-            const bool ok = j < rb && dd < r2;
+            const bool ok = j < rb && dd < lim2;
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             const int pos = nc + __popc(m & lt_mask);
             if (ok && pos < NS2_CAP) { s_d[wib][pos] = dd; s_i[wib][pos] = ii; s_s[wib][pos] = j; }
@@ -649,7 +659,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         }
       }
       __syncwarp();
-      if (nc > NS2_CAP) break;   // too dense for the buffer: general kernel
+      if (nc > NS2_CAP) { if (lane == 0) atomicAdd(queue_n + 2, 1); break; }   // too dense for the buffer: general kernel
       // ---- candidates -> registers (round-robin), statistics ----
       double d[NS2_CHUNKS]; int idx[NS2_CHUNKS], sl[NS2_CHUNKS];
       double dmax = 0.0;
@@ -703,18 +713,10 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         for (int c = 0; c < NS2_CHUNKS; c++)
           if (bin[c] > B || (bin[c] == B && (d[c] > td || (d[c] == td && idx[c] > ti)))) sl[c] = -1;
       }
-      // ---- exact?  k-th inside the scanned block, or the block covers the whole radius ----
-      double bound = INFINITY;
-      if (cx - R > 0) bound = fmin(bound, qx - (g.origin[0] + (double)(cx - R) * g.cell));
-      if (cx + R < nx - 1) bound = fmin(bound, (g.origin[0] + (double)(cx + R + 1) * g.cell) - qx);
-      if (cy - R > 0) bound = fmin(bound, qy - (g.origin[1] + (double)(cy - R) * g.cell));
-      if (cy + R < ny - 1) bound = fmin(bound, (g.origin[1] + (double)(cy + R + 1) * g.cell) - qy);
-      if (cz - R > 0) bound = fmin(bound, qz - (g.origin[2] + (double)(cz - R) * g.cell));
-      if (cz + R < nz - 1) bound = fmin(bound, (g.origin[2] + (double)(cz + R + 1) * g.cell) - qz);
-      if (bound != INFINITY) { bound -= eps; if (bound < 0.0) bound = 0.0; }
-      const double b2 = bound == INFINITY ? INFINITY : bound * bound;
-      const double kth = nc > knn ? td : INFINITY;   // k or fewer inside the radius so far: exact only if the block covers the radius
-      if (!(b2 > fmin(kth, r2))) continue;           // grow the block
+      // ---- exact?  every candidate kept lies strictly inside the guaranteed ball (radius sqrt(lim2) <= distance to the
+      // nearest block face), so k kept candidates contain the true k nearest; fewer than k is final only when the
+      // block covers the whole search radius ----
+      if (!(nc >= knn || b2 > r2)) continue;         // grow the block
       // ---- cumulants of the selected candidates, butterfly sum over the warp ----
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
@@ -731,6 +733,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         for (int o = 16; o > 0; o >>= 1) c9[t] += __shfl_xor_sync(0xffffffffu, c9[t], o);
       }
       resolved = true;
+      if (lane == 0 && R > 1) atomicAdd(queue_n + 2 + R, 1);   // statistics (B2S_DEBUG_NORMALS): resolved at R = 2 / 3
     }
     if (!resolved) {
       if (lane == 0) { queue[atomicAdd(queue_n, 1)] = s; cum[10 * (size_t)tq + 9] = -1.0; }
@@ -843,7 +846,7 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
     cudaMemcpyAsync(hq, qn, 24, cudaMemcpyDeviceToHost, h->stream);
     cudaMemcpyAsync(&gh, hdr, sizeof(gh), cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
-    fprintf(stderr, "[b2s normals] too-many %d kth-outside %d fewer-than-k %d\n", hq[2], hq[3], hq[4]);
+    fprintf(stderr, "[b2s normals] select2: over-capacity %d, resolved at R=2 %d, at R=3 %d\n", hq[2], hq[4], hq[5]);
     fprintf(stderr, "[b2s normals] indexed %d queries %d fallback %d cell %.3f dims %dx%dx%d\n", gh.n, flags ? hq[1] : gh.n, hq[0], gh.cell,
             gh.dims[0], gh.dims[1], gh.dims[2]);
   }

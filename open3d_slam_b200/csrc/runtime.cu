@@ -114,10 +114,9 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 #define FLAG_AGG (1ull << 62)
 #define FLAG_PREFIX (2ull << 62)
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                                                     const int32_t* __restrict__ d_n, int32_t n_host,
-                                                                     unsigned long long* state, int32_t* tile_counter,
-                                                                     int32_t* d_total) {
+__device__ __forceinline__ void scan_lookback_body(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                   const int32_t* __restrict__ d_n, int32_t n_host, unsigned long long* state,
+                                                   int32_t* tile_counter, int32_t* d_total) {
   __shared__ int s_tile;
   __shared__ int s_warp[SCAN_THREADS / 32];
   __shared__ int s_prefix;
@@ -200,6 +199,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32
     out[n] = s_prefix + agg;
     if (d_total) *d_total = s_prefix + agg;
   }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                                     const int32_t* __restrict__ d_n, int32_t n_host,
+                                                                     unsigned long long* state, int32_t* tile_counter,
+                                                                     int32_t* d_total) {
+  scan_lookback_body(in, out, d_n, n_host, state, tile_counter, d_total);
+}
+
+// blockIdx.y = job: independent scans of different arrays in one launch (batched index builds)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_batch_kernel(const ScanJob* __restrict__ jobs) {
+  const ScanJob j = jobs[blockIdx.y];
+  scan_lookback_body(j.in, j.out, j.d_n, 0, j.state, j.counter, nullptr);
+}
+
+size_t scan_state_bytes(size_t n_max) {
+  size_t ntiles = (n_max + SCAN_TILE - 1) / SCAN_TILE;
+  if (ntiles < 1) ntiles = 1;
+  return ntiles * 8 + 64;
+}
+
+// jobs_dev[k].state / .counter must point into zeroed memory of scan_state_bytes(n_max) each (counter = state + ntiles)
+int32_t scan_exclusive_i32_batch(b2s_handle* h, const ScanJob* jobs_dev, int njobs, size_t n_max) {
+  int ntiles = (int)((n_max + SCAN_TILE - 1) / SCAN_TILE);
+  if (ntiles < 1) ntiles = 1;
+  scan_lookback_batch_kernel<<<dim3(ntiles, njobs), SCAN_THREADS, 0, h->stream>>>(jobs_dev);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
 }
 
 static int32_t scan_impl(b2s_handle* h, const int32_t* in, int32_t* out, const int32_t* d_n, int32_t n_host, size_t n_max,
@@ -439,7 +467,8 @@ static bool use_multi_kernel_sort() {
 template <typename K>
 static int32_t radix_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& keys_alt, uint32_t*& vals_alt, const int32_t* d_n,
                                size_t n_max, int key_bits) {
-  if (!use_multi_kernel_sort()) return cluster_sort_impl<K>(h, keys, vals, keys_alt, vals_alt, d_n, key_bits);
+  // one cluster (8 SMs) wins while the sort is launch-latency bound; from ~1e6 keys on the whole GPU has to work on it
+  if (!use_multi_kernel_sort() && n_max <= ((size_t)3 << 18)) return cluster_sort_impl<K>(h, keys, vals, keys_alt, vals_alt, d_n, key_bits);
   int nblocks = (int)((n_max + RS_TILE - 1) / RS_TILE);
   if (nblocks < 1) nblocks = 1;
   size_t hist_n = (size_t)256 * nblocks;

@@ -315,6 +315,77 @@ __global__ void __launch_bounds__(VX_THREADS) select_mark_kernel(const int32_t* 
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < (int)k; j += gridDim.x * blockDim.x) flags[vals[j]] = 1;
 }
 
+// k-th smallest hash by radix SELECT (no sort): one CTA walks the four digits from the top, each pass histograms the
+// keys that match the prefix found so far.  sel[0] = the k-th smallest key, sel[1] = how many of the keys EQUAL to it
+// belong to the k smallest (ties go to the lower index, like the stable sort / the oracle's (hash, index) order),
+// sel[2] = how many keys equal it, sel[3] = k.
+constexpr int SK_THREADS = 1024;
+__global__ void __launch_bounds__(SK_THREADS) select_kth_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ d_n,
+                                                                double ratio, uint32_t* __restrict__ sel) {
+  __shared__ int s_hist[256];
+  __shared__ int s_scan[8];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_rem, s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = *d_n;
+  size_t k = (size_t)((double)n * ratio);  // [O3D]: size_t(points_.size() * sampling_ratio)
+  if (k > (size_t)n) k = (size_t)n;
+  if (k == 0) { if (tid < 4) sel[tid] = 0; return; }
+  uint32_t prefix = 0;
+  int rem = (int)k;
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = 8 * pass;
+    const uint32_t hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SK_THREADS) {
+      const uint32_t key = keys[i];
+      if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFF], 1);
+    }
+    __syncthreads();
+    int h = 0, inc = 0;
+    if (tid < 256) {
+      h = s_hist[tid];
+      inc = h;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_scan[warp] = inc;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      for (int w = 0; w < warp; ++w) inc += s_scan[w];
+      const int exc = inc - h;
+      if (exc < rem && rem <= inc) { s_prefix = prefix | ((uint32_t)tid << shift); s_rem = rem - exc; s_cnt = h; }
+    }
+    __syncthreads();
+    prefix = s_prefix; rem = s_rem;
+    __syncthreads();
+  }
+  if (tid == 0) { sel[0] = prefix; sel[1] = (uint32_t)rem; sel[2] = (uint32_t)s_cnt; sel[3] = (uint32_t)k; }
+}
+
+__global__ void __launch_bounds__(VX_THREADS) select_mark_kth_kernel(const int32_t* __restrict__ d_n, const uint32_t* __restrict__ keys,
+                                                                     const uint32_t* __restrict__ sel, int32_t* __restrict__ flags) {
+  const int n = *d_n;
+  const uint32_t kth = sel[0], need = sel[1], cnt_eq = sel[2], k = sel[3];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t key = keys[i];
+    int f = 0;
+    if (k > 0) {
+      if (key < kth) f = 1;
+      else if (key == kth) {
+        if (need == cnt_eq) f = 1;
+        else {   // several points share the threshold hash and only some belong: lowest indices first (vanishingly rare)
+          uint32_t before = 0;
+          for (int j = 0; j < i; ++j) before += keys[j] == kth;
+          f = before < need;
+        }
+      }
+    }
+    flags[i] = f;
+  }
+}
+
 // Selection flags of the seeded down-sample, one int per point of `in`, left in h->flags (ratio < 1 only).
 // The hash depends on the point POSITION only, so the flags can be computed before the normals exist: the fused
 // pre-processing chain estimates normals for the selected points only (their neighbours still come from the full
@@ -331,6 +402,17 @@ int32_t select_flags(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t 
   select_keys_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), in->dn.as<int32_t>(), seed, keys, vals,
                                                            h->flags.as<int32_t>());
   h->launches++;
+  static const bool sort_select = getenv("B2S_SELECT_SORT") != nullptr;   // A/B knob: the full sort this replaced
+  if (!sort_select && n_max <= ((size_t)1 << 18)) {
+    ProfScope prof(h, PK_SELECT);
+    B2S_TRY(h->misc.ensure(256, h->stream));
+    uint32_t* sel = h->misc.as<uint32_t>() + 32;   // words 0..11 of misc hold the voxel bounding box
+    select_kth_kernel<<<1, SK_THREADS, 0, h->stream>>>(keys, in->dn.as<int32_t>(), ratio, sel);
+    select_mark_kth_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), keys, sel, h->flags.as<int32_t>());
+    h->launches += 2;
+    B2S_CUDA(cudaGetLastError());
+    return B2S_OK;
+  }
   B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, in->dn.as<int32_t>(), n_max, 32));
   select_mark_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), ratio, vals, h->flags.as<int32_t>());
   h->launches++;

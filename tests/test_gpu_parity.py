@@ -3,6 +3,8 @@
 Tolerances: the north star asks for 1e-4 relative on the converged SE(3); because the device path is fp64 and
 reproduces the oracle's neighbour decisions bit-for-bit, the tests hold it to 1e-9 (transform) / 1e-12 (voxel means).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -402,6 +404,63 @@ def test_mapper_step_host_matches_device_chain(engine_factory, graph):
             raise L.B2SError(L.E_CAPACITY, "eager mode grows the staging cloud")
         big = np.zeros((65537, 3), np.float32)
         m2.addRangeMeasurementHost(big.ctypes.data, big.shape[0], np.eye(4))
+
+
+def test_config3_voxel_normals_1m(engine_factory):
+    """BASELINE config 3 at full size: 21 scans in the map frame cut to 1 048 576 points, voxel 0.1, knn 20, radius 3.0."""
+    sc = synth.Scene(); poses = synth.loop_trajectory(600)
+    parts = []
+    for i in range(21):
+        T = poses[(i * 37) % 600]
+        s = synth.lidar_scan(sc, T, seed=1000 + i).astype(np.float64)
+        parts.append(s @ T[:3, :3].T + T[:3, 3])
+    xyz = np.ascontiguousarray(np.vstack(parts)[:1 << 20])   # scans lose their sky rays: 21 scans give > 2^20 returns
+    assert xyz.shape[0] == 1 << 20
+    eng = engine_factory(lua_params())
+    vox = E.voxelize(eng, eng.cloud(xyz), 0.1)
+    gx, _ = vox.download()
+    ox, _ = O.voxel_down_sample(xyz, 0.1)
+    assert gx.shape == ox.shape
+    og, gg = np.lexsort(ox.T[::-1]), np.lexsort(gx.T[::-1])
+    assert np.array_equal(ox[og], gx[gg])          # same voxels, same members summed in the same order: bit-identical means
+    L.check(L.lib().b2s_estimate_normals(eng._h, vox._c, 20, C.c_double(3.0)))
+    gx2, gn = vox.download()
+    assert np.array_equal(gx2, gx)
+    on = O.estimate_normals(gx, 20, 3.0)
+    assert np.abs(on - gn).max() < 1e-9
+    assert np.abs(np.linalg.norm(gn, axis=1) - 1.0).max() < 1e-12
+    assert np.all(np.sum(gn * gx, axis=1) <= 0.0)   # oriented towards the origin (OrientNormalsTowardsCameraLocation)
+
+
+def test_config4_scan_submap_pairs_batch(engine_factory):
+    """BASELINE config 4 (a handful of its 512 pairs): oracle-built 20 m submaps, sources displaced by a random SE(3)
+    within (+-0.5 m, +-5 deg), r = 0.3, max_iter = 100 (core/src/PlaceRecognition.cpp:45-46,111), one batched launch."""
+    p = lua_params()
+    p.icp.maxCorrespondenceDistance = 0.3
+    p.icp.maxNumIter = 100
+    eng = engine_factory(p)
+    reg = E.RegistrationIcpPointToPlane(eng)
+    sc = synth.Scene(); poses = synth.loop_trajectory(600)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0); mapc = O.cropper("MaxRadius", 0.0, 20.0)
+    rng = np.random.default_rng(44)
+    srcs, tgts, inits, refs = [], [], [], []
+    for pair in range(5):
+        k0 = 97 * pair
+        mx = np.zeros((0, 3)); mn = np.zeros((0, 3))
+        for k in range(k0, k0 + 3):       # submap from three consecutive scans at their true poses
+            (ax, an), _ = O.process_scan(synth.lidar_scan(sc, poses[k], seed=k), wide, wide, 0.1, 20, 3.0, 1.0, 0)
+            c = O.cropper("MaxRadius", 0.0, 20.0, center=tuple(poses[k][:3, 3]))
+            mx, mn = O.submap_insert_scan(mx, mn, ax, an, poses[k], 0.1, c)
+        _, (sx, sn) = O.process_scan(synth.lidar_scan(sc, poses[k0 + 3], seed=k0 + 3), wide, wide, 0.1, 20, 3.0, 0.3, 7)
+        d = synth.se3(*np.deg2rad(rng.uniform(-5, 5, 3)), rng.uniform(-0.5, 0.5, 3) * (0.2 if pair < 3 else 1.0))
+        init = poses[k0 + 3] @ d
+        srcs.append(sx); tgts.append((mx, mn)); inits.append(init)
+        refs.append(O.registration_icp_p2plane(sx, mx, mn, 0.3, init, max_iter=100))
+    res = reg.registerCloudsBatch([eng.cloud(s) for s in srcs], [eng.cloud(x, n) for x, n in tgts], inits)
+    for r, ref in zip(res, refs):
+        assert r.iters == ref.iters and r.n_corr == ref.n_corr
+        assert abs(r.fitness_ - ref.fitness) < 1e-12 and abs(r.inlier_rmse_ - ref.inlier_rmse) < 1e-9
+        assert rel_rot(r.transformation_, ref.T) < 1e-8 and rel_trans(r.transformation_, ref.T) < 1e-8
 
 
 def test_dense_map_running_sums(engine_factory):
