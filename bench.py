@@ -278,7 +278,10 @@ def run_b2s_arm(args):
     # one host thread per chain: the ctypes calls release the GIL, so the ~80 kernel launches of the chains are issued
     # concurrently (each on its own stream) instead of one chain after the other
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=min(chains, args.host_threads)) if args.host_threads > 1 else None
+    # graph replay: a step is a handful of enqueue calls per chain, one host thread keeps all chains busy (measured: no
+    # difference between 1 and 8 threads); eager launches (~45 per scan and chain) need the threads
+    host_threads = args.host_threads if args.host_threads > 0 else (1 if use_graph else 8)
+    pool = ThreadPoolExecutor(max_workers=min(chains, host_threads)) if host_threads > 1 else None
 
     def fan_out(fn):
         if pool is None:
@@ -375,13 +378,14 @@ def run_b2s_arm(args):
             c_.free()
     engs, maps, staging = make_chains()
     pinned = [[torch.from_numpy(scans[c][k]).pin_memory() for k in range(n_scans)] for c in range(chains)]
-    e2e_last = [None] * chains
+    res_sz = ctypes.sizeof(L.Result)
+    res_pinned = torch.zeros((chains, n_scans, res_sz), dtype=torch.uint8).pin_memory()   # every step's RegistrationResult lands here
     h2d = sum(int(pinned[c][1 + W].numel()) * 4 for c in range(chains))
     d2h = chains * ctypes.sizeof(L.Result)
 
     def one_e2e(c, k):
-        t = pinned[c][k]   # one C call: H2D of the float32 scan, the whole chain, D2H of the RegistrationResult
-        e2e_last[c] = maps[c].addRangeMeasurementHost(t.data_ptr(), t.shape[0], deltas[k])
+        t = pinned[c][k]   # one C call enqueues: H2D of the float32 scan, the whole chain, D2H of the RegistrationResult
+        maps[c].addRangeMeasurementHostAsync(t.data_ptr(), t.shape[0], deltas[k], res_pinned[c, k].data_ptr())
 
     def step_e2e(k):
         fan_out(lambda c: one_e2e(c, k))
@@ -392,6 +396,9 @@ def run_b2s_arm(args):
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
     e2e_value = world * chains * K / (ms_e2e * 1e-3)
+    e2e_res = [[L.Result.from_buffer_copy(res_pinned[c, k].numpy().tobytes()) for k in range(1 + W, 1 + W + K)] for c in range(chains)]
+    e2e_fit = float(min(r.fitness for rc in e2e_res for r in rc))
+    e2e_same = all(e2e_res[c][k].iters == int(iters[c][k]) for c in range(chains) for k in range(K))   # same scans as the resident leg
 
     line = None
     if rank == 0:
@@ -406,7 +413,8 @@ def run_b2s_arm(args):
                            "mean_source_points": float(nsrc.mean()), "min_fitness": float(fit.min()), "final_pose_err_m": pose_err,
                            "l2": "256 MiB write between timed steps (outside the event brackets)", "parallelism": f"{world}x{chains} independent chains"},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+                        "min_fitness": e2e_fit, "same_iteration_counts_as_resident_leg": bool(e2e_same)},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "profile_chain0": profile, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
@@ -426,7 +434,7 @@ def main():
     ap.add_argument("--ratio", type=float, default=0.3, help="scan_processing.downsampling_ratio (Lua default 0.3)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="scans in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--host-threads", type=int, default=8, help="host threads issuing the chains' launches (1 = serial)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads issuing the chains' launches (0 = auto: 1 with graph replay, 8 eager)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per scan")
     ap.add_argument("--nn-cell", type=float, default=0.0, help="NN grid cell edge in metres (0 = max_corr_dist / 4)")
     args = ap.parse_args()

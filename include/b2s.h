@@ -197,6 +197,11 @@ int32_t b2s_scan_result_fetch(b2s_handle* h, int32_t slot, b2s_result* out);   /
 int32_t b2s_mapper_step_host(b2s_handle* h, b2s_submap* sm, const void* xyz_f32, size_t n, size_t stride_bytes,
                              const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
                              b2s_result* out);
+/* the same without waiting: the upload, the chain and the copy of the result into *out_pinned (page-locked host memory,
+ * valid after the next b2s_synchronize) are only enqueued -- one host thread can keep many mappers (handles) busy */
+int32_t b2s_mapper_step_host_async(b2s_handle* h, b2s_submap* sm, const void* xyz_f32, size_t n, size_t stride_bytes,
+                                   const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
+                                   b2s_result* out_pinned);
 /* CUDA-graph replay of b2s_mapper_step_async for this submap: after two eager steps the ~45 launches of one scan are
  * captured once and replayed with a single cudaGraphLaunch.  Every scan must be uploaded (b2s_cloud_upload_f32/_f64) or
  * copied (b2s_cloud_copy) into the returned fixed-capacity staging cloud, which is then passed as raw_scan; the slot

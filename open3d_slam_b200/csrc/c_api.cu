@@ -154,6 +154,8 @@ static int32_t mapper_step_graph(b2s_handle* h, b2s_submap* sm, const b2s_cloud*
   B2S_REQUIRE(raw_scan == sm->staging, B2S_E_INVALID, "graph mode: the scan must be uploaded into the staging cloud of b2s_mapper_graph_enable");
   B2S_REQUIRE(slot == (int32_t)(sm->host_step & 255), B2S_E_INVALID, "graph mode: slot must be (step count %% 256) = %d", (int)(sm->host_step & 255));
   B2S_TRY(h->results.ensure(sizeof(b2s_result), h->stream));
+  // the odometry ring has 64 entries and the host may run ahead of the device: never by more than 32 steps
+  if ((sm->host_step & 31) == 0) B2S_CUDA(cudaStreamSynchronize(h->stream));
   memcpy(sm->odom_ring + (sm->host_step & 63) * 16, odometry_motion, 128);   // read by graph_begin_kernel of this step
   sm->host_step++;
   if (sm->gexec) {
@@ -715,6 +717,20 @@ int32_t b2s_mapper_step_host(b2s_handle* h, b2s_submap* sm, const void* xyz_f32,
   const int32_t slot = sm->graph_mode ? (int32_t)(sm->host_step & 255) : 0;
   B2S_TRY(b2s_mapper_step_async(h, sm, dst, odometry_motion, min_refinement_fitness, ignore_min_fitness, slot));
   return b2s_scan_result_fetch(h, slot, out);
+}
+
+int32_t b2s_mapper_step_host_async(b2s_handle* h, b2s_submap* sm, const void* xyz_f32, size_t n, size_t stride_bytes,
+                                   const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
+                                   b2s_result* out_pinned) {
+  B2S_REQUIRE(h && sm && xyz_f32 && odometry_motion && out_pinned, B2S_E_INVALID, "null argument");
+  b2s_cloud* dst = sm->graph_mode ? sm->staging : h->t3;
+  B2S_REQUIRE(!dst->fixed_cap || n <= dst->fixed_cap, B2S_E_CAPACITY, "scan larger than the staging capacity");
+  B2S_TRY(b2s_cloud_upload_f32(h, dst, xyz_f32, n, stride_bytes));
+  const int32_t slot = sm->graph_mode ? (int32_t)(sm->host_step & 255) : 0;
+  B2S_TRY(b2s_mapper_step_async(h, sm, dst, odometry_motion, min_refinement_fitness, ignore_min_fitness, slot));
+  LOCK(h);
+  B2S_CUDA(cudaMemcpyAsync(out_pinned, h->slots.as<b2s_result>() + slot, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
+  return B2S_OK;
 }
 
 int32_t b2s_scan_result_fetch(b2s_handle* h, int32_t slot, b2s_result* out) {

@@ -537,6 +537,16 @@ class Mapper:
             self._gstep += 1
         return _res(r)
 
+    def addRangeMeasurementHostAsync(self, xyz_f32_ptr: int, n: int, odometryMotion, out_pinned_ptr: int, stride: int = 12) -> None:
+        """Like addRangeMeasurementHost but only enqueues: the b2s_result lands at out_pinned_ptr (page-locked host memory,
+        ctypes layout _lib.Result) once the engine's stream has been synchronised."""
+        M = _mat(odometryMotion)
+        L.check(L.lib().b2s_mapper_step_host_async(self.eng._h, self.submap._s, C.c_void_p(xyz_f32_ptr), C.c_size_t(n), C.c_size_t(stride), _pd(M),
+                                                   C.c_double(self.params_.minRefinementFitness),
+                                                   C.c_int32(int(self.params_.isIgnoreMinRefinementFitness)), C.c_void_p(out_pinned_ptr)))
+        if getattr(self, "_staging", None) is not None:
+            self._gstep += 1
+
     def fetchResult(self, slot: int = 0) -> RegistrationResult:
         r = L.Result()
         L.check(L.lib().b2s_scan_result_fetch(self.eng._h, C.c_int32(slot), C.byref(r)))

@@ -406,6 +406,30 @@ def test_mapper_step_host_matches_device_chain(engine_factory, graph):
         m2.addRangeMeasurementHost(big.ctypes.data, big.shape[0], np.eye(4))
 
 
+def test_mapper_step_host_async_results_land_in_pinned_memory(engine_factory):
+    import torch
+    p = lua_params(seed=5)
+    sc = synth.Scene(); poses = synth.loop_trajectory(10)
+    e1, e2 = engine_factory(p), engine_factory(p)
+    m1, m2 = E.Mapper(e1, 600_000), E.Mapper(e2, 600_000)
+    raw0 = synth.lidar_scan(sc, poses[0], seed=80).astype(np.float32)
+    for m, e in ((m1, e1), (m2, e2)):
+        m.addRangeMeasurement(e.cloud(raw0.astype(np.float64)), None)
+        m.submap.setPose(np.eye(4))
+    m2.enableGraph(65536)
+    n = 6
+    scans = [torch.from_numpy(np.ascontiguousarray(synth.lidar_scan(sc, poses[k], seed=80 + k).astype(np.float32))).pin_memory() for k in range(1, n)]
+    out = torch.zeros((n, C.sizeof(L.Result)), dtype=torch.uint8).pin_memory()
+    for k in range(1, n):      # enqueue everything, synchronise once
+        m2.addRangeMeasurementHostAsync(scans[k - 1].data_ptr(), scans[k - 1].shape[0], np.linalg.inv(poses[k - 1]) @ poses[k], out[k].data_ptr())
+    e2.synchronize()
+    for k in range(1, n):
+        r1 = m1.addRangeMeasurementHost(scans[k - 1].data_ptr(), scans[k - 1].shape[0], np.linalg.inv(poses[k - 1]) @ poses[k])
+        r2 = L.Result.from_buffer_copy(out[k].numpy().tobytes())
+        assert r1.iters == r2.iters and r1.n_corr == r2.n_corr
+        assert np.abs(r1.transformation_ - np.array(r2.T).reshape(4, 4)).max() < 1e-12
+
+
 def test_config3_voxel_normals_1m(engine_factory):
     """BASELINE config 3 at full size: 21 scans in the map frame cut to 1 048 576 points, voxel 0.1, knn 20, radius 3.0."""
     sc = synth.Scene(); poses = synth.loop_trajectory(600)
