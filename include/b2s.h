@@ -165,6 +165,18 @@ void b2s_submap_destroy(b2s_submap* sm);
 /* F1  Submap::insertScan without carving: transform, append, voxelizeWithinCroppingVolume around the sensor
  *     src/Submap.cpp:39-75, src/helpers.cpp:115-183 */
 int32_t b2s_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* preprocessed_scan, const double map_to_sensor[16]);
+/* C1  Submap::carve of the sparse map (space carving)   src/Submap.cpp:55-60,109-123, src/helpers.cpp:235-271,
+ *     src/Voxel.cpp:123-149.  The caller keeps the reference's schedule (nScansInsertedMap_ % carveSpaceEveryNscans_ == 1,
+ *     before the scan is appended) and passes the pose the map-builder cropper was LAST set to (the previous insertion:
+ *     src/Submap.cpp:59 runs before :71).  raw_scan is in the sensor frame.  n_removed may be NULL (no synchronisation). */
+typedef struct b2s_carving_params {     /* SpaceCarvingParameters, include/open3d_slam/Parameters.hpp:85-92 */
+  double voxel_size;                    /* voxelSize_ = 0.1 */
+  double max_raytracing_length;         /* maxRaytracingLength_ = 20.0 */
+  double truncation_distance;           /* truncationDistance_ = 0.1 */
+  double min_dot_product_with_normal;   /* minDotProductWithNormal_ = 0.5 */
+} b2s_carving_params;
+int32_t b2s_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
+                         const double cropper_pose[16], const b2s_carving_params* params, size_t* n_removed);
 /* F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert           src/Submap.cpp:77-92, src/Voxel.cpp:66-88 */
 int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                                 const b2s_cropper* dense_cropper);

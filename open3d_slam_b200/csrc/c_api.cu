@@ -54,7 +54,8 @@ static double nn_cell(const b2s_handle* h, double max_corr) {
 }
 
 static int32_t check_icp_params(const b2s_icp_params& p) {
-  B2S_REQUIRE(p.reg_type == B2S_REG_POINT_TO_PLANE, B2S_E_UNSUPPORTED, "only PointToPlaneIcp is implemented on the device");
+  B2S_REQUIRE(p.reg_type == B2S_REG_POINT_TO_PLANE || p.reg_type == B2S_REG_POINT_TO_POINT, B2S_E_UNSUPPORTED,
+              "PointToPlaneIcp and PointToPointIcp are implemented on the device; GeneralizedIcp is not");
   B2S_REQUIRE(p.max_corr_dist > 0.0, B2S_E_INVALID, "[RegistrationICP] Invalid max_correspondence_distance.");
   B2S_REQUIRE(p.max_iter >= 0, B2S_E_INVALID, "max_iter must be >= 0");
   return B2S_OK;
@@ -77,6 +78,7 @@ static void fill_problem(b2s_handle* h, IcpProblem* P, const b2s_cloud* src, con
   P->rel_rmse = h->cfg.icp.rel_rmse;
   P->max_iter = h->cfg.icp.max_iter;
   P->src_n_max = (int32_t)src->n_max;
+  P->estimator = h->cfg.icp.reg_type;
   P->out = out_dev;
 }
 
@@ -444,7 +446,8 @@ int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* ta
   B2S_REQUIRE(h && source && target && init && out, B2S_E_INVALID, "null argument");
   LOCK(h);
   B2S_TRY(check_icp_params(h->cfg.icp));
-  B2S_REQUIRE(target->has_normals, B2S_E_NO_NORMALS, "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
+  B2S_REQUIRE(target->has_normals || h->cfg.icp.reg_type != B2S_REG_POINT_TO_PLANE, B2S_E_NO_NORMALS,
+              "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
   B2S_TRY(grid_build(h, &h->grid_a, target, nn_cell(h, h->cfg.icp.max_corr_dist), nullptr, true));
   B2S_TRY(h->work_xyz.ensure((source->n_max + 1) * 24, h->stream));
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
@@ -468,7 +471,8 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   size_t work_total = 0, max_src = 0;
   for (int i = 0; i < n; i++) {
     B2S_REQUIRE(sources[i] && targets[i], B2S_E_INVALID, "null cloud in batch");
-    B2S_REQUIRE(targets[i]->has_normals, B2S_E_NO_NORMALS, "[RegistrationICP] target %d has no normals", i);
+    B2S_REQUIRE(targets[i]->has_normals || h->cfg.icp.reg_type != B2S_REG_POINT_TO_PLANE, B2S_E_NO_NORMALS,
+                "[RegistrationICP] target %d has no normals", i);
     int gi = -1;
     for (size_t k = 0; k < seen.size(); k++) if (seen[k] == targets[i]) { gi = (int)k; break; }
     if (gi < 0) {
@@ -501,7 +505,8 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
 int32_t b2s_register_host(b2s_handle* h, const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_normals, size_t n_tgt,
                           const double init[16], b2s_result* out) {
   B2S_REQUIRE(h && init && out, B2S_E_INVALID, "null argument");
-  B2S_REQUIRE(tgt_normals != nullptr, B2S_E_NO_NORMALS, "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
+  B2S_REQUIRE(tgt_normals != nullptr || h->cfg.icp.reg_type != B2S_REG_POINT_TO_PLANE, B2S_E_NO_NORMALS,
+              "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
   B2S_TRY(b2s_cloud_upload_f64(h, h->t2, src_xyz, nullptr, n_src));
   B2S_TRY(b2s_cloud_upload_f64(h, h->t3, tgt_xyz, tgt_normals, n_tgt));
   return b2s_register(h, h->t2, h->t3, init, out);
@@ -524,7 +529,7 @@ int32_t b2s_submap_create(b2s_handle* h, size_t capacity_points, b2s_submap** ou
     B2S_TRY(cloud_set_count(h, sm->cloud[i], 0));
     sm->cloud[i]->has_normals = true;
   }
-  B2S_TRY(sm->pose.ensure(4 * 16 * 8, h->stream));
+  B2S_TRY(sm->pose.ensure(6 * 16 * 8, h->stream));   // pose state, insertion pose, odometry, guess, carving pose, spare
   const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   B2S_TRY(pose_to_device(h, I, sm->pose.as<double>()));
   *out = sm;
@@ -565,6 +570,27 @@ int32_t b2s_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, 
   double* Td = sm->pose.as<double>() + 16;  // slot 1: pose used by this insertion
   B2S_TRY(pose_to_device(h, T, Td));
   return op_submap_insert(h, sm, scan, Td, nullptr);
+}
+
+int32_t b2s_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double T[16], const double cropper_pose[16],
+                         const b2s_carving_params* prm, size_t* n_removed) {
+  B2S_REQUIRE(h && sm && raw_scan && T && cropper_pose && prm, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(prm->voxel_size > 0.0, B2S_E_INVALID, "carving voxel size must be > 0");
+  B2S_REQUIRE(!sm->graph_mode, B2S_E_UNSUPPORTED, "carving is not part of the captured per-scan graph");
+  LOCK(h);
+  double* Td = sm->pose.as<double>() + 64;   // slot 4: pose of the carving scan
+  B2S_TRY(pose_to_device(h, T, Td));
+  b2s_cropper c = h->cfg.scan.map_builder_cropper;   // mapBuilderCropper_ at the pose of the previous insertion
+  c.center[0] = cropper_pose[3]; c.center[1] = cropper_pose[7]; c.center[2] = cropper_pose[11];
+  int32_t* removed_dev = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 8);
+  B2S_TRY(op_submap_carve(h, sm, raw_scan, Td, make_crop(&c), *prm, removed_dev));
+  if (!n_removed) return B2S_OK;
+  B2S_TRY(ensure_pinned(h, 4096));
+  int32_t* pr = reinterpret_cast<int32_t*>(static_cast<char*>(h->pinned) + 512);
+  B2S_CUDA(cudaMemcpyAsync(pr, removed_dev, 4, cudaMemcpyDeviceToHost, h->stream));
+  const int32_t rc = check_status(h);   // synchronises
+  *n_removed = (size_t)*pr;
+  return rc;
 }
 
 int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double T[16], const b2s_cropper* crop) {

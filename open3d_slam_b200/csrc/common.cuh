@@ -245,12 +245,17 @@ struct IcpProblem {
   double rel_fitness, rel_rmse;
   int32_t max_iter;
   int32_t src_n_max;
+  int32_t estimator;        // B2S_REG_POINT_TO_PLANE / B2S_REG_POINT_TO_POINT
+  int32_t pad;
   b2s_result* out;
 };
 // single_host != nullptr: one registration, the problem travels as a kernel argument (no copy, no sync)
 int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
 
 int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev);
+// C1 space carving of the sparse map (carve.cu); removed_dev (optional) receives the number of removed points
+int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double* T_dev, const CropDev& crop,
+                        const b2s_carving_params& prm, int32_t* removed_dev);
 int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const b2s_cropper* crop);
 
 inline int grid_for(size_t n, int threads, int max_blocks = 148 * 16) {

@@ -262,6 +262,89 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
 constexpr int ICP_FIXED_SMEM_DOUBLES = ICP_WARPS * NACC + 2 * NACC + NACC + 16 + 16 + 8;
 constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4;  // working point, previous-neighbour slot, phase-2 queue entry
 
+// point-to-point ([O3D] TransformationEstimationPointToPoint = Eigen::umeyama): sums for the means and the cross moments
+//   acc[0..2] = sum source, acc[3..5] = sum target, acc[6 + 3a + b] = sum target_a * source_b
+__device__ __forceinline__ void icp_accumulate_p2p(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz) {
+  const double4 q = g.pts[slot];
+  acc[0] += px; acc[1] += py; acc[2] += pz;
+  acc[3] += q.x; acc[4] += q.y; acc[5] += q.z;
+  acc[6] += q.x * px; acc[7] += q.x * py; acc[8] += q.x * pz;
+  acc[9] += q.y * px; acc[10] += q.y * py; acc[11] += q.y * pz;
+  acc[12] += q.z * px; acc[13] += q.z * py; acc[14] += q.z * pz;
+  acc[27] += d2;
+  acc[28] += 1.0;
+}
+
+// 3x3 SVD by one-sided Jacobi (Hestenes), singular values sorted descending like Eigen's JacobiSVD (the rotation that
+// umeyama builds from it is unique for rank >= 2, so the SVD algorithm itself need not be Eigen's).  One thread, a few
+// hundred flops per registration iteration.
+__device__ void svd3_dev(const double* A, double* U, double* S, double* V) {
+  double W[9], Vm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; i++) W[i] = A[i];
+  for (int sweep = 0; sweep < 60; sweep++) {
+    bool rotated = false;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; i++) { alpha += W[3 * i + p] * W[3 * i + p]; beta += W[3 * i + q] * W[3 * i + q]; gamma += W[3 * i + p] * W[3 * i + q]; }
+        if (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int i = 0; i < 3; i++) {
+          const double wp = W[3 * i + p], wq = W[3 * i + q];
+          W[3 * i + p] = c * wp - sn * wq; W[3 * i + q] = sn * wp + c * wq;
+          const double vp = Vm[3 * i + p], vq = Vm[3 * i + q];
+          Vm[3 * i + p] = c * vp - sn * vq; Vm[3 * i + q] = sn * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double sv[3]; int ord[3] = {0, 1, 2};
+  for (int j = 0; j < 3; j++) sv[j] = sqrt(W[j] * W[j] + W[3 + j] * W[3 + j] + W[6 + j] * W[6 + j]);
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2 - a; b++) if (sv[ord[b]] < sv[ord[b + 1]]) { const int t = ord[b]; ord[b] = ord[b + 1]; ord[b + 1] = t; }
+  const double tiny = 1e-300;
+  for (int j = 0; j < 3; j++) {
+    const int o = ord[j];
+    S[j] = sv[o];
+    for (int i = 0; i < 3; i++) { V[3 * i + j] = Vm[3 * i + o]; U[3 * i + j] = sv[o] > tiny ? W[3 * i + o] / sv[o] : 0.0; }
+  }
+  if (!(S[0] > tiny)) { for (int i = 0; i < 9; i++) U[i] = (i % 4 == 0) ? 1.0 : 0.0; return; }
+  if (!(S[1] > tiny)) {
+    const double u0[3] = {U[0], U[3], U[6]};
+    const int k = fabs(u0[0]) <= fabs(u0[1]) ? (fabs(u0[0]) <= fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) <= fabs(u0[2]) ? 1 : 2);
+    double e[3] = {0, 0, 0}; e[k] = 1.0;
+    const double d = e[0] * u0[0] + e[1] * u0[1] + e[2] * u0[2];
+    const double v[3] = {e[0] - d * u0[0], e[1] - d * u0[1], e[2] - d * u0[2]};
+    const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    U[1] = v[0] / nv; U[4] = v[1] / nv; U[7] = v[2] / nv;
+  }
+  if (!(S[2] > tiny)) { U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1]; }
+}
+
+__device__ __forceinline__ double det3_dev(const double* M) {
+  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+// Eigen::umeyama without scaling from the accumulated moments (tot as filled by icp_accumulate_p2p, tot[28] = n)
+__device__ void umeyama_from_moments(const double* tot, double* Upd) {
+  const double one_over_n = 1.0 / tot[28];
+  double ms[3], mt[3], sigma[9];
+  for (int a = 0; a < 3; a++) { ms[a] = tot[a] * one_over_n; mt[a] = tot[3 + a] * one_over_n; }
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) sigma[3 * a + b] = tot[6 + 3 * a + b] * one_over_n - mt[a] * ms[b];
+  double U[9], S[3], V[9];
+  svd3_dev(sigma, U, S, V);
+  const double sgn = det3_dev(U) * det3_dev(V) < 0 ? -1.0 : 1.0;
+  for (int i = 0; i < 16; i++) Upd[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) Upd[4 * a + b] = U[3 * a] * V[3 * b] + U[3 * a + 1] * V[3 * b + 1] + sgn * U[3 * a + 2] * V[3 * b + 2];
+    Upd[4 * a + 3] = mt[a] - (Upd[4 * a] * ms[0] + Upd[4 * a + 1] * ms[1] + Upd[4 * a + 2] * ms[2]);
+  }
+}
+
 __device__ __forceinline__ void icp_accumulate(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz) {
   const double4 q = g.pts[slot];
   const double4 nn = g.nrm[slot];
@@ -337,6 +420,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
   g.nrm = reinterpret_cast<const double4*>(P.tgt_nrm);
   const double r2 = P.max_corr * P.max_corr;
   const int max_iter = P.max_iter;
+  const bool p2p = P.estimator == B2S_REG_POINT_TO_POINT;
 
   for (int e = 0;; ++e) {
     if (dbg_on && e < 64) dbg[4 * e] = clock64();
@@ -378,7 +462,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       }
       if (in_smem) s_prev[i] = st.bslot;
       if (done) {
-        if (st.bslot >= 0) icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+        if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
       } else {
         s_queue[atomicAdd(s_qn, 1)] = i;
       }
@@ -416,7 +500,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
         nn_phase2_warp(g, px, py, pz, st);
         if (lane == 0) {
           rp[i] = st.bslot;
-          if (st.bslot >= 0) icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+          if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
         }
       }
     }
@@ -464,7 +548,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       if (e >= max_iter) done = true;
       if (!done) {
         double Upd[16];
-        if (c > 0.0) {
+        if (c > 0.0 && p2p) {
+          umeyama_from_moments(s_tot, Upd);
+        } else if (c > 0.0) {
           double A[6][6], b[6], x[6];
           {
             int k = 0;

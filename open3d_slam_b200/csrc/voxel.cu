@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(VX_THREADS) compact_kernel(const double* __res
   }
 }
 
-static int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out) {
+int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out) {
   const size_t n_max = in->n_max;
   B2S_TRY(h->offs.ensure((n_max + 2) * 4, h->stream));
   B2S_TRY(cloud_reserve(h, out, n_max, in->has_normals));

@@ -57,9 +57,23 @@ class ScanProcessingParameters:
 
 
 @dataclass
+class SpaceCarvingParameters:
+    """include/open3d_slam/Parameters.hpp:85-92"""
+    voxelSize: float = 0.1
+    maxRaytracingLength: float = 20.0
+    truncationDistance: float = 0.1
+    carveSpaceEveryNscans: int = 10
+    minDotProductWithNormal: float = 0.5
+
+    def to_c(self) -> L.CarvingParams:
+        return L.CarvingParams(self.voxelSize, self.maxRaytracingLength, self.truncationDistance, self.minDotProductWithNormal)
+
+
+@dataclass
 class MapBuilderParameters:
     mapVoxelSize: float = 0.1
     cropper: ScanCroppingParameters = field(default_factory=ScanCroppingParameters)
+    carving: SpaceCarvingParameters = field(default_factory=SpaceCarvingParameters)
 
 
 @dataclass
@@ -82,11 +96,11 @@ class MapperParameters:
     nnCellSize: float = 0.0  # engine knob: NN grid cell (0 = maxCorrespondenceDistance / 4)
 
     def to_config(self) -> L.Config:
-        if self.scanToMapRegType != "PointToPlaneIcp":
+        if self.scanToMapRegType not in ("PointToPlaneIcp", "PointToPointIcp"):
             raise L.B2SError(L.E_UNSUPPORTED, f"registration type {self.scanToMapRegType} is not implemented on the device")
         cfg = L.Config()
         L.lib().b2s_default_config(C.byref(cfg))
-        cfg.icp.reg_type = L.REG_POINT_TO_PLANE
+        cfg.icp.reg_type = L.REG_POINT_TO_PLANE if self.scanToMapRegType == "PointToPlaneIcp" else L.REG_POINT_TO_POINT
         cfg.icp.max_iter = int(self.icp.maxNumIter)
         cfg.icp.max_corr_dist = float(self.icp.maxCorrespondenceDistance)
         cfg.icp.knn = int(self.icp.knn)
@@ -299,13 +313,17 @@ class RegistrationIcpPointToPlane(CloudRegistration):
         self.maxRadiusNormalEstimation_ = p.icp.maxDistanceKnn
         self.max_iteration_ = p.icp.maxNumIter
 
+    _regType = "PointToPlaneIcp"
+
     def _apply(self):
         mp = self.eng.params
-        if (mp.icp.maxCorrespondenceDistance, mp.icp.maxNumIter) != (self.maxCorrespondenceDistance_, self.max_iteration_):
+        if (mp.icp.maxCorrespondenceDistance, mp.icp.maxNumIter, mp.scanToMapRegType) != (self.maxCorrespondenceDistance_, self.max_iteration_,
+                                                                                         self._regType):
             import copy
             mp = copy.deepcopy(mp)
             mp.icp.maxCorrespondenceDistance = self.maxCorrespondenceDistance_
             mp.icp.maxNumIter = self.max_iteration_
+            mp.scanToMapRegType = self._regType
             self.eng.set_parameters(mp)
 
     def registerClouds(self, source: Cloud, target: Cloud, init) -> RegistrationResult:
@@ -330,11 +348,22 @@ class RegistrationIcpPointToPlane(CloudRegistration):
                                              C.c_double(self.maxRadiusNormalEstimation_)))
 
 
+class RegistrationIcpPointToPoint(RegistrationIcpPointToPlane):
+    """src/CloudRegistration.cpp:69-82: RegistrationICP with TransformationEstimationPointToPoint (Eigen::umeyama updates).
+    The target needs no normals and estimateNormalsOrCovariancesIfNeeded is the base-class no-op."""
+    _regType = "PointToPointIcp"
+
+    def estimateNormalsOrCovariancesIfNeeded(self, cloud: Cloud) -> None:
+        return None
+
+
 def cloudRegistrationFactory(eng: Engine, p: CloudRegistrationParameters) -> CloudRegistration:
     """src/CloudRegistration.cpp:85-100"""
     if p.regType == "PointToPlaneIcp":
         return RegistrationIcpPointToPlane(eng, p)
-    if p.regType in ("PointToPointIcp", "GeneralizedIcp"):
+    if p.regType == "PointToPointIcp":
+        return RegistrationIcpPointToPoint(eng, p)
+    if p.regType == "GeneralizedIcp":
         raise L.B2SError(L.E_UNSUPPORTED, f"{p.regType} is not implemented on the device (SURVEY.md 8f rank 3)")
     raise RuntimeError("cloud: unknown type of cloud registration")
 
@@ -353,6 +382,8 @@ class Submap:
         L.check(L.lib().b2s_submap_create(eng._h, C.c_size_t(capacity_points), C.byref(self._s)))
         self.capacity = capacity_points
         self.nScansInsertedMap_ = 0
+        self._cropperPose = np.eye(4)   # mapBuilderCropper_'s pose: set AFTER each insertion (Submap.cpp:71), Identity before the first
+        self.lastCarvedCount = 0
 
     def isEmpty(self) -> bool:
         return self.size() == 0
@@ -363,12 +394,26 @@ class Submap:
         return int(n.value)
 
     def insertScan(self, rawScan, preProcessedScan: Cloud, mapToRangeSensor, time=None, isPerformCarving=False) -> bool:
-        if isPerformCarving:
-            raise L.B2SError(L.E_UNSUPPORTED, "space carving is not implemented yet (SURVEY.md 8f rank 1)")
         T = _mat(mapToRangeSensor)
+        if isPerformCarving:
+            self.carve(rawScan, T, self.eng.params.mapBuilder.carving)
         L.check(L.lib().b2s_submap_insert(self.eng._h, self._s, preProcessedScan._c, _pd(T)))
+        self._cropperPose = T.copy()
         self.nScansInsertedMap_ += 1
         return True
+
+    def carve(self, rawScan: Cloud, mapToRangeSensor, params: "SpaceCarvingParameters", force: bool = False) -> int:
+        """Submap::carve (src/Submap.cpp:109-123): only when nScansInsertedMap_ % carveSpaceEveryNscans_ == 1 and the map is
+        not empty; the candidates are the map points inside the map-builder cropper at its LAST pose."""
+        if not force and not (self.nScansInsertedMap_ % params.carveSpaceEveryNscans == 1):
+            return 0
+        if self.size() == 0:
+            return 0
+        T = _mat(mapToRangeSensor); P = np.ascontiguousarray(self._cropperPose, dtype=np.float64)
+        prm = params.to_c(); n = C.c_size_t()
+        L.check(L.lib().b2s_submap_carve(self.eng._h, self._s, rawScan._c, _pd(T), _pd(P), C.byref(prm), C.byref(n)))
+        self.lastCarvedCount = int(n.value)
+        return self.lastCarvedCount
 
     def insertScanDenseMap(self, rawScan: Cloud, mapToRangeSensor, denseCropper: L.Cropper | None = None) -> bool:
         T = _mat(mapToRangeSensor)

@@ -150,3 +150,78 @@ def voxelize_within_cropping_volume(voxel, inside_mask, xyz, nrm):
         z = np.linalg.norm(n)
         out[k] = (sp / c, n / z if z > 0 else n)
     return xyz[~inside_mask], nrm[~inside_mask], out
+
+
+def carve(map_xyz, map_nrm, inside_mask, scan_map_frame, sensor, voxel, max_len, trunc, min_dot):
+    """Submap::carve -> getIdxsOfCarvedPoints (core/src/helpers.cpp:235-271) restated with numpy: all rays are marched
+    together, one step of all rays at a time; voxels are looked up through a dict of integer keys."""
+    inv = 1.0 / voxel
+    vox = {}
+    for i in np.nonzero(inside_mask)[0]:
+        vox.setdefault(tuple(np.floor(map_xyz[i] * inv).astype(np.int64)), []).append(int(i))
+    d = scan_map_frame - sensor
+    length = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    u = d / length[:, None]
+    mp = np.maximum(voxel, np.minimum(length - trunc, max_len))
+    nn = np.sqrt((map_nrm * map_nrm).sum(axis=1))
+    nhat = np.where(nn[:, None] > 0, map_nrm / np.where(nn > 0, nn, 1.0)[:, None], map_nrm)
+    removed = np.zeros(len(map_xyz), dtype=bool)
+    dist = 0.0
+    alive = np.ones(len(d), dtype=bool)
+    while True:
+        alive &= dist < mp
+        if not alive.any():
+            break
+        rays = np.nonzero(alive)[0]
+        pos = dist * u[rays] + sensor
+        keys = np.floor(pos * inv).astype(np.int64)
+        for r, k in zip(rays, map(tuple, keys)):
+            ids = vox.get(k)
+            if ids is None:
+                continue
+            for j in ids:
+                if abs(float(u[r] @ nhat[j])) > min_dot:
+                    removed[j] = True
+        dist += voxel
+    return removed
+
+
+def icp_p2point(src, tgt, r, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """[O3D] RegistrationICP with TransformationEstimationPointToPoint = Eigen::umeyama(no scaling), LAPACK SVD."""
+    T = np.eye(4) if init is None else np.array(init, dtype=np.float64)
+    tree = cKDTree(tgt)
+    pcd = src.copy()
+    if not np.allclose(T, np.eye(4), rtol=0, atol=1e-12):
+        pcd = pcd @ T[:3, :3].T + T[:3, 3]
+
+    def evaluate(p):
+        d, j = tree.query(p, k=1)
+        d2 = ((p - tgt[np.minimum(j, len(tgt) - 1)]) ** 2).sum(axis=1)
+        ok = (j < len(tgt)) & (d2 < r * r)
+        n = int(ok.sum())
+        if n == 0:
+            return ok, j, 0.0, 0.0
+        return ok, j, n / len(p), float(np.sqrt(d2[ok].sum() / n))
+
+    ok, j, fit, rmse = evaluate(pcd)
+    iters = 0
+    for i in range(max_iter):
+        U = np.eye(4)
+        if ok.any():
+            vs = pcd[ok]; vt = tgt[j[ok]]
+            ms, mt = vs.mean(axis=0), vt.mean(axis=0)
+            sigma = (vt - mt).T @ (vs - ms) / len(vs)
+            Us, S, Vt = np.linalg.svd(sigma)
+            D = np.eye(3)
+            if np.linalg.det(Us) * np.linalg.det(Vt) < 0:
+                D[2, 2] = -1.0
+            U[:3, :3] = Us @ D @ Vt
+            U[:3, 3] = mt - U[:3, :3] @ ms
+        T = U @ T
+        pcd = pcd @ U[:3, :3].T + U[:3, 3]
+        bfit, brmse = fit, rmse
+        ok, j, fit, rmse = evaluate(pcd)
+        iters = i + 1
+        if abs(bfit - fit) < rel_fitness and abs(brmse - rmse) < rel_rmse:
+            break
+    return T, fit, rmse, int(ok.sum()), iters

@@ -742,6 +742,121 @@ ORC_EXPORT int orc_registration_icp_p2plane(const double* src_xyz, size_t n_src,
   return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/*  R1' point-to-point ICP ("next" row)                     */
+/*      RegistrationIcpPointToPoint::registerClouds  core/src/CloudRegistration.cpp:69-75 */
+/*      -> [O3D] RegistrationICP(..., TransformationEstimationPointToPoint())  */
+/*      ComputeTransformation = Eigen::umeyama(source_mat, target_mat, with_scaling = false) */
+/* ------------------------------------------------------------------------- */
+/* 3x3 SVD A = U diag(s) V^T by one-sided Jacobi (Hestenes), singular values sorted descending like Eigen's JacobiSVD.
+ * Columns of U that belong to a zero singular value are completed to an orthonormal basis. */
+ORC_EXPORT void orc_svd3(const double* A, double* U, double* S, double* V) {
+  double W[9], Vm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  memcpy(W, A, sizeof(W));
+  for (int sweep = 0; sweep < 60; sweep++) {
+    int rotated = 0;
+    for (int p = 0; p < 2; p++) for (int q = p + 1; q < 3; q++) {
+      double alpha = 0, beta = 0, gamma = 0;
+      for (int i = 0; i < 3; i++) { alpha += W[3 * i + p] * W[3 * i + p]; beta += W[3 * i + q] * W[3 * i + q]; gamma += W[3 * i + p] * W[3 * i + q]; }
+      if (gamma == 0.0 || fabs(gamma) <= 1e-16 * sqrt(alpha * beta)) continue;
+      rotated = 1;
+      double zeta = (beta - alpha) / (2.0 * gamma);
+      double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+      double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+      for (int i = 0; i < 3; i++) {
+        double wp = W[3 * i + p], wq = W[3 * i + q];
+        W[3 * i + p] = c * wp - sn * wq; W[3 * i + q] = sn * wp + c * wq;
+        double vp = Vm[3 * i + p], vq = Vm[3 * i + q];
+        Vm[3 * i + p] = c * vp - sn * vq; Vm[3 * i + q] = sn * vp + c * vq;
+      }
+    }
+    if (!rotated) break;
+  }
+  double sv[3]; int ord[3] = {0, 1, 2};
+  for (int j = 0; j < 3; j++) sv[j] = sqrt(W[j] * W[j] + W[3 + j] * W[3 + j] + W[6 + j] * W[6 + j]);
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2 - a; b++) if (sv[ord[b]] < sv[ord[b + 1]]) { int t = ord[b]; ord[b] = ord[b + 1]; ord[b + 1] = t; }
+  const double tiny = 1e-300;
+  for (int j = 0; j < 3; j++) {
+    int o = ord[j];
+    S[j] = sv[o];
+    for (int i = 0; i < 3; i++) { V[3 * i + j] = Vm[3 * i + o]; U[3 * i + j] = sv[o] > tiny ? W[3 * i + o] / sv[o] : 0.0; }
+  }
+  /* complete U for vanishing singular values (sorted: they are the trailing columns) */
+  if (!(S[0] > tiny)) { double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(U, I, sizeof(I)); return; }
+  if (!(S[1] > tiny)) {   /* any unit vector orthogonal to u0 */
+    double u0[3] = {U[0], U[3], U[6]};
+    int k = fabs(u0[0]) <= fabs(u0[1]) ? (fabs(u0[0]) <= fabs(u0[2]) ? 0 : 2) : (fabs(u0[1]) <= fabs(u0[2]) ? 1 : 2);
+    double e[3] = {0, 0, 0}; e[k] = 1.0;
+    double d = e[0] * u0[0] + e[1] * u0[1] + e[2] * u0[2];
+    double v[3] = {e[0] - d * u0[0], e[1] - d * u0[1], e[2] - d * u0[2]};
+    double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    U[1] = v[0] / nv; U[4] = v[1] / nv; U[7] = v[2] / nv;
+  }
+  if (!(S[2] > tiny)) {   /* u2 = u0 x u1 */
+    U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+  }
+}
+
+static double det3(const double* M) {
+  return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+
+/* Eigen::umeyama without scaling, from the correspondences (source i -> target corr[i]); two passes like Eigen
+ * (means, then the covariance of the demeaned columns) */
+static void p2point_update(const double* src, const double* tgt, const int* corr, size_t n_src, double* update) {
+  size_t n = 0;
+  double ms[3] = {0, 0, 0}, mt[3] = {0, 0, 0};
+  for (size_t i = 0; i < n_src; i++) { int j = corr[i]; if (j < 0) continue; n++; for (int a = 0; a < 3; a++) { ms[a] += src[3 * i + a]; mt[a] += tgt[3 * (size_t)j + a]; } }
+  if (n == 0) { mat4_identity(update); return; }
+  const double one_over_n = 1.0 / (double)n;
+  for (int a = 0; a < 3; a++) { ms[a] *= one_over_n; mt[a] *= one_over_n; }
+  double sigma[9] = {0};
+  for (size_t i = 0; i < n_src; i++) {
+    int j = corr[i]; if (j < 0) continue;
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) sigma[3 * a + b] += (tgt[3 * (size_t)j + a] - mt[a]) * (src[3 * i + b] - ms[b]);
+  }
+  for (int a = 0; a < 9; a++) sigma[a] *= one_over_n;
+  double U[9], S[3], V[9];
+  orc_svd3(sigma, U, S, V);
+  double sgn = det3(U) * det3(V) < 0 ? -1.0 : 1.0;   /* Eq. (39): S(m-1) = -1 */
+  double R[9];
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) R[3 * a + b] = U[3 * a] * V[3 * b] + U[3 * a + 1] * V[3 * b + 1] + sgn * U[3 * a + 2] * V[3 * b + 2];
+  mat4_identity(update);
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) update[4 * a + b] = R[3 * a + b];
+    update[4 * a + 3] = mt[a] - (R[3 * a] * ms[0] + R[3 * a + 1] * ms[1] + R[3 * a + 2] * ms[2]);
+  }
+}
+
+ORC_EXPORT int orc_registration_icp_p2point(const double* src_xyz, size_t n_src, const double* tgt_xyz, size_t n_tgt, double max_corr_dist,
+                                            const double* init, int max_iter, double rel_fitness, double rel_rmse, orc_icp_result* out) {
+  if (max_corr_dist <= 0.0) return -1;       /* [O3D] LogError */
+  double T[16]; memcpy(T, init, sizeof(T));
+  kd_tree* t = kd_build(tgt_xyz, (int)n_tgt);
+  double* pcd = (double*)malloc(24 * (n_src ? n_src : 1));
+  memcpy(pcd, src_xyz, 24 * n_src);
+  if (!mat4_is_identity(init)) transform_points(init, pcd, n_src);
+  int* corr = (int*)malloc(sizeof(int) * (n_src ? n_src : 1));
+  double* d2 = (double*)malloc(sizeof(double) * (n_src ? n_src : 1));
+  double fit, rmse; int nc;
+  icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+  int it = 0;
+  for (int i = 0; i < max_iter; i++) {
+    double upd[16];
+    p2point_update(pcd, tgt_xyz, corr, n_src, upd);
+    mat4_mul(upd, T, T);
+    transform_points(upd, pcd, n_src);
+    double bfit = fit, brmse = rmse;
+    icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+    it = i + 1;
+    if (fabs(bfit - fit) < rel_fitness && fabs(brmse - rmse) < rel_rmse) break;
+  }
+  memcpy(out->T, T, sizeof(T));
+  out->fitness = fit; out->inlier_rmse = rmse; out->n_corr = nc; out->iters = it;
+  free(pcd); free(corr); free(d2); kd_free(t);
+  return 0;
+}
+
 /* Brute-force single evaluation (for cross-checking the tree): fitness/rmse/JTJ/JTr at transform T */
 ORC_EXPORT void orc_icp_evaluate_bruteforce(const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_nrm,
                                             size_t n_tgt, double r, const double* T, double* fitness, double* rmse,
@@ -973,6 +1088,75 @@ ORC_EXPORT int orc_process_scan(const double* raw_xyz, size_t n, const orc_cropp
   *n_match = orc_crop(&c1, merge_xyz, merge_nrm, k, match_xyz, match_nrm);
   free(a); free(b); free(bn);
   return (*n_merge > 0 && *n_match > 0) ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------------- */
+/*  C1  space carving of the sparse map ("next" row)       */
+/*      Submap::carve  core/src/Submap.cpp:109-123                             */
+/*      getIdxsOfCarvedPoints  core/src/helpers.cpp:235-271                    */
+/*      VoxelMap::insertCloud / getIndicesInVoxel  core/src/Voxel.cpp:123-149  */
+/*  scan_xyz: the raw scan ALREADY in the map frame (carve() transforms it);   */
+/*  only the map points inside `cropper` are candidates (getIndicesWithinVolume)*/
+/*  removed[i] = 1 for every map point hit by a ray that is not (nearly)        */
+/*  parallel to its surface.  Returns the number of removed points.             */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  double voxel_size, max_raytracing_length, truncation_distance, min_dot_product_with_normal;
+} orc_carving_params;
+
+ORC_EXPORT size_t orc_carve(const double* map_xyz, const double* map_nrm, size_t n_map, const double* scan_xyz, size_t n_scan,
+                            const double* sensor, const orc_cropper* cropper, const orc_carving_params* prm, uint8_t* removed) {
+  memset(removed, 0, n_map);
+  if (n_map == 0) return 0;
+  const double inv = 1.0 / prm->voxel_size;   /* VoxelHashMap.hpp:43-45 fromVoxelSize */
+  /* voxel -> chained list of the map indices inside the cropper */
+  vhash h; vh_init(&h, n_map);
+  int32_t* head = (int32_t*)malloc(sizeof(int32_t) * (n_map + 1));
+  int32_t* next = (int32_t*)malloc(sizeof(int32_t) * (n_map + 1));
+  for (size_t i = 0; i < n_map; i++) {
+    next[i] = -1;
+    if (!orc_within(cropper, map_xyz + 3 * i)) continue;
+    const double* p = map_xyz + 3 * i;
+    int is_new = 0;
+    int32_t slot = vh_get(&h, (int32_t)floor(p[0] * inv), (int32_t)floor(p[1] * inv), (int32_t)floor(p[2] * inv), 1, &is_new);
+    if (is_new) head[slot] = -1;
+    next[i] = head[slot]; head[slot] = (int32_t)i;
+  }
+  const double step = prm->voxel_size;
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n_scan; i++) {
+    const double* p = scan_xyz + 3 * i;
+    const double dx = p[0] - sensor[0], dy = p[1] - sensor[1], dz = p[2] - sensor[2];
+    const double length = sqrt(dx * dx + dy * dy + dz * dz);
+    const double dir[3] = {dx / length, dy / length, dz / length};
+    double mp = length - prm->truncation_distance;
+    if (prm->max_raytracing_length < mp) mp = prm->max_raytracing_length;       /* std::min */
+    if (prm->voxel_size > mp) mp = prm->voxel_size;                              /* std::max */
+    if (!(mp == mp)) continue;                                                   /* NaN ray: the while condition is false */
+    double distance = 0.0;
+    while (distance < mp) {
+      const double cx = distance * dir[0] + sensor[0], cy = distance * dir[1] + sensor[1], cz = distance * dir[2] + sensor[2];
+      int32_t slot = vh_get(&h, (int32_t)floor(cx * inv), (int32_t)floor(cy * inv), (int32_t)floor(cz * inv), 0, NULL);
+      if (slot >= 0) {
+        for (int32_t id = head[slot]; id >= 0; id = next[id]) {
+          int rm = 1;
+          if (map_nrm) {
+            const double* n = map_nrm + 3 * (size_t)id;
+            double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            double nx = n[0], ny = n[1], nz = n[2];
+            if (nn > 0.0) { nx /= nn; ny /= nn; nz /= nn; }                      /* Eigen normalized(): unchanged when the norm is 0 */
+            rm = fabs(dir[0] * nx + dir[1] * ny + dir[2] * nz) > prm->min_dot_product_with_normal;
+          }
+          if (rm) removed[id] = 1;                                               /* set insert: idempotent */
+        }
+      }
+      distance += step;
+    }
+  }
+  vh_free(&h); free(head); free(next);
+  size_t cnt = 0;
+  for (size_t i = 0; i < n_map; i++) cnt += removed[i];
+  return cnt;
 }
 
 ORC_EXPORT int orc_num_threads(void) {

@@ -152,6 +152,25 @@ def registration_icp_p2plane(src, tgt, tgt_nrm, max_corr_dist, init=None, max_it
                      None if tr is None else tr[:res.iters].copy())
 
 
+def registration_icp_p2point(src, tgt, max_corr_dist, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6) -> IcpResult:
+    """RegistrationIcpPointToPoint::registerClouds (core/src/CloudRegistration.cpp:69-75): ICP with Eigen::umeyama updates."""
+    src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3)
+    init = np.eye(4) if init is None else _f64(init).reshape(4, 4)
+    res = IcpResultC()
+    rc = lib().orc_registration_icp_p2point(_p(src), C.c_size_t(len(src)), _p(tgt), C.c_size_t(len(tgt)), C.c_double(max_corr_dist), _p(init),
+                                            C.c_int(max_iter), C.c_double(rel_fitness), C.c_double(rel_rmse), C.byref(res))
+    if rc != 0:
+        raise RuntimeError(f"orc_registration_icp_p2point failed: {rc}")
+    return IcpResult(np.array(res.T).reshape(4, 4), res.fitness, res.inlier_rmse, res.n_corr, res.iters, None)
+
+
+def svd3(A):
+    A = _f64(A).reshape(3, 3)
+    U = np.empty((3, 3)); S = np.empty(3); V = np.empty((3, 3))
+    lib().orc_svd3(_p(A), _p(U), _p(S), _p(V))
+    return U, S, V
+
+
 def icp_evaluate_bruteforce(src, tgt, tgt_nrm, r, T):
     src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); tgt_nrm = _f64(tgt_nrm).reshape(-1, 3)
     T = _f64(T).reshape(4, 4)
@@ -260,6 +279,27 @@ def kdtree_search_hybrid(pts, q, radius, max_nn):
         out.append((idx[:k].copy(), d2[:k].copy()))
     lib().orc_kdtree_free(t)
     return out
+
+
+class CarvingParams(C.Structure):
+    """SpaceCarvingParameters (core/include/open3d_slam/Parameters.hpp:85-92), the fields getIdxsOfCarvedPoints reads."""
+    _fields_ = [("voxel_size", C.c_double), ("max_raytracing_length", C.c_double), ("truncation_distance", C.c_double),
+                ("min_dot_product_with_normal", C.c_double)]
+
+
+def carve(map_xyz, map_nrm, scan_xyz_map_frame, sensor, cropper_: Cropper, voxel_size=0.1, max_raytracing_length=20.0,
+          truncation_distance=0.1, min_dot_product_with_normal=0.5):
+    """Boolean mask of the map points space carving removes (Submap::carve -> getIdxsOfCarvedPoints)."""
+    map_xyz = _f64(map_xyz).reshape(-1, 3)
+    map_nrm = None if map_nrm is None else _f64(map_nrm).reshape(-1, 3)
+    scan = _f64(scan_xyz_map_frame).reshape(-1, 3)
+    s = _f64(sensor).reshape(3)
+    prm = CarvingParams(voxel_size, max_raytracing_length, truncation_distance, min_dot_product_with_normal)
+    removed = np.zeros(len(map_xyz), dtype=np.uint8)
+    lib().orc_carve.restype = C.c_size_t
+    lib().orc_carve(_p(map_xyz), _p(map_nrm), C.c_size_t(len(map_xyz)), _p(scan), C.c_size_t(len(scan)), _p(s), C.byref(cropper_),
+                    C.byref(prm), removed.ctypes.data_as(C.c_void_p))
+    return removed.astype(bool)
 
 
 def num_threads() -> int:

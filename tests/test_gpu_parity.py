@@ -487,6 +487,94 @@ def test_config4_scan_submap_pairs_batch(engine_factory):
         assert rel_rot(r.transformation_, ref.T) < 1e-8 and rel_trans(r.transformation_, ref.T) < 1e-8
 
 
+def test_point_to_point_icp_matches_oracle(engine_factory):
+    """R1' (SURVEY 8f rank 3): RegistrationIcpPointToPoint -- [O3D] RegistrationICP with Eigen::umeyama updates."""
+    src, tgt, nrm, T_true = synth.planar_cloud_config1(noise=0.01)
+    p = lua_params()
+    p.icp.maxCorrespondenceDistance = 1.0
+    p.icp.maxNumIter = 50
+    eng = engine_factory(p)
+    reg = E.cloudRegistrationFactory(eng, E.CloudRegistrationParameters(regType="PointToPointIcp", icp=p.icp))
+    assert isinstance(reg, E.RegistrationIcpPointToPoint)
+    tcloud = eng.cloud(tgt)                                   # no normals: point-to-point does not need them
+    for init in (np.eye(4), synth.se3(0.01, -0.02, 0.03, (0.05, 0.02, -0.01))):
+        res = reg.registerClouds(eng.cloud(src), tcloud, init)
+        ref = O.registration_icp_p2point(src, tgt, 1.0, init, max_iter=50)
+        assert res.iters == ref.iters and res.n_corr == ref.n_corr
+        assert abs(res.fitness_ - ref.fitness) < 1e-12 and abs(res.inlier_rmse_ - ref.inlier_rmse) < 1e-9
+        assert rel_rot(res.transformation_, ref.T) < 1e-8 and rel_trans(res.transformation_, ref.T) < 1e-8
+    # iteration cap and the batched launch (one scan-submap-sized pair among them)
+    sc = synth.Scene(); poses = synth.loop_trajectory(600)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0)
+    (mx, mn), _ = O.process_scan(synth.lidar_scan(sc, poses[0], seed=0), wide, wide, 0.1, 20, 3.0, 1.0, 0)
+    _, (sx, sn) = O.process_scan(synth.lidar_scan(sc, poses[1], seed=1), wide, wide, 0.1, 20, 3.0, 0.3, 7)
+    init1 = np.linalg.inv(poses[0]) @ poses[1] @ synth.se3(0.0, 0.0, np.deg2rad(1.0), (0.1, -0.05, 0.0))
+    reg.max_iteration_ = 7
+    batch = reg.registerCloudsBatch([eng.cloud(src), eng.cloud(sx)], [tcloud, eng.cloud(mx, mn)], [np.eye(4), init1])
+    refs = [O.registration_icp_p2point(src, tgt, 1.0, np.eye(4), max_iter=7), O.registration_icp_p2point(sx, mx, 1.0, init1, max_iter=7)]
+    for b, ref in zip(batch, refs):
+        assert b.iters == ref.iters and b.n_corr == ref.n_corr
+        assert rel_rot(b.transformation_, ref.T) < 1e-8 and rel_trans(b.transformation_, ref.T) < 1e-8
+    # the plane estimator still refuses a target without normals on the same engine
+    with pytest.raises(L.B2SError) as ei:
+        E.RegistrationIcpPointToPlane(eng).registerClouds(eng.cloud(src), tcloud, np.eye(4))
+    assert ei.value.code == L.E_NO_NORMALS
+
+
+def _carving_case():
+    """A three-scan oracle submap plus floating clutter in free space, and the next raw scan with its pose."""
+    sc = synth.Scene(); poses = synth.loop_trajectory(600)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0)
+    mx = np.zeros((0, 3)); mn = np.zeros((0, 3))
+    for k in range(3):
+        (ax, an), _ = O.process_scan(synth.lidar_scan(sc, poses[k], seed=k), wide, wide, 0.1, 20, 3.0, 1.0, 0)
+        mx, mn = O.submap_insert_scan(mx, mn, ax, an, poses[k], 0.1, O.cropper("MaxRadius", 0.0, 20.0, center=tuple(poses[k][:3, 3])))
+    rng = np.random.default_rng(0)
+    clutter = rng.uniform([-6, -6, -1.5], [6, 6, 1.5], (800, 3)); cn = rng.normal(size=(800, 3))
+    cn[:50] = 0.0                                    # zero normals: normalized() leaves them, |dir . 0| = 0 never exceeds the threshold
+    return np.vstack([mx, clutter]), np.vstack([mn, cn]), synth.lidar_scan(sc, poses[3], seed=3).astype(np.float64), poses[3], poses[2]
+
+
+@pytest.mark.parametrize("voxel,min_dot,trunc", [(0.1, 0.5, 0.1), (0.25, 0.2, 0.5)])
+def test_space_carving_matches_oracle(engine_factory, voxel, min_dot, trunc):
+    """C1 (SURVEY 8f rank 1): Submap::carve -> getIdxsOfCarvedPoints; the surviving map must be the oracle's, in order, bit-exact."""
+    mx, mn, raw, T, Tprev = _carving_case()
+    p = lua_params()
+    p.mapBuilder.cropper = E.ScanCroppingParameters(cropperName="MaxRadius", croppingMaxRadius=20.0)
+    p.mapBuilder.carving = E.SpaceCarvingParameters(voxelSize=voxel, maxRaytracingLength=20.0, truncationDistance=trunc, minDotProductWithNormal=min_dot)
+    eng = engine_factory(p)
+    sm = E.Submap(eng, 400_000)
+    sm.setMapPointCloud(eng.cloud(mx, mn))
+    sm._cropperPose = Tprev                       # mapBuilderCropper_ still sits at the previous insertion (Submap.cpp:59 vs :71)
+    n_removed = sm.carve(eng.cloud(raw), T, p.mapBuilder.carving, force=True)
+    scan_map, _ = O.transform(T, raw)
+    rem = O.carve(mx, mn, scan_map, T[:3, 3], O.cropper("MaxRadius", 0.0, 20.0, center=tuple(Tprev[:3, 3])), voxel, 20.0, trunc, min_dot)
+    assert 0 < rem.sum() < len(mx) and rem[len(mx) - 800:].sum() > 0
+    assert n_removed == int(rem.sum())
+    gx, gn = sm.getMapPointCloud()
+    assert np.array_equal(gx, mx[~rem]) and np.array_equal(gn, mn[~rem])
+
+
+def test_insert_scan_with_carving_schedule(engine_factory):
+    """Submap.insertScan(isPerformCarving=True) carves only when nScansInsertedMap_ % carveSpaceEveryNscans_ == 1."""
+    p = lua_params()
+    p.mapBuilder.carving.carveSpaceEveryNscans = 2
+    eng = engine_factory(p)
+    icp = E.ScanToMapIcp(eng)
+    sc = synth.Scene(); poses = synth.loop_trajectory(8)
+    sm = E.Submap(eng, 400_000)
+    carved = []
+    for k in range(4):
+        raw = eng.cloud(synth.lidar_scan(sc, poses[k], seed=k).astype(np.float64))
+        ps = icp.processForScanMatchingAndMerging(raw)
+        sm.lastCarvedCount = -1
+        sm.insertScan(raw, ps.merge_, poses[k], isPerformCarving=True)
+        carved.append(sm.lastCarvedCount)
+    assert carved[0] == -1 and carved[2] == -1          # 0 % 2, 2 % 2 != 1: skipped
+    assert carved[1] >= 0 and carved[3] >= 0            # 1 % 2 == 1, 3 % 2 == 1: carved
+    assert sm.size() > 0
+
+
 def test_dense_map_running_sums(engine_factory):
     p = lua_params()
     eng = engine_factory(p)

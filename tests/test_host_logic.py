@@ -36,7 +36,9 @@ def test_factories_mirror_the_reference_errors():
     with pytest.raises(RuntimeError):
         E.cloudRegistrationFactory(None, E.CloudRegistrationParameters(regType="NoSuchIcp"))
     with pytest.raises(L.B2SError):
-        E.cloudRegistrationFactory(None, E.CloudRegistrationParameters(regType="PointToPointIcp"))
+        E.cloudRegistrationFactory(None, E.CloudRegistrationParameters(regType="GeneralizedIcp"))
+    p.scanToMapRegType = "PointToPointIcp"
+    assert p.to_config().icp.reg_type == L.REG_POINT_TO_POINT
 
 
 def test_synthetic_data_is_deterministic_and_sane():

@@ -231,3 +231,56 @@ def test_process_scan_matches_golden():
     assert d.max() == 0.0 and np.abs((mn * g["merge_nrm"][j]).sum(1)).min() > 1 - 1e-12
     with pytest.raises(RuntimeError):
         O.process_scan(np.array([[100.0, 0, 0]]), O.cropper("MinMaxRadius", 2.0, 30.0), O.cropper("MinMaxRadius", 2.0, 25.0), 0.1, 20, 3.0, 1.0, 0)
+
+
+def test_space_carving_c_vs_numpy_and_hand_case():
+    """C1: orc_carve against the numpy restatement and a hand-built case."""
+    # hand case: sensor at the origin looking along +x at a wall point 5 m away; map points on the ray with normals
+    # facing the sensor are carved, one with a perpendicular normal stays, one beyond (length - truncation) stays,
+    # one outside the cropper stays although a ray crosses its voxel
+    scan = np.array([[5.0, 0.02, 0.03], [0.03, 12.0, 0.02]])
+    mx = np.array([[1.04, 0.02, 0.03], [2.03, 0.01, 0.02], [4.96, 0.02, 0.03], [3.05, 0.02, 0.01], [0.02, 11.03, 0.03]])
+    mn = np.array([[-1.0, 0, 0], [0, 1.0, 0], [-1.0, 0, 0], [-0.9, 0.1, 0], [0, -1.0, 0]])
+    crop = O.cropper("MaxRadius", 0.0, 8.0)
+    rem = O.carve(mx, mn, scan, np.zeros(3), crop, 0.1, 20.0, 0.1, 0.5)
+    assert rem.tolist() == [True, False, False, True, False]
+    # random case vs numpy
+    rng = np.random.default_rng(5)
+    mx = rng.uniform(-4, 4, (3000, 3)); mn = rng.normal(size=(3000, 3)); mn[:20] = 0.0
+    scan = rng.normal(size=(400, 3)); scan = scan / np.linalg.norm(scan, axis=1)[:, None] * rng.uniform(2, 9, (400, 1)) + [0.3, -0.2, 0.1]
+    sensor = np.array([0.3, -0.2, 0.1])
+    crop = O.cropper("MaxRadius", 0.0, 3.5, center=(0.5, 0.5, 0.0))
+    inside = NP.within("MaxRadius", mx, (0.5, 0.5, 0.0), rmax=3.5)
+    for voxel, trunc, mind in ((0.1, 0.1, 0.5), (0.3, 0.6, 0.2)):
+        rem = O.carve(mx, mn, scan, sensor, crop, voxel, 6.0, trunc, mind)
+        ref = NP.carve(mx, mn, inside, scan, sensor, voxel, 6.0, trunc, mind)
+        assert rem.sum() > 10 and np.array_equal(rem, ref)
+        assert not rem[~inside].any() and not rem[:20].any()
+
+
+def test_point_to_point_icp_c_vs_numpy_and_closed_form():
+    """R1' (SURVEY 8f rank 3): orc_svd3 against LAPACK, umeyama ICP against the numpy restatement and the exact answer."""
+    rng = np.random.default_rng(11)
+    for k in range(50):
+        A = rng.normal(size=(3, 3)) * 10.0 ** rng.uniform(-3, 3)
+        if k % 5 == 0:
+            A[:, 2] = A[:, 0] * 0.5 - A[:, 1]          # rank 2
+        if k % 10 == 0:
+            A = np.outer(A[:, 0], A[0])                  # rank 1
+        U, S, V = O.svd3(A)
+        assert np.abs(U @ np.diag(S) @ V.T - A).max() < 1e-12 * max(1.0, np.abs(A).max())
+        assert np.abs(U.T @ U - np.eye(3)).max() < 1e-12 and np.abs(V.T @ V - np.eye(3)).max() < 1e-12
+        assert S[0] >= S[1] >= S[2] >= 0 and np.abs(S - np.linalg.svd(A, compute_uv=False)).max() < 1e-12 * max(1.0, S[0])
+    # exact correspondences within r: one umeyama step recovers the rigid motion exactly
+    tgt = rng.uniform(-5, 5, (400, 3))
+    T0 = synth.se3(0.01, -0.02, 0.015, (0.02, -0.01, 0.03))
+    src = (tgt - T0[:3, 3]) @ T0[:3, :3]                 # T0 * src = tgt
+    r = O.registration_icp_p2point(src, tgt, 0.5, np.eye(4), max_iter=30)
+    assert r.fitness == 1.0 and np.abs(r.T - T0).max() < 1e-12 and r.inlier_rmse < 1e-12
+    # config 1 (noisy): C vs numpy
+    src, tgt, nrm, T_true = synth.planar_cloud_config1(noise=0.01)
+    for init in (np.eye(4), synth.se3(0.01, 0.0, -0.01, (0.02, 0.0, 0.01))):
+        rc = O.registration_icp_p2point(src, tgt, 1.0, init, max_iter=50)
+        T2, f2, e2, n2, i2 = NP.icp_p2point(src, tgt, 1.0, init, max_iter=50)
+        assert rc.iters == i2 and rc.n_corr == n2
+        assert np.abs(rc.T - T2).max() < 1e-10 and abs(rc.inlier_rmse - e2) < 1e-12
