@@ -115,6 +115,50 @@ void RegistrationIcpPointToPlaneB200::estimateNormalsOrCovariancesIfNeeded(Point
   cloud->normals_ = d.download()->normals_;
 }
 
+RegistrationIcpPointToPointB200::RegistrationIcpPointToPointB200(const CloudRegistrationParameters& p) : cfg_(b2sConfigFrom(p.icp_, nullptr, nullptr)) {
+  cfg_.icp.reg_type = B2S_REG_POINT_TO_POINT;
+}
+
+RegistrationResult RegistrationIcpPointToPointB200::registerClouds(const PointCloud& source, const PointCloud& target, const Transform& init) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  double T0[16];
+  toRowMajor(init.matrix(), T0);
+  b2s_result r;
+  int32_t rc = b2s_register_host(h, source.points_.empty() ? nullptr : source.points_.front().data(), source.points_.size(),
+                                 target.points_.empty() ? nullptr : target.points_.front().data(), nullptr, target.points_.size(), T0, &r);
+  if (rc != B2S_OK) b2sThrow(rc);
+  return toResult(r);
+}
+
+void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, const Transform& cropperPose, const MapBuilderParameters& p,
+               PointCloud* map) {
+  if (map->points_.empty()) return;   // Submap.cpp:111
+  IcpParameters unused;
+  b2s_config cfg = b2sConfigFrom(unused, nullptr, &p);
+  b2s_handle* h = b2sThreadHandle(cfg);
+  DeviceCloud raw(h, rawScan, false), dmap(h, *map, true);
+  b2s_submap* sm = nullptr;
+  int32_t rc = b2s_submap_create(h, map->points_.size() + 1, &sm);
+  if (rc != B2S_OK) b2sThrow(rc);
+  rc = b2s_submap_set_cloud(h, sm, dmap.c);
+  double Ts[16], Tc[16];
+  toRowMajor(mapToRangeSensor.matrix(), Ts);
+  toRowMajor(cropperPose.matrix(), Tc);
+  const b2s_carving_params prm = {p.carving_.voxelSize_, p.carving_.maxRaytracingLength_, p.carving_.truncationDistance_,
+                                  p.carving_.minDotProductWithNormal_};
+  size_t removed = 0;
+  if (rc == B2S_OK) rc = b2s_submap_carve(h, sm, raw.c, Ts, Tc, &prm, &removed);
+  size_t n = 0;
+  if (rc == B2S_OK) rc = b2s_submap_size(h, sm, &n);
+  if (rc == B2S_OK) {
+    map->points_.resize(n);
+    if (map->HasNormals() || n == 0) map->normals_.resize(n);
+    rc = b2s_submap_download(h, sm, n ? map->points_.front().data() : nullptr, (n && !map->normals_.empty()) ? map->normals_.front().data() : nullptr, n, &n);
+  }
+  b2s_submap_destroy(sm);
+  if (rc != B2S_OK) b2sThrow(rc);
+}
+
 ScanToMapIcpB200::ScanToMapIcpB200(const MapperParameters& p) : cfg_(b2sConfigFrom(p.scanMatcher_.icp_, &p.scanProcessing_, &p.mapBuilder_)) {}
 
 ProcessedScans ScanToMapIcpB200::processForScanMatchingAndMerging(const PointCloud& in, const Transform&) const {

@@ -34,6 +34,21 @@ class RegistrationIcpPointToPlaneB200 : public CloudRegistration {
   b2s_config cfg_;
 };
 
+// RegistrationIcpPointToPoint (src/CloudRegistration.cpp:69-82) on the device: same ICP loop, Eigen::umeyama updates
+class RegistrationIcpPointToPointB200 : public CloudRegistration {
+ public:
+  explicit RegistrationIcpPointToPointB200(const CloudRegistrationParameters& p);
+  RegistrationResult registerClouds(const PointCloud& source, const PointCloud& target, const Transform& init) const final;
+
+ private:
+  b2s_config cfg_;
+};
+
+// Submap::carve for the sparse map (src/Submap.cpp:109-123): removes the carved points from *map in place.  cropperPose is
+// the pose mapBuilderCropper_ currently holds (the previous insertion); the caller keeps the every-N-scans schedule.
+void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, const Transform& cropperPose, const MapBuilderParameters& p,
+               PointCloud* map);
+
 class ScanToMapIcpB200 : public ScanToMapRegistration {
  public:
   explicit ScanToMapIcpB200(const MapperParameters& p);
