@@ -367,8 +367,14 @@ def run_b2s_arm(args):
     else:
         dom_for_roof = dom
     achieved = ab / (dur_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None   # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        ent = json.load(open(tpath)).get(dom_for_roof)
+        if ent:
+            traffic, traffic_src = ent["bytes_per_launch"], ent["source"]
     roofline = {"bound": "hbm", "kernel": dom_for_roof, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_launch": ab, "avg_launch_ms": dur_ms,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": ab, "avg_launch_ms": dur_ms,
                 "note": "latency-bound: a single registration's working set is L2-resident and its iterations are sequential (SURVEY.md 8d)"}
     profile = {k: {"ms_per_scan": v[0] / kp, "launch_groups_per_scan": v[1] / kp} for k, v in prof.items()}
 

@@ -177,6 +177,15 @@ typedef struct b2s_carving_params {     /* SpaceCarvingParameters, include/open3
 } b2s_carving_params;
 int32_t b2s_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                          const double cropper_pose[16], const b2s_carving_params* params, size_t* n_removed);
+/* L1  the two steps either side of the loop-closure ICP (src/PlaceRecognition.cpp:103-111,148; src/constraint_builders.cpp:54,71)
+ *     computeIndicesOfOverlappingPoints + SelectByIndex   src/helpers.cpp:307-332 : the points of source / target whose
+ *     voxel (edge voxel_size, source moved by source_to_target) holds >= min_points_per_voxel points of BOTH clouds, in
+ *     their original order (the reference's index lists come in hash-map order; only the sets matter to its callers).
+ *     [O3D] GetInformationMatrixFromPointClouds(source, target, max_correspondence_distance, transformation): 6x6, row-major. */
+int32_t b2s_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double source_to_target[16], double voxel_size,
+                    int32_t min_points_per_voxel, b2s_cloud* source_overlap, b2s_cloud* target_overlap);
+int32_t b2s_information_matrix(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, double max_correspondence_distance,
+                               const double transformation[16], double info_out[36]);
 /* F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert           src/Submap.cpp:77-92, src/Voxel.cpp:66-88 */
 int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                                 const b2s_cropper* dense_cropper);

@@ -502,6 +502,38 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   return check_status(h);
 }
 
+int32_t b2s_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double T[16], double voxel, int32_t min_pts,
+                    b2s_cloud* source_overlap, b2s_cloud* target_overlap) {
+  B2S_REQUIRE(h && source && target && T && source_overlap && target_overlap, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(source_overlap != target_overlap && source_overlap != source && target_overlap != target, B2S_E_INVALID, "aliased clouds");
+  B2S_REQUIRE(voxel > 0.0, B2S_E_INVALID, "voxel size must be > 0");
+  B2S_REQUIRE(min_pts >= 1, B2S_E_INVALID, "minNumPointsPerVoxel must be >= 1");   // assert_ge at helpers.cpp:310
+  LOCK(h);
+  B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream, true));
+  double* Td = h->poses.as<double>() + 16 * 62;   // slot 62: sourceToTarget of this call
+  B2S_TRY(pose_to_device(h, T, Td));
+  return op_overlap(h, source, target, Td, voxel, min_pts, source_overlap, target_overlap);
+}
+
+int32_t b2s_information_matrix(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, double max_corr, const double T[16],
+                               double info_out[36]) {
+  B2S_REQUIRE(h && source && target && T && info_out, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(max_corr > 0.0, B2S_E_INVALID, "[GetInformationMatrixFromPointClouds] Invalid max_correspondence_distance.");
+  LOCK(h);
+  B2S_TRY(grid_build(h, &h->grid_a, target, max_corr * 0.25, nullptr, false));
+  B2S_TRY(h->work_xyz.ensure((source->n_max + 1) * 24, h->stream));
+  B2S_TRY(h->results.ensure(sizeof(b2s_result) + 36 * 8 + 64, h->stream));
+  IcpProblem P;
+  fill_problem(h, &P, source, &h->grid_a, T, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
+  P.max_corr = max_corr;
+  P.max_iter = 0;
+  P.estimator = EST_INFORMATION;
+  P.info_out = reinterpret_cast<double*>(h->results.as<b2s_result>() + 1);
+  B2S_TRY(icp_launch(h, &P, nullptr, 1, source->n_max));
+  B2S_CUDA(cudaMemcpyAsync(info_out, P.info_out, 36 * 8, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
 int32_t b2s_register_host(b2s_handle* h, const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_normals, size_t n_tgt,
                           const double init[16], b2s_result* out) {
   B2S_REQUIRE(h && init && out, B2S_E_INVALID, "null argument");

@@ -245,14 +245,19 @@ struct IcpProblem {
   double rel_fitness, rel_rmse;
   int32_t max_iter;
   int32_t src_n_max;
-  int32_t estimator;        // B2S_REG_POINT_TO_PLANE / B2S_REG_POINT_TO_POINT
+  int32_t estimator;        // B2S_REG_POINT_TO_PLANE / B2S_REG_POINT_TO_POINT / EST_INFORMATION
   int32_t pad;
   b2s_result* out;
+  double* info_out;         // EST_INFORMATION: 36 doubles, row-major 6x6
 };
+constexpr int EST_INFORMATION = 3;   // internal estimator code: a single evaluation that outputs [O3D]'s information matrix
 // single_host != nullptr: one registration, the problem travels as a kernel argument (no copy, no sync)
 int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
 
 int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev);
+// L1 overlap selection in front of the loop-closure ICP (overlap.cu); T_dev = sourceToTarget (device, row-major)
+int32_t op_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double* T_dev, double voxel, int min_pts,
+                   b2s_cloud* source_overlap, b2s_cloud* target_overlap);
 // C1 space carving of the sparse map (carve.cu); removed_dev (optional) receives the number of removed points
 int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double* T_dev, const CropDev& crop,
                         const b2s_carving_params& prm, int32_t* removed_dev);

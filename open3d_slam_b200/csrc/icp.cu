@@ -275,6 +275,26 @@ __device__ __forceinline__ void icp_accumulate_p2p(double (&acc)[NACC], const Gr
   acc[28] += 1.0;
 }
 
+// information matrix ([O3D] GetInformationMatrixFromPointClouds): first and second moments of the matched TARGET points
+//   acc[0..2] = sum (x, y, z), acc[3..5] = sum (x2, y2, z2), acc[6..8] = sum (xy, xz, yz)
+__device__ __forceinline__ void icp_accumulate_info(double (&acc)[NACC], const GridView& g, int slot, double d2) {
+  const double4 q = g.pts[slot];
+  acc[0] += q.x; acc[1] += q.y; acc[2] += q.z;
+  acc[3] += q.x * q.x; acc[4] += q.y * q.y; acc[5] += q.z * q.z;
+  acc[6] += q.x * q.y; acc[7] += q.x * q.z; acc[8] += q.y * q.z;
+  acc[27] += d2;
+  acc[28] += 1.0;
+}
+
+// GTG = sum over matched target points of the three rank-one terms of [O3D]: rows (0,z,-y,1,0,0), (-z,0,x,0,1,0), (y,-x,0,0,0,1)
+__device__ void info_from_moments(const double* t, double* G) {
+  const double sx = t[0], sy = t[1], sz = t[2], xx = t[3], yy = t[4], zz = t[5], xy = t[6], xz = t[7], yz = t[8], n = t[28];
+  const double M[6][6] = {{zz + yy, -xy, -xz, 0.0, -sz, sy}, {-xy, zz + xx, -yz, sz, 0.0, -sx}, {-xz, -yz, yy + xx, -sy, sx, 0.0},
+                          {0.0, sz, -sy, n, 0.0, 0.0},       {-sz, 0.0, sx, 0.0, n, 0.0},       {sy, -sx, 0.0, 0.0, 0.0, n}};
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) G[6 * a + b] = M[a][b];
+}
+
 // 3x3 SVD by one-sided Jacobi (Hestenes), singular values sorted descending like Eigen's JacobiSVD (the rotation that
 // umeyama builds from it is unique for rank >= 2, so the SVD algorithm itself need not be Eigen's).  One thread, a few
 // hundred flops per registration iteration.
@@ -421,6 +441,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
   const double r2 = P.max_corr * P.max_corr;
   const int max_iter = P.max_iter;
   const bool p2p = P.estimator == B2S_REG_POINT_TO_POINT;
+  const bool info = P.estimator == EST_INFORMATION;   // one evaluation, output = 6x6 information matrix
 
   for (int e = 0;; ++e) {
     if (dbg_on && e < 64) dbg[4 * e] = clock64();
@@ -462,7 +483,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       }
       if (in_smem) s_prev[i] = st.bslot;
       if (done) {
-        if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
+        if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else if (info) icp_accumulate_info(acc, g, st.bslot, st.best); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
       } else {
         s_queue[atomicAdd(s_qn, 1)] = i;
       }
@@ -500,7 +521,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
         nn_phase2_warp(g, px, py, pz, st);
         if (lane == 0) {
           rp[i] = st.bslot;
-          if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
+          if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else if (info) icp_accumulate_info(acc, g, st.bslot, st.best); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
         }
       }
     }
@@ -546,6 +567,10 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       bool done = false;
       if (e > 0 && fabs(s_misc[0] - fit) < P.rel_fitness && fabs(s_misc[1] - rmse) < P.rel_rmse) done = true;
       if (e >= max_iter) done = true;
+      if (info) {
+        done = true;
+        if (crank == 0 && P.info_out) info_from_moments(s_tot, P.info_out);
+      }
       if (!done) {
         double Upd[16];
         if (c > 0.0 && p2p) {

@@ -294,6 +294,22 @@ def transform(eng: Engine, T, cloud: Cloud) -> Cloud:
 # --------------------------------------------------------------------------------------------------------------------
 
 
+def computeOverlappingClouds(eng: Engine, source: Cloud, target: Cloud, sourceToTarget, voxelSize: float, minNumPointsPerVoxel: int = 1):
+    """computeIndicesOfOverlappingPoints + SelectByIndex (src/helpers.cpp:307-332, src/PlaceRecognition.cpp:103-106):
+    returns (sourceOverlap, targetOverlap), the selected points in their original order."""
+    so, to = Cloud(eng), Cloud(eng)
+    L.check(L.lib().b2s_overlap(eng._h, source._c, target._c, _pd(_mat(sourceToTarget)), C.c_double(voxelSize), C.c_int32(minNumPointsPerVoxel),
+                                so._c, to._c))
+    return so, to
+
+
+def getInformationMatrixFromPointClouds(eng: Engine, source: Cloud, target: Cloud, maxCorrespondenceDistance: float, transformation) -> np.ndarray:
+    """[O3D] GetInformationMatrixFromPointClouds as called at src/PlaceRecognition.cpp:148 and src/constraint_builders.cpp:71."""
+    G = np.zeros((6, 6))
+    L.check(L.lib().b2s_information_matrix(eng._h, source._c, target._c, C.c_double(maxCorrespondenceDistance), _pd(_mat(transformation)), _pd(G)))
+    return G
+
+
 class CloudRegistration:
     def registerClouds(self, source: Cloud, target: Cloud, init) -> RegistrationResult:  # pragma: no cover - abstract
         raise NotImplementedError

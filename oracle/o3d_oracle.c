@@ -1159,6 +1159,66 @@ ORC_EXPORT size_t orc_carve(const double* map_xyz, const double* map_nrm, size_t
   return cnt;
 }
 
+/* ------------------------------------------------------------------------- */
+/*  L1  overlap selection + information matrix around the loop-closure ICP      */
+/*      ("next" row)                                       */
+/*      computeIndicesOfOverlappingPoints  core/src/helpers.cpp:307-332         */
+/*      [O3D] GetInformationMatrixFromPointClouds (core/src/PlaceRecognition.cpp:148, */
+/*      core/src/constraint_builders.cpp:71)                                    */
+/* ------------------------------------------------------------------------- */
+/* flags (0/1) per source / target point: the point lies in a voxel (key = floor(p * (1/voxel)), source transformed by T
+ * like [O3D] PointCloud::Transform) that holds >= min_pts source AND >= min_pts target points.  The reference returns
+ * index lists in hash-map order; callers only use them through SelectByIndex, so the sets are what matters. */
+ORC_EXPORT void orc_overlap_flags(const double* src, size_t n_src, const double* tgt, size_t n_tgt, const double* T, double voxel,
+                                  size_t min_pts, uint8_t* src_flag, uint8_t* tgt_flag) {
+  const double inv = 1.0 / voxel;
+  double* st = (double*)malloc(24 * (n_src ? n_src : 1));
+  memcpy(st, src, 24 * n_src);
+  transform_points(T, st, n_src);   /* sourceTransformed.Transform(sourceToTarget.matrix()) -- unconditional here */
+  vhash h; vh_init(&h, n_src + n_tgt);
+  int32_t* cs = (int32_t*)calloc(n_src + n_tgt + 1, sizeof(int32_t));
+  int32_t* ct = (int32_t*)calloc(n_src + n_tgt + 1, sizeof(int32_t));
+  int32_t* ss = (int32_t*)malloc(sizeof(int32_t) * (n_src ? n_src : 1));
+  int32_t* ts = (int32_t*)malloc(sizeof(int32_t) * (n_tgt ? n_tgt : 1));
+  for (size_t j = 0; j < n_tgt; j++) {
+    const double* p = tgt + 3 * j;
+    ts[j] = vh_get(&h, (int32_t)floor(p[0] * inv), (int32_t)floor(p[1] * inv), (int32_t)floor(p[2] * inv), 1, NULL);
+    ct[ts[j]]++;
+  }
+  for (size_t i = 0; i < n_src; i++) {
+    const double* p = st + 3 * i;
+    ss[i] = vh_get(&h, (int32_t)floor(p[0] * inv), (int32_t)floor(p[1] * inv), (int32_t)floor(p[2] * inv), 1, NULL);
+    cs[ss[i]]++;
+  }
+  for (size_t i = 0; i < n_src; i++) src_flag[i] = (size_t)cs[ss[i]] >= min_pts && (size_t)ct[ss[i]] >= min_pts;
+  for (size_t j = 0; j < n_tgt; j++) tgt_flag[j] = (size_t)cs[ts[j]] >= min_pts && (size_t)ct[ts[j]] >= min_pts;
+  vh_free(&h); free(cs); free(ct); free(ss); free(ts); free(st);
+}
+
+/* [O3D] GetInformationMatrixFromPointClouds(source, target, max_correspondence_distance, transformation): 6x6 row-major */
+ORC_EXPORT int orc_information_matrix(const double* src, size_t n_src, const double* tgt, size_t n_tgt, double max_corr_dist,
+                                      const double* T, double* info36) {
+  if (max_corr_dist <= 0.0) return -1;
+  double* pcd = (double*)malloc(24 * (n_src ? n_src : 1));
+  memcpy(pcd, src, 24 * n_src);
+  if (!mat4_is_identity(T)) transform_points(T, pcd, n_src);
+  kd_tree* t = kd_build(tgt, (int)n_tgt);
+  int* corr = (int*)malloc(sizeof(int) * (n_src ? n_src : 1));
+  double* d2 = (double*)malloc(sizeof(double) * (n_src ? n_src : 1));
+  double fit, rmse; int nc;
+  icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+  double G[36] = {0};
+  for (size_t i = 0; i < n_src; i++) {
+    int j = corr[i]; if (j < 0) continue;
+    const double x = tgt[3 * (size_t)j], y = tgt[3 * (size_t)j + 1], z = tgt[3 * (size_t)j + 2];
+    const double r[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
+    for (int k = 0; k < 3; k++) for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) G[6 * a + b] += r[k][a] * r[k][b];
+  }
+  memcpy(info36, G, sizeof(G));
+  free(pcd); free(corr); free(d2); kd_free(t);
+  return 0;
+}
+
 ORC_EXPORT int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -302,5 +302,23 @@ def carve(map_xyz, map_nrm, scan_xyz_map_frame, sensor, cropper_: Cropper, voxel
     return removed.astype(bool)
 
 
+def overlap_flags(src, tgt, T, voxel, min_pts=1):
+    """computeIndicesOfOverlappingPoints (core/src/helpers.cpp:307-332) as boolean masks over source and target."""
+    src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); T = _f64(T).reshape(4, 4)
+    fs = np.zeros(len(src), dtype=np.uint8); ft = np.zeros(len(tgt), dtype=np.uint8)
+    lib().orc_overlap_flags(_p(src), C.c_size_t(len(src)), _p(tgt), C.c_size_t(len(tgt)), _p(T), C.c_double(voxel), C.c_size_t(min_pts),
+                            fs.ctypes.data_as(C.c_void_p), ft.ctypes.data_as(C.c_void_p))
+    return fs.astype(bool), ft.astype(bool)
+
+
+def information_matrix(src, tgt, max_corr_dist, T):
+    """[O3D] GetInformationMatrixFromPointClouds (called at core/src/PlaceRecognition.cpp:148)."""
+    src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); T = _f64(T).reshape(4, 4)
+    G = np.zeros((6, 6))
+    if lib().orc_information_matrix(_p(src), C.c_size_t(len(src)), _p(tgt), C.c_size_t(len(tgt)), C.c_double(max_corr_dist), _p(T), _p(G)) != 0:
+        raise RuntimeError("invalid max_correspondence_distance")
+    return G
+
+
 def num_threads() -> int:
     return int(lib().orc_num_threads())

@@ -521,6 +521,88 @@ def test_point_to_point_icp_matches_oracle(engine_factory):
     assert ei.value.code == L.E_NO_NORMALS
 
 
+def test_edge_cases_empty_inputs_and_capacity(engine_factory):
+    """Empty and overflowing inputs: the reference's asserts become error codes, everything else degrades like [O3D]."""
+    src, tgt, nrm, _ = synth.planar_cloud_config1()
+    p = lua_params()
+    eng = engine_factory(p)
+    empty = eng.cloud(np.zeros((0, 3)))
+    assert len(E.voxelize(eng, empty, 0.1)) == 0
+    assert len(E.random_down_sample(eng, empty, 0.5, 1)) == 0
+    assert len(E.transform(eng, synth.se3(0.1, 0, 0, (1, 2, 3)), empty)) == 0
+    assert len(E.crop(eng, empty, E.ScanCroppingParameters().to_c())) == 0
+    L.check(L.lib().b2s_estimate_normals(eng._h, empty._c, 20, C.c_double(3.0)))       # no points: nothing to do, no error
+    reg = E.RegistrationIcpPointToPlane(eng)
+    # empty source: no correspondences -> identity updates, fitness 0, one iteration until the criteria see 0 == 0
+    r = reg.registerClouds(empty, eng.cloud(tgt, nrm), np.eye(4))
+    ref = O.registration_icp_p2plane(np.zeros((0, 3)), tgt, nrm, 1.0, np.eye(4), max_iter=50)
+    assert (r.iters, r.n_corr, r.fitness_, r.inlier_rmse_) == (ref.iters, 0, 0.0, 0.0) and np.array_equal(r.transformation_, np.eye(4))
+    # empty target (with a normals array of length 0): same outcome, the initial guess comes back untouched
+    init = synth.se3(0.0, 0.0, 0.1, (1.0, 0.0, 0.0))
+    r = reg.registerClouds(eng.cloud(src), eng.cloud(np.zeros((0, 3)), np.zeros((0, 3))), init)
+    assert r.n_corr == 0 and r.fitness_ == 0.0 and np.array_equal(r.transformation_, init)
+    # everything cropped away: ScanToMapIcp's assert_gt(cropped size, 0)  (ScanToMapRegistration.cpp:51-52)
+    far = eng.cloud(np.array([[100.0, 0, 0], [0, 120.0, 1.0], [90.0, 90.0, 0.0]]))
+    with pytest.raises(L.B2SError) as ei:
+        E.ScanToMapIcp(eng).processForScanMatchingAndMerging(far)
+    assert ei.value.code == L.E_EMPTY
+    # a submap that cannot hold the scan answers B2S_E_CAPACITY instead of writing out of bounds
+    sc = synth.Scene(); poses = synth.loop_trajectory(4)
+    ps = E.ScanToMapIcp(eng).processForScanMatchingAndMerging(eng.cloud(synth.lidar_scan(sc, poses[0], seed=0).astype(np.float64)))
+    small = E.Submap(eng, 2000)
+    with pytest.raises(L.B2SError) as ei:
+        small.insertScan(None, ps.merge_, np.eye(4))
+    assert ei.value.code == L.E_CAPACITY
+    # invalid parameters are refused like the reference's asserts (CloudRegistration.cpp:50-51, [O3D] r <= 0)
+    with pytest.raises(L.B2SError):
+        L.check(L.lib().b2s_estimate_normals(eng._h, eng.cloud(src)._c, 0, C.c_double(3.0)))
+    bad = lua_params(); bad.icp.maxCorrespondenceDistance = 0.0
+    with pytest.raises(L.B2SError) as ei:
+        E.RegistrationIcpPointToPlane(engine_factory(bad)).registerClouds(eng.cloud(src), eng.cloud(tgt, nrm), np.eye(4))
+    assert ei.value.code == L.E_INVALID
+
+
+def test_loop_closure_overlap_and_information_matrix(engine_factory):
+    """L1: overlap selection -> ICP on the overlap -> information matrix, the sequence of
+    PlaceRecognition::buildLoopClosureConstraints (src/PlaceRecognition.cpp:103-148) on two oracle-built submaps."""
+    sc = synth.Scene(); poses = synth.loop_trajectory(600)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0)
+    subs = []
+    for k0 in (0, 8):                       # two submaps 4 m apart
+        mx = np.zeros((0, 3)); mn = np.zeros((0, 3))
+        for k in range(k0, k0 + 3):
+            (ax, an), _ = O.process_scan(synth.lidar_scan(sc, poses[k], seed=k), wide, wide, 0.1, 20, 3.0, 1.0, 0)
+            mx, mn = O.submap_insert_scan(mx, mn, ax, an, poses[k], 0.1, O.cropper("MaxRadius", 0.0, 20.0, center=tuple(poses[k][:3, 3])))
+        subs.append((mx, mn))
+    (sx, sn), (tx, tn) = subs
+    guess = synth.se3(0.0, 0.0, np.deg2rad(0.8), (0.08, -0.05, 0.02))          # stands in for the RANSAC result
+    p = lua_params()
+    p.icp.maxCorrespondenceDistance = 0.3
+    p.icp.maxNumIter = 100
+    eng = engine_factory(p)
+    src, tgt = eng.cloud(sx, sn), eng.cloud(tx, tn)
+    for voxel, m in ((0.3, 1), (0.5, 4)):                                        # 3 x map voxel, minNumPointsPerVoxel = 1 is the reference's call
+        so, to = E.computeOverlappingClouds(eng, src, tgt, guess, voxel, m)
+        fs, ft = O.overlap_flags(sx, tx, guess, voxel, m)
+        gsx, gsn = so.download(); gtx, gtn = to.download()
+        assert 0 < fs.sum() < len(sx) and 0 < ft.sum() < len(tx)
+        assert np.array_equal(gsx, sx[fs]) and np.array_equal(gsn, sn[fs]) and np.array_equal(gtx, tx[ft]) and np.array_equal(gtn, tn[ft])
+    so, to = E.computeOverlappingClouds(eng, src, tgt, guess, 0.3, 1)
+    fs, ft = O.overlap_flags(sx, tx, guess, 0.3, 1)
+    res = E.RegistrationIcpPointToPlane(eng).registerClouds(so, to, guess)
+    ref = O.registration_icp_p2plane(sx[fs], tx[ft], tn[ft], 0.3, guess, max_iter=100)
+    assert res.iters == ref.iters and res.n_corr == ref.n_corr and np.abs(res.transformation_ - ref.T).max() < 1e-8
+    G = E.getInformationMatrixFromPointClouds(eng, so, to, 0.3, ref.T)      # the same transformation on both sides
+    Gref = O.information_matrix(sx[fs], tx[ft], 0.3, ref.T)
+    assert G[3, 3] == Gref[3, 3] > 1000 and np.abs(G - Gref).max() < 1e-9 * np.abs(Gref).max()
+    assert np.array_equal(G, G.T)
+    # identity transformation: [O3D] skips the Transform (isIdentity) -- same matrix as with an explicit identity
+    G0 = E.getInformationMatrixFromPointClouds(eng, so, to, 0.3, np.eye(4))
+    assert np.abs(G0 - O.information_matrix(sx[fs], tx[ft], 0.3, np.eye(4))).max() < 1e-9 * np.abs(Gref).max()
+    with pytest.raises(L.B2SError):
+        E.computeOverlappingClouds(eng, src, tgt, guess, 0.3, 0)
+
+
 def _carving_case():
     """A three-scan oracle submap plus floating clutter in free space, and the next raw scan with its pose."""
     sc = synth.Scene(); poses = synth.loop_trajectory(600)

@@ -284,3 +284,28 @@ def test_point_to_point_icp_c_vs_numpy_and_closed_form():
         T2, f2, e2, n2, i2 = NP.icp_p2point(src, tgt, 1.0, init, max_iter=50)
         assert rc.iters == i2 and rc.n_corr == n2
         assert np.abs(rc.T - T2).max() < 1e-10 and abs(rc.inlier_rmse - e2) < 1e-12
+
+
+def test_overlap_and_information_matrix_vs_numpy():
+    """L1: computeIndicesOfOverlappingPoints and [O3D] GetInformationMatrixFromPointClouds."""
+    rng = np.random.default_rng(21)
+    tgt = rng.uniform(-3, 3, (4000, 3)); src = rng.uniform(-1, 5, (3000, 3))
+    T = synth.se3(0.02, -0.01, 0.3, (0.4, -0.2, 0.1))
+    for voxel, m in ((0.5, 1), (0.8, 3)):
+        fs, ft = O.overlap_flags(src, tgt, T, voxel, m)
+        st = src @ T[:3, :3].T + T[:3, 3]
+        ks = np.floor(st * (1.0 / voxel)).astype(np.int64); kt = np.floor(tgt * (1.0 / voxel)).astype(np.int64)
+        from collections import Counter
+        cs = Counter(map(tuple, ks)); ct = Counter(map(tuple, kt))
+        rs = np.array([cs[tuple(k)] >= m and ct.get(tuple(k), 0) >= m for k in ks]); rt = np.array([ct[tuple(k)] >= m and cs.get(tuple(k), 0) >= m for k in kt])
+        assert np.array_equal(fs, rs) and np.array_equal(ft, rt) and 0 < fs.sum() < len(src)
+    G = O.information_matrix(src, tgt, 0.3, T)
+    st = src @ T[:3, :3].T + T[:3, 3]
+    d, j = cKDTree(tgt).query(st)
+    ok = d < 0.3
+    ref = np.zeros((6, 6))
+    for x, y, z in tgt[j[ok]]:
+        for r in (np.array([0, z, -y, 1, 0, 0.0]), np.array([-z, 0, x, 0, 1, 0.0]), np.array([y, -x, 0, 0, 0, 1.0])):
+            ref += np.outer(r, r)
+    assert ok.sum() > 50 and np.abs(G - ref).max() < 1e-9 * np.abs(ref).max()
+    assert np.array_equal(G, G.T) and G[3, 3] == G[4, 4] == G[5, 5] == float(ok.sum())
