@@ -177,6 +177,11 @@ typedef struct b2s_carving_params {     /* SpaceCarvingParameters, include/open3
 } b2s_carving_params;
 int32_t b2s_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                          const double cropper_pose[16], const b2s_carving_params* params, size_t* n_removed);
+/* D1  ConstantVelocityMotionCompensation::undistortInputPointCloud (src/MotionCompensation.cpp:64-139): per-point motion
+ *     compensation by azimuth phase (computePhase), for the linear / angular (roll-pitch-yaw) velocity the host estimated from
+ *     its pose buffer (estimateLinearAndAngularVelocity, :33-57).  in != out; the output carries no normals. */
+int32_t b2s_undistort(b2s_handle* h, const b2s_cloud* in, const double linear_velocity[3], const double angular_velocity_rpy[3],
+                      double scan_duration, int32_t is_spinning_clockwise, b2s_cloud* out);
 /* L1  the two steps either side of the loop-closure ICP (src/PlaceRecognition.cpp:103-111,148; src/constraint_builders.cpp:54,71)
  *     computeIndicesOfOverlappingPoints + SelectByIndex   src/helpers.cpp:307-332 : the points of source / target whose
  *     voxel (edge voxel_size, source moved by source_to_target) holds >= min_points_per_voxel points of BOTH clouds, in

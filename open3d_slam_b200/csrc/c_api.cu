@@ -502,6 +502,14 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   return check_status(h);
 }
 
+int32_t b2s_undistort(b2s_handle* h, const b2s_cloud* in, const double lin_vel[3], const double ang_vel_rpy[3], double scan_duration,
+                      int32_t clockwise, b2s_cloud* out) {
+  B2S_REQUIRE(h && in && out && lin_vel && ang_vel_rpy && in != out, B2S_E_INVALID, "bad argument");
+  B2S_REQUIRE(scan_duration > 0.0, B2S_E_INVALID, "lidar scanDuration_: must be > 0");   // assert_gt at MotionCompensation.cpp:61
+  LOCK(h);
+  return op_undistort(h, in, lin_vel, ang_vel_rpy, scan_duration, clockwise ? 1 : 0, out);
+}
+
 int32_t b2s_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double T[16], double voxel, int32_t min_pts,
                     b2s_cloud* source_overlap, b2s_cloud* target_overlap) {
   B2S_REQUIRE(h && source && target && T && source_overlap && target_overlap, B2S_E_INVALID, "null argument");

@@ -511,4 +511,61 @@ int32_t op_transform(b2s_handle* h, const b2s_cloud* in, const double* T_host, b
   return B2S_OK;
 }
 
+// ---- D1: constant-velocity de-skew ------------------------------------------------------------
+// ConstantVelocityMotionCompensation::undistortInputPointCloud / computePhase (core/src/MotionCompensation.cpp:64-139):
+// every point is moved by the sensor motion accumulated up to its azimuth phase: p' = R(q) p + t with
+// t = phase * scanDuration * v, q = fromRPY(phase * scanDuration * w).normalized() = qz * qy * qx (core/src/math.cpp:32-37),
+// R(q) as Eigen::Quaternion::toRotationMatrix.  The velocities come from the host's pose buffer (two poses).
+__global__ void __launch_bounds__(VX_THREADS) undistort_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double vx, double vy,
+                                                               double vz, double wr, double wp, double wy, double duration, int clockwise,
+                                                               double* __restrict__ out, int32_t* out_n) {
+  const int n = *d_n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = n;
+  const double two_pi = 2.0 * 3.14159265358979323846;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    const double angle = atan2(py, px);
+    const double wrapped = angle < 0.0 ? (angle + two_pi) : angle;
+    double phase = 0.0;
+    if (wrapped != 0.0) phase = clockwise ? 1.0 - wrapped / two_pi : wrapped / two_pi;
+    const double s = phase * duration;
+    const double tx_ = s * vx, ty_ = s * vy, tz_ = s * vz;
+    const double r = s * wr, pi_ = s * wp, yw = s * wy;
+    double sr, cr, sp, cp, sy, cy;
+    sincos(0.5 * r, &sr, &cr); sincos(0.5 * pi_, &sp, &cp); sincos(0.5 * yw, &sy, &cy);
+    // qzy = qz * qy with qz = (cy,0,0,sy), qy = (cp,0,sp,0);  q = qzy * qx with qx = (cr,sr,0,0)   (Eigen's product, all terms kept)
+    const double a0 = cy * cp - 0.0 * 0.0 - 0.0 * sp - sy * 0.0;
+    const double a1 = cy * 0.0 + 0.0 * cp + 0.0 * 0.0 - sy * sp;
+    const double a2 = cy * sp + 0.0 * cp + sy * 0.0 - 0.0 * 0.0;
+    const double a3 = cy * 0.0 + sy * cp + 0.0 * sp - 0.0 * 0.0;
+    double w = a0 * cr - a1 * sr - a2 * 0.0 - a3 * 0.0;
+    double x = a0 * sr + a1 * cr + a2 * 0.0 - a3 * 0.0;
+    double y = a0 * 0.0 + a2 * cr + a3 * sr - a1 * 0.0;
+    double z = a0 * 0.0 + a3 * cr + a1 * 0.0 - a2 * sr;
+    const double n2 = w * w + x * x + y * y + z * z;
+    if (n2 > 0.0) { const double nn = sqrt(n2); w /= nn; x /= nn; y /= nn; z /= nn; }
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x,
+                 tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    out[3 * i] = ((1 - (tyy + tzz)) * px + (txy - twz) * py + (txz + twy) * pz) + tx_;
+    out[3 * i + 1] = ((txy + twz) * px + (1 - (txx + tzz)) * py + (tyz - twx) * pz) + ty_;
+    out[3 * i + 2] = ((txz - twy) * px + (tyz + twx) * py + (1 - (txx + tyy)) * pz) + tz_;
+  }
+}
+
+int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, const double* ang_vel_rpy, double scan_duration, int clockwise,
+                     b2s_cloud* out) {
+  const size_t n_max = in->n_max > 0 ? in->n_max : 1;
+  B2S_TRY(cloud_reserve(h, out, n_max, false));
+  ProfScope prof(h, PK_CROP);
+  undistort_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), in->dn.as<int32_t>(), lin_vel[0], lin_vel[1],
+                                                                              lin_vel[2], ang_vel_rpy[0], ang_vel_rpy[1], ang_vel_rpy[2],
+                                                                              scan_duration, clockwise, out->xyz.as<double>(), out->dn.as<int32_t>());
+  h->launches++;
+  out->has_normals = false;   // the reference copies the input cloud and rewrites points_ only; raw scans carry no normals
+  out->n_max = in->n_max;
+  out->n_known = in->n_known;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
 }  // namespace b2s

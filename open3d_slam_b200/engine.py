@@ -294,6 +294,35 @@ def transform(eng: Engine, T, cloud: Cloud) -> Cloud:
 # --------------------------------------------------------------------------------------------------------------------
 
 
+class ConstantVelocityMotionCompensation:
+    """src/MotionCompensation.cpp:31-139.  The velocity estimate (two poses of the caller's buffer, :33-57) is host logic;
+    the per-point correction runs on the device (b2s_undistort)."""
+
+    def __init__(self, eng: Engine, isSpinningClockwise: bool = True, scanDuration: float = 0.1, numPosesVelocityEstimation: int = 3):
+        if not scanDuration > 0.0:
+            raise RuntimeError("lidar scanDuration_: must be > 0")   # assert_gt, :61
+        self.eng = eng
+        self.isSpinningClockwise_ = isSpinningClockwise
+        self.scanDuration_ = scanDuration
+        self.numPosesVelocityEstimation_ = numPosesVelocityEstimation
+
+    @staticmethod
+    def estimateLinearAndAngularVelocity(startPose, finishPose, dt: float):
+        """:41-52 -- dT = start^-1 * finish; v = dT.translation / (dt + 1e-6); w = toRPY(dT.rotation) / (dt + 1e-6)."""
+        dT = np.linalg.inv(_mat(startPose)) @ _mat(finishPose)
+        R = dT[:3, :3]
+        roll = np.arctan2(R[2, 1], R[2, 2]); pitch = np.arcsin(-R[2, 0]); yaw = np.arctan2(R[1, 0], R[0, 0])
+        return dT[:3, 3] / (dt + 1e-6), np.array([roll, pitch, yaw]) / (dt + 1e-6)
+
+    def undistortInputPointCloud(self, cloud: Cloud, linearVelocity, angularVelocityRpy) -> Cloud:
+        out = Cloud(self.eng)
+        lv = np.ascontiguousarray(np.asarray(linearVelocity, dtype=np.float64).reshape(3))
+        av = np.ascontiguousarray(np.asarray(angularVelocityRpy, dtype=np.float64).reshape(3))
+        L.check(L.lib().b2s_undistort(self.eng._h, cloud._c, _pd(lv), _pd(av), C.c_double(self.scanDuration_), C.c_int32(int(self.isSpinningClockwise_)),
+                                      out._c))
+        return out
+
+
 def computeOverlappingClouds(eng: Engine, source: Cloud, target: Cloud, sourceToTarget, voxelSize: float, minNumPointsPerVoxel: int = 1):
     """computeIndicesOfOverlappingPoints + SelectByIndex (src/helpers.cpp:307-332, src/PlaceRecognition.cpp:103-106):
     returns (sourceOverlap, targetOverlap), the selected points in their original order."""

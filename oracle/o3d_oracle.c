@@ -1219,6 +1219,49 @@ ORC_EXPORT int orc_information_matrix(const double* src, size_t n_src, const dou
   return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/*  D1  constant-velocity de-skew ("next" row)             */
+/*      ConstantVelocityMotionCompensation::undistortInputPointCloud / computePhase */
+/*      core/src/MotionCompensation.cpp:64-139 ; fromRPY core/src/math.cpp:32-37 */
+/*      makeTransform(xyz, q) * p  =  R(q) p + xyz  (Eigen toRotationMatrix)     */
+/* ------------------------------------------------------------------------- */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+static void quat_mul(const double* a, const double* b, double* o) {   /* (w,x,y,z), Eigen's product */
+  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+  o[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+}
+ORC_EXPORT double orc_compute_phase(double x, double y, int spinning_clockwise) {
+  const double angle = atan2(y, x);
+  const double wrapped = angle < 0.0 ? (angle + 2.0 * M_PI) : angle;
+  if (wrapped == 0.0) return 0.0;
+  return spinning_clockwise ? 1.0 - wrapped / (2.0 * M_PI) : wrapped / (2.0 * M_PI);
+}
+ORC_EXPORT void orc_undistort(const double* xyz, size_t n, const double* lin_vel, const double* ang_vel_rpy, double scan_duration,
+                              int spinning_clockwise, double* out) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; i++) {
+    const double* p = xyz + 3 * i;
+    const double phase = orc_compute_phase(p[0], p[1], spinning_clockwise);
+    const double s = phase * scan_duration;
+    const double t[3] = {s * lin_vel[0], s * lin_vel[1], s * lin_vel[2]};
+    const double r = s * ang_vel_rpy[0], pi = s * ang_vel_rpy[1], yw = s * ang_vel_rpy[2];
+    const double qx[4] = {cos(0.5 * r), sin(0.5 * r), 0, 0}, qy[4] = {cos(0.5 * pi), 0, sin(0.5 * pi), 0}, qz[4] = {cos(0.5 * yw), 0, 0, sin(0.5 * yw)};
+    double qzy[4], q[4];
+    quat_mul(qz, qy, qzy); quat_mul(qzy, qx, q);                 /* yaw * pitch * roll */
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (n2 > 0.0) { const double nn = sqrt(n2); for (int k = 0; k < 4; k++) q[k] /= nn; }   /* .normalized() */
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x,
+                 tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const double R[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+    for (int a = 0; a < 3; a++) out[3 * i + a] = (R[3 * a] * p[0] + R[3 * a + 1] * p[1] + R[3 * a + 2] * p[2]) + t[a];
+  }
+}
+
 ORC_EXPORT int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

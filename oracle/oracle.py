@@ -320,5 +320,14 @@ def information_matrix(src, tgt, max_corr_dist, T):
     return G
 
 
+def undistort(xyz, linear_velocity, angular_velocity_rpy, scan_duration=0.1, spinning_clockwise=True):
+    """ConstantVelocityMotionCompensation::undistortInputPointCloud (core/src/MotionCompensation.cpp:64-110) for given velocities."""
+    xyz = _f64(xyz).reshape(-1, 3)
+    lv = _f64(linear_velocity).reshape(3); av = _f64(angular_velocity_rpy).reshape(3)
+    out = np.empty_like(xyz)
+    lib().orc_undistort(_p(xyz), C.c_size_t(len(xyz)), _p(lv), _p(av), C.c_double(scan_duration), C.c_int(int(spinning_clockwise)), _p(out))
+    return out
+
+
 def num_threads() -> int:
     return int(lib().orc_num_threads())

@@ -603,6 +603,29 @@ def test_loop_closure_overlap_and_information_matrix(engine_factory):
         E.computeOverlappingClouds(eng, src, tgt, guess, 0.3, 0)
 
 
+def test_constant_velocity_deskew_matches_oracle(engine_factory):
+    """D1: undistortInputPointCloud on a full 64x1024 scan, float32 wire input, both spin directions."""
+    sc = synth.Scene(); poses = synth.loop_trajectory(8)
+    raw32 = np.ascontiguousarray(synth.lidar_scan(sc, poses[2], seed=2))
+    raw = raw32.astype(np.float64)
+    raw[0] = [3.0, 0.0, 1.0]                                   # azimuth exactly 0 -> phase 0 -> untouched
+    eng = engine_factory(lua_params())
+    lv, av = E.ConstantVelocityMotionCompensation.estimateLinearAndAngularVelocity(poses[0], poses[2], 0.2)
+    assert abs(np.linalg.norm(lv) - 5.0) < 0.1                 # the synthetic trajectory moves 0.5 m per 0.1 s scan
+    av = av + np.array([0.03, -0.02, 0.4])                     # some rotation too
+    for cw in (True, False):
+        mc = E.ConstantVelocityMotionCompensation(eng, isSpinningClockwise=cw, scanDuration=0.1)
+        out, _ = mc.undistortInputPointCloud(eng.cloud(raw), lv, av).download()
+        ref = O.undistort(raw, lv, av, 0.1, cw)
+        assert out.shape == ref.shape and np.abs(out - ref).max() < 1e-12     # libm (atan2, sincos) is the only difference
+        assert np.array_equal(out[0], raw[0])
+        assert 0.05 < np.abs(out - raw).max() < 10.0           # it actually moved points (translation + lever arm of the rotation)
+    zero = E.ConstantVelocityMotionCompensation(eng).undistortInputPointCloud(eng.cloud(raw), np.zeros(3), np.zeros(3)).download()[0]
+    assert np.array_equal(zero, raw)
+    with pytest.raises(RuntimeError):
+        E.ConstantVelocityMotionCompensation(eng, scanDuration=0.0)
+
+
 def _carving_case():
     """A three-scan oracle submap plus floating clutter in free space, and the next raw scan with its pose."""
     sc = synth.Scene(); poses = synth.loop_trajectory(600)

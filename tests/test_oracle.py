@@ -309,3 +309,22 @@ def test_overlap_and_information_matrix_vs_numpy():
             ref += np.outer(r, r)
     assert ok.sum() > 50 and np.abs(G - ref).max() < 1e-9 * np.abs(ref).max()
     assert np.array_equal(G, G.T) and G[3, 3] == G[4, 4] == G[5, 5] == float(ok.sum())
+
+
+def test_constant_velocity_deskew_vs_numpy():
+    """D1: undistortInputPointCloud restated vs scipy Rotation (Rz Ry Rx) and the phase convention."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-20, 20, (500, 3)); pts[0] = [3.0, 0.0, 1.0]; pts[1] = [-2.0, 0.0, 0.5]; pts[2] = [0.0, 0.0, 1.0]
+    lv = np.array([5.0, -0.4, 0.1]); av = np.array([0.02, -0.05, 0.8])
+    for cw in (True, False):
+        out = O.undistort(pts, lv, av, 0.1, cw)
+        ang = np.arctan2(pts[:, 1], pts[:, 0]); ang = np.where(ang < 0, ang + 2 * np.pi, ang)
+        phase = np.where(ang == 0.0, 0.0, 1.0 - ang / (2 * np.pi) if cw else ang / (2 * np.pi))
+        ref = np.empty_like(pts)
+        for i, (p, ph) in enumerate(zip(pts, phase)):
+            R = Rotation.from_euler("ZYX", (ph * 0.1 * av)[::-1]).as_matrix()      # Rz(yaw) Ry(pitch) Rx(roll)
+            ref[i] = R @ p + ph * 0.1 * lv
+        assert np.abs(out - ref).max() < 1e-12
+        assert np.array_equal(out[0], pts[0])                   # angle 0 -> phase 0 -> untouched
+    assert np.array_equal(O.undistort(pts, np.zeros(3), np.zeros(3)), pts)   # zero velocities: identity motion
