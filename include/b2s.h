@@ -194,6 +194,14 @@ int32_t b2s_information_matrix(b2s_handle* h, const b2s_cloud* source, const b2s
 /* F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert           src/Submap.cpp:77-92, src/Voxel.cpp:66-88 */
 int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                                 const b2s_cropper* dense_cropper);
+/* F2  VoxelHashMap<Voxel> query interface (include/open3d_slam/VoxelHashMap.hpp:104-158) on the dense map, batched over
+ *     the points of a device cloud:  hasVoxelContainingPoint / getVoxelContainingPointPtr -> counts[i] (0 = no voxel) and,
+ *     optionally, the aggregated position (AggregatedVoxel::getAggregatedPosition, src/Voxel.cpp:35-40) in means_xyz[3i..];
+ *     removeKey(getKey(p)) for every point; size(); clear().  Host arrays must hold `capacity` >= cloud size entries. */
+int32_t b2s_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* points, int32_t* counts, double* means_xyz, size_t capacity);
+int32_t b2s_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* points);
+int32_t b2s_dense_size(b2s_handle* h, const b2s_submap* sm, size_t* n_voxels);
+int32_t b2s_dense_clear(b2s_handle* h, b2s_submap* sm);
 /* Submap::getMapPointCloud (copy-out)                                       src/Submap.cpp:184-191 */
 int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n);
 int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, size_t capacity, size_t* n);

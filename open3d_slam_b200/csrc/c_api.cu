@@ -502,6 +502,47 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   return check_status(h);
 }
 
+int32_t b2s_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* points, int32_t* counts, double* means_xyz, size_t capacity) {
+  B2S_REQUIRE(h && sm && points && counts, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  size_t n = 0;
+  B2S_TRY(cloud_count_sync(h, points, &n));
+  B2S_REQUIRE(n <= capacity, B2S_E_CAPACITY, "output arrays hold %zu entries, the cloud has %zu points", capacity, n);
+  if (n == 0) return B2S_OK;
+  B2S_TRY(h->tmp_i32.ensure((n + 64) * 4, h->stream));
+  if (means_xyz) B2S_TRY(h->tmp_f64.ensure((n + 1) * 24, h->stream));
+  B2S_TRY(op_dense_query(h, sm, points, h->tmp_i32.as<int32_t>(), means_xyz ? h->tmp_f64.as<double>() : nullptr));
+  B2S_CUDA(cudaMemcpyAsync(counts, h->tmp_i32.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (means_xyz) B2S_CUDA(cudaMemcpyAsync(means_xyz, h->tmp_f64.p, n * 24, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int32_t b2s_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* points) {
+  B2S_REQUIRE(h && sm && points, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  return op_dense_remove(h, sm, points);
+}
+
+int32_t b2s_dense_size(b2s_handle* h, const b2s_submap* sm, size_t* n_voxels) {
+  B2S_REQUIRE(h && sm && n_voxels, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  int32_t* d = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 12);
+  B2S_TRY(op_dense_count(h, sm, d));
+  B2S_TRY(ensure_pinned(h, 4096));
+  int32_t* pr = reinterpret_cast<int32_t*>(static_cast<char*>(h->pinned) + 768);
+  B2S_CUDA(cudaMemcpyAsync(pr, d, 4, cudaMemcpyDeviceToHost, h->stream));
+  const int32_t rc = check_status(h);
+  *n_voxels = (size_t)*pr;
+  return rc;
+}
+
+int32_t b2s_dense_clear(b2s_handle* h, b2s_submap* sm) {
+  B2S_REQUIRE(h && sm, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  if (sm->dense_cap == 0) return B2S_OK;
+  return dense_init(h, sm, sm->dense_cap, sm->dense_voxel);
+}
+
 int32_t b2s_undistort(b2s_handle* h, const b2s_cloud* in, const double lin_vel[3], const double ang_vel_rpy[3], double scan_duration,
                       int32_t clockwise, b2s_cloud* out) {
   B2S_REQUIRE(h && in && out && lin_vel && ang_vel_rpy && in != out, B2S_E_INVALID, "bad argument");

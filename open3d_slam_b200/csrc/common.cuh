@@ -255,6 +255,10 @@ constexpr int EST_INFORMATION = 3;   // internal estimator code: a single evalua
 int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
 
 int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev);
+// F2 VoxelHashMap queries on the dense map (fuse.cu)
+int32_t op_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* pts, int32_t* count_dev, double* mean_dev);
+int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts);
+int32_t op_dense_count(b2s_handle* h, const b2s_submap* sm, int32_t* out_dev);
 // D1 constant-velocity de-skew (voxel.cu)
 int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, const double* ang_vel_rpy, double scan_duration, int clockwise,
                      b2s_cloud* out);

@@ -379,4 +379,88 @@ int32_t dense_to_cloud(b2s_handle* h, b2s_submap* sm, double* d_xyz, int32_t* d_
   return B2S_OK;
 }
 
+// =====================================================================================================================
+//  F2  VoxelHashMap query API on the dense map (core/include/open3d_slam/VoxelHashMap.hpp:104-158), batched:
+//      hasVoxelContainingPoint / getVoxelContainingPointPtr (-> aggregated content), removeKey(getKey(p)), size, clear.
+//  A removed voxel keeps its key in the table with count 0 (= absent for every reader); inserting into it again simply
+//  re-populates the slot, so no tombstone handling is needed.
+// =====================================================================================================================
+__device__ __forceinline__ long long dense_find(const unsigned long long* __restrict__ keys, size_t cap, double x, double y, double z, double inv) {
+  const double fx = floor(__dmul_rn(x, inv)), fy = floor(__dmul_rn(y, inv)), fz = floor(__dmul_rn(z, inv));   // getVoxelIdx(p, inverseVoxelSize_)
+  if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) return -1;
+  const unsigned long long key = dense_pack((int)fx, (int)fy, (int)fz);
+  size_t slot = (size_t)(dense_hash(key) % cap);
+  for (size_t probe = 0; probe < cap; ++probe) {
+    const unsigned long long k = keys[slot];
+    if (k == DENSE_EMPTY) return -1;
+    if (k == key) return (long long)slot;
+    slot = slot + 1 == cap ? 0 : slot + 1;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(FZ_THREADS) dense_query_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double inv,
+                                                                 const unsigned long long* __restrict__ keys, const double* __restrict__ sums,
+                                                                 const int32_t* __restrict__ cnts, size_t cap, int32_t* __restrict__ count_out,
+                                                                 double* __restrict__ mean_out) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const long long s = dense_find(keys, cap, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], inv);
+    const int c = s >= 0 ? cnts[s] : 0;
+    count_out[i] = c;
+    if (mean_out) {
+      const double cd = (double)c;
+      for (int k = 0; k < 3; k++) mean_out[3 * i + k] = c > 0 ? sums[6 * s + k] / cd : 0.0;   // AggregatedVoxel::getAggregatedPosition
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FZ_THREADS) dense_remove_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double inv,
+                                                                  const unsigned long long* __restrict__ keys, double* __restrict__ sums,
+                                                                  int32_t* __restrict__ cnts, size_t cap) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const long long s = dense_find(keys, cap, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], inv);
+    if (s < 0) continue;
+    cnts[s] = 0;   // several points of the same voxel write the same zeros
+    for (int k = 0; k < 6; k++) sums[6 * s + k] = 0.0;
+  }
+}
+
+__global__ void dense_count_kernel(const int32_t* __restrict__ cnts, size_t cap, int32_t* out) {
+  int c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) c += cnts[i] > 0;
+  c = warp_sum_i(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int32_t op_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* pts, int32_t* count_dev, double* mean_dev) {
+  B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
+  dense_query_kernel<<<grid_for(pts->n_max > 0 ? pts->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+      pts->xyz.as<double>(), pts->dn.as<int32_t>(), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
+      sm->dense_cnt.as<int32_t>(), sm->dense_cap, count_dev, mean_dev);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts) {
+  B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
+  dense_remove_kernel<<<grid_for(pts->n_max > 0 ? pts->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+      pts->xyz.as<double>(), pts->dn.as<int32_t>(), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
+      sm->dense_cnt.as<int32_t>(), sm->dense_cap);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t op_dense_count(b2s_handle* h, const b2s_submap* sm, int32_t* out_dev) {
+  B2S_CUDA(cudaMemsetAsync(out_dev, 0, 4, h->stream));
+  if (sm->dense_cap == 0) return B2S_OK;
+  dense_count_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_cnt.as<int32_t>(), sm->dense_cap, out_dev);
+  h->launches++;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
 }  // namespace b2s

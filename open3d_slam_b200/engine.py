@@ -477,6 +477,27 @@ class Submap:
                                                   C.c_size_t(capacity), C.byref(m)))
         return xyz[:m.value].copy(), keys[:m.value].copy()
 
+    # ---- VoxelHashMap query interface on the dense map (include/open3d_slam/VoxelHashMap.hpp:104-158), batched ----
+    def denseQuery(self, points: Cloud, with_means: bool = True):
+        """hasVoxelContainingPoint / getVoxelContainingPointPtr for every point: (counts, aggregated positions or None)."""
+        n = len(points)
+        counts = np.zeros(n, dtype=np.int32); means = np.zeros((n, 3)) if with_means else None
+        L.check(L.lib().b2s_dense_query(self.eng._h, self._s, points._c, counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        _pd(means) if with_means else None, C.c_size_t(n)))
+        return counts, means
+
+    def denseRemove(self, points: Cloud) -> None:
+        """removeKey(getKey(p)) for every point."""
+        L.check(L.lib().b2s_dense_remove(self.eng._h, self._s, points._c))
+
+    def denseSize(self) -> int:
+        n = C.c_size_t()
+        L.check(L.lib().b2s_dense_size(self.eng._h, self._s, C.byref(n)))
+        return int(n.value)
+
+    def denseClear(self) -> None:
+        L.check(L.lib().b2s_dense_clear(self.eng._h, self._s))
+
     def setMapPointCloud(self, cloud: Cloud):
         L.check(L.lib().b2s_submap_set_cloud(self.eng._h, self._s, cloud._c))
 

@@ -699,3 +699,26 @@ def test_dense_map_running_sums(engine_factory):
     o1 = np.lexsort((gk[:, 2], gk[:, 1], gk[:, 0])); o2 = np.lexsort((rk[:, 2], rk[:, 1], rk[:, 0]))
     assert np.array_equal(gk[o1], rk[o2])
     assert np.abs(gx[o1] - rx[o2]).max() < 1e-12      # atomics change the summation order, not the members
+    # F2: the VoxelHashMap query interface, batched -- has / content / remove / size / clear against the oracle's voxel set
+    assert sm.denseSize() == len(rx)
+    table = {tuple(k): x for k, x in zip(rk, rx)}
+    rng = np.random.default_rng(9)
+    q = np.vstack([rx[::7] + rng.uniform(-0.02, 0.02, (len(rx[::7]), 3)), rng.uniform(-30, 30, (2000, 3))])
+    counts, means = sm.denseQuery(eng.cloud(q))
+    keys = np.floor(q * (1.0 / 0.05)).astype(np.int64)
+    has = np.array([tuple(k) in table for k in keys])
+    assert np.array_equal(counts > 0, has) and has.sum() > 1000 and (~has).sum() > 1000
+    exp = np.array([table[tuple(k)] if h else np.zeros(3) for k, h in zip(keys, has)])
+    assert np.abs(means - exp).max() < 1e-12
+    victims = q[has][::3]
+    sm.denseRemove(eng.cloud(victims))
+    gone = {tuple(k) for k in np.floor(victims * (1.0 / 0.05)).astype(np.int64)}
+    assert sm.denseSize() == len(rx) - len(gone)
+    counts2, _ = sm.denseQuery(eng.cloud(q), with_means=False)
+    assert np.array_equal(counts2 > 0, np.array([h and tuple(k) not in gone for k, h in zip(keys, has)]))
+    gx2, gk2 = sm.getDenseMap()
+    assert {tuple(k) for k in gk2} == set(table) - gone
+    sm.insertScanDenseMap(eng.cloud(raw), poses[2], cp.to_c())          # removed voxels can be populated again
+    assert sm.denseSize() > len(rx) - len(gone)
+    sm.denseClear()
+    assert sm.denseSize() == 0 and len(sm.getDenseMap()[0]) == 0
