@@ -54,8 +54,8 @@ static double nn_cell(const b2s_handle* h, double max_corr) {
 }
 
 static int32_t check_icp_params(const b2s_icp_params& p) {
-  B2S_REQUIRE(p.reg_type == B2S_REG_POINT_TO_PLANE || p.reg_type == B2S_REG_POINT_TO_POINT, B2S_E_UNSUPPORTED,
-              "PointToPlaneIcp and PointToPointIcp are implemented on the device; GeneralizedIcp is not");
+  B2S_REQUIRE(p.reg_type == B2S_REG_POINT_TO_PLANE || p.reg_type == B2S_REG_POINT_TO_POINT || p.reg_type == B2S_REG_GENERALIZED,
+              B2S_E_UNSUPPORTED, "unknown registration type %d", (int)p.reg_type);
   B2S_REQUIRE(p.max_corr_dist > 0.0, B2S_E_INVALID, "[RegistrationICP] Invalid max_correspondence_distance.");
   B2S_REQUIRE(p.max_iter >= 0, B2S_E_INVALID, "max_iter must be >= 0");
   return B2S_OK;
@@ -79,6 +79,8 @@ static void fill_problem(b2s_handle* h, IcpProblem* P, const b2s_cloud* src, con
   P->max_iter = h->cfg.icp.max_iter;
   P->src_n_max = (int32_t)src->n_max;
   P->estimator = h->cfg.icp.reg_type;
+  P->src_nrm = src->has_normals ? src->nrm.as<double>() : nullptr;
+  P->gicp_eps = 1e-3;   // TransformationEstimationForGeneralizedICP() default, the object the reference holds (CloudRegistration.hpp)
   P->out = out_dev;
 }
 
@@ -446,8 +448,10 @@ int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* ta
   B2S_REQUIRE(h && source && target && init && out, B2S_E_INVALID, "null argument");
   LOCK(h);
   B2S_TRY(check_icp_params(h->cfg.icp));
-  B2S_REQUIRE(target->has_normals || h->cfg.icp.reg_type != B2S_REG_POINT_TO_PLANE, B2S_E_NO_NORMALS,
+  B2S_REQUIRE(target->has_normals || h->cfg.icp.reg_type == B2S_REG_POINT_TO_POINT, B2S_E_NO_NORMALS,
               "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
+  B2S_REQUIRE(source->has_normals || h->cfg.icp.reg_type != B2S_REG_GENERALIZED, B2S_E_NO_NORMALS,
+              "GeneralizedIcp on the device derives the covariances from normals: call estimateNormalsOrCovariancesIfNeeded on both clouds");
   B2S_TRY(grid_build(h, &h->grid_a, target, nn_cell(h, h->cfg.icp.max_corr_dist), nullptr, true));
   B2S_TRY(h->work_xyz.ensure((source->n_max + 1) * 24, h->stream));
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
@@ -471,8 +475,9 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   size_t work_total = 0, max_src = 0;
   for (int i = 0; i < n; i++) {
     B2S_REQUIRE(sources[i] && targets[i], B2S_E_INVALID, "null cloud in batch");
-    B2S_REQUIRE(targets[i]->has_normals || h->cfg.icp.reg_type != B2S_REG_POINT_TO_PLANE, B2S_E_NO_NORMALS,
+    B2S_REQUIRE(targets[i]->has_normals || h->cfg.icp.reg_type == B2S_REG_POINT_TO_POINT, B2S_E_NO_NORMALS,
                 "[RegistrationICP] target %d has no normals", i);
+    B2S_REQUIRE(sources[i]->has_normals || h->cfg.icp.reg_type != B2S_REG_GENERALIZED, B2S_E_NO_NORMALS, "GeneralizedIcp: source %d has no normals", i);
     int gi = -1;
     for (size_t k = 0; k < seen.size(); k++) if (seen[k] == targets[i]) { gi = (int)k; break; }
     if (gi < 0) {
@@ -738,6 +743,7 @@ int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* clo
 static int32_t register_to_submap_async(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double* sensor_pose_host,
                                         const double* sensor_pose_dev, const double* init_host, const double* init_dev, b2s_result* out_dev) {
   B2S_TRY(check_icp_params(h->cfg.icp));
+  B2S_REQUIRE(scan->has_normals || h->cfg.icp.reg_type != B2S_REG_GENERALIZED, B2S_E_NO_NORMALS, "GeneralizedIcp: the scan has no normals");
   const b2s_cloud* map = sm->cloud[0];
   b2s_cropper c = h->cfg.scan.scan_matcher_cropper;  // ScanToMapRegistration.cpp:58 setPose(mapToRangeSensor)
   if (sensor_pose_host) { c.center[0] = sensor_pose_host[3]; c.center[1] = sensor_pose_host[7]; c.center[2] = sensor_pose_host[11]; }

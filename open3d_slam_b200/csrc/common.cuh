@@ -249,6 +249,8 @@ struct IcpProblem {
   int32_t pad;
   b2s_result* out;
   double* info_out;         // EST_INFORMATION: 36 doubles, row-major 6x6
+  const double* src_nrm;    // B2S_REG_GENERALIZED: source normals (3 x f64 per point, source order)
+  double gicp_eps;          // TransformationEstimationForGeneralizedICP::epsilon_ (1e-3)
 };
 constexpr int EST_INFORMATION = 3;   // internal estimator code: a single evaluation that outputs [O3D]'s information matrix
 // single_host != nullptr: one registration, the problem travels as a kernel argument (no copy, no sync)

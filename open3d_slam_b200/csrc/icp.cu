@@ -383,12 +383,89 @@ __device__ __forceinline__ void icp_accumulate(double (&acc)[NACC], const GridVi
   acc[28] += 1.0;
 }
 
+// ---- Generalized ICP ([O3D] pipelines/registration/GeneralizedICP.cpp) --------------------------------------------
+// covariance of a point from its normal: Rx diag(eps, 1, 1) Rx^T with Rx = GetRotationFromE1ToX(n) (identity when
+// e1 . n < -0.99), every product written out like the reference does
+__device__ __forceinline__ void gicp_cov_from_normal(double nx, double ny, double nz, double eps, double (&C)[9]) {
+  double Rx[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (!(nx < -0.99)) {
+    const double v1 = -nz, v2 = ny;                       // v = e1 x n = (0, -nz, ny)
+    const double sv[9] = {0, -v2, v1, v2, 0, -0.0, -v1, 0.0, 0};
+    const double f = 1 / (1 + nx);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const double sv2 = sv[3 * i] * sv[j] + sv[3 * i + 1] * sv[3 + j] + sv[3 * i + 2] * sv[6 + j];
+        Rx[3 * i + j] = (i == j ? 1.0 : 0.0) + sv[3 * i + j] + sv2 * f;
+      }
+  }
+  double t[9];   // Rx * D
+#pragma unroll
+  for (int i = 0; i < 3; i++) { t[3 * i] = Rx[3 * i] * eps; t[3 * i + 1] = Rx[3 * i + 1]; t[3 * i + 2] = Rx[3 * i + 2]; }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = t[3 * i] * Rx[3 * j] + t[3 * i + 1] * Rx[3 * j + 1] + t[3 * i + 2] * Rx[3 * j + 2];
+}
+
+// one correspondence of TransformationEstimationForGeneralizedICP: M = Ct + R Cs0 R^T, J = M^-1/2 [-skew(p) | I],
+// r = M^-1/2 (p - q); accumulated as J^T J = A^T M^-1 A and J^T r = A^T M^-1 d (the square root only appears squared)
+__device__ __forceinline__ void icp_accumulate_gicp(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz,
+                                                    const double* __restrict__ R, const double* __restrict__ sn, double eps) {
+  const double4 q = g.pts[slot];
+  const double4 nt = g.nrm[slot];
+  double Ct[9], Cs0[9], M[9];
+  gicp_cov_from_normal(nt.x, nt.y, nt.z, eps, Ct);
+  gicp_cov_from_normal(sn[0], sn[1], sn[2], eps, Cs0);
+  {
+    double t[9];   // R * Cs0, then (R Cs0) R^T   ([O3D] TransformCovariances)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) t[3 * i + j] = R[3 * i] * Cs0[j] + R[3 * i + 1] * Cs0[3 + j] + R[3 * i + 2] * Cs0[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) M[3 * i + j] = Ct[3 * i + j] + (t[3 * i] * R[3 * j] + t[3 * i + 1] * R[3 * j + 1] + t[3 * i + 2] * R[3 * j + 2]);
+  }
+  double Mi[9];
+  {
+    const double a = M[0], b = M[1], c = M[2], d = M[3], e = M[4], f = M[5], gg = M[6], h = M[7], i = M[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * gg) + c * (d * h - e * gg);
+    const double id = 1.0 / det;
+    Mi[0] = (e * i - f * h) * id; Mi[1] = (c * h - b * i) * id; Mi[2] = (b * f - c * e) * id;
+    Mi[3] = (f * gg - d * i) * id; Mi[4] = (a * i - c * gg) * id; Mi[5] = (c * d - a * f) * id;
+    Mi[6] = (d * h - e * gg) * id; Mi[7] = (b * gg - a * h) * id; Mi[8] = (a * e - b * d) * id;
+  }
+  const double dd[3] = {px - q.x, py - q.y, pz - q.z};
+  const double A[18] = {0, pz, -py, 1, 0, 0, -pz, 0, px, 0, 1, 0, py, -px, 0, 0, 0, 1};
+  double MA[18], Md[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) MA[6 * r + c] = Mi[3 * r] * A[c] + Mi[3 * r + 1] * A[6 + c] + Mi[3 * r + 2] * A[12 + c];
+    Md[r] = Mi[3 * r] * dd[0] + Mi[3 * r + 1] * dd[1] + Mi[3 * r + 2] * dd[2];
+  }
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) acc[k++] += A[a] * MA[b] + A[6 + a] * MA[6 + b] + A[12 + a] * MA[12 + b];
+#pragma unroll
+  for (int a = 0; a < 6; a++) acc[21 + a] += A[a] * Md[0] + A[6 + a] * Md[1] + A[12 + a] * Md[2];
+  acc[27] += d2;
+  acc[28] += 1.0;
+}
+
 // `single` carries the problem by value (kernel parameter space) for the one-registration calls, so that no
 // host->device copy -- and no implicit stream synchronisation of a pageable copy -- sits in front of the launch;
 // batches pass an array.  dbg (optional): clock64 stamps of problem 0 / CTA 0 per evaluation {start, search, reduce, solve}.
-__global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __grid_constant__ IcpProblem single,
-                                                                     const IcpProblem* __restrict__ problems, int smem_pts_cap,
-                                                                     long long* dbg) {
+// GICP = true compiles the generalized-ICP accumulation in (its register footprint would otherwise tax the other estimators)
+template <bool GICP>
+__global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_constant__ IcpProblem single,
+                                                             const IcpProblem* __restrict__ problems, int smem_pts_cap,
+                                                             long long* dbg) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const unsigned csize = cluster.num_blocks();
@@ -452,6 +529,14 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
     double U[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) U[i] = s_U[i];
+    double RT[9];   // GICP: rotation of the accumulated transformation = what [O3D] has applied to the source covariances so far
+    if (GICP) {
+      const bool moved = e > 0 || apply;   // identity init is not applied at all (isIdentity), like the covariance transform
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) RT[3 * i + j] = moved ? s_T[4 * i + j] : (i == j ? 1.0 : 0.0);
+    }
 
     double acc[NACC];
 #pragma unroll
@@ -483,7 +568,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
       }
       if (in_smem) s_prev[i] = st.bslot;
       if (done) {
-        if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else if (info) icp_accumulate_info(acc, g, st.bslot, st.best); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
+        if (st.bslot >= 0) {
+          if (GICP) icp_accumulate_gicp(acc, g, st.bslot, st.best, px, py, pz, RT, P.src_nrm + 3 * (size_t)(lo + i), P.gicp_eps);
+          else if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz);
+          else if (info) icp_accumulate_info(acc, g, st.bslot, st.best);
+          else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+        }
       } else {
         s_queue[atomicAdd(s_qn, 1)] = i;
       }
@@ -521,7 +611,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_p2plane_kernel(const __gri
         nn_phase2_warp(g, px, py, pz, st);
         if (lane == 0) {
           rp[i] = st.bslot;
-          if (st.bslot >= 0) { if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz); else if (info) icp_accumulate_info(acc, g, st.bslot, st.best); else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz); }
+          if (st.bslot >= 0) {
+            if (GICP) icp_accumulate_gicp(acc, g, st.bslot, st.best, px, py, pz, RT, P.src_nrm + 3 * (size_t)(min(r * chunk, n) + i), P.gicp_eps);
+            else if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz);
+            else if (info) icp_accumulate_info(acc, g, st.bslot, st.best);
+            else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+          }
         }
       }
     }
@@ -630,9 +725,11 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   memset(&single, 0, sizeof(single));
   if (single_host) { single = *single_host; problems_dev = nullptr; n_problems = 1; }
   if (!g_icp_attr_set) {
-    B2S_CUDA(cudaFuncSetAttribute(icp_p2plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
+    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
+    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
     g_icp_attr_set = true;
   }
+  const int estimator = single_host ? single_host->estimator : h->cfg.icp.reg_type;   // uniform over a batch
   int csize = 1;
   while (csize < 8 && (size_t)csize * ICP_THREADS * 2 < max_src_points) csize *= 2;
   const int fixed = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16 + 16;
@@ -665,7 +762,8 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(h, PK_ICP);
-  B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_p2plane_kernel, single, problems_dev, pts_cap, h->icp_dbg));
+  if (estimator == B2S_REG_GENERALIZED) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<true>, single, problems_dev, pts_cap, h->icp_dbg));
+  else B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<false>, single, problems_dev, pts_cap, h->icp_dbg));
   h->launches++;
   return B2S_OK;
 }

@@ -96,11 +96,12 @@ class MapperParameters:
     nnCellSize: float = 0.0  # engine knob: NN grid cell (0 = maxCorrespondenceDistance / 4)
 
     def to_config(self) -> L.Config:
-        if self.scanToMapRegType not in ("PointToPlaneIcp", "PointToPointIcp"):
-            raise L.B2SError(L.E_UNSUPPORTED, f"registration type {self.scanToMapRegType} is not implemented on the device")
+        types = {"PointToPlaneIcp": L.REG_POINT_TO_PLANE, "PointToPointIcp": L.REG_POINT_TO_POINT, "GeneralizedIcp": L.REG_GENERALIZED}
+        if self.scanToMapRegType not in types:   # Parameters.hpp:37-49 ; unknown -> the factories throw
+            raise L.B2SError(L.E_UNSUPPORTED, f"unknown registration type {self.scanToMapRegType}")
         cfg = L.Config()
         L.lib().b2s_default_config(C.byref(cfg))
-        cfg.icp.reg_type = L.REG_POINT_TO_PLANE if self.scanToMapRegType == "PointToPlaneIcp" else L.REG_POINT_TO_POINT
+        cfg.icp.reg_type = types[self.scanToMapRegType]
         cfg.icp.max_iter = int(self.icp.maxNumIter)
         cfg.icp.max_corr_dist = float(self.icp.maxCorrespondenceDistance)
         cfg.icp.knn = int(self.icp.knn)
@@ -402,6 +403,13 @@ class RegistrationIcpPointToPoint(RegistrationIcpPointToPlane):
         return None
 
 
+class RegistrationIcpGeneralized(RegistrationIcpPointToPlane):
+    """src/CloudRegistration.cpp:15-38: [O3D] RegistrationGeneralizedICP.  estimateNormalsOrCovariancesIfNeeded estimates
+    NORMALS exactly like the point-to-plane class (the reference's EstimateCovariances call is commented out, :29), and [O3D]
+    derives the per-point covariances from them -- so both clouds must carry normals."""
+    _regType = "GeneralizedIcp"
+
+
 def cloudRegistrationFactory(eng: Engine, p: CloudRegistrationParameters) -> CloudRegistration:
     """src/CloudRegistration.cpp:85-100"""
     if p.regType == "PointToPlaneIcp":
@@ -409,7 +417,7 @@ def cloudRegistrationFactory(eng: Engine, p: CloudRegistrationParameters) -> Clo
     if p.regType == "PointToPointIcp":
         return RegistrationIcpPointToPoint(eng, p)
     if p.regType == "GeneralizedIcp":
-        raise L.B2SError(L.E_UNSUPPORTED, f"{p.regType} is not implemented on the device (SURVEY.md 8f rank 3)")
+        return RegistrationIcpGeneralized(eng, p)
     raise RuntimeError("cloud: unknown type of cloud registration")
 
 

@@ -225,3 +225,65 @@ def icp_p2point(src, tgt, r, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=
         if abs(bfit - fit) < rel_fitness and abs(brmse - rmse) < rel_rmse:
             break
     return T, fit, rmse, int(ok.sum()), iters
+
+
+def gicp_covariances_from_normals(nrm, eps=1e-3):
+    """[O3D] InitializePointCloudForGeneralizedICP, normals branch: Rx diag(eps,1,1) Rx^T with Rx = GetRotationFromE1ToX(n)."""
+    out = np.empty((len(nrm), 3, 3))
+    for i, x in enumerate(nrm):
+        e1 = np.array([1.0, 0.0, 0.0])
+        v = np.cross(e1, x); c = float(e1 @ x)
+        if c < -0.99:
+            Rx = np.eye(3)
+        else:
+            sv = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+            Rx = np.eye(3) + sv + (sv @ sv) * (1.0 / (1.0 + c))
+        out[i] = Rx @ np.diag([eps, 1.0, 1.0]) @ Rx.T
+    return out
+
+
+def icp_gicp(src, src_nrm, tgt, tgt_nrm, r, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6, eps=1e-3):
+    """[O3D] RegistrationGeneralizedICP, written with the matrix square root W = (Ct + Cs)^-1/2 exactly as
+    TransformationEstimationForGeneralizedICP::ComputeTransformation states it (rows of W [-skew(vs) | I], W d)."""
+    T = np.eye(4) if init is None else np.array(init, dtype=np.float64)
+    tree = cKDTree(tgt)
+    pcd = src.copy()
+    Cs = gicp_covariances_from_normals(src_nrm, eps); Ct = gicp_covariances_from_normals(tgt_nrm, eps)
+    if not np.allclose(T, np.eye(4), rtol=0, atol=1e-12):
+        pcd = pcd @ T[:3, :3].T + T[:3, 3]
+        Cs = T[:3, :3] @ Cs @ T[:3, :3].T
+
+    def evaluate(p):
+        d, j = tree.query(p, k=1)
+        d2 = ((p - tgt[np.minimum(j, len(tgt) - 1)]) ** 2).sum(axis=1)
+        ok = (j < len(tgt)) & (d2 < r * r)
+        n = int(ok.sum())
+        if n == 0:
+            return ok, j, 0.0, 0.0
+        return ok, j, n / len(p), float(np.sqrt(d2[ok].sum() / n))
+
+    ok, j, fit, rmse = evaluate(pcd)
+    iters = 0
+    for i in range(max_iter):
+        U = np.eye(4)
+        if ok.any():
+            JTJ = np.zeros((6, 6)); JTr = np.zeros(6)
+            for k in np.nonzero(ok)[0]:
+                vs = pcd[k]; vt = tgt[j[k]]
+                M = Ct[j[k]] + Cs[k]
+                w, V = np.linalg.eigh(np.linalg.inv(M))
+                W = V @ np.diag(np.sqrt(w)) @ V.T                      # symmetric positive definite square root
+                A = np.hstack([-np.array([[0, -vs[2], vs[1]], [vs[2], 0, -vs[0]], [-vs[1], vs[0], 0]]), np.eye(3)])
+                J = W @ A; res = W @ (vs - vt)
+                JTJ += J.T @ J; JTr += J.T @ res
+            x = np.linalg.solve(JTJ, -JTr)
+            U[:3, :3] = rot_zyx(x[0], x[1], x[2]); U[:3, 3] = x[3:]
+        T = U @ T
+        pcd = pcd @ U[:3, :3].T + U[:3, 3]
+        Cs = U[:3, :3] @ Cs @ U[:3, :3].T
+        bfit, brmse = fit, rmse
+        ok, j, fit, rmse = evaluate(pcd)
+        iters = i + 1
+        if abs(bfit - fit) < rel_fitness and abs(brmse - rmse) < rel_rmse:
+            break
+    return T, fit, rmse, int(ok.sum()), iters

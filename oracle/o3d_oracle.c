@@ -857,6 +857,125 @@ ORC_EXPORT int orc_registration_icp_p2point(const double* src_xyz, size_t n_src,
   return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/*  R1'' Generalized ICP ("next" row, SURVEY.md 8f rank 3, second half)          */
+/*      RegistrationIcpGeneralized::registerClouds  core/src/CloudRegistration.cpp:15-20 */
+/*      -> [O3D] RegistrationGeneralizedICP(source, target, r, init, TransformationEstimationForGeneralizedICP(eps = 1e-3)) */
+/*      pipelines/registration/GeneralizedICP.cpp: covariances from normals (GetRotationFromE1ToX),  */
+/*      per correspondence M = Ct + Cs, W = M^-1/2, rows of W [-skew(vs) | I] and W d, then the     */
+/*      same 6x6 solve / update / convergence loop as point-to-plane; the source covariances are   */
+/*      rotated with the cloud by every PointCloud::Transform.                                      */
+/* ------------------------------------------------------------------------- */
+static void mat3_mul(const double* A, const double* B, double* C) {
+  double t[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  memcpy(C, t, sizeof(t));
+}
+static void mat3_mul_bt(const double* A, const double* B, double* C) {   /* A * B^T */
+  double t[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1] + A[3 * i + 2] * B[3 * j + 2];
+  memcpy(C, t, sizeof(t));
+}
+/* [O3D] GetRotationFromE1ToX + Rx * diag(eps,1,1) * Rx^T, row-major 3x3 */
+ORC_EXPORT void orc_gicp_covariance_from_normal(const double* n, double eps, double* C) {
+  const double c = n[0];                                   /* e1 . x */
+  double Rx[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (!(c < -0.99)) {
+    const double v[3] = {0.0, -n[2], n[1]};                /* e1 x x */
+    const double sv[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+    double sv2[9]; mat3_mul(sv, sv, sv2);
+    const double factor = 1 / (1 + c);
+    for (int k = 0; k < 9; k++) Rx[k] = (k % 4 == 0 ? 1.0 : 0.0) + sv[k] + sv2[k] * factor;
+  }
+  const double D[9] = {eps, 0, 0, 0, 1, 0, 0, 0, 1};
+  double t[9]; mat3_mul(Rx, D, t); mat3_mul_bt(t, Rx, C);
+}
+static int inv3(const double* M, double* Mi) {
+  const double a = M[0], b = M[1], c = M[2], d = M[3], e = M[4], f = M[5], g = M[6], h = M[7], i = M[8];
+  const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  const double id = 1.0 / det;
+  Mi[0] = (e * i - f * h) * id; Mi[1] = (c * h - b * i) * id; Mi[2] = (b * f - c * e) * id;
+  Mi[3] = (f * g - d * i) * id; Mi[4] = (a * i - c * g) * id; Mi[5] = (c * d - a * f) * id;
+  Mi[6] = (d * h - e * g) * id; Mi[7] = (b * g - a * h) * id; Mi[8] = (a * e - b * d) * id;
+  return det != 0.0;
+}
+/* J^T J and J^T r of one correspondence with J = W A, r = W d, W = (Ct+Cs)^-1/2, A = [-skew(vs) | I]:
+ *   J^T J = A^T M^-1 A,  J^T r = A^T M^-1 d   (W only ever appears squared) */
+static void gicp_update(const double* src, const double* src_cov, const double* tgt, const double* tgt_cov, const int* corr, size_t n_src,
+                        double* update) {
+  double JTJ[36] = {0}, JTr[6] = {0};
+  size_t ncorr = 0;
+  for (size_t c0 = 0; c0 < n_src; c0 += 1024) {
+    double Acc[36] = {0}, g[6] = {0};
+    size_t c1 = c0 + 1024 < n_src ? c0 + 1024 : n_src;
+    for (size_t i = c0; i < c1; i++) {
+      int j = corr[i]; if (j < 0) continue;
+      ncorr++;
+      const double* vs = src + 3 * i; const double* vt = tgt + 3 * (size_t)j;
+      double M[9], Mi[9];
+      for (int k = 0; k < 9; k++) M[k] = tgt_cov[9 * (size_t)j + k] + src_cov[9 * i + k];
+      inv3(M, Mi);
+      const double d[3] = {vs[0] - vt[0], vs[1] - vt[1], vs[2] - vt[2]};
+      /* A (3x6) = [-skew(vs) | I] */
+      const double A[18] = {0, vs[2], -vs[1], 1, 0, 0, -vs[2], 0, vs[0], 0, 1, 0, vs[1], -vs[0], 0, 0, 0, 1};
+      double MA[18];                                       /* M^-1 A */
+      for (int r = 0; r < 3; r++) for (int q = 0; q < 6; q++) MA[6 * r + q] = Mi[3 * r] * A[q] + Mi[3 * r + 1] * A[6 + q] + Mi[3 * r + 2] * A[12 + q];
+      const double Md[3] = {Mi[0] * d[0] + Mi[1] * d[1] + Mi[2] * d[2], Mi[3] * d[0] + Mi[4] * d[1] + Mi[5] * d[2], Mi[6] * d[0] + Mi[7] * d[1] + Mi[8] * d[2]};
+      for (int a = 0; a < 6; a++) {
+        for (int b = 0; b < 6; b++) Acc[6 * a + b] += A[a] * MA[b] + A[6 + a] * MA[6 + b] + A[12 + a] * MA[12 + b];
+        g[a] += A[a] * Md[0] + A[6 + a] * Md[1] + A[12 + a] * Md[2];
+      }
+    }
+    for (int a = 0; a < 36; a++) JTJ[a] += Acc[a];
+    for (int a = 0; a < 6; a++) JTr[a] += g[a];
+  }
+  if (ncorr == 0) { mat4_identity(update); return; }
+  double nb[6], x[6];
+  for (int a = 0; a < 6; a++) nb[a] = -JTr[a];
+  orc_ldlt6_solve(JTJ, nb, x);
+  orc_vec6_to_mat4(x, update);
+}
+static void transform_covariances(const double* T, double* cov, size_t n) {   /* [O3D] TransformCovariances: R C R^T */
+  const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  for (size_t i = 0; i < n; i++) { double t[9]; mat3_mul(R, cov + 9 * i, t); mat3_mul_bt(t, R, cov + 9 * i); }
+}
+
+ORC_EXPORT int orc_registration_gicp(const double* src_xyz, const double* src_nrm, size_t n_src, const double* tgt_xyz, const double* tgt_nrm,
+                                     size_t n_tgt, double max_corr_dist, const double* init, int max_iter, double rel_fitness, double rel_rmse,
+                                     double epsilon, orc_icp_result* out) {
+  if (max_corr_dist <= 0.0) return -1;
+  if (!src_nrm || !tgt_nrm) return -2;   /* this restatement covers the normals -> covariances branch the reference takes */
+  double T[16]; memcpy(T, init, sizeof(T));
+  double* sc = (double*)malloc(72 * (n_src ? n_src : 1));
+  double* tc = (double*)malloc(72 * (n_tgt ? n_tgt : 1));
+  for (size_t i = 0; i < n_src; i++) orc_gicp_covariance_from_normal(src_nrm + 3 * i, epsilon, sc + 9 * i);
+  for (size_t j = 0; j < n_tgt; j++) orc_gicp_covariance_from_normal(tgt_nrm + 3 * j, epsilon, tc + 9 * j);
+  kd_tree* t = kd_build(tgt_xyz, (int)n_tgt);
+  double* pcd = (double*)malloc(24 * (n_src ? n_src : 1));
+  memcpy(pcd, src_xyz, 24 * n_src);
+  if (!mat4_is_identity(init)) { transform_points(init, pcd, n_src); transform_covariances(init, sc, n_src); }
+  int* corr = (int*)malloc(sizeof(int) * (n_src ? n_src : 1));
+  double* d2 = (double*)malloc(sizeof(double) * (n_src ? n_src : 1));
+  double fit, rmse; int nc;
+  icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+  int it = 0;
+  for (int i = 0; i < max_iter; i++) {
+    double upd[16];
+    gicp_update(pcd, sc, tgt_xyz, tc, corr, n_src, upd);
+    mat4_mul(upd, T, T);
+    transform_points(upd, pcd, n_src);
+    transform_covariances(upd, sc, n_src);
+    double bfit = fit, brmse = rmse;
+    icp_correspondences(t, pcd, n_src, max_corr_dist, corr, d2, &fit, &rmse, &nc);
+    it = i + 1;
+    if (fabs(bfit - fit) < rel_fitness && fabs(brmse - rmse) < rel_rmse) break;
+  }
+  memcpy(out->T, T, sizeof(T));
+  out->fitness = fit; out->inlier_rmse = rmse; out->n_corr = nc; out->iters = it;
+  free(pcd); free(corr); free(d2); free(sc); free(tc); kd_free(t);
+  return 0;
+}
+
 /* Brute-force single evaluation (for cross-checking the tree): fitness/rmse/JTJ/JTr at transform T */
 ORC_EXPORT void orc_icp_evaluate_bruteforce(const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_nrm,
                                             size_t n_tgt, double r, const double* T, double* fitness, double* rmse,

@@ -171,6 +171,24 @@ def svd3(A):
     return U, S, V
 
 
+def registration_gicp(src, src_nrm, tgt, tgt_nrm, max_corr_dist, init=None, max_iter=30, rel_fitness=1e-6, rel_rmse=1e-6, epsilon=1e-3) -> IcpResult:
+    """RegistrationIcpGeneralized::registerClouds (core/src/CloudRegistration.cpp:15-20) for clouds that carry normals."""
+    src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); src_nrm = _f64(src_nrm).reshape(-1, 3); tgt_nrm = _f64(tgt_nrm).reshape(-1, 3)
+    init = np.eye(4) if init is None else _f64(init).reshape(4, 4)
+    res = IcpResultC()
+    rc = lib().orc_registration_gicp(_p(src), _p(src_nrm), C.c_size_t(len(src)), _p(tgt), _p(tgt_nrm), C.c_size_t(len(tgt)), C.c_double(max_corr_dist),
+                                     _p(init), C.c_int(max_iter), C.c_double(rel_fitness), C.c_double(rel_rmse), C.c_double(epsilon), C.byref(res))
+    if rc != 0:
+        raise RuntimeError(f"orc_registration_gicp failed: {rc}")
+    return IcpResult(np.array(res.T).reshape(4, 4), res.fitness, res.inlier_rmse, res.n_corr, res.iters, None)
+
+
+def gicp_covariance_from_normal(n, epsilon=1e-3):
+    n = _f64(n).reshape(3); Cm = np.empty((3, 3))
+    lib().orc_gicp_covariance_from_normal(_p(n), C.c_double(epsilon), _p(Cm))
+    return Cm
+
+
 def icp_evaluate_bruteforce(src, tgt, tgt_nrm, r, T):
     src = _f64(src).reshape(-1, 3); tgt = _f64(tgt).reshape(-1, 3); tgt_nrm = _f64(tgt_nrm).reshape(-1, 3)
     T = _f64(T).reshape(4, 4)

@@ -130,6 +130,29 @@ RegistrationResult RegistrationIcpPointToPointB200::registerClouds(const PointCl
   return toResult(r);
 }
 
+RegistrationIcpGeneralizedB200::RegistrationIcpGeneralizedB200(const CloudRegistrationParameters& p) : cfg_(b2sConfigFrom(p.icp_, nullptr, nullptr)) {
+  cfg_.icp.reg_type = B2S_REG_GENERALIZED;
+}
+
+RegistrationResult RegistrationIcpGeneralizedB200::registerClouds(const PointCloud& source, const PointCloud& target, const Transform& init) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  DeviceCloud ds(h, source, true), dt(h, target, true);   // both with normals: the covariances are derived from them on the device
+  double T0[16];
+  toRowMajor(init.matrix(), T0);
+  b2s_result r;
+  int32_t rc = b2s_register(h, ds.c, dt.c, T0, &r);
+  if (rc != B2S_OK) b2sThrow(rc);
+  return toResult(r);
+}
+
+void RegistrationIcpGeneralizedB200::estimateNormalsOrCovariancesIfNeeded(PointCloud* cloud) const {
+  b2s_handle* h = b2sThreadHandle(cfg_);
+  DeviceCloud d(h, *cloud, false);
+  int32_t rc = b2s_estimate_normals(h, d.c, cfg_.icp.knn, cfg_.icp.knn_radius);   // src/CloudRegistration.cpp:21-30
+  if (rc != B2S_OK) b2sThrow(rc);
+  cloud->normals_ = d.download()->normals_;
+}
+
 void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, const Transform& cropperPose, const MapBuilderParameters& p,
                PointCloud* map) {
   if (map->points_.empty()) return;   // Submap.cpp:111

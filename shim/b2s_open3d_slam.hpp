@@ -44,6 +44,18 @@ class RegistrationIcpPointToPointB200 : public CloudRegistration {
   b2s_config cfg_;
 };
 
+// RegistrationIcpGeneralized (src/CloudRegistration.cpp:15-38) on the device: covariances from the normals the reference's own
+// estimateNormalsOrCovariancesIfNeeded leaves on the clouds ([O3D] InitializePointCloudForGeneralizedICP, normals branch)
+class RegistrationIcpGeneralizedB200 : public CloudRegistration {
+ public:
+  explicit RegistrationIcpGeneralizedB200(const CloudRegistrationParameters& p);
+  RegistrationResult registerClouds(const PointCloud& source, const PointCloud& target, const Transform& init) const final;
+  void estimateNormalsOrCovariancesIfNeeded(PointCloud* cloud) const final;
+
+ private:
+  b2s_config cfg_;
+};
+
 // Submap::carve for the sparse map (src/Submap.cpp:109-123): removes the carved points from *map in place.  cropperPose is
 // the pose mapBuilderCropper_ currently holds (the previous insertion); the caller keeps the every-N-scans schedule.
 void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, const Transform& cropperPose, const MapBuilderParameters& p,

@@ -521,6 +521,41 @@ def test_point_to_point_icp_matches_oracle(engine_factory):
     assert ei.value.code == L.E_NO_NORMALS
 
 
+def test_generalized_icp_matches_oracle(engine_factory):
+    """R1'' (second half): RegistrationIcpGeneralized -- [O3D] RegistrationGeneralizedICP with the
+    covariances derived from the normals (what the reference's estimateNormalsOrCovariancesIfNeeded leaves on the clouds)."""
+    src, tgt, nrm, T_true = synth.planar_cloud_config1(noise=0.01)
+    snrm = O.estimate_normals(src, 10, 2.0)
+    p = lua_params()
+    p.icp.maxCorrespondenceDistance = 1.0
+    p.icp.maxNumIter = 30
+    eng = engine_factory(p)
+    reg = E.cloudRegistrationFactory(eng, E.CloudRegistrationParameters(regType="GeneralizedIcp", icp=p.icp))
+    assert isinstance(reg, E.RegistrationIcpGeneralized)
+    tcloud = eng.cloud(tgt, nrm)
+    for init in (np.eye(4), synth.se3(0.01, -0.02, 0.03, (0.05, 0.02, -0.01))):
+        res = reg.registerClouds(eng.cloud(src, snrm), tcloud, init)
+        ref = O.registration_gicp(src, snrm, tgt, nrm, 1.0, init, max_iter=30)
+        assert res.iters == ref.iters and res.n_corr == ref.n_corr
+        assert abs(res.fitness_ - ref.fitness) < 1e-12 and abs(res.inlier_rmse_ - ref.inlier_rmse) < 1e-9
+        assert rel_rot(res.transformation_, ref.T) < 1e-8 and rel_trans(res.transformation_, ref.T) < 1e-8
+    # a scan against a submap-sized target, batched with the small pair, iteration cap 6
+    sc = synth.Scene(); poses = synth.loop_trajectory(600)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0)
+    (mx, mn), _ = O.process_scan(synth.lidar_scan(sc, poses[0], seed=0), wide, wide, 0.1, 20, 3.0, 1.0, 0)
+    _, (sx, sn) = O.process_scan(synth.lidar_scan(sc, poses[1], seed=1), wide, wide, 0.1, 20, 3.0, 0.3, 7)
+    init1 = np.linalg.inv(poses[0]) @ poses[1] @ synth.se3(0.0, 0.0, np.deg2rad(1.0), (0.1, -0.05, 0.0))
+    reg.max_iteration_ = 6
+    batch = reg.registerCloudsBatch([eng.cloud(src, snrm), eng.cloud(sx, sn)], [tcloud, eng.cloud(mx, mn)], [np.eye(4), init1])
+    refs = [O.registration_gicp(src, snrm, tgt, nrm, 1.0, np.eye(4), max_iter=6), O.registration_gicp(sx, sn, mx, mn, 1.0, init1, max_iter=6)]
+    for b, ref in zip(batch, refs):
+        assert b.iters == ref.iters and b.n_corr == ref.n_corr
+        assert rel_rot(b.transformation_, ref.T) < 1e-8 and rel_trans(b.transformation_, ref.T) < 1e-8
+    with pytest.raises(L.B2SError) as ei:                       # covariances come from normals: both clouds need them
+        reg.registerClouds(eng.cloud(src), tcloud, np.eye(4))
+    assert ei.value.code == L.E_NO_NORMALS
+
+
 def test_edge_cases_empty_inputs_and_capacity(engine_factory):
     """Empty and overflowing inputs: the reference's asserts become error codes, everything else degrades like [O3D]."""
     src, tgt, nrm, _ = synth.planar_cloud_config1()

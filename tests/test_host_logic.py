@@ -29,14 +29,14 @@ def test_parameter_mapping():
 
 def test_factories_mirror_the_reference_errors():
     p = E.MapperParameters()
-    p.scanToMapRegType = "GeneralizedIcp"
+    p.scanToMapRegType = "NoSuchIcp"
     with pytest.raises(L.B2SError) as ei:
         p.to_config()
     assert ei.value.code == L.E_UNSUPPORTED
+    p.scanToMapRegType = "GeneralizedIcp"
+    assert p.to_config().icp.reg_type == L.REG_GENERALIZED
     with pytest.raises(RuntimeError):
         E.cloudRegistrationFactory(None, E.CloudRegistrationParameters(regType="NoSuchIcp"))
-    with pytest.raises(L.B2SError):
-        E.cloudRegistrationFactory(None, E.CloudRegistrationParameters(regType="GeneralizedIcp"))
     p.scanToMapRegType = "PointToPointIcp"
     assert p.to_config().icp.reg_type == L.REG_POINT_TO_POINT
 

@@ -328,3 +328,27 @@ def test_constant_velocity_deskew_vs_numpy():
         assert np.abs(out - ref).max() < 1e-12
         assert np.array_equal(out[0], pts[0])                   # angle 0 -> phase 0 -> untouched
     assert np.array_equal(O.undistort(pts, np.zeros(3), np.zeros(3)), pts)   # zero velocities: identity motion
+
+
+def test_generalized_icp_c_vs_numpy():
+    """R1'' (SURVEY 8f rank 3): orc_registration_gicp (J^T J = A^T M^-1 A) against the numpy restatement that forms
+    W = (Ct + Cs)^-1/2 explicitly like [O3D] does, and the covariance-from-normal construction."""
+    rng = np.random.default_rng(8)
+    for k in range(20):
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        if k == 0:
+            n = np.array([-1.0, 0.0, 0.0])                      # the c < -0.99 branch: Rx = I
+        if k == 1:
+            n = np.array([-0.995, 0.0998749, 0.0])
+        Cm = O.gicp_covariance_from_normal(n)
+        assert np.abs(Cm - NP.gicp_covariances_from_normals(n[None])[0]).max() < 1e-15
+        if n[0] >= -0.99:                                        # proper rotation: I - (1 - eps) n n^T
+            assert np.abs(Cm - (np.eye(3) - (1 - 1e-3) * np.outer(n, n))).max() < 1e-12
+    src, tgt, nrm, T_true = synth.planar_cloud_config1(n=600, noise=0.01)
+    snrm = O.estimate_normals(src, 10, 2.0)
+    for init in (np.eye(4), synth.se3(0.01, 0.0, -0.01, (0.02, 0.0, 0.01))):
+        rc = O.registration_gicp(src, snrm, tgt, nrm, 1.0, init, max_iter=30)
+        T2, f2, e2, n2, i2 = NP.icp_gicp(src, snrm, tgt, nrm, 1.0, init, max_iter=30)
+        assert rc.iters == i2 and rc.n_corr == n2
+        assert np.abs(rc.T - T2).max() < 1e-9 and abs(rc.inlier_rmse - e2) < 1e-10
+        assert np.linalg.norm(rc.T[:3, 3] - np.linalg.inv(T_true)[:3, 3]) < 0.02
