@@ -63,7 +63,8 @@ typedef struct b2s_cropper {
   double center[3];
 } b2s_cropper;
 
-/* CloudRegistrationType (Parameters.hpp:37).  Only point-to-plane is implemented in this round. */
+/* CloudRegistrationType (Parameters.hpp:37).  All three estimators run on the device; GeneralizedIcp derives the per-point
+ * covariances from the clouds' normals like [O3D] does when no covariances are present. */
 enum { B2S_REG_POINT_TO_PLANE = 0, B2S_REG_POINT_TO_POINT = 1, B2S_REG_GENERALIZED = 2 };
 
 /* IcpParameters + ICPConvergenceCriteria (Parameters.hpp:66-71; src/CloudRegistration.cpp:58-66; [O3D] defaults
@@ -174,6 +175,7 @@ typedef struct b2s_carving_params {     /* SpaceCarvingParameters, include/open3
   double max_raytracing_length;         /* maxRaytracingLength_ = 20.0 */
   double truncation_distance;           /* truncationDistance_ = 0.1 */
   double min_dot_product_with_normal;   /* minDotProductWithNormal_ = 0.5 */
+  double neighborhood_radius_dense_map; /* neighborhoodRadiusDenseMap_ = 0.1 (dense map only) */
 } b2s_carving_params;
 int32_t b2s_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                          const double cropper_pose[16], const b2s_carving_params* params, size_t* n_removed);
@@ -191,6 +193,12 @@ int32_t b2s_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* tar
                     int32_t min_points_per_voxel, b2s_cloud* source_overlap, b2s_cloud* target_overlap);
 int32_t b2s_information_matrix(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, double max_correspondence_distance,
                                const double transformation[16], double info_out[36]);
+/* C2  Submap::carve of the DENSE map   src/Submap.cpp:86-89,125-136, src/helpers.cpp:347-377, src/VoxelHashMap.cpp:13-45,
+ *     src/Voxel.cpp:162-192.  `scan` is used in the frame the caller hands over (the reference passes the raw scan together with
+ *     the map-frame sensor position); the every-N-scans schedule stays with the caller.  Uses voxel = dense_voxel_size,
+ *     neighborhood_radius_dense_map, truncation_distance, max_raytracing_length.  n_removed may be NULL (no synchronisation). */
+int32_t b2s_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double sensor_position[3],
+                        const b2s_carving_params* params, size_t* n_removed);
 /* F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert           src/Submap.cpp:77-92, src/Voxel.cpp:66-88 */
 int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double map_to_sensor[16],
                                 const b2s_cropper* dense_cropper);

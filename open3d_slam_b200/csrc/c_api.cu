@@ -507,6 +507,21 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
   return check_status(h);
 }
 
+int32_t b2s_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double sensor[3], const b2s_carving_params* prm, size_t* n_removed) {
+  B2S_REQUIRE(h && sm && scan && sensor && prm, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  if (sm->dense_cap == 0) { if (n_removed) *n_removed = 0; return B2S_OK; }   // cloud->empty(): nothing to carve (Submap.cpp:127)
+  int32_t* removed_dev = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 8);
+  B2S_TRY(op_dense_carve(h, sm, scan, sensor, prm->neighborhood_radius_dense_map, prm->truncation_distance, prm->max_raytracing_length, removed_dev));
+  if (!n_removed) return B2S_OK;
+  B2S_TRY(ensure_pinned(h, 4096));
+  int32_t* pr = reinterpret_cast<int32_t*>(static_cast<char*>(h->pinned) + 512);
+  B2S_CUDA(cudaMemcpyAsync(pr, removed_dev, 4, cudaMemcpyDeviceToHost, h->stream));
+  const int32_t rc = check_status(h);
+  *n_removed = (size_t)*pr;
+  return rc;
+}
+
 int32_t b2s_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* points, int32_t* counts, double* means_xyz, size_t capacity) {
   B2S_REQUIRE(h && sm && points && counts, B2S_E_INVALID, "null argument");
   LOCK(h);

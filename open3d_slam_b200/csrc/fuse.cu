@@ -463,4 +463,136 @@ int32_t op_dense_count(b2s_handle* h, const b2s_submap* sm, int32_t* out_dev) {
   return B2S_OK;
 }
 
+// =====================================================================================================================
+//  C2  space carving of the dense map: Submap::carve(scan, sensorPosition, param, VoxelizedPointCloud*)
+//      core/src/Submap.cpp:125-136 -> removeDuplicatePointsWithinSameVoxels (core/src/Voxel.cpp:162-192),
+//      getKeysOfCarvedPoints (core/src/helpers.cpp:347-377), getVoxelsWithinPointNeighborhood (core/src/VoxelHashMap.cpp:13-45)
+//  (1) first point of every voxel of the scan = the ray set (atomicMin of the index per voxel of a scratch hash);
+//  (2) one thread per ray: steps of 2*radius, at every step the reference's dx/dy/dz loops (floating accumulation kept as
+//      written) enumerate test points; a test point within `radius` of its voxel centre nominates that voxel; nominated
+//      voxels that exist in the dense map are flagged; (3) flagged voxels are emptied (removeKey).
+// =====================================================================================================================
+__device__ __forceinline__ long long dense_find_key(const unsigned long long* __restrict__ keys, size_t cap, int kx, int ky, int kz) {
+  if (!(abs(kx) < 1048575 && abs(ky) < 1048575 && abs(kz) < 1048575)) return -1;
+  const unsigned long long key = dense_pack(kx, ky, kz);
+  size_t slot = (size_t)(dense_hash(key) % cap);
+  for (size_t probe = 0; probe < cap; ++probe) {
+    const unsigned long long k = keys[slot];
+    if (k == DENSE_EMPTY) return -1;
+    if (k == key) return (long long)slot;
+    slot = slot + 1 == cap ? 0 : slot + 1;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(FZ_THREADS) dcarve_first_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double inv,
+                                                                  unsigned long long* keys, int32_t* first, size_t mask,
+                                                                  int32_t* __restrict__ slot_of) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double fx = floor(__dmul_rn(xyz[3 * i], inv)), fy = floor(__dmul_rn(xyz[3 * i + 1], inv)), fz = floor(__dmul_rn(xyz[3 * i + 2], inv));
+    slot_of[i] = -1;
+    if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) continue;   // NaN / far away: never a ray
+    const unsigned long long key = dense_pack((int)fx, (int)fy, (int)fz);
+    size_t s = (size_t)dense_hash(key) & mask;
+    for (size_t probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
+      const unsigned long long old = atomicCAS(&keys[s], DENSE_EMPTY, key);
+      if (old == DENSE_EMPTY || old == key) { atomicMin(&first[s], i); slot_of[i] = (int32_t)s; break; }
+    }
+  }
+}
+
+__global__ void dcarve_init_kernel(unsigned long long* keys, int32_t* first, size_t cap, int32_t* rm, size_t dense_cap) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) { keys[i] = DENSE_EMPTY; first[i] = 0x7fffffff; }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dense_cap; i += (size_t)gridDim.x * blockDim.x) rm[i] = 0;
+}
+
+__global__ void __launch_bounds__(FZ_THREADS) dcarve_march_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
+                                                                  const int32_t* __restrict__ slot_of, const int32_t* __restrict__ first,
+                                                                  double sx, double sy, double sz, double voxel, double radius, double trunc,
+                                                                  double max_len, const unsigned long long* __restrict__ dkeys,
+                                                                  const int32_t* __restrict__ dcnt, size_t dcap, int32_t* __restrict__ rm) {
+  const int n = *d_n;
+  const double step = 2.0 * radius;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int so = slot_of[i];
+    if (so < 0 || first[so] != i) continue;       // removeDuplicatePointsWithinSameVoxels keeps the first point of a voxel
+    const double dx = xyz[3 * i] - sx, dy = xyz[3 * i + 1] - sy, dz = xyz[3 * i + 2] - sz;
+    const double length = sqrt(dx * dx + dy * dy + dz * dz);
+    const double ux = dx / length, uy = dy / length, uz = dz / length;
+    double mp = length - trunc;
+    if (max_len < mp) mp = max_len;
+    if (step > mp) mp = step;
+    if (!(mp == mp)) continue;
+    double distance = 0.0;
+    while (distance < mp) {
+      const double cx = distance * ux + sx, cy = distance * uy + sy, cz = distance * uz + sz;
+      const int ckx = (int)floor(cx / voxel), cky = (int)floor(cy / voxel), ckz = (int)floor(cz / voxel);
+      bool center_added = false;
+      if (radius > 0.0) {
+        for (double ox = -radius; ox <= radius; ox += voxel)
+          for (double oy = -radius; oy <= radius; oy += voxel)
+            for (double oz = -radius; oz <= radius; oz += voxel) {
+              const double tx = cx + ox, ty = cy + oy, tz = cz + oz;
+              const int kx = (int)floor(tx / voxel), ky = (int)floor(ty / voxel), kz = (int)floor(tz / voxel);
+              const double ex = tx - ((double)kx * voxel + voxel * 0.5), ey = ty - ((double)ky * voxel + voxel * 0.5),
+                           ez = tz - ((double)kz * voxel + voxel * 0.5);
+              if (sqrt(ex * ex + ey * ey + ez * ez) <= radius) {
+                const long long s = dense_find_key(dkeys, dcap, kx, ky, kz);
+                if (s >= 0 && dcnt[s] > 0) rm[s] = 1;
+                if (kx == ckx && ky == cky && kz == ckz) center_added = true;
+              }
+            }
+      }
+      if (!center_added) {
+        const long long s = dense_find_key(dkeys, dcap, ckx, cky, ckz);
+        if (s >= 0 && dcnt[s] > 0) rm[s] = 1;
+      }
+      distance += step;
+    }
+  }
+}
+
+__global__ void dcarve_apply_kernel(const int32_t* __restrict__ rm, size_t cap, double* __restrict__ sums, int32_t* __restrict__ cnts, int32_t* removed) {
+  int c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    if (!rm[i]) continue;
+    cnts[i] = 0;
+    for (int k = 0; k < 6; k++) sums[6 * i + k] = 0.0;
+    c++;
+  }
+  c = warp_sum_i(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(removed, c);
+}
+
+int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* sensor, double radius, double trunc, double max_len,
+                       int32_t* removed_dev) {
+  B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
+  const size_t n_max = scan->n_max > 0 ? scan->n_max : 1;
+  size_t cap = 1024;
+  while (cap < 2 * n_max) cap <<= 1;
+  B2S_TRY(h->keys.ensure(cap * 8, h->stream));
+  B2S_TRY(h->vals.ensure(cap * 4, h->stream));
+  B2S_TRY(h->tmp_i32.ensure((n_max + 64) * 4, h->stream));
+  B2S_TRY(h->offs.ensure((sm->dense_cap + 2) * 4, h->stream));   // removal flags per dense slot
+  unsigned long long* keys = h->keys.as<unsigned long long>();
+  int32_t* first = h->vals.as<int32_t>();
+  int32_t* slot_of = h->tmp_i32.as<int32_t>();
+  int32_t* rm = h->offs.as<int32_t>();
+  const double voxel = sm->dense_voxel;
+  ProfScope prof(h, PK_FUSE);
+  B2S_CUDA(cudaMemsetAsync(removed_dev, 0, 4, h->stream));
+  dcarve_init_kernel<<<148 * 8, 256, 0, h->stream>>>(keys, first, cap, rm, sm->dense_cap);
+  dcarve_first_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), 1.0 / voxel, keys, first,
+                                                                                cap - 1, slot_of);
+  dcarve_march_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), slot_of, first, sensor[0],
+                                                                                sensor[1], sensor[2], voxel, radius, trunc, max_len,
+                                                                                sm->dense_keys.as<unsigned long long>(), sm->dense_cnt.as<int32_t>(),
+                                                                                sm->dense_cap, rm);
+  dcarve_apply_kernel<<<148 * 8, 256, 0, h->stream>>>(rm, sm->dense_cap, sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), removed_dev);
+  h->launches += 4;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
 }  // namespace b2s

@@ -64,9 +64,11 @@ class SpaceCarvingParameters:
     truncationDistance: float = 0.1
     carveSpaceEveryNscans: int = 10
     minDotProductWithNormal: float = 0.5
+    neighborhoodRadiusDenseMap: float = 0.1
 
     def to_c(self) -> L.CarvingParams:
-        return L.CarvingParams(self.voxelSize, self.maxRaytracingLength, self.truncationDistance, self.minDotProductWithNormal)
+        return L.CarvingParams(self.voxelSize, self.maxRaytracingLength, self.truncationDistance, self.minDotProductWithNormal,
+                               self.neighborhoodRadiusDenseMap)
 
 
 @dataclass
@@ -435,6 +437,7 @@ class Submap:
         L.check(L.lib().b2s_submap_create(eng._h, C.c_size_t(capacity_points), C.byref(self._s)))
         self.capacity = capacity_points
         self.nScansInsertedMap_ = 0
+        self.nScansInsertedDenseMap_ = 0
         self._cropperPose = np.eye(4)   # mapBuilderCropper_'s pose: set AFTER each insertion (Submap.cpp:71), Identity before the first
         self.lastCarvedCount = 0
 
@@ -468,10 +471,22 @@ class Submap:
         self.lastCarvedCount = int(n.value)
         return self.lastCarvedCount
 
-    def insertScanDenseMap(self, rawScan: Cloud, mapToRangeSensor, denseCropper: L.Cropper | None = None) -> bool:
+    def insertScanDenseMap(self, rawScan: Cloud, mapToRangeSensor, denseCropper: L.Cropper | None = None, isPerformCarving: bool = False,
+                           carving: "SpaceCarvingParameters | None" = None) -> bool:
         T = _mat(mapToRangeSensor)
         L.check(L.lib().b2s_submap_insert_dense(self.eng._h, self._s, rawScan._c, _pd(T), C.byref(denseCropper) if denseCropper else None))
+        if isPerformCarving:   # Submap.cpp:86-89: after the insertion, with the raw scan and the map-frame sensor position
+            prm = carving or self.eng.params.mapBuilder.carving
+            if self.nScansInsertedDenseMap_ % prm.carveSpaceEveryNscans == 1:
+                self.carveDenseMap(rawScan, T[:3, 3], prm)
+        self.nScansInsertedDenseMap_ += 1
         return True
+
+    def carveDenseMap(self, scan: Cloud, sensorPosition, params: "SpaceCarvingParameters") -> int:
+        """Submap::carve(scan, sensorPosition, param, &denseMap_) (src/Submap.cpp:125-136), unconditionally."""
+        s = np.ascontiguousarray(np.asarray(sensorPosition, dtype=np.float64).reshape(3)); prm = params.to_c(); n = C.c_size_t()
+        L.check(L.lib().b2s_dense_carve(self.eng._h, self._s, scan._c, _pd(s), C.byref(prm), C.byref(n)))
+        return int(n.value)
 
     def getMapPointCloud(self):
         n = self.size()

@@ -1183,6 +1183,74 @@ ORC_EXPORT size_t orc_dense_to_cloud(void* p, double* out_xyz, double* out_nrm, 
   return m;
 }
 
+/* C2  space carving of the DENSE map ("next" row, SURVEY.md 8f rank 1, second half)
+ *     Submap::carve(scan, sensorPosition, param, VoxelizedPointCloud*)  core/src/Submap.cpp:125-136
+ *     removeDuplicatePointsWithinSameVoxels  core/src/Voxel.cpp:162-192 ; getKeysOfCarvedPoints  core/src/helpers.cpp:347-377
+ *     getVoxelsWithinPointNeighborhood  core/src/VoxelHashMap.cpp:13-45 (keys by DIVISION: getVoxelIdx(p, voxelSize))
+ *     `scan` is used in whatever frame the caller hands over (the reference passes the raw scan with the map-frame
+ *     sensor position, core/src/Submap.cpp:88).  Returns the number of voxels removed. */
+ORC_EXPORT size_t orc_dense_carve(void* pd, const double* scan, size_t n, const double* sensor, double voxel, double radius,
+                                  double truncation, double max_len) {
+  orc_dense* d = (orc_dense*)pd;
+  /* removeDuplicatePointsWithinSameVoxels: the first point of every voxel (key by multiplication with 1/voxel) */
+  vhash seen; vh_init(&seen, n);
+  uint8_t* first = (uint8_t*)calloc(n ? n : 1, 1);
+  const double inv = 1.0 / voxel;
+  for (size_t i = 0; i < n; i++) {
+    int is_new = 0;
+    vh_get(&seen, (int32_t)floor(scan[3 * i] * inv), (int32_t)floor(scan[3 * i + 1] * inv), (int32_t)floor(scan[3 * i + 2] * inv), 1, &is_new);
+    first[i] = (uint8_t)is_new;
+  }
+  vh_free(&seen);
+  uint8_t* rm = (uint8_t*)calloc(d->h.cnt ? d->h.cnt : 1, 1);
+  const double step = 2.0 * radius;
+  for (size_t i = 0; i < n; i++) {
+    if (!first[i]) continue;
+    const double* p = scan + 3 * i;
+    const double dx = p[0] - sensor[0], dy = p[1] - sensor[1], dz = p[2] - sensor[2];
+    const double length = sqrt(dx * dx + dy * dy + dz * dz);
+    const double dir[3] = {dx / length, dy / length, dz / length};
+    double mp = length - truncation;
+    if (max_len < mp) mp = max_len;
+    if (step > mp) mp = step;
+    if (!(mp == mp)) continue;
+    double distance = 0.0;
+    while (distance < mp) {
+      const double c[3] = {distance * dir[0] + sensor[0], distance * dir[1] + sensor[1], distance * dir[2] + sensor[2]};
+      const int32_t ck[3] = {(int32_t)floor(c[0] / voxel), (int32_t)floor(c[1] / voxel), (int32_t)floor(c[2] / voxel)};
+      int center_added = 0;
+      if (radius <= 0.0) {
+        int32_t s0 = vh_get(&d->h, ck[0], ck[1], ck[2], 0, NULL);
+        if (s0 >= 0 && d->cnt[s0] > 0) rm[s0] = 1;
+        center_added = 1;
+      } else {
+        for (double ox = -radius; ox <= radius; ox += voxel)
+          for (double oy = -radius; oy <= radius; oy += voxel)
+            for (double oz = -radius; oz <= radius; oz += voxel) {
+              const double t[3] = {c[0] + ox, c[1] + oy, c[2] + oz};
+              const int32_t k[3] = {(int32_t)floor(t[0] / voxel), (int32_t)floor(t[1] / voxel), (int32_t)floor(t[2] / voxel)};
+              const double e[3] = {t[0] - ((double)k[0] * voxel + voxel * 0.5), t[1] - ((double)k[1] * voxel + voxel * 0.5),
+                                   t[2] - ((double)k[2] * voxel + voxel * 0.5)};
+              if (sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) <= radius) {
+                int32_t s0 = vh_get(&d->h, k[0], k[1], k[2], 0, NULL);
+                if (s0 >= 0 && d->cnt[s0] > 0) rm[s0] = 1;
+                if (k[0] == ck[0] && k[1] == ck[1] && k[2] == ck[2]) center_added = 1;
+              }
+            }
+      }
+      if (!center_added) {
+        int32_t s0 = vh_get(&d->h, ck[0], ck[1], ck[2], 0, NULL);
+        if (s0 >= 0 && d->cnt[s0] > 0) rm[s0] = 1;
+      }
+      distance += step;
+    }
+  }
+  size_t removed = 0;
+  for (size_t s0 = 0; s0 < d->h.cnt; s0++) if (rm[s0]) { d->cnt[s0] = 0; for (int k = 0; k < 6; k++) d->sum[6 * s0 + k] = 0.0; removed++; }   /* removeKey */
+  free(first); free(rm);
+  return removed;
+}
+
 /* ------------------------------------------------------------------------- */
 /*  S1  ScanToMapIcp::preprocess + processForScanMatchingAndMerging            */
 /*      core/src/ScanToMapRegistration.cpp:35-54 (also Odometry.cpp:25-30)     */

@@ -260,6 +260,13 @@ class DenseMap:
         if lib().orc_dense_insert(self._h, _p(xyz), _p(nrm), C.c_size_t(len(xyz))) != 0:
             raise RuntimeError("dense map capacity exceeded")
 
+    def carve(self, scan, sensor, voxel, radius=0.1, truncation=0.1, max_len=20.0) -> int:
+        """Submap::carve on the dense map (core/src/Submap.cpp:125-136): returns the number of removed voxels."""
+        scan = _f64(scan).reshape(-1, 3); s = _f64(sensor).reshape(3)
+        lib().orc_dense_carve.restype = C.c_size_t
+        return int(lib().orc_dense_carve(self._h, _p(scan), C.c_size_t(len(scan)), _p(s), C.c_double(voxel), C.c_double(radius),
+                                         C.c_double(truncation), C.c_double(max_len)))
+
     def to_cloud(self):
         ox = np.empty((self._cap, 3)); on = np.empty((self._cap, 3)); keys = np.empty((self._cap, 3), dtype=np.int32)
         m = lib().orc_dense_to_cloud(self._h, _p(ox), _p(on), _p(keys))

@@ -168,7 +168,7 @@ void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, con
   toRowMajor(mapToRangeSensor.matrix(), Ts);
   toRowMajor(cropperPose.matrix(), Tc);
   const b2s_carving_params prm = {p.carving_.voxelSize_, p.carving_.maxRaytracingLength_, p.carving_.truncationDistance_,
-                                  p.carving_.minDotProductWithNormal_};
+                                  p.carving_.minDotProductWithNormal_, p.carving_.neighborhoodRadiusDenseMap_};
   size_t removed = 0;
   if (rc == B2S_OK) rc = b2s_submap_carve(h, sm, raw.c, Ts, Tc, &prm, &removed);
   size_t n = 0;

@@ -638,6 +638,37 @@ def test_loop_closure_overlap_and_information_matrix(engine_factory):
         E.computeOverlappingClouds(eng, src, tgt, guess, 0.3, 0)
 
 
+def test_dense_map_carving_matches_oracle(engine_factory):
+    """C2: Submap::carve on the dense map -- first-point-per-voxel ray set, neighbourhood enumeration with the reference's
+    floating loops, removal of every nominated voxel that exists.  Same surviving voxel set and sums as the oracle."""
+    p = lua_params()
+    eng = engine_factory(p)
+    sc = synth.Scene(); poses = synth.loop_trajectory(8)
+    sm = E.Submap(eng, 10_000)
+    dm = O.DenseMap(0.05, 1 << 21)
+    cp = E.ScanCroppingParameters("MaxRadius", 0.0, 15.0)
+    for k in range(2):
+        raw = synth.lidar_scan(sc, poses[k], seed=k).astype(np.float64)
+        sm.insertScanDenseMap(eng.cloud(raw), poses[k], cp.to_c())
+        kept, _ = O.crop(O.cropper("MaxRadius", 0.0, 15.0), raw)
+        dm.insert(O.transform(poses[k], kept)[0])
+    clutter = np.random.default_rng(1).uniform([-4, -4, -1], [4, 4, 1], (3000, 3))
+    Tc = synth.se3(0.0, 0.0, 0.2, (0.5, -0.3, 0.1))                  # floating clutter in free space, to be carved
+    sm.insertScanDenseMap(eng.cloud(clutter), Tc, None)
+    dm.insert(O.transform(Tc, clutter)[0])
+    n0 = sm.denseSize()
+    raw = synth.lidar_scan(sc, poses[2], seed=2).astype(np.float64)[::4]
+    scan = raw @ poses[2][:3, :3].T + poses[2][:3, 3]
+    prm = E.SpaceCarvingParameters(maxRaytracingLength=20.0, truncationDistance=0.3, neighborhoodRadiusDenseMap=0.1)
+    removed = sm.carveDenseMap(eng.cloud(scan), poses[2][:3, 3], prm)
+    ref_removed = dm.carve(scan, poses[2][:3, 3], 0.05, 0.1, 0.3, 20.0)
+    assert removed == ref_removed and 0 < removed < n0
+    gx, gk = sm.getDenseMap(); rx, _rn, rk = dm.to_cloud()
+    o1 = np.lexsort((gk[:, 2], gk[:, 1], gk[:, 0])); o2 = np.lexsort((rk[:, 2], rk[:, 1], rk[:, 0]))
+    assert np.array_equal(gk[o1], rk[o2]) and np.abs(gx[o1] - rx[o2]).max() < 1e-12
+    assert sm.denseSize() == n0 - removed
+
+
 def test_constant_velocity_deskew_matches_oracle(engine_factory):
     """D1: undistortInputPointCloud on a full 64x1024 scan, float32 wire input, both spin directions."""
     sc = synth.Scene(); poses = synth.loop_trajectory(8)

@@ -352,3 +352,51 @@ def test_generalized_icp_c_vs_numpy():
         assert rc.iters == i2 and rc.n_corr == n2
         assert np.abs(rc.T - T2).max() < 1e-9 and abs(rc.inlier_rmse - e2) < 1e-10
         assert np.linalg.norm(rc.T[:3, 3] - np.linalg.inv(T_true)[:3, 3]) < 0.02
+
+
+def test_dense_map_carving_vs_python_restatement():
+    """C2: orc_dense_carve against a literal Python transcription of getKeysOfCarvedPoints / getVoxelsWithinPointNeighborhood."""
+    import math
+    rng = np.random.default_rng(13)
+    voxel, radius, trunc, maxlen = 0.05, 0.1, 0.15, 3.0
+    pts = rng.uniform(-1.5, 1.5, (6000, 3))
+    dm = O.DenseMap(voxel, 1 << 16); dm.insert(pts)
+    sensor = np.array([0.1, -0.05, 0.02])
+    scan = rng.normal(size=(40, 3)); scan = scan / np.linalg.norm(scan, axis=1)[:, None] * rng.uniform(0.5, 2.5, (40, 1)) + sensor
+    scan = np.vstack([scan, scan[:5] + 1e-4])                  # same voxel as an earlier point: dropped by the de-duplication
+    present = {tuple(k) for k in dm.to_cloud()[2]}
+    inv = 1.0 / voxel
+    seen, rays = set(), []
+    for p in scan:
+        k = tuple(math.floor(v * inv) for v in p)
+        if k not in seen:
+            seen.add(k); rays.append(p)
+    remove = set()
+    step = 2.0 * radius
+    for p in rays:
+        d = p - sensor; length = math.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); u = d / length
+        mp = max(step, min(length - trunc, maxlen)); dist = 0.0
+        while dist < mp:
+            c = dist * u + sensor
+            ck = tuple(math.floor(v / voxel) for v in c); added = False
+            ox = -radius
+            while ox <= radius:
+                oy = -radius
+                while oy <= radius:
+                    oz = -radius
+                    while oz <= radius:
+                        t = c + np.array([ox, oy, oz]); k = tuple(math.floor(v / voxel) for v in t)
+                        e = t - (np.array(k, dtype=np.float64) * voxel + voxel * 0.5)
+                        if math.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) <= radius:
+                            if k in present:
+                                remove.add(k)
+                            added = added or k == ck
+                        oz += voxel
+                    oy += voxel
+                ox += voxel
+            if not added and ck in present:
+                remove.add(ck)
+            dist += step
+    n = dm.carve(scan, sensor, voxel, radius, trunc, maxlen)
+    assert n == len(remove) and 0 < n < len(present)
+    assert {tuple(k) for k in dm.to_cloud()[2]} == present - remove
