@@ -577,6 +577,8 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
   __shared__ int s_i[NK_THREADS / 32][NS2_CAP];
   __shared__ int s_s[NK_THREADS / 32][NS2_CAP];
   __shared__ int s_hist[NK_THREADS / 32][32];
+  __shared__ int s_ra[NK_THREADS / 32][64];   // first slot of every (y, z) row of the current block ((2*3+1)^2 = 49 rows at most)
+  __shared__ int s_rp[NK_THREADS / 32][65];   // exclusive prefix of the row sizes
   if (threadIdx.x == 0) g = *hdr;
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -630,33 +632,44 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       const double b2 = bound == INFINITY ? INFINITY : bound * bound;
       const double lim2 = fmin(r2, b2);   // candidates beyond the guaranteed ball cannot be certified at this R: drop them
       int nc = 0;
-      for (int t0 = 0; t0 < side * side; t0 += 32) {
+      // rows of the block -> (first slot, exclusive prefix of the row sizes) in shared memory; the candidates are then
+      // walked as ONE flat sequence, 32 per step, so that short rows (a handful of points each) do not leave lanes idle
+      int total = 0;
+      const int nrows = (side * side + 31) & ~31;
+      for (int t0 = 0; t0 < nrows; t0 += 32) {
         int a = 0, b = 0;
         const int t = t0 + lane;
         if (t < side * side) {
           const int z = cz - R + t / side, y = cy - R + t % side;
           if (z >= 0 && z < nz && y >= 0 && y < ny) { const int row = (z * ny + y) * nx; a = cs[row + x0]; b = cs[row + x1 + 1]; }
         }
-        unsigned rows = __ballot_sync(0xffffffffu, b > a);
-        while (rows) {
-          const int src_lane = __ffs(rows) - 1;
-          rows &= rows - 1;
-          const int ra = __shfl_sync(0xffffffffu, a, src_lane), rb = __shfl_sync(0xffffffffu, b, src_lane);
-          for (int j0 = ra; j0 < rb; j0 += 32) {
-            const int j = j0 + lane;
-            double dd = INFINITY; int ii = 0x7fffffff;
-            if (j < rb) {
-              const double4 p = pts[j];
-              dd = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-              ii = (int)__double_as_longlong(p.w);
-            }
-            const bool ok = j < rb && dd < lim2;
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const int pos = nc + __popc(m & lt_mask);
-            if (ok && pos < NS2_CAP) { s_d[wib][pos] = dd; s_i[wib][pos] = ii; s_s[wib][pos] = j; }
-            nc += __popc(m);
-          }
+        const int cnt = b - a;
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        s_ra[wib][t] = a;
+        s_rp[wib][t] = total + inc - cnt;
+        total += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) s_rp[wib][nrows] = total;
+      __syncwarp();
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        double dd = INFINITY; int ii = 0x7fffffff, j = -1;
+        if (t < total) {
+          int lo = 0, hi = nrows;   // first index whose prefix exceeds t; s_rp[nrows] = total > t
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_rp[wib][mid] > t) hi = mid; else lo = mid + 1; }
+          const int r = lo - 1;
+          j = s_ra[wib][r] + (t - s_rp[wib][r]);
+          const double4 p = pts[j];
+          dd = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+          ii = (int)__double_as_longlong(p.w);
         }
+        const bool ok = j >= 0 && dd < lim2;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int pos = nc + __popc(m & lt_mask);
+        if (ok && pos < NS2_CAP) { s_d[wib][pos] = dd; s_i[wib][pos] = ii; s_s[wib][pos] = j; }
+        nc += __popc(m);
       }
       __syncwarp();
       if (nc > NS2_CAP) { if (lane == 0) atomicAdd(queue_n + 2, 1); break; }   // too dense for the buffer: general kernel
