@@ -461,8 +461,9 @@ __device__ __forceinline__ void icp_accumulate_gicp(double (&acc)[NACC], const G
 // `single` carries the problem by value (kernel parameter space) for the one-registration calls, so that no
 // host->device copy -- and no implicit stream synchronisation of a pageable copy -- sits in front of the launch;
 // batches pass an array.  dbg (optional): clock64 stamps of problem 0 / CTA 0 per evaluation {start, search, reduce, solve}.
-// GICP = true compiles the generalized-ICP accumulation in (its register footprint would otherwise tax the other estimators)
-template <bool GICP>
+// MODE selects what is compiled in, so that the headline point-to-plane path carries no code (registers, stack) of the others:
+//   0 = point-to-plane only, 1 = point-to-point + information matrix (+ plane), 2 = generalized ICP
+template <int MODE>
 __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_constant__ IcpProblem single,
                                                              const IcpProblem* __restrict__ problems, int smem_pts_cap,
                                                              long long* dbg) {
@@ -517,8 +518,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   g.nrm = reinterpret_cast<const double4*>(P.tgt_nrm);
   const double r2 = P.max_corr * P.max_corr;
   const int max_iter = P.max_iter;
-  const bool p2p = P.estimator == B2S_REG_POINT_TO_POINT;
-  const bool info = P.estimator == EST_INFORMATION;   // one evaluation, output = 6x6 information matrix
+  constexpr bool GICP = MODE == 2;
+  const bool p2p = MODE == 1 && P.estimator == B2S_REG_POINT_TO_POINT;
+  const bool info = MODE == 1 && P.estimator == EST_INFORMATION;   // one evaluation, output = 6x6 information matrix
 
   for (int e = 0;; ++e) {
     if (dbg_on && e < 64) dbg[4 * e] = clock64();
@@ -725,8 +727,9 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   memset(&single, 0, sizeof(single));
   if (single_host) { single = *single_host; problems_dev = nullptr; n_problems = 1; }
   if (!g_icp_attr_set) {
-    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
-    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
+    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
+    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
+    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
     g_icp_attr_set = true;
   }
   const int estimator = single_host ? single_host->estimator : h->cfg.icp.reg_type;   // uniform over a batch
@@ -762,8 +765,9 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ProfScope prof(h, PK_ICP);
-  if (estimator == B2S_REG_GENERALIZED) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<true>, single, problems_dev, pts_cap, h->icp_dbg));
-  else B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<false>, single, problems_dev, pts_cap, h->icp_dbg));
+  if (estimator == B2S_REG_GENERALIZED) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<2>, single, problems_dev, pts_cap, h->icp_dbg));
+  else if (estimator == B2S_REG_POINT_TO_PLANE) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<0>, single, problems_dev, pts_cap, h->icp_dbg));
+  else B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<1>, single, problems_dev, pts_cap, h->icp_dbg));
   h->launches++;
   return B2S_OK;
 }
