@@ -106,6 +106,21 @@ __device__ __forceinline__ void cell_of(const GridView& g, double qx, double qy,
   cz = (int)fmin(fmax(floor((qz - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
 }
 
+// every cell overlapping the box [q - rad, q + rad]: one contiguous slot range per (y, z) row
+__device__ __forceinline__ void nn_scan_box(const GridView& g, double qx, double qy, double qz, double rad, NNState& st) {
+  const int ix0 = (int)fmin(fmax(floor((qx - rad - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+  const int ix1 = (int)fmin(fmax(floor((qx + rad - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+  const int iy0 = (int)fmin(fmax(floor((qy - rad - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  const int iy1 = (int)fmin(fmax(floor((qy + rad - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
+  const int iz0 = (int)fmin(fmax(floor((qz - rad - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+  const int iz1 = (int)fmin(fmax(floor((qz + rad - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
+  for (int z = iz0; z <= iz1; ++z)
+    for (int y = iy0; y <= iy1; ++y) {
+      const int row = (z * g.ny + y) * g.nx;
+      nn_scan_range(g.pts, g.cs[row + ix0], g.cs[row + ix1 + 1], qx, qy, qz, st);
+    }
+}
+
 // phase 1 (one thread): BOX QUERY.  The previous iteration's neighbour (`hint`, -1 = none) is almost always still the
 // nearest or next to it, so the exact answer lies within its distance d_h of the query: scan exactly the cells that
 // overlap the box [q - d_h, q + d_h] (one contiguous slot range per (y, z) row) -- a handful of candidates, no ring
@@ -125,17 +140,17 @@ __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double q
   }
   const double radm = sqrt(rad2) * (1.0 + 1e-12) + 1e-300;
   if (radm > 2.0 * g.cell) return false;
-  const int ix0 = (int)fmin(fmax(floor((qx - radm - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
-  const int ix1 = (int)fmin(fmax(floor((qx + radm - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
-  const int iy0 = (int)fmin(fmax(floor((qy - radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
-  const int iy1 = (int)fmin(fmax(floor((qy + radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
-  const int iz0 = (int)fmin(fmax(floor((qz - radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
-  const int iz1 = (int)fmin(fmax(floor((qz + radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
-  for (int z = iz0; z <= iz1; ++z)
-    for (int y = iy0; y <= iy1; ++y) {
-      const int row = (z * g.ny + y) * g.nx;
-      nn_scan_range(g.pts, g.cs[row + ix0], g.cs[row + ix1 + 1], qx, qy, qz, st);
+  if (!seeded) {
+    // stage A: a half-cell box first (at most 2 x 2 x 2 cells instead of 3 x 3 x 3).  Every point within half a cell edge of
+    // the query lies inside it, so a hit at that distance is already exact -- which is the case for almost every inlier
+    // of the first evaluation, the one that has no neighbours to start from.
+    const double ra = 0.5 * g.cell;
+    if (ra * ra < rad2) {
+      nn_scan_box(g, qx, qy, qz, ra, st);
+      if (st.bslot >= 0 && st.best <= ra * ra) return true;
     }
+  }
+  nn_scan_box(g, qx, qy, qz, radm, st);   // cells seen in stage A are seen again: an equal candidate never replaces the best
   // seeded: every point at distance <= d_h was scanned.  unseeded: exact iff the best lies within the box radius.
   return seeded || (st.bslot >= 0 && st.best <= rad2);
 }

@@ -521,6 +521,29 @@ def test_point_to_point_icp_matches_oracle(engine_factory):
     assert ei.value.code == L.E_NO_NORMALS
 
 
+def test_icp_properties_permutation_and_rigid_invariance(engine_factory):
+    """SURVEY 8c test 7 on the device: the result does not depend on the order of the points (the grid index re-orders the
+    target, the cluster splits the source) and is covariant under a common rigid motion of source, target and guess."""
+    rng = np.random.default_rng(31)
+    src, tgt, nrm, _ = synth.planar_cloud_config1(noise=0.01)
+    p = lua_params()
+    p.icp.maxCorrespondenceDistance = 0.8
+    eng = engine_factory(p)
+    reg = E.RegistrationIcpPointToPlane(eng)
+    init = synth.se3(0.005, -0.01, 0.01, (0.02, 0.01, -0.01))
+    base = reg.registerClouds(eng.cloud(src), eng.cloud(tgt, nrm), init)
+    assert 0.0 <= base.fitness_ <= 1.0 and base.inlier_rmse_ <= 0.8
+    ps, pt = rng.permutation(len(src)), rng.permutation(len(tgt))
+    perm = reg.registerClouds(eng.cloud(src[ps]), eng.cloud(tgt[pt], nrm[pt]), init)
+    assert perm.iters == base.iters and perm.n_corr == base.n_corr
+    assert np.abs(perm.transformation_ - base.transformation_).max() < 1e-9
+    G = synth.se3(0.3, -0.2, 1.1, (4.0, -7.0, 2.5))                    # common rigid motion
+    R = G[:3, :3]
+    moved = reg.registerClouds(eng.cloud(src @ R.T + G[:3, 3]), eng.cloud(tgt @ R.T + G[:3, 3], nrm @ R.T), G @ init @ np.linalg.inv(G))
+    assert moved.n_corr == base.n_corr and abs(moved.inlier_rmse_ - base.inlier_rmse_) < 1e-9
+    assert np.abs(moved.transformation_ - G @ base.transformation_ @ np.linalg.inv(G)).max() < 1e-7
+
+
 def test_generalized_icp_matches_oracle(engine_factory):
     """R1'' (second half): RegistrationIcpGeneralized -- [O3D] RegistrationGeneralizedICP with the
     covariances derived from the normals (what the reference's estimateNormalsOrCovariancesIfNeeded leaves on the clouds)."""
