@@ -44,9 +44,30 @@ def main():
         raw = synth.lidar_scan(scene, poses[k], n_beams=16, n_az=512, seed=20 + k).astype(np.float64)
         (mx, mn), _ = O.process_scan(raw, wide, wide, 0.1, 20, 3.0, 1.0, 0)
         T = np.eye(4) if k == 0 else np.linalg.inv(poses[0]) @ poses[1]
-        map_x, map_n, keys = O.submap_insert_scan(map_x, map_n, mx, mn, T, 0.1, wide, return_keys=True)
+        c = O.cropper("MinMaxRadius", 2.0, 30.0, center=tuple(T[:3, 3]))   # mapBuilderCropper_->setPose(mapToRangeSensor), Submap.cpp:71
+        map_x, map_n, keys = O.submap_insert_scan(map_x, map_n, mx, mn, T, 0.1, c, return_keys=True)
     order = np.lexsort((map_x[:, 2], map_x[:, 1], map_x[:, 0], keys[:, 2], keys[:, 1], keys[:, 0]))
     np.savez_compressed(os.path.join(OUT, "fusion_two_scans.npz"), map_xyz=map_x[order], map_nrm=map_n[order], keys=keys[order])
+    # the "next" rows of SURVEY 8f on small inputs: point-to-point / generalized ICP on config 1, overlap + information
+    # matrix, sparse-map carving, de-skew (inputs are regenerated from seeds by the test; only the outputs are stored)
+    n = {}
+    src, tgt, nrm, _ = synth.planar_cloud_config1(n=800, noise=0.01)
+    snrm = O.estimate_normals(src, 10, 2.0)
+    init = synth.se3(0.01, -0.02, 0.03, (0.05, 0.02, -0.01))
+    r = O.registration_icp_p2point(src, tgt, 1.0, init, max_iter=50)
+    n["p2p_T"] = r.T; n["p2p_iters"] = r.iters; n["p2p_ncorr"] = r.n_corr; n["p2p_rmse"] = r.inlier_rmse
+    r = O.registration_gicp(src, snrm, tgt, nrm, 1.0, init, max_iter=30)
+    n["gicp_T"] = r.T; n["gicp_iters"] = r.iters; n["gicp_ncorr"] = r.n_corr; n["gicp_rmse"] = r.inlier_rmse
+    fs, ft = O.overlap_flags(src, tgt, init, 0.5, 2)
+    n["overlap_src"] = np.packbits(fs); n["overlap_tgt"] = np.packbits(ft)
+    n["info"] = O.information_matrix(src, tgt, 0.3, init)
+    rng = np.random.default_rng(77)
+    raw = rng.normal(size=(300, 3)); raw = raw / np.linalg.norm(raw, axis=1)[:, None] * rng.uniform(3, 9, (300, 1))   # sensor frame
+    Ts = synth.se3(t=(5.0, 5.0, 1.0))
+    n["carved"] = np.packbits(O.carve(tgt, nrm, O.transform(Ts, raw)[0], Ts[:3, 3], O.cropper("MaxRadius", 0.0, 8.0, center=(5.0, 5.0, 0.0)), 0.25,
+                                      20.0, 0.1, 0.3))
+    n["deskew"] = O.undistort(src[:50], np.array([5.0, -0.4, 0.1]), np.array([0.02, -0.05, 0.8]), 0.1, True)
+    np.savez_compressed(os.path.join(OUT, "next_rows.npz"), **n)
     print("golden vectors written to", OUT)
 
 

@@ -400,3 +400,24 @@ def test_dense_map_carving_vs_python_restatement():
     n = dm.carve(scan, sensor, voxel, radius, trunc, maxlen)
     assert n == len(remove) and 0 < n < len(present)
     assert {tuple(k) for k in dm.to_cloud()[2]} == present - remove
+
+
+def test_next_rows_match_golden():
+    """The committed outputs of the "next" rows (tests/golden/next_rows.npz, written by make_golden.py) still come out."""
+    g = np.load(os.path.join(GOLD, "next_rows.npz"))
+    src, tgt, nrm, _ = synth.planar_cloud_config1(n=800, noise=0.01)
+    snrm = O.estimate_normals(src, 10, 2.0)
+    init = synth.se3(0.01, -0.02, 0.03, (0.05, 0.02, -0.01))
+    r = O.registration_icp_p2point(src, tgt, 1.0, init, max_iter=50)
+    assert r.iters == int(g["p2p_iters"]) and r.n_corr == int(g["p2p_ncorr"]) and np.abs(r.T - g["p2p_T"]).max() < 1e-12
+    r = O.registration_gicp(src, snrm, tgt, nrm, 1.0, init, max_iter=30)
+    assert r.iters == int(g["gicp_iters"]) and r.n_corr == int(g["gicp_ncorr"]) and np.abs(r.T - g["gicp_T"]).max() < 1e-12
+    fs, ft = O.overlap_flags(src, tgt, init, 0.5, 2)
+    assert np.array_equal(np.packbits(fs), g["overlap_src"]) and np.array_equal(np.packbits(ft), g["overlap_tgt"])
+    assert np.abs(O.information_matrix(src, tgt, 0.3, init) - g["info"]).max() < 1e-9
+    rng = np.random.default_rng(77)
+    raw = rng.normal(size=(300, 3)); raw = raw / np.linalg.norm(raw, axis=1)[:, None] * rng.uniform(3, 9, (300, 1))
+    Ts = synth.se3(t=(5.0, 5.0, 1.0))
+    rem = O.carve(tgt, nrm, O.transform(Ts, raw)[0], Ts[:3, 3], O.cropper("MaxRadius", 0.0, 8.0, center=(5.0, 5.0, 0.0)), 0.25, 20.0, 0.1, 0.3)
+    assert np.array_equal(np.packbits(rem), g["carved"]) and 0 < rem.sum() < len(tgt)
+    assert np.abs(O.undistort(src[:50], np.array([5.0, -0.4, 0.1]), np.array([0.02, -0.05, 0.8]), 0.1, True) - g["deskew"]).max() < 1e-13
