@@ -521,78 +521,6 @@ def test_point_to_point_icp_matches_oracle(engine_factory):
     assert ei.value.code == L.E_NO_NORMALS
 
 
-def test_device_against_committed_golden_fixtures(engine_factory):
-    """The CUDA path against tests/golden/*.npz directly (no oracle call): config-1 ICP, scan pre-processing, two-scan fusion
-    and the "next" rows.  The fixtures are written by tests/golden/make_golden.py."""
-    import os
-    from scipy.spatial import cKDTree
-    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    # config 1
-    g = np.load(os.path.join(gold, "config1_icp.npz"))
-    p = lua_params(); p.icp.maxCorrespondenceDistance = 1.0; p.icp.maxNumIter = 50
-    eng = engine_factory(p)
-    for tag, noise in (("clean", 0.0), ("noisy", 0.01)):
-        src, tgt, nrm, _ = synth.planar_cloud_config1(noise=noise)
-        r = E.RegistrationIcpPointToPlane(eng).registerClouds(eng.cloud(src), eng.cloud(tgt, nrm), np.eye(4))
-        assert r.iters == int(g[f"{tag}_iters"]) and r.n_corr == int(g[f"{tag}_ncorr"])
-        assert np.abs(r.transformation_ - g[f"{tag}_T"]).max() < 1e-9 and abs(r.inlier_rmse_ - float(g[f"{tag}_rmse"])) < 1e-10
-    # scan pre-processing (16 x 512 scan stored in the fixture)
-    g = np.load(os.path.join(gold, "scan_preprocess.npz"))
-    p2 = lua_params(seed=5); p2.scanProcessing.downSamplingRatio = 0.3
-    p2.scanProcessing.cropper = E.ScanCroppingParameters("MinMaxRadius", 2.0, 25.0)
-    e2 = engine_factory(p2)
-    raw = g["raw"].astype(np.float64)
-    vx, _ = E.voxelize(e2, e2.cloud(raw), 0.1).download()
-    o = np.lexsort(vx.T[::-1]); og = np.lexsort(g["voxel_means"].T[::-1])
-    assert np.array_equal(vx[o], g["voxel_means"][og])
-    ps = E.ScanToMapIcp(e2).processForScanMatchingAndMerging(e2.cloud(raw))
-    for got, (rx, rn) in ((ps.merge_, (g["merge_xyz"], g["merge_nrm"])), (ps.match_, (g["match_xyz"], g["match_nrm"]))):
-        gx, gn = got.download()
-        d, j = cKDTree(rx).query(gx)
-        assert len(gx) == len(rx) and d.max() == 0.0 and len(np.unique(j)) == len(rx) and np.abs(gn - rn[j]).max() < 1e-8
-    # fusion of two scans (first insertion with the identity: duplication quirk)
-    g = np.load(os.path.join(gold, "fusion_two_scans.npz"))
-    p3 = lua_params(); p3.scanProcessing.downSamplingRatio = 1.0
-    e3 = engine_factory(p3)
-    scene = synth.Scene(); poses = synth.loop_trajectory(4)
-    sm = E.Submap(e3, 200_000); s2m = E.ScanToMapIcp(e3)
-    for k in range(2):
-        raw = synth.lidar_scan(scene, poses[k], n_beams=16, n_az=512, seed=20 + k).astype(np.float64)
-        sm.insertScan(None, s2m.processForScanMatchingAndMerging(e3.cloud(raw)).merge_, np.eye(4) if k == 0 else np.linalg.inv(poses[0]) @ poses[1])
-    mx, mn = sm.getMapPointCloud()
-    d, j = cKDTree(g["map_xyz"]).query(mx)
-    assert len(mx) == len(g["map_xyz"]) and d.max() == 0.0 and len(np.unique(j)) == len(mx) and np.abs(mn - g["map_nrm"][j]).max() < 1e-8
-    # "next" rows
-    g = np.load(os.path.join(gold, "next_rows.npz"))
-    src, tgt, nrm, _ = synth.planar_cloud_config1(n=800, noise=0.01)
-    init = synth.se3(0.01, -0.02, 0.03, (0.05, 0.02, -0.01))
-    p4 = lua_params(); p4.icp.maxCorrespondenceDistance = 1.0; p4.icp.maxNumIter = 50; p4.icp.knn = 10; p4.icp.maxDistanceKnn = 2.0
-    e4 = engine_factory(p4)
-    r = E.RegistrationIcpPointToPoint(e4).registerClouds(e4.cloud(src), e4.cloud(tgt), init)
-    assert r.iters == int(g["p2p_iters"]) and r.n_corr == int(g["p2p_ncorr"]) and np.abs(r.transformation_ - g["p2p_T"]).max() < 1e-8
-    gicp = E.RegistrationIcpGeneralized(e4); gicp.max_iteration_ = 30
-    sc = e4.cloud(src); gicp.estimateNormalsOrCovariancesIfNeeded(sc)          # knn 10, radius 2.0 like the fixture's source normals
-    r = gicp.registerClouds(sc, e4.cloud(tgt, nrm), init)
-    assert r.iters == int(g["gicp_iters"]) and r.n_corr == int(g["gicp_ncorr"]) and np.abs(r.transformation_ - g["gicp_T"]).max() < 1e-7
-    so, to = E.computeOverlappingClouds(e4, e4.cloud(src), e4.cloud(tgt), init, 0.5, 2)
-    fs = np.unpackbits(g["overlap_src"])[:len(src)].astype(bool); ft = np.unpackbits(g["overlap_tgt"])[:len(tgt)].astype(bool)
-    assert np.array_equal(so.download()[0], src[fs]) and np.array_equal(to.download()[0], tgt[ft])
-    G = E.getInformationMatrixFromPointClouds(e4, e4.cloud(src), e4.cloud(tgt), 0.3, init)
-    assert np.abs(G - g["info"]).max() < 1e-9 * np.abs(g["info"]).max()
-    rng = np.random.default_rng(77)
-    raw = rng.normal(size=(300, 3)); raw = raw / np.linalg.norm(raw, axis=1)[:, None] * rng.uniform(3, 9, (300, 1))   # sensor frame
-    p5 = lua_params(); p5.mapBuilder.cropper = E.ScanCroppingParameters(cropperName="MaxRadius", croppingMaxRadius=8.0)
-    e5 = engine_factory(p5)
-    smc = E.Submap(e5, 10_000); smc.setMapPointCloud(e5.cloud(tgt, nrm))
-    smc._cropperPose = synth.se3(t=(5.0, 5.0, 0.0))
-    Ts = synth.se3(t=(5.0, 5.0, 1.0))                                            # sensor at (5, 5, 1)
-    smc.carve(e5.cloud(raw), Ts, E.SpaceCarvingParameters(voxelSize=0.25, truncationDistance=0.1, minDotProductWithNormal=0.3), force=True)
-    rem = np.unpackbits(g["carved"])[:len(tgt)].astype(bool)
-    assert np.array_equal(smc.getMapPointCloud()[0], tgt[~rem])
-    out = E.ConstantVelocityMotionCompensation(e5).undistortInputPointCloud(e5.cloud(src[:50]), [5.0, -0.4, 0.1], [0.02, -0.05, 0.8]).download()[0]
-    assert np.abs(out - g["deskew"]).max() < 1e-12
-
-
 def test_icp_properties_permutation_and_rigid_invariance(engine_factory):
     """SURVEY 8c test 7 on the device: the result does not depend on the order of the points (the grid index re-orders the
     target, the cluster splits the source) and is covariant under a common rigid motion of source, target and guess."""
@@ -883,3 +811,75 @@ def test_dense_map_running_sums(engine_factory):
     assert sm.denseSize() > len(rx) - len(gone)
     sm.denseClear()
     assert sm.denseSize() == 0 and len(sm.getDenseMap()[0]) == 0
+
+
+def test_device_against_committed_golden_fixtures(engine_factory):
+    """The CUDA path against tests/golden/*.npz directly (no oracle call): config-1 ICP, scan pre-processing, two-scan fusion
+    and the "next" rows.  The fixtures are written by tests/golden/make_golden.py."""
+    import os
+    from scipy.spatial import cKDTree
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    # config 1
+    g = np.load(os.path.join(gold, "config1_icp.npz"))
+    p = lua_params(); p.icp.maxCorrespondenceDistance = 1.0; p.icp.maxNumIter = 50
+    eng = engine_factory(p)
+    for tag, noise in (("clean", 0.0), ("noisy", 0.01)):
+        src, tgt, nrm, _ = synth.planar_cloud_config1(noise=noise)
+        r = E.RegistrationIcpPointToPlane(eng).registerClouds(eng.cloud(src), eng.cloud(tgt, nrm), np.eye(4))
+        assert r.iters == int(g[f"{tag}_iters"]) and r.n_corr == int(g[f"{tag}_ncorr"])
+        assert np.abs(r.transformation_ - g[f"{tag}_T"]).max() < 1e-9 and abs(r.inlier_rmse_ - float(g[f"{tag}_rmse"])) < 1e-10
+    # scan pre-processing (16 x 512 scan stored in the fixture)
+    g = np.load(os.path.join(gold, "scan_preprocess.npz"))
+    p2 = lua_params(seed=5); p2.scanProcessing.downSamplingRatio = 0.3
+    p2.scanProcessing.cropper = E.ScanCroppingParameters("MinMaxRadius", 2.0, 25.0)
+    e2 = engine_factory(p2)
+    raw = g["raw"].astype(np.float64)
+    vx, _ = E.voxelize(e2, e2.cloud(raw), 0.1).download()
+    o = np.lexsort(vx.T[::-1]); og = np.lexsort(g["voxel_means"].T[::-1])
+    assert np.array_equal(vx[o], g["voxel_means"][og])
+    ps = E.ScanToMapIcp(e2).processForScanMatchingAndMerging(e2.cloud(raw))
+    for got, (rx, rn) in ((ps.merge_, (g["merge_xyz"], g["merge_nrm"])), (ps.match_, (g["match_xyz"], g["match_nrm"]))):
+        gx, gn = got.download()
+        d, j = cKDTree(rx).query(gx)
+        assert len(gx) == len(rx) and d.max() == 0.0 and len(np.unique(j)) == len(rx) and np.abs(gn - rn[j]).max() < 1e-8
+    # fusion of two scans (first insertion with the identity: duplication quirk)
+    g = np.load(os.path.join(gold, "fusion_two_scans.npz"))
+    p3 = lua_params(); p3.scanProcessing.downSamplingRatio = 1.0
+    e3 = engine_factory(p3)
+    scene = synth.Scene(); poses = synth.loop_trajectory(4)
+    sm = E.Submap(e3, 200_000); s2m = E.ScanToMapIcp(e3)
+    for k in range(2):
+        raw = synth.lidar_scan(scene, poses[k], n_beams=16, n_az=512, seed=20 + k).astype(np.float64)
+        sm.insertScan(None, s2m.processForScanMatchingAndMerging(e3.cloud(raw)).merge_, np.eye(4) if k == 0 else np.linalg.inv(poses[0]) @ poses[1])
+    mx, mn = sm.getMapPointCloud()
+    d, j = cKDTree(g["map_xyz"]).query(mx)
+    assert len(mx) == len(g["map_xyz"]) and d.max() == 0.0 and len(np.unique(j)) == len(mx) and np.abs(mn - g["map_nrm"][j]).max() < 1e-8
+    # "next" rows
+    g = np.load(os.path.join(gold, "next_rows.npz"))
+    src, tgt, nrm, _ = synth.planar_cloud_config1(n=800, noise=0.01)
+    init = synth.se3(0.01, -0.02, 0.03, (0.05, 0.02, -0.01))
+    p4 = lua_params(); p4.icp.maxCorrespondenceDistance = 1.0; p4.icp.maxNumIter = 50; p4.icp.knn = 10; p4.icp.maxDistanceKnn = 2.0
+    e4 = engine_factory(p4)
+    r = E.RegistrationIcpPointToPoint(e4).registerClouds(e4.cloud(src), e4.cloud(tgt), init)
+    assert r.iters == int(g["p2p_iters"]) and r.n_corr == int(g["p2p_ncorr"]) and np.abs(r.transformation_ - g["p2p_T"]).max() < 1e-8
+    gicp = E.RegistrationIcpGeneralized(e4); gicp.max_iteration_ = 30
+    sc = e4.cloud(src); gicp.estimateNormalsOrCovariancesIfNeeded(sc)          # knn 10, radius 2.0 like the fixture's source normals
+    r = gicp.registerClouds(sc, e4.cloud(tgt, nrm), init)
+    assert r.iters == int(g["gicp_iters"]) and r.n_corr == int(g["gicp_ncorr"]) and np.abs(r.transformation_ - g["gicp_T"]).max() < 1e-7
+    so, to = E.computeOverlappingClouds(e4, e4.cloud(src), e4.cloud(tgt), init, 0.5, 2)
+    fs = np.unpackbits(g["overlap_src"])[:len(src)].astype(bool); ft = np.unpackbits(g["overlap_tgt"])[:len(tgt)].astype(bool)
+    assert np.array_equal(so.download()[0], src[fs]) and np.array_equal(to.download()[0], tgt[ft])
+    G = E.getInformationMatrixFromPointClouds(e4, e4.cloud(src), e4.cloud(tgt), 0.3, init)
+    assert np.abs(G - g["info"]).max() < 1e-9 * np.abs(g["info"]).max()
+    rng = np.random.default_rng(77)
+    raw = rng.normal(size=(300, 3)); raw = raw / np.linalg.norm(raw, axis=1)[:, None] * rng.uniform(3, 9, (300, 1))   # sensor frame
+    p5 = lua_params(); p5.mapBuilder.cropper = E.ScanCroppingParameters(cropperName="MaxRadius", croppingMaxRadius=8.0)
+    e5 = engine_factory(p5)
+    smc = E.Submap(e5, 10_000); smc.setMapPointCloud(e5.cloud(tgt, nrm))
+    smc._cropperPose = synth.se3(t=(5.0, 5.0, 0.0))
+    Ts = synth.se3(t=(5.0, 5.0, 1.0))                                            # sensor at (5, 5, 1)
+    smc.carve(e5.cloud(raw), Ts, E.SpaceCarvingParameters(voxelSize=0.25, truncationDistance=0.1, minDotProductWithNormal=0.3), force=True)
+    rem = np.unpackbits(g["carved"])[:len(tgt)].astype(bool)
+    assert np.array_equal(smc.getMapPointCloud()[0], tgt[~rem])
+    out = E.ConstantVelocityMotionCompensation(e5).undistortInputPointCloud(e5.cloud(src[:50]), [5.0, -0.4, 0.1], [0.02, -0.05, 0.8]).download()[0]
+    assert np.abs(out - g["deskew"]).max() < 1e-12
