@@ -1,24 +1,28 @@
-// icp.cu -- K-icp-iter: the whole point-to-plane ICP loop of one registration inside ONE persistent kernel.
+// icp.cu -- K-icp-iter: the whole ICP loop of one registration inside ONE persistent kernel.
 //
-// Replaces [O3D] RegistrationICP + TransformationEstimationPointToPlane as called by
-// RegistrationIcpPointToPlane::registerClouds (core/src/CloudRegistration.cpp:44-48), i.e. SURVEY.md 8a rows
-// R3 (correspondence search), R4 (JtJ / Jtr), R5 (6x6 solve, SE(3) update, convergence test).
+// Replaces [O3D] RegistrationICP as called by the reference's three CloudRegistration classes
+// (core/src/CloudRegistration.cpp:15-20 generalized, :44-48 point-to-plane, :69-75 point-to-point), i.e. SURVEY.md 8a rows
+// R3 (correspondence search), R4 (per-estimator sums), R5 (solve, SE(3) update, convergence test), plus one-evaluation
+// mode for [O3D] GetInformationMatrixFromPointClouds.  Three instantiations (icp_kernel<MODE>): 0 point-to-plane only
+// (the headline path carries no code of the others), 1 point-to-point + information matrix, 2 generalized ICP.
 //
 // Mapping to the machine:
 //   * one thread-block CLUSTER (1..8 CTAs, one per SM) per registration, blockIdx.y = registration in the batch;
 //   * the working copy of the source cloud lives in shared memory for the whole loop (each CTA owns a contiguous
 //     chunk) and is advanced by the per-iteration update like [O3D] pcd.Transform(update);
 //   * exact nearest neighbour with the strict d2 < r2 cut through the dense grid of grid_index.cu, in two phases:
-//       phase 1, one thread per point: rings 0..1 around the query cell, seeded by the previous iteration's
-//                neighbour (the seed only tightens the pruning radius) -- resolves almost every point;
-//       phase 2, one WARP per unresolved point (outliers / empty neighbourhoods, queued in shared memory):
-//                the rows of ring R are spread over the 32 lanes, followed by a warp lexicographic-min reduce.
-//     Without phase 2 a handful of outliers scanning hundreds of cells serially set the iteration time.
+//       phase 1, one thread per point: BOX QUERY -- the cells overlapping [q - d, q + d], one contiguous slot range per
+//                (y, z) row, with d = distance to the previous evaluation's neighbour (kept per point in shared
+//                memory); without a neighbour to start from (first evaluation) a half-cell box, then a one-cell box;
+//       phase 2, one WARP per unresolved point (outliers / empty neighbourhoods, queued in shared memory): the rows
+//                of the box around the search sphere are spread over the 32 lanes, then a warp lexicographic-min;
+//                the queues of all CTAs are drained by all warps of the cluster through distributed shared memory.
 //     Ties -> lower target index.  Gathers hit the L2-resident target.
-//   * per-thread fp64 accumulation of the 21 + 6 + 2 sums, warp-shuffle tree, CTA tree, then a DSMEM exchange:
-//     every CTA reads all cluster partials in rank order and redundantly solves the 6x6 system (LDLT with
-//     diagonal pivoting, fully unrolled into registers), so one cluster barrier per iteration is enough and no
-//     host round trip ever happens;
+//   * per-thread fp64 accumulation of 29 sums (plane / GICP: 21 JtJ + 6 Jtr; point-to-point: means + cross moments;
+//     information: target moments; + sum d2 + count), warp-shuffle tree, CTA tree, then a DSMEM exchange: every CTA
+//     reads all cluster partials in rank order and redundantly computes the update (6x6 LDLT with diagonal pivoting,
+//     fully unrolled into registers; or umeyama with a one-thread Jacobi SVD), so one cluster barrier per iteration
+//     is enough and no host round trip ever happens;
 //   * all arithmetic fp64; distances and the point transform use explicitly rounded ops (no FMA contraction) so
 //     that correspondences are bit-identical to the CPU oracle.
 #include <cooperative_groups.h>
