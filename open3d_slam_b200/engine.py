@@ -589,12 +589,14 @@ class ScanToMapIcp(ScanToMapRegistration):
 
 def scanToMapRegistrationFactory(eng: Engine, p: MapperParameters) -> ScanToMapRegistration:
     """src/ScanToMapRegistration.cpp:91-103"""
-    if p.scanToMapRegType in ("PointToPlaneIcp",):
+    if p.scanToMapRegType in ("PointToPlaneIcp", "GeneralizedIcp", "PointToPointIcp"):
+        # one ScanToMapIcp for all three, like the reference; its cloud registration follows toCloudRegistrationType (:105-129).
+        # Note for PointToPointIcp: the reference's estimateNormalsOrCovariancesIfNeeded is a no-op there, so its merge_/match_
+        # clouds and its map carry no normals; the device chain still estimates and carries them (the estimator ignores
+        # them and the map positions are the same).
         s = ScanToMapIcp(eng)
         s.setParameters(p)
         return s
-    if p.scanToMapRegType in ("GeneralizedIcp", "PointToPointIcp"):
-        raise L.B2SError(L.E_UNSUPPORTED, f"{p.scanToMapRegType} is not implemented on the device")
     raise RuntimeError("scanToMapRegistrationFactory: unknown type of registration scan to map")
 
 

@@ -322,6 +322,44 @@ def test_scan_to_map_registration_and_mapper_loop(engine_factory):
     assert np.linalg.norm(pose[:3, 3] - gt[:3, 3]) < 0.15
 
 
+@pytest.mark.parametrize("reg_type", ["GeneralizedIcp", "PointToPointIcp"])
+def test_scan_to_map_loop_with_the_other_estimators(engine_factory, reg_type):
+    """ScanToMapIcp serves all three registration types (src/ScanToMapRegistration.cpp:91-129): the device Mapper against the
+    oracle-only restatement of the loop with the matching oracle estimator."""
+    p = lua_params(seed=3)
+    p.scanToMapRegType = reg_type
+    p.scanProcessing.downSamplingRatio = 0.5
+    eng = engine_factory(p)
+    assert isinstance(E.scanToMapRegistrationFactory(eng, p), E.ScanToMapIcp)
+    sc = synth.Scene(); poses = synth.loop_trajectory(8)
+    mapper = E.Mapper(eng, 600_000)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0)
+    map_x = np.zeros((0, 3)); map_n = np.zeros((0, 3)); pose = np.eye(4)
+    for k in range(4):
+        raw = synth.lidar_scan(sc, poses[k], seed=300 + k)
+        delta = np.eye(4) if k == 0 else np.linalg.inv(poses[k - 1]) @ poses[k] @ synth.se3(0, 0, 1e-3, (0.02, -0.01, 0.005))
+        ok = mapper.addRangeMeasurement(eng.cloud(raw), delta)
+        (mx, mn), (ax, an) = O.process_scan(raw.astype(np.float64), wide, wide, 0.1, 20, 3.0, 0.5, 3)
+        if k == 0:
+            map_x, map_n = O.submap_insert_scan(map_x, map_n, mx, mn, np.eye(4), 0.1, wide)
+            continue
+        assert ok
+        guess = pose @ delta
+        px, pn = O.crop(O.cropper("MinMaxRadius", 2.0, 30.0, center=pose[:3, 3]), map_x, map_n)
+        if reg_type == "GeneralizedIcp":
+            ref = O.registration_gicp(ax, an, px, pn, 1.0, guess, max_iter=50)
+        else:
+            ref = O.registration_icp_p2point(ax, px, 1.0, guess, max_iter=50)
+        got = mapper.lastResult
+        assert got.iters == ref.iters and got.n_corr == ref.n_corr
+        assert rel_rot(got.transformation_, ref.T) < 1e-7 and rel_trans(got.transformation_, ref.T) < 1e-7
+        assert ref.fitness > 0.7
+        pose = ref.T
+        map_x, map_n = O.submap_insert_scan(map_x, map_n, mx, mn, pose, 0.1, O.cropper("MinMaxRadius", 2.0, 30.0, center=pose[:3, 3]))
+    gt = np.linalg.inv(poses[0]) @ poses[3]
+    assert np.linalg.norm(pose[:3, 3] - gt[:3, 3]) < 0.15
+
+
 def test_mapper_async_chain_matches_sync(engine_factory):
     p = lua_params(seed=3)
     p.scanProcessing.downSamplingRatio = 0.5
