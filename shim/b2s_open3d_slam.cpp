@@ -182,7 +182,13 @@ void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, con
   if (rc != B2S_OK) b2sThrow(rc);
 }
 
-ScanToMapIcpB200::ScanToMapIcpB200(const MapperParameters& p) : cfg_(b2sConfigFrom(p.scanMatcher_.icp_, &p.scanProcessing_, &p.mapBuilder_)) {}
+ScanToMapIcpB200::ScanToMapIcpB200(const MapperParameters& p) : cfg_(b2sConfigFrom(p.scanMatcher_.icp_, &p.scanProcessing_, &p.mapBuilder_)) {
+  switch (p.scanMatcher_.scanToMapRegType_) {   // toCloudRegistrationType, src/ScanToMapRegistration.cpp:105-129
+    case ScanToMapRegistrationType::PointToPointIcp: cfg_.icp.reg_type = B2S_REG_POINT_TO_POINT; break;
+    case ScanToMapRegistrationType::GeneralizedIcp: cfg_.icp.reg_type = B2S_REG_GENERALIZED; break;
+    default: cfg_.icp.reg_type = B2S_REG_POINT_TO_PLANE; break;
+  }
+}
 
 ProcessedScans ScanToMapIcpB200::processForScanMatchingAndMerging(const PointCloud& in, const Transform&) const {
   b2s_handle* h = b2sThreadHandle(cfg_);

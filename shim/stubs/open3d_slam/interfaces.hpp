@@ -21,7 +21,8 @@ struct IcpParameters { int maxNumIter_ = 50; double maxCorrespondenceDistance_ =
 struct CloudRegistrationParameters { IcpParameters icp_; };
 struct SpaceCarvingParameters { double voxelSize_ = 0.1, maxRaytracingLength_ = 20.0, truncationDistance_ = 0.1; int carveSpaceEveryNscans_ = 10; double minDotProductWithNormal_ = 0.5, neighborhoodRadiusDenseMap_ = 0.1; };
 struct MapBuilderParameters { double mapVoxelSize_ = 0.03; ScanCroppingParameters cropper_; SpaceCarvingParameters carving_; };
-struct ScanToMapRegistrationParameters { double minRefinementFitness_ = 0.7; IcpParameters icp_; };
+enum class ScanToMapRegistrationType : int { PointToPlaneIcp, PointToPointIcp, GeneralizedIcp };   // Parameters.hpp:44-49
+struct ScanToMapRegistrationParameters { double minRefinementFitness_ = 0.7; IcpParameters icp_; ScanToMapRegistrationType scanToMapRegType_ = ScanToMapRegistrationType::PointToPlaneIcp; };
 struct MapperParameters { ScanToMapRegistrationParameters scanMatcher_; ScanProcessingParameters scanProcessing_; MapBuilderParameters mapBuilder_; };
 class Submap;  // the shim only needs getMapPointCloud(); see b2s_open3d_slam.cpp
 class CloudRegistration {
