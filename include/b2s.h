@@ -210,6 +210,11 @@ int32_t b2s_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* po
 int32_t b2s_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* points);
 int32_t b2s_dense_size(b2s_handle* h, const b2s_submap* sm, size_t* n_voxels);
 int32_t b2s_dense_clear(b2s_handle* h, b2s_submap* sm);
+/* Submap::transform (loop-closure correction of a whole submap)              src/Submap.cpp:94-107
+ *     mapCloud_.Transform(T) ([O3D] PointCloud::Transform: points T p / w, normals R n; no duplication quirk),
+ *     denseMap_.transform(T) (src/Voxel.cpp:49-64: applied to the voxel SUMS, keys unchanged -- kept as it is),
+ *     mapToRangeSensor_ = mapToRangeSensor_ * T (the pose state of b2s_submap_set_pose / b2s_submap_get_pose). */
+int32_t b2s_submap_transform(b2s_handle* h, b2s_submap* sm, const double T[16]);
 /* Submap::getMapPointCloud (copy-out)                                       src/Submap.cpp:184-191 */
 int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n);
 int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, size_t capacity, size_t* n);

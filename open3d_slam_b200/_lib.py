@@ -57,7 +57,7 @@ SYMBOLS = [
     "b2s_submap_dense_download", "b2s_submap_set_cloud", "b2s_register_to_submap", "b2s_submap_set_pose", "b2s_submap_get_pose",
     "b2s_mapper_step_async", "b2s_scan_result_fetch", "b2s_profile_enable", "b2s_profile_read", "b2s_mapper_graph_enable", "b2s_debug_icp_clocks",
     "b2s_mapper_step_host", "b2s_mapper_step_host_async", "b2s_submap_carve", "b2s_overlap", "b2s_information_matrix", "b2s_undistort",
-    "b2s_dense_query", "b2s_dense_remove", "b2s_dense_size", "b2s_dense_clear", "b2s_dense_carve",
+    "b2s_dense_query", "b2s_dense_remove", "b2s_dense_size", "b2s_dense_clear", "b2s_dense_carve", "b2s_submap_transform",
 ]
 PROFILE_KINDS = ["icp", "normals", "radix_sort", "nn_grid_build", "voxel", "fuse", "select", "crop"]
 

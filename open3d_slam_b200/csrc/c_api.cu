@@ -658,6 +658,12 @@ int32_t b2s_submap_set_pose(b2s_handle* h, b2s_submap* sm, const double T[16]) {
   return pose_to_device(h, T, sm->pose.as<double>());
 }
 
+int32_t b2s_submap_transform(b2s_handle* h, b2s_submap* sm, const double T[16]) {
+  B2S_REQUIRE(h && sm && T, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  return op_submap_transform(h, sm, T);
+}
+
 int32_t b2s_submap_get_pose(b2s_handle* h, const b2s_submap* sm, double T[16]) {
   B2S_REQUIRE(h && sm && T, B2S_E_INVALID, "null argument");
   LOCK(h);

@@ -263,6 +263,7 @@ int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts);
 int32_t op_dense_count(b2s_handle* h, const b2s_submap* sm, int32_t* out_dev);
 int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* sensor, double radius, double trunc, double max_len,
                        int32_t* removed_dev);
+int32_t op_submap_transform(b2s_handle* h, b2s_submap* sm, const double* T_host);   // Submap::transform (voxel.cu)
 // D1 constant-velocity de-skew (voxel.cu)
 int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, const double* ang_vel_rpy, double scan_duration, int clockwise,
                      b2s_cloud* out);

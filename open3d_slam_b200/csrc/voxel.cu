@@ -568,4 +568,69 @@ int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, 
   return B2S_OK;
 }
 
+// ---- Submap::transform (core/src/Submap.cpp:94-107): [O3D] PointCloud::Transform of the map cloud IN PLACE ----------------
+// TransformPoints: (T p).head3 / w ; TransformNormals: R n.  No near-identity duplication here (that quirk belongs to
+// o3d_slam::transform, helpers.cpp:273-305).  The pose state follows: mapToRangeSensor_ = mapToRangeSensor_ * T.
+struct Mat4 { double m[16]; };
+__global__ void __launch_bounds__(VX_THREADS) o3d_transform_inplace_kernel(double* __restrict__ xyz, double* __restrict__ nrm,
+                                                                           const int32_t* __restrict__ d_n, Mat4 M) {
+  const int n = *d_n;
+  const double* T = M.m;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
+    const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], px), __dmul_rn(T[5], py)), __dmul_rn(T[6], pz)), T[7]);
+    const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], px), __dmul_rn(T[9], py)), __dmul_rn(T[10], pz)), T[11]);
+    const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[12], px), __dmul_rn(T[13], py)), __dmul_rn(T[14], pz)), T[15]);
+    xyz[3 * i] = __ddiv_rn(x, w); xyz[3 * i + 1] = __ddiv_rn(y, w); xyz[3 * i + 2] = __ddiv_rn(z, w);
+    if (nrm) {
+      const double a = nrm[3 * i], b = nrm[3 * i + 1], c = nrm[3 * i + 2];
+      nrm[3 * i] = __dadd_rn(__dadd_rn(__dmul_rn(T[0], a), __dmul_rn(T[1], b)), __dmul_rn(T[2], c));
+      nrm[3 * i + 1] = __dadd_rn(__dadd_rn(__dmul_rn(T[4], a), __dmul_rn(T[5], b)), __dmul_rn(T[6], c));
+      nrm[3 * i + 2] = __dadd_rn(__dadd_rn(__dmul_rn(T[8], a), __dmul_rn(T[9], b)), __dmul_rn(T[10], c));
+    }
+  }
+}
+__global__ void pose_right_multiply_kernel(double* pose, Mat4 M) {   // pose = pose * T (row-major), one thread
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double P[16], R[16];
+  for (int i = 0; i < 16; i++) P[i] = pose[i];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 4; k++) s += P[4 * i + k] * M.m[4 * k + j];
+      R[4 * i + j] = s;
+    }
+  for (int i = 0; i < 16; i++) pose[i] = R[i];
+}
+// VoxelizedPointCloud::transform (core/src/Voxel.cpp:49-64): the transform is applied to the position SUM, keys stay
+__global__ void dense_transform_kernel(double* __restrict__ sums, const int32_t* __restrict__ cnts, size_t cap, Mat4 M) {
+  const double* T = M.m;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+    if (cnts[i] <= 0) continue;
+    const double a = sums[6 * i], b = sums[6 * i + 1], c = sums[6 * i + 2];
+    sums[6 * i] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], a), __dmul_rn(T[1], b)), __dmul_rn(T[2], c)), T[3]);
+    sums[6 * i + 1] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], a), __dmul_rn(T[5], b)), __dmul_rn(T[6], c)), T[7]);
+    sums[6 * i + 2] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], a), __dmul_rn(T[9], b)), __dmul_rn(T[10], c)), T[11]);
+  }
+}
+
+int32_t op_submap_transform(b2s_handle* h, b2s_submap* sm, const double* T_host) {
+  Mat4 M;
+  for (int i = 0; i < 16; i++) M.m[i] = T_host[i];
+  b2s_cloud* map = sm->cloud[0];
+  const size_t n_max = map->n_max > 0 ? map->n_max : 1;
+  o3d_transform_inplace_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(map->xyz.as<double>(),
+                                                                                          map->has_normals ? map->nrm.as<double>() : nullptr,
+                                                                                          map->dn.as<int32_t>(), M);
+  pose_right_multiply_kernel<<<1, 32, 0, h->stream>>>(sm->pose.as<double>(), M);
+  h->launches += 2;
+  if (sm->dense_cap > 0) {
+    dense_transform_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, M);
+    h->launches++;
+  }
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
 }  // namespace b2s

@@ -521,6 +521,11 @@ class Submap:
     def denseClear(self) -> None:
         L.check(L.lib().b2s_dense_clear(self.eng._h, self._s))
 
+    def transform(self, T) -> None:
+        """Submap::transform (src/Submap.cpp:94-107): map cloud, dense map and mapToRangeSensor_ follow a loop-closure correction."""
+        L.check(L.lib().b2s_submap_transform(self.eng._h, self._s, _pd(_mat(T))))
+        self._cropperPose = self._cropperPose   # mapBuilderCropper_ keeps its pose in the reference as well
+
     def setMapPointCloud(self, cloud: Cloud):
         L.check(L.lib().b2s_submap_set_cloud(self.eng._h, self._s, cloud._c))
 

@@ -1449,6 +1449,32 @@ ORC_EXPORT void orc_undistort(const double* xyz, size_t n, const double* lin_vel
   }
 }
 
+/* ------------------------------------------------------------------------- */
+/*  Submap::transform  core/src/Submap.cpp:94-107 (loop-closure correction of a submap)   */
+/*  mapCloud_.Transform(mat) = [O3D] PointCloud::Transform: TransformPoints (T p / w),     */
+/*  TransformNormals (R n) -- no duplication quirk here; denseMap_.transform(T) =          */
+/*  VoxelizedPointCloud::transform (core/src/Voxel.cpp:49-64): the affine map is applied   */
+/*  to the SUMS and the keys stay (kept as it is).                                         */
+/* ------------------------------------------------------------------------- */
+ORC_EXPORT void orc_pointcloud_transform(const double* T, double* xyz, double* nrm, size_t n) {
+  transform_points(T, xyz, n);
+  if (nrm) for (size_t i = 0; i < n; i++) {
+    double* v = nrm + 3 * i;
+    const double a = T[0] * v[0] + T[1] * v[1] + T[2] * v[2], b = T[4] * v[0] + T[5] * v[1] + T[6] * v[2], c = T[8] * v[0] + T[9] * v[1] + T[10] * v[2];
+    v[0] = a; v[1] = b; v[2] = c;
+  }
+}
+ORC_EXPORT void orc_dense_transform(void* pd, const double* T) {
+  orc_dense* d = (orc_dense*)pd;
+  for (size_t s0 = 0; s0 < d->h.cnt; s0++) {
+    if (d->cnt[s0] <= 0) continue;
+    double* v = d->sum + 6 * s0;
+    const double a = (T[0] * v[0] + T[1] * v[1] + T[2] * v[2]) + T[3], b = (T[4] * v[0] + T[5] * v[1] + T[6] * v[2]) + T[7],
+                 c = (T[8] * v[0] + T[9] * v[1] + T[10] * v[2]) + T[11];
+    v[0] = a; v[1] = b; v[2] = c;
+  }
+}
+
 ORC_EXPORT int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -260,6 +260,11 @@ class DenseMap:
         if lib().orc_dense_insert(self._h, _p(xyz), _p(nrm), C.c_size_t(len(xyz))) != 0:
             raise RuntimeError("dense map capacity exceeded")
 
+    def transform(self, T) -> None:
+        """VoxelizedPointCloud::transform (core/src/Voxel.cpp:49-64)."""
+        T = _f64(T).reshape(4, 4)
+        lib().orc_dense_transform(self._h, _p(T))
+
     def carve(self, scan, sensor, voxel, radius=0.1, truncation=0.1, max_len=20.0) -> int:
         """Submap::carve on the dense map (core/src/Submap.cpp:125-136): returns the number of removed voxels."""
         scan = _f64(scan).reshape(-1, 3); s = _f64(sensor).reshape(3)
@@ -352,6 +357,13 @@ def undistort(xyz, linear_velocity, angular_velocity_rpy, scan_duration=0.1, spi
     out = np.empty_like(xyz)
     lib().orc_undistort(_p(xyz), C.c_size_t(len(xyz)), _p(lv), _p(av), C.c_double(scan_duration), C.c_int(int(spinning_clockwise)), _p(out))
     return out
+
+
+def pointcloud_transform(T, xyz, nrm=None):
+    """[O3D] PointCloud::Transform (points and normals, no duplication quirk): what Submap::transform applies to mapCloud_."""
+    T = _f64(T).reshape(4, 4); x = _f64(xyz).reshape(-1, 3).copy(); n = None if nrm is None else _f64(nrm).reshape(-1, 3).copy()
+    lib().orc_pointcloud_transform(_p(T), _p(x), _p(n), C.c_size_t(len(x)))
+    return x, n
 
 
 def num_threads() -> int:

@@ -922,3 +922,28 @@ def test_device_against_committed_golden_fixtures(engine_factory):
     assert np.array_equal(smc.getMapPointCloud()[0], tgt[~rem])
     out = E.ConstantVelocityMotionCompensation(e5).undistortInputPointCloud(e5.cloud(src[:50]), [5.0, -0.4, 0.1], [0.02, -0.05, 0.8]).download()[0]
     assert np.abs(out - g["deskew"]).max() < 1e-12
+
+
+def test_submap_transform_matches_oracle(engine_factory):
+    """Submap::transform (src/Submap.cpp:94-107): [O3D] PointCloud::Transform of the map in place (no duplication quirk),
+    VoxelizedPointCloud::transform of the dense map (sums moved, keys kept) and mapToRangeSensor_ * T."""
+    eng = engine_factory(lua_params())
+    sc = synth.Scene(); poses = synth.loop_trajectory(4)
+    wide = O.cropper("MinMaxRadius", 2.0, 30.0)
+    (mx, mn), _ = O.process_scan(synth.lidar_scan(sc, poses[0], seed=0), wide, wide, 0.1, 20, 3.0, 0.5, 1)
+    sm = E.Submap(eng, 100_000)
+    sm.setMapPointCloud(eng.cloud(mx, mn))
+    sm.setPose(poses[1])
+    raw = synth.lidar_scan(sc, poses[1], seed=1).astype(np.float64)[::8]
+    sm.insertScanDenseMap(eng.cloud(raw), poses[1], None)
+    dm = O.DenseMap(0.05, 1 << 18); dm.insert(O.transform(poses[1], raw)[0])
+    for T in (synth.se3(0.01, -0.02, 0.3, (0.5, -0.25, 0.1)), np.eye(4) + 0.0):   # the identity must NOT duplicate anything here
+        sm.transform(T)
+        mx, mn = O.pointcloud_transform(T, mx, mn)
+        dm.transform(T)
+    gx, gn = sm.getMapPointCloud()
+    assert np.array_equal(gx, mx) and np.array_equal(gn, mn)                      # same expressions, same order: bit-identical
+    assert np.abs(sm.getPose() - poses[1] @ synth.se3(0.01, -0.02, 0.3, (0.5, -0.25, 0.1))).max() < 1e-12
+    dx, dk = sm.getDenseMap(); rx, _rn, rk = dm.to_cloud()
+    o1 = np.lexsort((dk[:, 2], dk[:, 1], dk[:, 0])); o2 = np.lexsort((rk[:, 2], rk[:, 1], rk[:, 0]))
+    assert np.array_equal(dk[o1], rk[o2]) and np.abs(dx[o1] - rx[o2]).max() < 1e-9
