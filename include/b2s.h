@@ -257,6 +257,74 @@ int32_t b2s_mapper_step_host_async(b2s_handle* h, b2s_submap* sm, const void* xy
 int32_t b2s_mapper_graph_enable(b2s_handle* h, b2s_submap* sm, size_t raw_capacity_points, double min_refinement_fitness,
                                 int32_t ignore_min_fitness, b2s_cloud** staging_out);
 
+/* ---- options of the device-resident Mapper chain (b2s_mapper_step_async / _host / _host_async) -----------------------
+ * What Mapper::addRangeMeasurement and SubmapCollection::insertScan do around S1/S2/F1 with their default wiring:
+ *   - the minimum-motion gate in front of the map insertion                       src/Mapper.cpp:170-176
+ *   - Submap::insertScan(..., isPerformCarving = true): space carving of the sparse map every carveSpaceEveryNscans_
+ *     insertions (nScansInsertedMap_ % N == 1, map not empty), with the cropper at the pose of the LAST insertion
+ *                                                                                 src/SubmapCollection.cpp:178,205, src/Submap.cpp:55-60,109-123
+ *   - insertScanDenseMap(raw scan, mapToRangeSensor, carving = true) for every scan addRangeMeasurement accepted
+ *                                                                                 src/SlamWrapper.cpp:318-327,363-376, src/Submap.cpp:77-92,125-136
+ * All decisions are taken ON THE DEVICE from device-resident counters (the host never learns whether a scan passed
+ * the fitness gate before it reads the result), so the chain stays free of host round trips and graph-replayable.
+ * Options are per submap; changing them drops a captured graph (it is re-captured on the next step). */
+typedef struct b2s_mapper_options {
+  double min_movement_between_mapping_steps;   /* MapperParameters::minMovementBetweenMappingSteps_ (Parameters.hpp:161), default 0 */
+  int32_t carve_enabled;                       /* isPerformCarving of Submap::insertScan */
+  int32_t carve_every_n_scans;                 /* SpaceCarvingParameters::carveSpaceEveryNscans_ (Parameters.hpp:89), default 10 */
+  b2s_carving_params carving;                  /* mapBuilder_.carving_ */
+  int32_t dense_enabled;                       /* feed the dense map with every accepted raw scan */
+  int32_t dense_carve_every_n_scans;           /* denseMapBuilder_.carving_.carveSpaceEveryNscans_; 0 = no dense carving */
+  b2s_carving_params dense_carving;            /* denseMapBuilder_.carving_ */
+  b2s_cropper dense_cropper;                   /* denseMapBuilder_.cropper_ (applied in the sensor frame, Submap.cpp:78-79) */
+} b2s_mapper_options;
+void b2s_default_mapper_options(b2s_mapper_options* o);
+int32_t b2s_submap_set_mapper_options(b2s_handle* h, b2s_submap* sm, const b2s_mapper_options* o);
+/* device-side bookkeeping of the chain, read back (synchronises): what the reference keeps in Mapper / Submap members */
+typedef struct b2s_mapper_counters {
+  int64_t steps;                 /* scans that went through S1 + S2 on this submap */
+  int64_t accepted;              /* passed the fitness gate (addRangeMeasurement returned true) */
+  int64_t inserted_map;          /* Submap::nScansInsertedMap_ */
+  int64_t inserted_dense;        /* Submap::nScansInsertedDenseMap_ */
+  int64_t carve_runs;            /* how often the sparse carving actually ran */
+  int64_t carved_points_total;   /* map points removed by it */
+  int64_t dense_carve_runs;
+  int64_t carved_voxels_total;   /* dense voxels emptied */
+} b2s_mapper_counters;
+int32_t b2s_submap_get_mapper_counters(b2s_handle* h, const b2s_submap* sm, b2s_mapper_counters* out);
+
+/* ---- F4  o3d_slam::VoxelMap (include/open3d_slam/Voxel.hpp:19-36, src/Voxel.cpp:123-160): voxel -> per-layer lists of point indices.
+ *      Keys are getVoxelIdx(p, 1 / voxelSize) = floor(p * inv) per axis (VoxelHashMap.hpp:43-50).  Layers are integers
+ *      0..B2S_VOXEL_MAP_LAYERS-1 (the shim maps the reference's layer names, e.g. Submap::voxelMapLayer).  The users on this path:
+ *      the revisit check of SubmapCollection::isSwitchingSubmapsConsistant (src/SubmapCollection.cpp:352-364) =
+ *      b2s_voxel_map_has_voxel over the scan moved by mapToRangeSensor; Submap::computeFeatures fills it with
+ *      voxelMap_.clear(); voxelMap_.insertCloud(voxelMapLayer, mapCloud_) (src/Submap.cpp:235-236). ------------------------------ */
+#define B2S_VOXEL_MAP_LAYERS 4
+typedef struct b2s_voxel_map b2s_voxel_map;
+int32_t b2s_voxel_map_create(b2s_handle* h, const double voxel_size[3], size_t capacity_voxels, b2s_voxel_map** out);   /* VoxelMap(voxelSize) */
+void b2s_voxel_map_destroy(b2s_voxel_map* vm);
+int32_t b2s_voxel_map_clear(b2s_handle* h, b2s_voxel_map* vm);                                                        /* clear() */
+int32_t b2s_voxel_map_insert_cloud(b2s_handle* h, b2s_voxel_map* vm, int32_t layer, const b2s_cloud* cloud);          /* insertCloud(layer, cloud) */
+int32_t b2s_voxel_map_size(b2s_handle* h, const b2s_voxel_map* vm, size_t* n_voxels);                                 /* size() */
+/* hasVoxelContainingPoint for every point of `points` (moved by the isometry T first when T is given): flags (optional, one per
+ * point, `capacity` entries) and the number of hits */
+int32_t b2s_voxel_map_has_voxel(b2s_handle* h, const b2s_voxel_map* vm, const b2s_cloud* points, const double T_or_null[16],
+                                int32_t* flags_or_null, size_t capacity, size_t* n_hits);
+/* getIndicesInVoxel(layer, p) for every point: CSR answer, offsets[n + 1] and the concatenated index lists (each sorted ascending =
+ * insertion order of insertCloud(layer, cloud)).  indices may be NULL to query the sizes only. */
+int32_t b2s_voxel_map_indices_in_voxel(b2s_handle* h, const b2s_voxel_map* vm, int32_t layer, const b2s_cloud* points, int32_t* offsets,
+                                       size_t offsets_capacity, int32_t* indices, size_t indices_capacity, size_t* n_indices);
+/* copies of the clouds the last mapper step produced on this handle (ProcessedScans of Mapper.cpp:139; SubmapCollection keeps
+ * the merge_ cloud in its overlap buffer, src/SubmapCollection.cpp:83-92,180).  Either output may be NULL. */
+int32_t b2s_mapper_processed_scan(b2s_handle* h, b2s_cloud* merge_out, b2s_cloud* match_out);
+
+/* ---- device-to-device hand-over of a cloud's arrays (a submap that is the registration target on
+ *      several GPUs is built once by its owner and broadcast over NVLink by the host side -- torch.distributed / NCCL own
+ *      the transfer, this library only copies between its cloud and the caller's device buffers on the handle's stream).
+ *      xyz / normals are 3 x f64 per point, like every cloud.  export: synchronises (the count is returned). -------------- */
+int32_t b2s_cloud_export_device(b2s_handle* h, const b2s_cloud* c, void* xyz_dev, void* normals_dev_or_null, size_t capacity_points, size_t* n);
+int32_t b2s_cloud_import_device(b2s_handle* h, b2s_cloud* c, const void* xyz_dev, const void* normals_dev_or_null, size_t n);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -47,6 +47,17 @@ class CarvingParams(C.Structure):
                 ("min_dot_product_with_normal", C.c_double), ("neighborhood_radius_dense_map", C.c_double)]
 
 
+class MapperOptions(C.Structure):
+    _fields_ = [("min_movement_between_mapping_steps", C.c_double), ("carve_enabled", C.c_int32), ("carve_every_n_scans", C.c_int32),
+                ("carving", CarvingParams), ("dense_enabled", C.c_int32), ("dense_carve_every_n_scans", C.c_int32),
+                ("dense_carving", CarvingParams), ("dense_cropper", Cropper)]
+
+
+class MapperCounters(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("steps", "accepted", "inserted_map", "inserted_dense", "carve_runs", "carved_points_total",
+                                         "dense_carve_runs", "carved_voxels_total")]
+
+
 # every symbol include/b2s.h declares (checked by tests/test_abi.py without needing a GPU)
 SYMBOLS = [
     "b2s_default_config", "b2s_create", "b2s_destroy", "b2s_set_config", "b2s_synchronize", "b2s_last_error", "b2s_version",
@@ -58,6 +69,10 @@ SYMBOLS = [
     "b2s_mapper_step_async", "b2s_scan_result_fetch", "b2s_profile_enable", "b2s_profile_read", "b2s_mapper_graph_enable", "b2s_debug_icp_clocks",
     "b2s_mapper_step_host", "b2s_mapper_step_host_async", "b2s_submap_carve", "b2s_overlap", "b2s_information_matrix", "b2s_undistort",
     "b2s_dense_query", "b2s_dense_remove", "b2s_dense_size", "b2s_dense_clear", "b2s_dense_carve", "b2s_submap_transform",
+    "b2s_default_mapper_options", "b2s_submap_set_mapper_options", "b2s_submap_get_mapper_counters",
+    "b2s_voxel_map_create", "b2s_voxel_map_destroy", "b2s_voxel_map_clear", "b2s_voxel_map_insert_cloud", "b2s_voxel_map_size",
+    "b2s_voxel_map_has_voxel", "b2s_voxel_map_indices_in_voxel", "b2s_mapper_processed_scan",
+    "b2s_cloud_export_device", "b2s_cloud_import_device",
 ]
 PROFILE_KINDS = ["icp", "normals", "radix_sort", "nn_grid_build", "voxel", "fuse", "select", "crop"]
 
@@ -87,9 +102,12 @@ def lib():
         L.b2s_cloud_destroy.restype = None
         L.b2s_submap_destroy.restype = None
         L.b2s_default_config.restype = None
+        L.b2s_default_mapper_options.restype = None
         L.b2s_destroy.argtypes = [C.c_void_p]
         L.b2s_cloud_destroy.argtypes = [C.c_void_p]
         L.b2s_submap_destroy.argtypes = [C.c_void_p]
+        L.b2s_voxel_map_destroy.restype = None
+        L.b2s_voxel_map_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

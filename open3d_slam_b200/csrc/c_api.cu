@@ -39,13 +39,42 @@ __global__ void compose_kernel(const double* __restrict__ A, const double* __res
   }
 }
 
-// Mapper::addRangeMeasurement fitness gate (core/src/Mapper.cpp:151-160): accept -> mapToRangeSensor_ = result
-__global__ void gate_kernel(const b2s_result* __restrict__ res, double min_fitness, int ignore_fitness, double* pose_state, int32_t* gate) {
-  if (threadIdx.x == 0) {
-    const bool ok = ignore_fitness || !(res->fitness < min_fitness);
-    *gate = ok ? 1 : 0;
-    if (ok) for (int i = 0; i < 16; i++) pose_state[i] = res->T[i];
+// Everything Mapper::addRangeMeasurement decides after the registration (core/src/Mapper.cpp:151-177), on the device:
+//   fitness gate (:151)            accepted -> mapToRangeSensor_ = result (pose slot 0)
+//   minimum-motion gate (:170-176) sensorMotion = mapToRangeSensorLastScanInsertion_^-1 * mapToRangeSensor_ (pose slot 5)
+//   carving schedule               Submap::carve: map not empty and nScansInsertedMap_ % N == 1 (Submap.cpp:111)
+//   dense map                      fed with every accepted scan (SlamWrapper.cpp:318-327), carved when nScansInsertedDenseMap_ % N == 1
+// and the copy of the result into this step's slot of the result ring (slots == nullptr: the result already sits in its slot).
+struct GateArgs {
+  double min_fitness, min_move;
+  int ignore_fitness, carve_on, carve_n, dense_on, dcarve_n, pad;
+};
+__global__ void mapper_gate_kernel(const b2s_result* __restrict__ res, GateArgs a, double* pose, int32_t* ms, const int32_t* __restrict__ map_n,
+                                   b2s_result* slots, const int32_t* __restrict__ gstate) {
+  if (threadIdx.x != 0) return;
+  const bool accepted = a.ignore_fitness || !(res->fitness < a.min_fitness);
+  if (accepted) for (int i = 0; i < 16; i++) pose[i] = res->T[i];
+  bool insert = accepted;
+  if (accepted && a.min_move > 0.0) {
+    // Eigen: inverse of an isometry = (R^T, -(R^T t)); translation of the product A * B = A.linear() * B.translation() + A.translation()
+    const double* L = pose + 5 * 16;
+    const double* P = pose;
+    double it[3], m[3];
+    for (int i = 0; i < 3; i++) it[i] = -(L[i] * L[3] + L[4 + i] * L[7] + L[8 + i] * L[11]);
+    for (int i = 0; i < 3; i++) m[i] = (L[i] * P[3] + L[4 + i] * P[7] + L[8 + i] * P[11]) + it[i];
+    const double moved = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+    insert = !(moved < a.min_move);
   }
+  const bool carve = insert && a.carve_on && a.carve_n > 0 && *map_n > 0 && (ms[MS_NINS] % a.carve_n == 1);
+  const bool dense = accepted && a.dense_on;
+  const bool dcarve = dense && a.dcarve_n > 0 && (ms[MS_NDENSE] % a.dcarve_n == 1);
+  ms[MS_ACCEPT] = accepted; ms[MS_INSERT] = insert; ms[MS_CARVE] = carve; ms[MS_DENSE] = dense; ms[MS_DCARVE] = dcarve;
+  ms[MS_NSTEPS] += 1; ms[MS_NACCEPT] += accepted ? 1 : 0;
+  if (slots) slots[gstate[1]] = *res;
+}
+// end of a step that fed the dense map: ++nScansInsertedDenseMap_ (Submap.cpp:90)
+__global__ void mapper_post_kernel(int32_t* ms) {
+  if (threadIdx.x == 0 && ms[MS_DENSE]) ms[MS_NDENSE] += 1;
 }
 
 static double nn_cell(const b2s_handle* h, double max_corr) {
@@ -123,22 +152,42 @@ __global__ void graph_begin_kernel(const double* __restrict__ ring, int32_t* gst
   if (threadIdx.x == 0) { gstate[0] = step + 1; gstate[1] = step & 255; }
 }
 
-// fitness gate (Mapper.cpp:151-160) + copy of the result into this step's slot
-__global__ void gate_slot_kernel(const b2s_result* __restrict__ res, double min_fitness, int ignore_fitness, double* pose_state, int32_t* gate,
-                                 b2s_result* slots, const int32_t* gstate) {
-  if (threadIdx.x == 0) {
-    const bool ok = ignore_fitness || !(res->fitness < min_fitness);
-    *gate = ok ? 1 : 0;
-    if (ok) for (int i = 0; i < 16; i++) pose_state[i] = res->T[i];
-    slots[gstate[1]] = *res;
+// what follows the registration in every variant of the chain: gates, [carving], F1, [dense map]
+static int32_t mapper_chain_tail(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const b2s_cloud* merge, const b2s_result* res,
+                                 double min_fitness, int ignore_fitness, b2s_result* slots, const int32_t* gstate) {
+  const b2s_mapper_options& o = sm->opts;
+  double* pose_state = sm->pose.as<double>();
+  int32_t* ms = sm->mstate.as<int32_t>();
+  GateArgs ga;
+  ga.min_fitness = min_fitness; ga.min_move = o.min_movement_between_mapping_steps; ga.ignore_fitness = ignore_fitness;
+  ga.carve_on = o.carve_enabled; ga.carve_n = o.carve_every_n_scans; ga.dense_on = o.dense_enabled; ga.dcarve_n = o.dense_carve_every_n_scans; ga.pad = 0;
+  mapper_gate_kernel<<<1, 32, 0, h->stream>>>(res, ga, pose_state, ms, sm->cloud[0]->dn.as<int32_t>(), slots, gstate);
+  h->launches++;
+  if (o.carve_enabled) {   // Submap::insertScan: carve BEFORE the scan is appended, cropper still at the pose of the last insertion
+    B2S_REQUIRE(o.carving.voxel_size > 0.0, B2S_E_INVALID, "carving voxel size must be > 0");
+    CropDev crop = make_crop(&h->cfg.scan.map_builder_cropper, pose_state + 5 * 16);
+    B2S_TRY(op_submap_carve(h, sm, raw_scan, pose_state, crop, o.carving, nullptr, ms + MS_CARVE));
   }
+  B2S_TRY(op_submap_insert(h, sm, merge, pose_state, ms + MS_INSERT));                                  // Mapper.cpp:174
+  if (o.dense_enabled) {
+    if (sm->dense_cap == 0) {
+      B2S_REQUIRE(h->cfg.dense_voxel_size > 0.0, B2S_E_INVALID, "dense_voxel_size must be > 0");
+      B2S_TRY(dense_init(h, sm, (size_t)1 << 22, h->cfg.dense_voxel_size));
+    }
+    B2S_TRY(op_dense_insert(h, sm, raw_scan, nullptr, pose_state, &o.dense_cropper, ms + MS_DENSE));
+    if (o.dense_carve_every_n_scans > 0)
+      B2S_TRY(op_dense_carve(h, sm, raw_scan, nullptr, pose_state, o.dense_carving.neighborhood_radius_dense_map, o.dense_carving.truncation_distance,
+                             o.dense_carving.max_raytracing_length, ms + MS_TMP + 1, ms + MS_DCARVE));
+    mapper_post_kernel<<<1, 32, 0, h->stream>>>(ms);
+    h->launches++;
+  }
+  return B2S_OK;
 }
 
 static int32_t mapper_chain_graphable(b2s_handle* h, b2s_submap* sm) {
   double* pose_state = sm->pose.as<double>();
   double* odom = pose_state + 32;
   double* guess = pose_state + 48;
-  int32_t* gate = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 4);
   int32_t* gstate = sm->gstate.as<int32_t>();
   b2s_result* res = h->results.as<b2s_result>();
   double* ring_dev = nullptr;
@@ -149,9 +198,7 @@ static int32_t mapper_chain_graphable(b2s_handle* h, b2s_submap* sm) {
   compose_kernel<<<1, 32, 0, h->stream>>>(pose_state, odom, guess);
   h->launches++;
   B2S_TRY(::register_to_submap_async(h, h->t2, sm, nullptr, pose_state, nullptr, guess, res));
-  gate_slot_kernel<<<1, 32, 0, h->stream>>>(res, sm->g_min_fitness, sm->g_ignore_fitness, pose_state, gate, h->slots.as<b2s_result>(), gstate);
-  h->launches++;
-  return op_submap_insert(h, sm, h->t1, pose_state, gate);
+  return mapper_chain_tail(h, sm, sm->staging, h->t1, res, sm->g_min_fitness, sm->g_ignore_fitness, h->slots.as<b2s_result>(), gstate);
 }
 
 static int32_t mapper_step_graph(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double* odometry_motion, int32_t slot) {
@@ -162,6 +209,14 @@ static int32_t mapper_step_graph(b2s_handle* h, b2s_submap* sm, const b2s_cloud*
   if ((sm->host_step & 31) == 0) B2S_CUDA(cudaStreamSynchronize(h->stream));
   memcpy(sm->odom_ring + (sm->host_step & 63) * 16, odometry_motion, 128);   // read by graph_begin_kernel of this step
   sm->host_step++;
+  if (sm->gexec && (sm->graph_alloc_gen != __atomic_load_n(&g_alloc_generation, __ATOMIC_RELAXED) || sm->graph_cfg_gen != h->cfg_gen)) {
+    // a device buffer was re-allocated since the capture (any call that grows a scratch buffer): the graph holds the old
+    // address -- or b2s_set_config changed what the captured launches were built from.  Drop it; this step runs eagerly (which also re-sizes the scratch), the next one re-captures.
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    cudaGraphExecDestroy(sm->gexec);
+    sm->gexec = nullptr;
+    sm->graph_warm = 1;
+  }
   if (sm->gexec) {
     B2S_CUDA(cudaGraphLaunch(sm->gexec, h->stream));
     h->launches += sm->graph_kernels;
@@ -195,6 +250,8 @@ static int32_t mapper_step_graph(b2s_handle* h, b2s_submap* sm, const b2s_cloud*
   cudaGraphDestroy(graph);
   if (ce != cudaSuccess) { sm->gexec = nullptr; sm->graph_warm = 1 << 30; cudaGetLastError(); return mapper_chain_graphable(h, sm); }
   sm->graph_kernels = captured_kernels;
+  sm->graph_alloc_gen = __atomic_load_n(&g_alloc_generation, __ATOMIC_RELAXED);
+  sm->graph_cfg_gen = h->cfg_gen;
   B2S_CUDA(cudaGraphLaunch(sm->gexec, h->stream));
   h->launches += sm->graph_kernels;
   return B2S_OK;
@@ -271,6 +328,7 @@ int32_t b2s_set_config(b2s_handle* h, const b2s_config* cfg) {
   B2S_REQUIRE(h && cfg, B2S_E_INVALID, "null argument");
   LOCK(h);
   h->cfg = *cfg;
+  h->cfg_gen++;
   return B2S_OK;
 }
 
@@ -398,6 +456,32 @@ int32_t b2s_cloud_download(b2s_handle* h, const b2s_cloud* c, double* xyz, doubl
   return check_status(h);
 }
 
+int32_t b2s_cloud_export_device(b2s_handle* h, const b2s_cloud* c, void* xyz_dev, void* normals_dev, size_t capacity, size_t* n_out) {
+  B2S_REQUIRE(h && c && xyz_dev, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  size_t n = 0;
+  B2S_TRY(cloud_count_sync(h, c, &n));
+  if (n_out) *n_out = n;
+  B2S_REQUIRE(n <= capacity, B2S_E_CAPACITY, "device buffer too small: %zu points, capacity %zu", n, capacity);
+  if (n) B2S_CUDA(cudaMemcpyAsync(xyz_dev, c->xyz.p, n * 24, cudaMemcpyDeviceToDevice, h->stream));
+  if (n && normals_dev) {
+    B2S_REQUIRE(c->has_normals, B2S_E_NO_NORMALS, "cloud has no normals");
+    B2S_CUDA(cudaMemcpyAsync(normals_dev, c->nrm.p, n * 24, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return check_status(h);
+}
+
+int32_t b2s_cloud_import_device(b2s_handle* h, b2s_cloud* c, const void* xyz_dev, const void* normals_dev, size_t n) {
+  B2S_REQUIRE(h && c && (xyz_dev || n == 0), B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(n < (size_t)0x7fffffff / 4, B2S_E_INVALID, "cloud too large");
+  LOCK(h);
+  B2S_TRY(cloud_reserve(h, c, n, normals_dev != nullptr));
+  if (n) B2S_CUDA(cudaMemcpyAsync(c->xyz.p, xyz_dev, n * 24, cudaMemcpyDeviceToDevice, h->stream));
+  if (n && normals_dev) B2S_CUDA(cudaMemcpyAsync(c->nrm.p, normals_dev, n * 24, cudaMemcpyDeviceToDevice, h->stream));
+  c->has_normals = normals_dev != nullptr;
+  return cloud_set_count(h, c, n);
+}
+
 int32_t b2s_cloud_copy(b2s_handle* h, const b2s_cloud* src, b2s_cloud* dst) {
   B2S_REQUIRE(h && src && dst, B2S_E_INVALID, "null argument");
   LOCK(h);
@@ -512,7 +596,7 @@ int32_t b2s_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, co
   LOCK(h);
   if (sm->dense_cap == 0) { if (n_removed) *n_removed = 0; return B2S_OK; }   // cloud->empty(): nothing to carve (Submap.cpp:127)
   int32_t* removed_dev = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 8);
-  B2S_TRY(op_dense_carve(h, sm, scan, sensor, prm->neighborhood_radius_dense_map, prm->truncation_distance, prm->max_raytracing_length, removed_dev));
+  B2S_TRY(op_dense_carve(h, sm, scan, sensor, nullptr, prm->neighborhood_radius_dense_map, prm->truncation_distance, prm->max_raytracing_length, removed_dev));
   if (!n_removed) return B2S_OK;
   B2S_TRY(ensure_pinned(h, 4096));
   int32_t* pr = reinterpret_cast<int32_t*>(static_cast<char*>(h->pinned) + 512);
@@ -630,9 +714,15 @@ int32_t b2s_submap_create(b2s_handle* h, size_t capacity_points, b2s_submap** ou
     B2S_TRY(cloud_set_count(h, sm->cloud[i], 0));
     sm->cloud[i]->has_normals = true;
   }
-  B2S_TRY(sm->pose.ensure(6 * 16 * 8, h->stream));   // pose state, insertion pose, odometry, guess, carving pose, spare
+  // pose slots: [0] mapToRangeSensor_, [1] pose of a host-driven insertion, [2] odometry motion, [3] initial guess, [4] carving pose,
+  //             [5] pose of the last insertion (= mapToRangeSensorLastScanInsertion_ = mapBuilderCropper_'s pose; Identity before the first)
+  B2S_TRY(sm->pose.ensure(8 * 16 * 8, h->stream));
   const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   B2S_TRY(pose_to_device(h, I, sm->pose.as<double>()));
+  B2S_TRY(pose_to_device(h, I, sm->pose.as<double>() + 5 * 16));
+  B2S_TRY(sm->mstate.ensure(MS_WORDS * 4, h->stream));
+  B2S_CUDA(cudaMemsetAsync(sm->mstate.p, 0, MS_WORDS * 4, h->stream));
+  b2s_default_mapper_options(&sm->opts);
   *out = sm;
   return B2S_OK;
 }
@@ -647,7 +737,7 @@ void b2s_submap_destroy(b2s_submap* sm) {
   if (sm->gexec) cudaGraphExecDestroy(sm->gexec);
   if (sm->odom_ring) cudaFreeHost(sm->odom_ring);
   if (sm->staging) { sm->staging->xyz.release(); sm->staging->nrm.release(); sm->staging->dn.release(); delete sm->staging; }
-  sm->gstate.release();
+  sm->gstate.release(); sm->mstate.release();
   if (sm->cnt_ev) cudaEventDestroy(sm->cnt_ev);
   delete sm;
 }
@@ -683,7 +773,6 @@ int32_t b2s_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_sca
                          const b2s_carving_params* prm, size_t* n_removed) {
   B2S_REQUIRE(h && sm && raw_scan && T && cropper_pose && prm, B2S_E_INVALID, "null argument");
   B2S_REQUIRE(prm->voxel_size > 0.0, B2S_E_INVALID, "carving voxel size must be > 0");
-  B2S_REQUIRE(!sm->graph_mode, B2S_E_UNSUPPORTED, "carving is not part of the captured per-scan graph");
   LOCK(h);
   double* Td = sm->pose.as<double>() + 64;   // slot 4: pose of the carving scan
   B2S_TRY(pose_to_device(h, T, Td));
@@ -707,7 +796,7 @@ int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* 
     B2S_REQUIRE(h->cfg.dense_voxel_size > 0.0, B2S_E_INVALID, "dense_voxel_size must be > 0");
     B2S_TRY(dense_init(h, sm, (size_t)1 << 22, h->cfg.dense_voxel_size));
   }
-  return op_dense_insert(h, sm, raw, T, crop);
+  return op_dense_insert(h, sm, raw, T, nullptr, crop);
 }
 
 int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n) {
@@ -800,16 +889,52 @@ int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* ra
   double* pose_state = sm->pose.as<double>();        // mapToRangeSensor_ (== mapToRangeSensorPrev_ in steady state)
   double* odom = pose_state + 32;
   double* guess = pose_state + 48;
-  int32_t* gate = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 4);
   b2s_result* res = h->slots.as<b2s_result>() + slot;
   B2S_TRY(process_scan_impl(h, raw_scan, h->t1, h->t2));                      // Mapper.cpp:139
   B2S_TRY(pose_to_device(h, odometry_motion, odom));
   compose_kernel<<<1, 32, 0, h->stream>>>(pose_state, odom, guess);           // Mapper.cpp:130-137
   h->launches++;
   B2S_TRY(register_to_submap_async(h, h->t2, sm, nullptr, pose_state, nullptr, guess, res));  // Mapper.cpp:140-141
-  gate_kernel<<<1, 32, 0, h->stream>>>(res, min_refinement_fitness, ignore_min_fitness, pose_state, gate);  // Mapper.cpp:151-160
-  h->launches++;
-  return op_submap_insert(h, sm, h->t1, pose_state, gate);                   // Mapper.cpp:174
+  return mapper_chain_tail(h, sm, raw_scan, h->t1, res, min_refinement_fitness, ignore_min_fitness, nullptr, nullptr);   // Mapper.cpp:151-177
+}
+
+void b2s_default_mapper_options(b2s_mapper_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->min_movement_between_mapping_steps = 0.0;
+  o->carve_enabled = 0; o->carve_every_n_scans = 10;
+  o->carving.voxel_size = 0.1; o->carving.max_raytracing_length = 20.0; o->carving.truncation_distance = 0.1;
+  o->carving.min_dot_product_with_normal = 0.5; o->carving.neighborhood_radius_dense_map = 0.1;
+  o->dense_enabled = 0; o->dense_carve_every_n_scans = 0;
+  o->dense_carving = o->carving;
+  o->dense_cropper.kind = B2S_CROP_NONE;
+}
+
+int32_t b2s_submap_set_mapper_options(b2s_handle* h, b2s_submap* sm, const b2s_mapper_options* o) {
+  B2S_REQUIRE(h && sm && o, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(!o->carve_enabled || (o->carve_every_n_scans > 0 && o->carving.voxel_size > 0.0), B2S_E_INVALID, "invalid carving parameters");
+  B2S_REQUIRE(o->dense_carve_every_n_scans >= 0 && o->min_movement_between_mapping_steps >= 0.0, B2S_E_INVALID, "invalid mapper options");
+  LOCK(h);
+  sm->opts = *o;
+  if (sm->gexec) {   // the options are baked into the captured chain
+    B2S_CUDA(cudaStreamSynchronize(h->stream));
+    cudaGraphExecDestroy(sm->gexec);
+    sm->gexec = nullptr;
+    sm->graph_warm = 1;
+  }
+  return B2S_OK;
+}
+
+int32_t b2s_submap_get_mapper_counters(b2s_handle* h, const b2s_submap* sm, b2s_mapper_counters* out) {
+  B2S_REQUIRE(h && sm && out, B2S_E_INVALID, "null argument");
+  LOCK(h);
+  B2S_TRY(ensure_pinned(h, 4096));
+  int32_t* pw = reinterpret_cast<int32_t*>(static_cast<char*>(h->pinned) + 1024);
+  B2S_CUDA(cudaMemcpyAsync(pw, sm->mstate.p, MS_WORDS * 4, cudaMemcpyDeviceToHost, h->stream));
+  const int32_t rc = check_status(h);   // synchronises
+  out->steps = pw[MS_NSTEPS]; out->accepted = pw[MS_NACCEPT]; out->inserted_map = pw[MS_NINS]; out->inserted_dense = pw[MS_NDENSE];
+  out->carve_runs = pw[MS_NCARVE]; out->carved_points_total = pw[MS_CARVED]; out->dense_carve_runs = pw[MS_NDCARVE];
+  out->carved_voxels_total = pw[MS_DCARVED];
+  return rc;
 }
 
 // Turns b2s_mapper_step_async into a CUDA-graph replay for this submap: the ~45 kernel launches of one scan collapse
@@ -864,6 +989,14 @@ int32_t b2s_mapper_step_host_async(b2s_handle* h, b2s_submap* sm, const void* xy
   B2S_TRY(b2s_mapper_step_async(h, sm, dst, odometry_motion, min_refinement_fitness, ignore_min_fitness, slot));
   LOCK(h);
   B2S_CUDA(cudaMemcpyAsync(out_pinned, h->slots.as<b2s_result>() + slot, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
+  return B2S_OK;
+}
+
+int32_t b2s_mapper_processed_scan(b2s_handle* h, b2s_cloud* merge_out, b2s_cloud* match_out) {
+  B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
+  LOCK(h);
+  if (merge_out) B2S_TRY(op_voxel_down_sample(h, h->t1, nullptr, 0.0, merge_out));   // voxel <= 0: plain copy
+  if (match_out) B2S_TRY(op_voxel_down_sample(h, h->t2, nullptr, 0.0, match_out));
   return B2S_OK;
 }
 

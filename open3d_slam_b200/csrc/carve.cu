@@ -33,15 +33,23 @@ __device__ __forceinline__ bool cv_key_of(double x, double y, double z, double i
   return true;
 }
 
+// enable (optional): device-side schedule of the mapper chain -- every kernel of the carving sequence returns at once unless
+// *enable != 0; n_eff (optional) receives the point count the compaction works on (0 when skipped)
 __global__ void __launch_bounds__(CV_THREADS) carve_init_kernel(unsigned long long* __restrict__ keys, int32_t* __restrict__ head, size_t cap,
-                                                                int32_t* __restrict__ keep, int n_max) {
+                                                                int32_t* __restrict__ keep, int n_max, const int32_t* __restrict__ enable,
+                                                                const int32_t* __restrict__ d_nmap, int32_t* n_eff) {
+  const bool on = enable == nullptr || *enable != 0;
+  if (n_eff && blockIdx.x == 0 && threadIdx.x == 0) *n_eff = on ? *d_nmap : 0;
+  if (!on) return;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) { keys[i] = CV_EMPTY; head[i] = -1; }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_max; i += gridDim.x * blockDim.x) keep[i] = 1;
 }
 
 __global__ void __launch_bounds__(CV_THREADS) carve_insert_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, CropDev crop,
                                                                   double inv, unsigned long long* keys, int32_t* head,
-                                                                  int32_t* __restrict__ next, size_t mask, uint32_t* status) {
+                                                                  int32_t* __restrict__ next, size_t mask, uint32_t* status,
+                                                                  const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
@@ -62,7 +70,9 @@ __global__ void __launch_bounds__(CV_THREADS) carve_march_kernel(const double* _
                                                                  const double* __restrict__ Tdev, const double* __restrict__ map_nrm,
                                                                  const unsigned long long* __restrict__ keys, const int32_t* __restrict__ head,
                                                                  const int32_t* __restrict__ next, size_t mask, double voxel, double inv,
-                                                                 double max_len, double trunc, double min_dot, int32_t* keep) {
+                                                                 double max_len, double trunc, double min_dot, int32_t* keep,
+                                                                 const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   const int n = *d_nscan;
   double T[16];
 #pragma unroll
@@ -110,17 +120,39 @@ __global__ void __launch_bounds__(CV_THREADS) carve_march_kernel(const double* _
   }
 }
 
-__global__ void carve_count_kernel(const int32_t* __restrict__ before, const int32_t* __restrict__ after, int32_t* removed) {
-  *removed = *before - *after;
+// commit of the compacted map back into the map's own buffers (captured graphs and indices hold their addresses), the
+// removed count, and the chain's carving counters
+__global__ void __launch_bounds__(CV_THREADS) carve_commit_kernel(const double* __restrict__ txyz, const double* __restrict__ tnrm,
+                                                                  const int32_t* __restrict__ d_after, double* __restrict__ mxyz,
+                                                                  double* __restrict__ mnrm, int32_t* d_nmap, int32_t* removed,
+                                                                  const int32_t* __restrict__ enable, int32_t* mstate) {
+  if (enable != nullptr && *enable == 0) { if (removed && blockIdx.x == 0 && threadIdx.x == 0) *removed = 0; return; }
+  const int before = *d_nmap, n = *d_after;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += gridDim.x * blockDim.x) { mxyz[i] = txyz[i]; if (mnrm) mnrm[i] = tnrm[i]; }
+  // d_nmap is read by every block before any block can reach this point of a LATER kernel; within this kernel only block 0
+  // writes it, after its own copy loop -- other blocks may still read `before`, so the write goes through a grid-wide
+  // ticket: the last block to finish publishes the new count
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&mstate[MS_TMP], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    mstate[MS_TMP] = 0;
+    *d_nmap = n;
+    if (removed) *removed = before - n;
+    mstate[MS_NCARVE] += 1;
+    mstate[MS_CARVED] += before - n;
+  }
 }
 
-int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out);   // voxel.cu
+int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out, const int32_t* d_n_override = nullptr);   // voxel.cu
 
 int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double* T_dev, const CropDev& crop,
-                        const b2s_carving_params& prm, int32_t* removed_dev) {
+                        const b2s_carving_params& prm, int32_t* removed_dev, const int32_t* enable_dev) {
   b2s_cloud* map = sm->cloud[0];
   b2s_cloud* tmp = sm->cloud[1];
-  const size_t n_max = map->n_max > 0 ? map->n_max : 1;
+  // graph replay: constant launch dimensions (the map's host-side bound moves from scan to scan)
+  const size_t n_max = sm->graph_mode ? sm->capacity : (map->n_max > 0 ? map->n_max : 1);
   size_t cap = 1024;
   while (cap < 2 * n_max) cap <<= 1;
   B2S_TRY(h->keys.ensure(cap * 8, h->stream));                    // packed voxel keys
@@ -131,24 +163,28 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
   int32_t* head = h->vals.as<int32_t>();
   int32_t* next = h->tmp_i32.as<int32_t>();
   int32_t* keep = h->flags.as<int32_t>();
+  int32_t* ms = sm->mstate.as<int32_t>();
+  int32_t* n_eff = ms + MS_CARVE_N;
   const double inv = 1.0 / prm.voxel_size;   // fromVoxelSize (VoxelHashMap.hpp:43-45)
   ProfScope prof(h, PK_FUSE);
-  carve_init_kernel<<<grid_for(cap, CV_THREADS), CV_THREADS, 0, h->stream>>>(keys, head, cap, keep, (int)n_max);
+  carve_init_kernel<<<grid_for(cap, CV_THREADS), CV_THREADS, 0, h->stream>>>(keys, head, cap, keep, (int)n_max, enable_dev, map->dn.as<int32_t>(),
+                                                                             n_eff);
   carve_insert_kernel<<<grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(), crop, inv, keys,
-                                                                                head, next, cap - 1, h->status.as<uint32_t>());
+                                                                                head, next, cap - 1, h->status.as<uint32_t>(), enable_dev);
   carve_march_kernel<<<grid_for(raw_scan->n_max > 0 ? raw_scan->n_max : 1, CV_THREADS), CV_THREADS, 0, h->stream>>>(
       raw_scan->xyz.as<double>(), raw_scan->dn.as<int32_t>(), T_dev, map->has_normals ? map->nrm.as<double>() : nullptr, keys, head, next,
-      cap - 1, prm.voxel_size, inv, prm.max_raytracing_length, prm.truncation_distance, prm.min_dot_product_with_normal, keep);
+      cap - 1, prm.voxel_size, inv, prm.max_raytracing_length, prm.truncation_distance, prm.min_dot_product_with_normal, keep, enable_dev);
   h->launches += 3;
-  B2S_TRY(compact_cloud(h, map, keep, tmp));
-  if (removed_dev) {
-    carve_count_kernel<<<1, 1, 0, h->stream>>>(map->dn.as<int32_t>(), tmp->dn.as<int32_t>(), removed_dev);
-    h->launches++;
-  }
-  // copy back: the map keeps its buffers (captured graphs and indices hold their addresses)
-  B2S_CUDA(cudaMemcpyAsync(map->xyz.p, tmp->xyz.p, n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
-  if (map->has_normals) B2S_CUDA(cudaMemcpyAsync(map->nrm.p, tmp->nrm.p, n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
-  B2S_CUDA(cudaMemcpyAsync(map->dn.p, tmp->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+  const size_t keep_n_max = map->n_max;
+  if (sm->graph_mode) map->n_max = n_max;
+  const int32_t rc = compact_cloud(h, map, keep, tmp, n_eff);   // order-preserving (removeByIds = SelectByIndex(invert))
+  map->n_max = keep_n_max;
+  B2S_TRY(rc);
+  carve_commit_kernel<<<grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream>>>(tmp->xyz.as<double>(), tmp->nrm.as<double>(),
+                                                                               tmp->dn.as<int32_t>(), map->xyz.as<double>(),
+                                                                               map->has_normals ? map->nrm.as<double>() : nullptr,
+                                                                               map->dn.as<int32_t>(), removed_dev, enable_dev, ms);
+  h->launches++;
   map->n_known = -1;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;

@@ -137,9 +137,31 @@ struct b2s_submap {
   b2s::DevBuf gstate;                 // int32 [0] device step counter, [1] current result slot
   double g_min_fitness = 0.0;
   int g_ignore_fitness = 0;
+  // Mapper / SubmapCollection wiring of the device chain (b2s_mapper_options) and its device-side state words (MS_*)
+  b2s_mapper_options opts;
+  b2s::DevBuf mstate;                 // int32 [MS_WORDS]: gates and counters of the chain, see the MS_* indices below
+  unsigned long long graph_alloc_gen = 0;   // value of b2s::g_alloc_generation when the graph was captured
+  unsigned long long graph_cfg_gen = 0;     // value of b2s_handle::cfg_gen when the graph was captured
 };
 
 namespace b2s {
+// device-side state words of the mapper chain (b2s_submap::mstate)
+enum MapperStateWord {
+  MS_ACCEPT = 0,      // this step passed the fitness gate (Mapper.cpp:151)
+  MS_INSERT = 1,      // ... and the minimum-motion gate (Mapper.cpp:170-176): F1 runs
+  MS_CARVE = 2,       // sparse-map carving runs in this step (Submap.cpp:111)
+  MS_DENSE = 3,       // dense-map insertion runs in this step
+  MS_DCARVE = 4,      // dense-map carving runs in this step (Submap.cpp:127)
+  MS_NINS = 5,        // Submap::nScansInsertedMap_
+  MS_NDENSE = 6,      // Submap::nScansInsertedDenseMap_
+  MS_NSTEPS = 7, MS_NACCEPT = 8, MS_NCARVE = 9, MS_CARVED = 10, MS_NDCARVE = 11, MS_DCARVED = 12,
+  MS_CARVE_N = 13,    // point count the carving compaction works on (0 when carving is skipped)
+  MS_TMP = 14,
+  MS_WORDS = 32
+};
+// bumped by every DevBuf re-allocation: a captured graph holds raw pointers of the scratch buffers, so a graph captured
+// under an older generation is re-captured before it is replayed again
+extern unsigned long long g_alloc_generation;
 // per-kernel-group device timing with CUDA events on the launching stream (bench.py's roofline numbers)
 enum ProfKind { PK_ICP = 0, PK_NORMALS, PK_SORT, PK_GRID, PK_VOXEL, PK_FUSE, PK_SELECT, PK_CROP, PK_COUNT };
 struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -161,6 +183,7 @@ struct b2s_handle {
   bool own_stream = false;
   std::mutex mu;
   b2s_config cfg;
+  unsigned long long cfg_gen = 1;     // bumped by b2s_set_config: captured graphs bake the configuration in
   int64_t launches = 0;
 
   b2s::DevBuf status;                 // uint32 device status word
@@ -218,6 +241,7 @@ int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double c
 // the same for n clouds at once (batched registration: every pair brings its own target), blockIdx.y = cloud
 int32_t grid_build_batch(b2s_handle* h, GridIndex* const* g, const b2s_cloud* const* clouds, int n, double cell, bool with_normals);
 
+int32_t pose_to_device(b2s_handle* h, const double* T, double* dst);   // host 4x4 -> device slot, no staging buffer (voxel.cu)
 int32_t cloud_reserve(b2s_handle* h, b2s_cloud* c, size_t n, bool normals);
 int32_t cloud_set_count(b2s_handle* h, b2s_cloud* c, size_t n);
 
@@ -261,8 +285,10 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
 int32_t op_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* pts, int32_t* count_dev, double* mean_dev);
 int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts);
 int32_t op_dense_count(b2s_handle* h, const b2s_submap* sm, int32_t* out_dev);
-int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* sensor, double radius, double trunc, double max_len,
-                       int32_t* removed_dev);
+// sensor_dev != nullptr: the sensor position is the translation of that device-resident 4x4; enable_dev (optional): the
+// kernels return at once unless *enable_dev != 0 (device-side schedule of the mapper chain)
+int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* sensor, const double* sensor_dev, double radius,
+                       double trunc, double max_len, int32_t* removed_dev, const int32_t* enable_dev = nullptr);
 int32_t op_submap_transform(b2s_handle* h, b2s_submap* sm, const double* T_host);   // Submap::transform (voxel.cu)
 // D1 constant-velocity de-skew (voxel.cu)
 int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, const double* ang_vel_rpy, double scan_duration, int clockwise,
@@ -272,8 +298,10 @@ int32_t op_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* targ
                    b2s_cloud* source_overlap, b2s_cloud* target_overlap);
 // C1 space carving of the sparse map (carve.cu); removed_dev (optional) receives the number of removed points
 int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan, const double* T_dev, const CropDev& crop,
-                        const b2s_carving_params& prm, int32_t* removed_dev);
-int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const b2s_cropper* crop);
+                        const b2s_carving_params& prm, int32_t* removed_dev, const int32_t* enable_dev = nullptr);
+// T_dev != nullptr: device-resident pose (T_host ignored)
+int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const double* T_dev, const b2s_cropper* crop,
+                        const int32_t* enable_dev = nullptr);
 
 inline int grid_for(size_t n, int threads, int max_blocks = 148 * 16) {
   size_t b = (n + (size_t)threads - 1) / (size_t)threads;

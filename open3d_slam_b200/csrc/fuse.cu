@@ -150,12 +150,19 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_mean_kernel(const K* __restri
   }
 }
 
+// mstate / last_pose: Submap::nScansInsertedMap_ and the pose mapBuilderCropper_ was last set to (Submap.cpp:71,73), which is
+// also Mapper::mapToRangeSensorLastScanInsertion_ (Mapper.cpp:175) -- kept on the device for the chain's own gates
 __global__ void __launch_bounds__(FZ_THREADS) fuse_commit_kernel(const double* __restrict__ oxyz, const double* __restrict__ onrm,
                                                                  const int32_t* __restrict__ d_out_n, const int32_t* __restrict__ d_tot,
-                                                                 double* __restrict__ mxyz, double* __restrict__ mnrm, int32_t* d_nmap) {
+                                                                 double* __restrict__ mxyz, double* __restrict__ mnrm, int32_t* d_nmap,
+                                                                 int32_t* mstate, double* last_pose, const double* __restrict__ Tdev) {
   if (*d_tot <= 0) return;  // gate closed, empty scan or capacity error: the map stays as it was
   const int n = *d_out_n;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *d_nmap = n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *d_nmap = n;
+    if (mstate) mstate[MS_NINS] += 1;
+    if (last_pose) for (int i = 0; i < 16; i++) last_pose[i] = Tdev[i];
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += gridDim.x * blockDim.x) { mxyz[i] = oxyz[i]; mnrm[i] = onrm[i]; }
 }
 
@@ -204,7 +211,8 @@ static int32_t fuse_impl(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
                                                             map->xyz.as<double>(), map->nrm.as<double>(), tmp->xyz.as<double>(),
                                                             tmp->nrm.as<double>(), d_out_n);
   fuse_commit_kernel<<<blocks, FZ_THREADS, 0, h->stream>>>(tmp->xyz.as<double>(), tmp->nrm.as<double>(), d_out_n, d_tot,
-                                                           map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>());
+                                                           map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>(),
+                                                           sm->mstate.as<int32_t>(), sm->pose.as<double>() + 5 * 16, T_dev);
   h->launches += 2;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
@@ -272,38 +280,54 @@ __device__ __forceinline__ unsigned long long dense_hash(unsigned long long k) {
   return k;
 }
 
+__device__ __forceinline__ void dense_add_point(double x, double y, double z, double inv, unsigned long long* __restrict__ keys,
+                                                double* __restrict__ sums, int32_t* __restrict__ cnts, size_t cap, int32_t* used, uint32_t* status) {
+  const double fx = floor(__dmul_rn(x, inv)), fy = floor(__dmul_rn(y, inv)), fz = floor(__dmul_rn(z, inv));
+  if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) { atomicOr(status, ST_KEY_OVERFLOW); return; }
+  const unsigned long long key = dense_pack((int)fx, (int)fy, (int)fz);
+  size_t slot = (size_t)(dense_hash(key) % cap);
+  for (size_t probe = 0; probe < cap; ++probe) {
+    unsigned long long prev = atomicCAS(&keys[slot], DENSE_EMPTY, key);
+    if (prev == DENSE_EMPTY) {
+      if ((size_t)atomicAdd(used, 1) + 1 > cap - cap / 8) atomicOr(status, ST_HASH_FULL);
+      prev = key;
+    }
+    if (prev == key) {
+      atomicAdd(&sums[6 * slot], x); atomicAdd(&sums[6 * slot + 1], y); atomicAdd(&sums[6 * slot + 2], z);
+      atomicAdd(&cnts[slot], 1);
+      return;
+    }
+    slot = slot + 1 == cap ? 0 : slot + 1;
+  }
+}
+
+// Submap::insertScanDenseMap goes through o3d_slam::transform (Submap.cpp:80), so its near-identity duplication quirk
+// (helpers.cpp:275-292: |T - I|_max < 1e-4 -> the untransformed cloud is copied first and every transformed point is
+// appended as well) applies: such a scan lands in the dense map twice.  Kept.
 __global__ void __launch_bounds__(FZ_THREADS) dense_insert_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                                   const double* __restrict__ Tdev, CropDev crop, double inv,
                                                                   unsigned long long* __restrict__ keys, double* __restrict__ sums,
-                                                                  int32_t* __restrict__ cnts, size_t cap, int32_t* used, uint32_t* status) {
+                                                                  int32_t* __restrict__ cnts, size_t cap, int32_t* used, uint32_t* status,
+                                                                  const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   double T[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) T[i] = Tdev[i];
+  double mx = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) mx = fmax(mx, fabs(T[i] - ((i % 5 == 0) ? 1.0 : 0.0)));
+  const bool ident = mx < 1e-4;  // helpers.cpp:275
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
     if (!(px == px && py == py && pz == pz)) continue;
     if (!crop_within(crop, px, py, pz)) continue;  // denseMapCropper_ at identity, applied in the sensor frame (Submap.cpp:78-79)
+    if (ident) dense_add_point(px, py, pz, inv, keys, sums, cnts, cap, used, status);
     const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
     const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], px), __dmul_rn(T[5], py)), __dmul_rn(T[6], pz)), T[7]);
     const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], px), __dmul_rn(T[9], py)), __dmul_rn(T[10], pz)), T[11]);
-    const double fx = floor(__dmul_rn(x, inv)), fy = floor(__dmul_rn(y, inv)), fz = floor(__dmul_rn(z, inv));
-    if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) { atomicOr(status, ST_KEY_OVERFLOW); continue; }
-    const unsigned long long key = dense_pack((int)fx, (int)fy, (int)fz);
-    size_t slot = (size_t)(dense_hash(key) % cap);
-    for (size_t probe = 0; probe < cap; ++probe) {
-      unsigned long long prev = atomicCAS(&keys[slot], DENSE_EMPTY, key);
-      if (prev == DENSE_EMPTY) {
-        if ((size_t)atomicAdd(used, 1) + 1 > cap - cap / 8) atomicOr(status, ST_HASH_FULL);
-        prev = key;
-      }
-      if (prev == key) {
-        atomicAdd(&sums[6 * slot], x); atomicAdd(&sums[6 * slot + 1], y); atomicAdd(&sums[6 * slot + 2], z);
-        atomicAdd(&cnts[slot], 1);
-        break;
-      }
-      slot = slot + 1 == cap ? 0 : slot + 1;
-    }
+    const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[12], px), __dmul_rn(T[13], py)), __dmul_rn(T[14], pz)), T[15]);
+    dense_add_point(__ddiv_rn(x, w), __ddiv_rn(y, w), __ddiv_rn(z, w), inv, keys, sums, cnts, cap, used, status);
   }
 }
 
@@ -328,18 +352,23 @@ int32_t dense_init(b2s_handle* h, b2s_submap* sm, size_t cap, double voxel) {
   return B2S_OK;
 }
 
-int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const b2s_cropper* crop) {
+int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const double* T_dev, const b2s_cropper* crop,
+                        const int32_t* enable_dev) {
   B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
-  B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream, true));
-  double* Td = h->poses.as<double>() + 16 * 62;
-  B2S_TRY(pose_to_device(h, T_host, Td));
+  const double* Td = T_dev;
+  if (!Td) {
+    B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream, true));
+    double* slot = h->poses.as<double>() + 16 * 62;
+    B2S_TRY(pose_to_device(h, T_host, slot));
+    Td = slot;
+  }
   b2s_cropper c0;
   memset(&c0, 0, sizeof(c0));
   if (crop) c0 = *crop;
   c0.center[0] = c0.center[1] = c0.center[2] = 0.0;  // Submap.cpp:78 setPose(Identity)
   dense_insert_kernel<<<grid_for(raw->n_max > 0 ? raw->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
       raw->xyz.as<double>(), raw->dn.as<int32_t>(), Td, make_crop(&c0), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(),
-      sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, sm->dense_used.as<int32_t>(), h->status.as<uint32_t>());
+      sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, sm->dense_used.as<int32_t>(), h->status.as<uint32_t>(), enable_dev);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
@@ -487,7 +516,8 @@ __device__ __forceinline__ long long dense_find_key(const unsigned long long* __
 
 __global__ void __launch_bounds__(FZ_THREADS) dcarve_first_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double inv,
                                                                   unsigned long long* keys, int32_t* first, size_t mask,
-                                                                  int32_t* __restrict__ slot_of) {
+                                                                  int32_t* __restrict__ slot_of, const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double fx = floor(__dmul_rn(xyz[3 * i], inv)), fy = floor(__dmul_rn(xyz[3 * i + 1], inv)), fz = floor(__dmul_rn(xyz[3 * i + 2], inv));
@@ -502,16 +532,23 @@ __global__ void __launch_bounds__(FZ_THREADS) dcarve_first_kernel(const double* 
   }
 }
 
-__global__ void dcarve_init_kernel(unsigned long long* keys, int32_t* first, size_t cap, int32_t* rm, size_t dense_cap) {
+__global__ void dcarve_init_kernel(unsigned long long* keys, int32_t* first, size_t cap, int32_t* rm, size_t dense_cap,
+                                   const int32_t* __restrict__ enable, int32_t* removed) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && removed) *removed = 0;
+  if (enable != nullptr && *enable == 0) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) { keys[i] = DENSE_EMPTY; first[i] = 0x7fffffff; }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dense_cap; i += (size_t)gridDim.x * blockDim.x) rm[i] = 0;
 }
 
 __global__ void __launch_bounds__(FZ_THREADS) dcarve_march_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                                   const int32_t* __restrict__ slot_of, const int32_t* __restrict__ first,
-                                                                  double sx, double sy, double sz, double voxel, double radius, double trunc,
+                                                                  double sx, double sy, double sz, const double* __restrict__ sensor_dev,
+                                                                  double voxel, double radius, double trunc,
                                                                   double max_len, const unsigned long long* __restrict__ dkeys,
-                                                                  const int32_t* __restrict__ dcnt, size_t dcap, int32_t* __restrict__ rm) {
+                                                                  const int32_t* __restrict__ dcnt, size_t dcap, int32_t* __restrict__ rm,
+                                                                  const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
+  if (sensor_dev) { sx = sensor_dev[3]; sy = sensor_dev[7]; sz = sensor_dev[11]; }   // mapToRangeSensor.translation()
   const int n = *d_n;
   const double step = 2.0 * radius;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -553,7 +590,10 @@ __global__ void __launch_bounds__(FZ_THREADS) dcarve_march_kernel(const double* 
   }
 }
 
-__global__ void dcarve_apply_kernel(const int32_t* __restrict__ rm, size_t cap, double* __restrict__ sums, int32_t* __restrict__ cnts, int32_t* removed) {
+__global__ void dcarve_apply_kernel(const int32_t* __restrict__ rm, size_t cap, double* __restrict__ sums, int32_t* __restrict__ cnts, int32_t* removed,
+                                    const int32_t* __restrict__ enable, int32_t* mstate) {
+  if (enable != nullptr && *enable == 0) return;
+  if (mstate && blockIdx.x == 0 && threadIdx.x == 0) mstate[MS_NDCARVE] += 1;
   int c = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     if (!rm[i]) continue;
@@ -562,11 +602,11 @@ __global__ void dcarve_apply_kernel(const int32_t* __restrict__ rm, size_t cap, 
     c++;
   }
   c = warp_sum_i(c);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(removed, c);
+  if ((threadIdx.x & 31) == 0 && c) { atomicAdd(removed, c); if (mstate) atomicAdd(&mstate[MS_DCARVED], c); }
 }
 
-int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* sensor, double radius, double trunc, double max_len,
-                       int32_t* removed_dev) {
+int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* sensor, const double* sensor_dev, double radius,
+                       double trunc, double max_len, int32_t* removed_dev, const int32_t* enable_dev) {
   B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
   const size_t n_max = scan->n_max > 0 ? scan->n_max : 1;
   size_t cap = 1024;
@@ -580,16 +620,17 @@ int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, con
   int32_t* slot_of = h->tmp_i32.as<int32_t>();
   int32_t* rm = h->offs.as<int32_t>();
   const double voxel = sm->dense_voxel;
+  const double s0 = sensor ? sensor[0] : 0.0, s1 = sensor ? sensor[1] : 0.0, s2 = sensor ? sensor[2] : 0.0;
   ProfScope prof(h, PK_FUSE);
-  B2S_CUDA(cudaMemsetAsync(removed_dev, 0, 4, h->stream));
-  dcarve_init_kernel<<<148 * 8, 256, 0, h->stream>>>(keys, first, cap, rm, sm->dense_cap);
+  dcarve_init_kernel<<<148 * 8, 256, 0, h->stream>>>(keys, first, cap, rm, sm->dense_cap, enable_dev, removed_dev);
   dcarve_first_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), 1.0 / voxel, keys, first,
-                                                                                cap - 1, slot_of);
-  dcarve_march_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), slot_of, first, sensor[0],
-                                                                                sensor[1], sensor[2], voxel, radius, trunc, max_len,
+                                                                                cap - 1, slot_of, enable_dev);
+  dcarve_march_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), slot_of, first, s0, s1, s2,
+                                                                                sensor_dev, voxel, radius, trunc, max_len,
                                                                                 sm->dense_keys.as<unsigned long long>(), sm->dense_cnt.as<int32_t>(),
-                                                                                sm->dense_cap, rm);
-  dcarve_apply_kernel<<<148 * 8, 256, 0, h->stream>>>(rm, sm->dense_cap, sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), removed_dev);
+                                                                                sm->dense_cap, rm, enable_dev);
+  dcarve_apply_kernel<<<148 * 8, 256, 0, h->stream>>>(rm, sm->dense_cap, sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), removed_dev, enable_dev,
+                                                      sm->mstate.as<int32_t>());
   h->launches += 4;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(OV_THREADS) ov_flags_kernel(const int32_t* __r
   }
 }
 
-int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out);   // voxel.cu
+int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out, const int32_t* d_n_override = nullptr);   // voxel.cu
 
 int32_t op_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* target, const double* T_dev, double voxel, int min_pts,
                    b2s_cloud* source_overlap, b2s_cloud* target_overlap) {

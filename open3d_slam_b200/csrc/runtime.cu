@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+unsigned long long g_alloc_generation = 1;
 thread_local bool g_capturing = false;
 thread_local bool g_capture_broken = false;
 
@@ -43,6 +44,7 @@ int32_t DevBuf::ensure(size_t bytes, cudaStream_t s, bool preserve) {
     B2S_CUDA(cudaStreamSynchronize(s));  // earlier kernels may still read the old allocation
     B2S_CUDA(cudaFree(p));
   }
+  if (p) __atomic_add_fetch(&g_alloc_generation, 1ull, __ATOMIC_RELAXED);   // captured graphs may hold the old address
   p = np;
   cap = ncap;
   return B2S_OK;

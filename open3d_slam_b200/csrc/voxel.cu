@@ -100,13 +100,15 @@ __global__ void __launch_bounds__(VX_THREADS) compact_kernel(const double* __res
   }
 }
 
-int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out) {
+int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out, const int32_t* d_n_override = nullptr);
+int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out, const int32_t* d_n_override) {
   const size_t n_max = in->n_max;
+  const int32_t* d_n = d_n_override ? d_n_override : in->dn.as<int32_t>();
   B2S_TRY(h->offs.ensure((n_max + 2) * 4, h->stream));
   B2S_TRY(cloud_reserve(h, out, n_max, in->has_normals));
-  B2S_TRY(scan_exclusive_i32(h, flags, h->offs.as<int32_t>(), in->dn.as<int32_t>(), n_max, nullptr));
+  B2S_TRY(scan_exclusive_i32(h, flags, h->offs.as<int32_t>(), d_n, n_max, nullptr));
   compact_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(
-      in->xyz.as<double>(), in->has_normals ? in->nrm.as<double>() : nullptr, in->dn.as<int32_t>(), flags, h->offs.as<int32_t>(),
+      in->xyz.as<double>(), in->has_normals ? in->nrm.as<double>() : nullptr, d_n, flags, h->offs.as<int32_t>(),
       out->xyz.as<double>(), in->has_normals ? out->nrm.as<double>() : nullptr, out->dn.as<int32_t>());
   h->launches++;
   out->has_normals = in->has_normals;

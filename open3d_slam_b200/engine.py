@@ -92,6 +92,8 @@ class MapperParameters:
     scanProcessing: ScanProcessingParameters = field(default_factory=ScanProcessingParameters)
     mapBuilder: MapBuilderParameters = field(default_factory=MapBuilderParameters)
     denseMapVoxelSize: float = 0.05
+    denseMapCropper: ScanCroppingParameters = field(default_factory=ScanCroppingParameters)       # denseMapBuilder_.cropper_
+    denseMapCarving: SpaceCarvingParameters = field(default_factory=SpaceCarvingParameters)       # denseMapBuilder_.carving_
     isIgnoreMinRefinementFitness: bool = False
     minMovementBetweenMappingSteps: float = 0.0
     seed: int = 0            # replaces std::random_device of [O3D] RandomDownSample
@@ -247,6 +249,17 @@ class Cloud:
         m = C.c_size_t()
         L.check(L.lib().b2s_cloud_download(self.eng._h, self._c, _pd(xyz), _pd(nrm) if hn else None, C.c_size_t(n), C.byref(m)))
         return xyz, nrm
+
+    def export_device(self, xyz_ptr: int, nrm_ptr: int | None, capacity_points: int) -> int:
+        """device-to-device copy of the arrays into caller-owned device buffers (3 x f64 per point); returns the point count"""
+        n = C.c_size_t()
+        L.check(L.lib().b2s_cloud_export_device(self.eng._h, self._c, C.c_void_p(xyz_ptr), C.c_void_p(nrm_ptr) if nrm_ptr else None,
+                                                C.c_size_t(capacity_points), C.byref(n)))
+        return int(n.value)
+
+    def import_device(self, xyz_ptr: int, nrm_ptr: int | None, n: int):
+        L.check(L.lib().b2s_cloud_import_device(self.eng._h, self._c, C.c_void_p(xyz_ptr), C.c_void_p(nrm_ptr) if nrm_ptr else None, C.c_size_t(n)))
+        return self
 
     def free(self):
         if self._c and not getattr(self, "_borrowed", False):
@@ -441,6 +454,29 @@ class Submap:
         self._cropperPose = np.eye(4)   # mapBuilderCropper_'s pose: set AFTER each insertion (Submap.cpp:71), Identity before the first
         self.lastCarvedCount = 0
 
+    def setMapperOptions(self, *, minMovement: float = 0.0, carving: "SpaceCarvingParameters | None" = None, dense: bool = False,
+                         denseCarving: "SpaceCarvingParameters | None" = None, denseCropper: "ScanCroppingParameters | None" = None) -> None:
+        """What Mapper / SubmapCollection / SlamWrapper wire around S1-S2-F1 for this submap, decided on the device by the chain:
+        minimum-motion gate (Mapper.cpp:170-176), carving every N insertions (Submap.cpp:55-60,109-123), dense-map feed with
+        every accepted scan and its carving (SlamWrapper.cpp:318-327,363-376; Submap.cpp:77-92,125-136)."""
+        o = L.MapperOptions()
+        L.lib().b2s_default_mapper_options(C.byref(o))
+        o.min_movement_between_mapping_steps = float(minMovement)
+        if carving is not None:
+            o.carve_enabled = 1; o.carve_every_n_scans = int(carving.carveSpaceEveryNscans); o.carving = carving.to_c()
+        if dense:
+            o.dense_enabled = 1
+            if denseCarving is not None:
+                o.dense_carve_every_n_scans = int(denseCarving.carveSpaceEveryNscans); o.dense_carving = denseCarving.to_c()
+            if denseCropper is not None:
+                o.dense_cropper = denseCropper.to_c()
+        L.check(L.lib().b2s_submap_set_mapper_options(self.eng._h, self._s, C.byref(o)))
+
+    def mapperCounters(self) -> dict:
+        c = L.MapperCounters()
+        L.check(L.lib().b2s_submap_get_mapper_counters(self.eng._h, self._s, C.byref(c)))
+        return {n: int(getattr(c, n)) for n, _ in L.MapperCounters._fields_}
+
     def isEmpty(self) -> bool:
         return self.size() == 0
 
@@ -542,6 +578,69 @@ class Submap:
         if self._s:
             L.lib().b2s_submap_destroy(self._s)
             self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class VoxelMap:
+    """o3d_slam::VoxelMap (include/open3d_slam/Voxel.hpp:19-36, src/Voxel.cpp:123-160) on the device; layers are named like
+    the reference's and mapped to small integers."""
+
+    def __init__(self, eng: Engine, voxelSize=0.25, capacity_voxels: int = 1 << 20):
+        self.eng = eng
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(voxelSize, dtype=np.float64), (3,)))
+        self._v = C.c_void_p()
+        L.check(L.lib().b2s_voxel_map_create(eng._h, _pd(v), C.c_size_t(capacity_voxels), C.byref(self._v)))
+        self._layers = {}
+
+    def _layer(self, name: str) -> int:
+        if name not in self._layers:
+            self._layers[name] = len(self._layers)
+        return self._layers[name]
+
+    def clear(self) -> None:
+        L.check(L.lib().b2s_voxel_map_clear(self.eng._h, self._v))
+
+    def insertCloud(self, layer: str, cloud: Cloud) -> None:
+        L.check(L.lib().b2s_voxel_map_insert_cloud(self.eng._h, self._v, C.c_int32(self._layer(layer)), cloud._c))
+
+    def size(self) -> int:
+        n = C.c_size_t()
+        L.check(L.lib().b2s_voxel_map_size(self.eng._h, self._v, C.byref(n)))
+        return int(n.value)
+
+    def hasVoxelContainingPoint(self, points: Cloud, T=None):
+        """batched: (flags per point, number of hits); T (optional) moves the points first (isSwitchingSubmapsConsistant)."""
+        n = len(points)
+        flags = np.zeros(max(n, 1), dtype=np.int32); hits = C.c_size_t()
+        Tm = _mat(T) if T is not None else None
+        L.check(L.lib().b2s_voxel_map_has_voxel(self.eng._h, self._v, points._c, _pd(Tm) if Tm is not None else None,
+                                                flags.ctypes.data_as(C.POINTER(C.c_int32)), C.c_size_t(len(flags)), C.byref(hits)))
+        return flags[:n].astype(bool), int(hits.value)
+
+    def getIndicesInVoxel(self, layer: str, points: Cloud):
+        """batched getIndicesInVoxel(layer, p): list of index arrays, one per query point."""
+        if layer not in self._layers:
+            return [np.zeros(0, dtype=np.int64) for _ in range(len(points))]
+        n = len(points)
+        offs = np.zeros(n + 1, dtype=np.int32); tot = C.c_size_t()
+        lay = C.c_int32(self._layers[layer])
+        L.check(L.lib().b2s_voxel_map_indices_in_voxel(self.eng._h, self._v, lay, points._c, offs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       C.c_size_t(n + 1), None, C.c_size_t(0), C.byref(tot)))
+        idx = np.zeros(max(int(tot.value), 1), dtype=np.int32)
+        L.check(L.lib().b2s_voxel_map_indices_in_voxel(self.eng._h, self._v, lay, points._c, offs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       C.c_size_t(n + 1), idx.ctypes.data_as(C.POINTER(C.c_int32)), C.c_size_t(len(idx)),
+                                                       C.byref(tot)))
+        return [idx[offs[i]:offs[i + 1]].astype(np.int64) for i in range(n)]
+
+    def free(self):
+        if self._v:
+            L.lib().b2s_voxel_map_destroy(self._v)
+            self._v = C.c_void_p()
 
     def __del__(self):
         try:
@@ -687,6 +786,14 @@ class Mapper:
                                                    C.c_int32(int(self.params_.isIgnoreMinRefinementFitness)), C.c_void_p(out_pinned_ptr)))
         if getattr(self, "_staging", None) is not None:
             self._gstep += 1
+
+    def lastProcessedScan(self, merge: bool = True, match: bool = False) -> ProcessedScans:
+        """Copies of the merge_ / match_ clouds the last device step produced (SubmapCollection buffers merge_ for the overlap
+        between consecutive submaps, src/SubmapCollection.cpp:83-92,180)."""
+        m = Cloud(self.eng) if merge else None
+        a = Cloud(self.eng) if match else None
+        L.check(L.lib().b2s_mapper_processed_scan(self.eng._h, m._c if m else None, a._c if a else None))
+        return ProcessedScans(m, a)
 
     def fetchResult(self, slot: int = 0) -> RegistrationResult:
         r = L.Result()

@@ -114,9 +114,8 @@ def lidar_scan(scene: Scene, pose: np.ndarray, n_beams=64, n_az=1024, max_range=
     return np.ascontiguousarray(pts.astype(dtype))
 
 
-def loop_trajectory(n_scans=600, step=0.5, half=8.0, corner_r=3.0, z=0.0):
-    """Rounded-rectangle loop (config 2): poses map->sensor, heading along the path, `step` metres per scan."""
-    # build the closed path as a dense polyline, then resample by arc length
+def _loop_path(half=8.0, corner_r=3.0):
+    """closed rounded-rectangle polyline and its cumulative arc length"""
     segs = []
     s = half - corner_r
     corners = [(s, -s, -np.pi / 2), (s, s, 0.0), (-s, s, np.pi / 2), (-s, -s, np.pi)]
@@ -126,6 +125,18 @@ def loop_trajectory(n_scans=600, step=0.5, half=8.0, corner_r=3.0, z=0.0):
     path = np.vstack(segs + [segs[0][:1]])
     seglen = np.linalg.norm(np.diff(path, axis=0), axis=1)
     cum = np.r_[0.0, np.cumsum(seglen)]
+    return path, seglen, cum
+
+
+def loop_length(half=8.0, corner_r=3.0) -> float:
+    """length of one lap of loop_trajectory()'s path"""
+    return float(_loop_path(half, corner_r)[2][-1])
+
+
+def loop_trajectory(n_scans=600, step=0.5, half=8.0, corner_r=3.0, z=0.0):
+    """Rounded-rectangle loop (config 2): poses map->sensor, heading along the path, `step` metres per scan."""
+    # the closed path is a dense polyline, resampled by arc length
+    path, seglen, cum = _loop_path(half, corner_r)
     total = cum[-1]
     poses = []
     for k in range(n_scans):

@@ -1204,6 +1204,9 @@ ORC_EXPORT size_t orc_dense_carve(void* pd, const double* scan, size_t n, const 
   vh_free(&seen);
   uint8_t* rm = (uint8_t*)calloc(d->h.cnt ? d->h.cnt : 1, 1);
   const double step = 2.0 * radius;
+  /* the reference marches the rays under "#pragma omp parallel for schedule(static)" (helpers.cpp:352); here every hit is
+   * an idempotent byte store into rm[], so no critical section is needed and the result does not depend on the schedule */
+#pragma omp parallel for schedule(dynamic, 256)
   for (size_t i = 0; i < n; i++) {
     if (!first[i]) continue;
     const double* p = scan + 3 * i;
