@@ -125,8 +125,10 @@ int64_t b2s_launch_count(const b2s_handle* h);
 #define B2S_PROFILE_KINDS 8
 int32_t b2s_profile_enable(b2s_handle* h, int32_t on);
 int32_t b2s_profile_read(b2s_handle* h, double* ms_by_kind, int64_t* count_by_kind, int32_t n_kinds);
-/* debug aid: clock64 stamps {start, search end, reduce end, solve end} x 64 evaluations of the ICP kernel (CTA 0) */
-int32_t b2s_debug_icp_clocks(b2s_handle* h, int32_t enable, long long* out_256);
+/* debug aid (1024 words): [0..255] clock64 stamps {start, search end, reduce end, solve end} x 64 evaluations of the ICP kernel (CTA 0),
+ * [256..511] per-CTA phase times, [512 + 8 e + 0..3] search statistics of evaluation e < 32 (candidates scanned in phase 1, point
+ * evaluations, points queued for phase 2, candidates scanned in phase 2) */
+int32_t b2s_debug_icp_clocks(b2s_handle* h, int32_t enable, long long* out_1024);
 
 /* ---- clouds (open3d::geometry::PointCloud points_/normals_) ------------------------------------------------ */
 int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out);

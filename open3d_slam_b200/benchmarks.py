@@ -153,7 +153,7 @@ def run_config4(dev, stream, world, rank, loop=None, n_pairs=512, n_targets=64, 
     peak, peak_src = hbm_peak()
     out = None
     if rank == 0:
-        iters, n_src = full[:, 18], full[:, 22]
+        iters, n_src = full[:, 18], full[:, 21]
         bytes_icp = float(np.sum(72.0 * n_src * (iters + 1)))          # algorithmic bytes of all ICP evaluations (fp64 layout)
         icp_ms = prof.get("icp", float("nan"))
         out = {"workload": "config4: %d scan-submap pairs over %d shared 20 m-radius targets, r=0.3, max_iter=100" % (n_pairs, n_targets),

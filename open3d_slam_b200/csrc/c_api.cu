@@ -1,6 +1,7 @@
 // c_api.cu -- the extern "C" boundary declared in include/b2s.h.  Host-side plumbing only: argument checks mirroring
 // the reference's asserts, device staging, kernel sequencing.  No arithmetic of the hot path runs on the host.
 #include <math.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -24,6 +25,8 @@ __global__ void f32_to_f64_kernel(const unsigned char* __restrict__ src, size_t 
     dst[3 * i] = (double)p[0]; dst[3 * i + 1] = (double)p[1]; dst[3 * i + 2] = (double)p[2];
   }
 }
+
+__global__ void pad_kernel() {}   // B2S_PAD_LAUNCHES=n: n empty launches per scan, to measure what a launch costs the chain (tuning aid)
 
 __global__ void empty_check_kernel(const int32_t* a, const int32_t* b, uint32_t* status) {
   if (*a <= 0 || *b <= 0) atomicOr(status, ST_EMPTY);
@@ -139,6 +142,8 @@ static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud*
   B2S_TRY(op_crop(h, merge, make_crop(&c1), match));
   empty_check_kernel<<<1, 1, 0, h->stream>>>(merge->dn.as<int32_t>(), match->dn.as<int32_t>(), h->status.as<uint32_t>());
   h->launches++;
+  static const int pad = getenv("B2S_PAD_LAUNCHES") ? atoi(getenv("B2S_PAD_LAUNCHES")) : 0;
+  for (int i = 0; i < pad; i++) pad_kernel<<<1, 32, 0, h->stream>>>();
   return B2S_OK;
 }
 
@@ -354,15 +359,15 @@ int32_t b2s_profile_read(b2s_handle* h, double* ms_by_kind, int64_t* count_by_ki
 }
 
 // debug aid: clock64 stamps {start, search end, reduce end, solve end} of up to 64 evaluations of the next registrations
-int32_t b2s_debug_icp_clocks(b2s_handle* h, int32_t enable, long long* out_256) {
+int32_t b2s_debug_icp_clocks(b2s_handle* h, int32_t enable, long long* out_1024) {
   B2S_REQUIRE(h, B2S_E_INVALID, "null handle");
   LOCK(h);
-  if (enable && !h->icp_dbg) { B2S_CUDA(cudaMalloc(&h->icp_dbg, 512 * 8)); }
-  if (h->icp_dbg && out_256) {
+  if (enable && !h->icp_dbg) { B2S_CUDA(cudaMalloc(&h->icp_dbg, 1024 * 8)); B2S_CUDA(cudaMemset(h->icp_dbg, 0, 1024 * 8)); }
+  if (h->icp_dbg && out_1024) {
     B2S_CUDA(cudaStreamSynchronize(h->stream));
-    B2S_CUDA(cudaMemcpy(out_256, h->icp_dbg, 512 * 8, cudaMemcpyDeviceToHost));
+    B2S_CUDA(cudaMemcpy(out_1024, h->icp_dbg, 1024 * 8, cudaMemcpyDeviceToHost));
   }
-  if (h->icp_dbg) B2S_CUDA(cudaMemsetAsync(h->icp_dbg, 0, 512 * 8, h->stream));
+  if (h->icp_dbg) B2S_CUDA(cudaMemsetAsync(h->icp_dbg, 0, 1024 * 8, h->stream));
   if (!enable && h->icp_dbg) { cudaFree(h->icp_dbg); h->icp_dbg = nullptr; }
   return B2S_OK;
 }
@@ -381,6 +386,7 @@ int32_t b2s_cloud_create(b2s_handle* h, b2s_cloud** out) {
   B2S_REQUIRE(c, B2S_E_INVALID, "out of host memory");
   c->h = h;
   c->device = h->device;
+  c->xyz.tracked = c->nrm.tracked = c->dn.tracked = false;   // caller-owned: never part of a captured chain
   B2S_TRY(cloud_reserve(h, c, 1, false));
   B2S_TRY(cloud_set_count(h, c, 0));
   *out = c;

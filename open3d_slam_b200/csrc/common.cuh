@@ -47,6 +47,7 @@ const char* get_error();
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool tracked = true;   // a re-allocation invalidates captured graphs (false for clouds the caller owns: a graph never holds them)
   int32_t ensure(size_t bytes, cudaStream_t s, bool preserve = false);
   void release();
   template <typename T>

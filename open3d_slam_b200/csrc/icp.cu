@@ -37,6 +37,36 @@ constexpr int ICP_THREADS = 512;
 constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
 constexpr int ICP_R1 = -1;  // phase 1 is a box query, not a ring walk: phase 2 starts its ring walk at ring 0
+constexpr int ICP_MAX_CLUSTER = 16;   // 8 is the portable limit; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
+
+// ---- bulk-async (TMA engine) staging of the source chunk: global -> shared, completion on an mbarrier --------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// cp.async.bulk: 16-byte aligned source / destination, size a multiple of 16 (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 struct GridView {
   double ox, oy, oz, cell, inv, eps;
@@ -49,6 +79,7 @@ struct GridView {
 struct NNState {
   double best;
   int bidx, bslot;
+  int scanned;   // candidates looked at (only read by the counting instantiation, icp_kernel<3>)
 };
 
 __device__ __forceinline__ double slab_gap(double q, double o, double cell, int i, int n, double eps) {
@@ -60,6 +91,7 @@ __device__ __forceinline__ double slab_gap(double q, double o, double cell, int 
 }
 
 __device__ __forceinline__ void nn_scan_range(const double4* __restrict__ pts, int s, int e, double qx, double qy, double qz, NNState& st) {
+  st.scanned += e > s ? e - s : 0;   // statistics (dead code unless the counting instantiation reads it)
 #pragma unroll 4
   for (int j = s; j < e; ++j) {
     const double4 p = pts[j];
@@ -133,7 +165,7 @@ __device__ __forceinline__ void nn_scan_box(const GridView& g, double qx, double
 // Cell indices use the same floor((v - o) * inv) expression as the index build, which is monotone in v, so no point
 // inside the box can sit in a cell outside the index range.  Returns true when st holds the exact answer.
 __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double qy, double qz, double r2, int hint, NNState& st) {
-  st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1;
+  st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
   if (!(qx == qx && qy == qy && qz == qz)) return true;
   double rad2 = fmin(r2, g.cell * g.cell);
   bool seeded = false;
@@ -278,7 +310,8 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
   return true;
 }
 
-constexpr int ICP_FIXED_SMEM_DOUBLES = ICP_WARPS * NACC + 2 * NACC + NACC + 16 + 16 + 8;
+constexpr int ICP_FIXED_SMEM_DOUBLES = (ICP_WARPS * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1;   // even: what follows stays 16-byte aligned
+constexpr int ICP_FIXED_SMEM_BYTES = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16 + 16;   // + header + queue length + mbarrier
 constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4;  // working point, previous-neighbour slot, phase-2 queue entry
 
 // point-to-point ([O3D] TransformationEstimationPointToPoint = Eigen::umeyama): sums for the means and the cross moments
@@ -481,7 +514,9 @@ __device__ __forceinline__ void icp_accumulate_gicp(double (&acc)[NACC], const G
 // host->device copy -- and no implicit stream synchronisation of a pageable copy -- sits in front of the launch;
 // batches pass an array.  dbg (optional): clock64 stamps of problem 0 / CTA 0 per evaluation {start, search, reduce, solve}.
 // MODE selects what is compiled in, so that the headline point-to-plane path carries no code (registers, stack) of the others:
-//   0 = point-to-plane only, 1 = point-to-point + information matrix (+ plane), 2 = generalized ICP
+//   0 = point-to-plane only, 1 = point-to-point + information matrix (+ plane), 2 = generalized ICP,
+//   3 = point-to-plane with search statistics (b2s_debug_icp_clocks): dbg[512 + 8 e + {0,1,2,3}] = candidates scanned in phase 1,
+//       point evaluations, points queued for phase 2, candidates scanned in phase 2 -- per evaluation e < 32, whole cluster
 template <int MODE>
 __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_constant__ IcpProblem single,
                                                              const IcpProblem* __restrict__ problems, int smem_pts_cap,
@@ -499,15 +534,16 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   double* s_U = s_tot + NACC;                           // [16] update of the current iteration
   double* s_T = s_U + 16;                               // [16] accumulated transformation
   double* s_misc = s_T + 16;                            // [0] prev fitness [1] prev rmse [2] done [3] apply
-  GridHeader* s_g = reinterpret_cast<GridHeader*>(s_misc + 8);
+  GridHeader* s_g = reinterpret_cast<GridHeader*>(smem_raw + ICP_FIXED_SMEM_DOUBLES * 8);
   int* s_qn = reinterpret_cast<int*>(s_g + 1);          // phase-2 queue length (16 bytes reserved)
-  double* s_pts = reinterpret_cast<double*>(s_qn + 4);
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_qn + 4);   // mbarrier of the bulk-async staging (16 bytes reserved)
+  double* s_pts = reinterpret_cast<double*>(smem_raw + ICP_FIXED_SMEM_BYTES);    // 16-byte aligned
   int* s_prev = reinterpret_cast<int*>(s_pts + 3 * (size_t)smem_pts_cap);  // previous neighbour slot per point (warm start)
   int* s_queue = s_prev + smem_pts_cap;                                    // local indices of points left to phase 2
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *P.src_n;
-  const int chunk = (n + (int)csize - 1) / (int)csize;
+  const int chunk = (((n + (int)csize - 1) / (int)csize) + 1) & ~1;   // even: every chunk starts on a 16-byte boundary of the 24-byte points
   const int lo = min((int)crank * chunk, n), hi = min(lo + chunk, n);
   const int cnt = hi - lo;
   const bool in_smem = chunk <= smem_pts_cap;   // uniform over the cluster (phase 2 shares work across CTAs)
@@ -520,11 +556,27 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
     s_misc[0] = 0.0; s_misc[1] = 0.0; s_misc[2] = 0.0;
     s_misc[3] = mat4_is_identity_dev(init) ? 0.0 : 1.0;  // [O3D]: if (!init.isIdentity()) pcd.Transform(init)
     *s_qn = 0;
+    if (in_smem) { mbar_init(s_bar, 1); mbar_fence_init(); }
   }
+  __syncthreads();
   {  // stage this CTA's chunk of the source cloud
     const double* src = P.src_xyz + 3 * (size_t)lo;
-    for (int i = tid; i < 3 * cnt; i += ICP_THREADS) work[i] = src[i];
-    if (in_smem) for (int i = tid; i < cnt; i += ICP_THREADS) s_prev[i] = -1;
+    if (in_smem) {
+      // one elected thread hands the chunk to the bulk-async copy engine (cp.async.bulk global -> shared, 48 bytes per pair of
+      // points keeps every transfer a multiple of 16 bytes); completion is counted in bytes on the mbarrier
+      const int cnt_even = cnt & ~1;
+      const uint32_t total = 24u * (uint32_t)cnt_even;
+      if (tid == 0 && total > 0) {
+        mbar_arrive_expect_tx(s_bar, total);
+        for (uint32_t off = 0; off < total; off += 32768u)
+          bulk_copy_g2s(reinterpret_cast<char*>(s_pts) + off, reinterpret_cast<const char*>(src) + off, min(32768u, total - off), s_bar);
+      }
+      if ((cnt & 1) && tid < 3) s_pts[3 * (cnt - 1) + tid] = src[3 * (cnt - 1) + tid];   // odd tail point
+      for (int i = tid; i < cnt; i += ICP_THREADS) s_prev[i] = -1;
+      if (total > 0) mbar_wait_parity(s_bar, 0);
+    } else {
+      for (int i = tid; i < 3 * cnt; i += ICP_THREADS) work[i] = src[i];
+    }
   }
   __syncthreads();
 
@@ -538,6 +590,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   const double r2 = P.max_corr * P.max_corr;
   const int max_iter = P.max_iter;
   constexpr bool GICP = MODE == 2;
+  constexpr bool COUNT = MODE == 3;
+  int n_scanned1 = 0, n_evals1 = 0, n_queued = 0, n_scanned2 = 0;
   const bool p2p = MODE == 1 && P.estimator == B2S_REG_POINT_TO_POINT;
   const bool info = MODE == 1 && P.estimator == EST_INFORMATION;   // one evaluation, output = 6x6 information matrix
 
@@ -588,6 +642,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
         done = true;
       }
       if (in_smem) s_prev[i] = st.bslot;
+      if (COUNT) { n_scanned1 += st.scanned; n_evals1++; n_queued += done ? 0 : 1; }
       if (done) {
         if (st.bslot >= 0) {
           if (GICP) icp_accumulate_gicp(acc, g, st.bslot, st.best, px, py, pz, RT, P.src_nrm + 3 * (size_t)(lo + i), P.gicp_eps);
@@ -608,21 +663,21 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
     // The sums are cluster totals anyway, so a point may be accumulated by any CTA.
     if (in_smem) {
       cluster.sync();  // every queue is complete
-      int qoff[9];
+      int qoff[ICP_MAX_CLUSTER + 1];
       qoff[0] = 0;
 #pragma unroll
-      for (int r = 0; r < 8; r++) qoff[r + 1] = qoff[r] + ((unsigned)r < csize ? *cluster.map_shared_rank(s_qn, r) : 0);
-      for (int gi = (int)crank * ICP_WARPS + warp; gi < qoff[8]; gi += (int)csize * ICP_WARPS) {
+      for (int r = 0; r < ICP_MAX_CLUSTER; r++) qoff[r + 1] = qoff[r] + ((unsigned)r < csize ? *cluster.map_shared_rank(s_qn, r) : 0);
+      for (int gi = (int)crank * ICP_WARPS + warp; gi < qoff[ICP_MAX_CLUSTER]; gi += (int)csize * ICP_WARPS) {
         int r = 0;
 #pragma unroll
-        for (int k = 1; k < 8; k++) if (gi >= qoff[k]) r = k;
+        for (int k = 1; k < ICP_MAX_CLUSTER; k++) if (gi >= qoff[k]) r = k;
         const int li = gi - qoff[r];
         const int i = cluster.map_shared_rank(s_queue, r)[li];
         const double* rw = cluster.map_shared_rank(s_pts, r);
         int* rp = cluster.map_shared_rank(s_prev, r);
         const double px = rw[3 * i], py = rw[3 * i + 1], pz = rw[3 * i + 2];
         NNState st;
-        st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1;
+        st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
         const int hs = rp[i];  // best of the box query (or the seed), -1 when nothing was in range
         if (hs >= 0) {
           const double4 p = g.pts[hs];
@@ -630,6 +685,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
           if (!(st.best < r2)) { st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; }
         }
         nn_phase2_warp(g, px, py, pz, st);
+        if (COUNT) n_scanned2 += st.scanned;
         if (lane == 0) {
           rp[i] = st.bslot;
           if (st.bslot >= 0) {
@@ -641,8 +697,18 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
         }
       }
     }
+    if (COUNT && dbg != nullptr && blockIdx.y == 0 && e < 32) {
+      const int a = warp_sum_i(n_scanned1), b = warp_sum_i(n_evals1), c = warp_sum_i(n_queued), d = warp_sum_i(n_scanned2);
+      if (lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 512 + 8 * e + 0, (unsigned long long)a);
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 512 + 8 * e + 1, (unsigned long long)b);
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 512 + 8 * e + 2, (unsigned long long)c);
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 512 + 8 * e + 3, (unsigned long long)d);
+      }
+      n_scanned1 = n_evals1 = n_queued = n_scanned2 = 0;
+    }
     if (dbg_on && e < 64) dbg[4 * e + 1] = clock64();
-    if (dbg != nullptr && blockIdx.y == 0 && e < 8) {   // per-CTA balance: {phase-1 end, phase-2 end (all warps), queue length, points}
+    if (dbg != nullptr && blockIdx.y == 0 && e < 8 && crank < 8) {   // per-CTA balance: {phase-1 end, phase-2 end (all warps), queue length, points}
       __syncthreads();
       if (tid == 0) {
         long long t_p2;
@@ -737,24 +803,45 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
-static bool g_icp_attr_set = false;
 constexpr int ICP_DYN_SMEM = 200 * 1024;
+
+// the opt-in attributes are per DEVICE (a process may hold handles on several GPUs): one flag per device, set under a lock
+static std::mutex g_icp_attr_mu;
+static bool g_icp_attr_set[64] = {false};
+
+static int icp_max_cluster() {   // B2S_ICP_MAX_CLUSTER=16 spreads one registration over 16 SMs (non-portable cluster size)
+  static const int v = getenv("B2S_ICP_MAX_CLUSTER") ? atoi(getenv("B2S_ICP_MAX_CLUSTER")) : 8;
+  return v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1)));
+}
+
+template <int MODE>
+static cudaError_t icp_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(icp_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(icp_kernel<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+}
 
 int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points) {
   if (n_problems <= 0) return B2S_OK;
   IcpProblem single;
   memset(&single, 0, sizeof(single));
   if (single_host) { single = *single_host; problems_dev = nullptr; n_problems = 1; }
-  if (!g_icp_attr_set) {
-    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
-    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
-    B2S_CUDA(cudaFuncSetAttribute(icp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ICP_DYN_SMEM));
-    g_icp_attr_set = true;
+  {
+    std::lock_guard<std::mutex> lk(g_icp_attr_mu);
+    const int d = h->device >= 0 && h->device < 64 ? h->device : 0;
+    if (!g_icp_attr_set[d]) {
+      B2S_CUDA(icp_set_attrs<0>());
+      B2S_CUDA(icp_set_attrs<1>());
+      B2S_CUDA(icp_set_attrs<2>());
+      B2S_CUDA(icp_set_attrs<3>());
+      g_icp_attr_set[d] = true;
+    }
   }
   const int estimator = single_host ? single_host->estimator : h->cfg.icp.reg_type;   // uniform over a batch
   int csize = 1;
-  while (csize < 8 && (size_t)csize * ICP_THREADS * 2 < max_src_points) csize *= 2;
-  const int fixed = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16 + 16;
+  const int cmax = icp_max_cluster();
+  while (csize < cmax && (size_t)csize * ICP_THREADS * (csize >= 8 ? 1 : 2) < max_src_points) csize *= 2;
+  const int fixed = ICP_FIXED_SMEM_BYTES;
   {
     // a batch that already fills the GPU is served better by small clusters (one CTA per SM is resident either way, and
     // every evaluation pays its barriers and reduction once per cluster): shrink while the chunk still fits shared memory
@@ -767,7 +854,7 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   // neighbouring queries hit the same lines (4 target points per 128-byte line)
   int pts_cap = (ICP_DYN_SMEM - fixed) / ICP_BYTES_PER_POINT;
   {
-    const size_t chunk = (max_src_points + (size_t)csize - 1) / (size_t)csize;
+    const size_t chunk = (((max_src_points + (size_t)csize - 1) / (size_t)csize) + 1) & ~(size_t)1;   // even, like the kernel's
     const size_t want = ((chunk + 63) / 64) * 64 + 64;
     if (want < (size_t)pts_cap) pts_cap = (int)want;
   }
@@ -785,6 +872,7 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   cfg.numAttrs = 1;
   ProfScope prof(h, PK_ICP);
   if (estimator == B2S_REG_GENERALIZED) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<2>, single, problems_dev, pts_cap, h->icp_dbg));
+  else if (estimator == B2S_REG_POINT_TO_PLANE && h->icp_dbg) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<3>, single, problems_dev, pts_cap, h->icp_dbg));
   else if (estimator == B2S_REG_POINT_TO_PLANE) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<0>, single, problems_dev, pts_cap, h->icp_dbg));
   else B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<1>, single, problems_dev, pts_cap, h->icp_dbg));
   h->launches++;

@@ -44,7 +44,7 @@ int32_t DevBuf::ensure(size_t bytes, cudaStream_t s, bool preserve) {
     B2S_CUDA(cudaStreamSynchronize(s));  // earlier kernels may still read the old allocation
     B2S_CUDA(cudaFree(p));
   }
-  if (p) __atomic_add_fetch(&g_alloc_generation, 1ull, __ATOMIC_RELAXED);   // captured graphs may hold the old address
+  if (p && tracked) __atomic_add_fetch(&g_alloc_generation, 1ull, __ATOMIC_RELAXED);   // captured graphs may hold the old address
   p = np;
   cap = ncap;
   return B2S_OK;

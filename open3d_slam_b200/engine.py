@@ -787,12 +787,13 @@ class Mapper:
         if getattr(self, "_staging", None) is not None:
             self._gstep += 1
 
-    def lastProcessedScan(self, merge: bool = True, match: bool = False) -> ProcessedScans:
+    def lastProcessedScan(self, merge: bool = True, match: bool = False, merge_into: "Cloud | None" = None) -> ProcessedScans:
         """Copies of the merge_ / match_ clouds the last device step produced (SubmapCollection buffers merge_ for the overlap
-        between consecutive submaps, src/SubmapCollection.cpp:83-92,180)."""
-        m = Cloud(self.eng) if merge else None
+        between consecutive submaps, src/SubmapCollection.cpp:83-92,180).  merge_into: an existing cloud to overwrite."""
+        m = merge_into if merge_into is not None else (Cloud(self.eng) if merge else None)
         a = Cloud(self.eng) if match else None
-        L.check(L.lib().b2s_mapper_processed_scan(self.eng._h, m._c if m else None, a._c if a else None))
+        # (Cloud has __len__: no truth tests on clouds)
+        L.check(L.lib().b2s_mapper_processed_scan(self.eng._h, m._c if m is not None else None, a._c if a is not None else None))
         return ProcessedScans(m, a)
 
     def fetchResult(self, slot: int = 0) -> RegistrationResult:

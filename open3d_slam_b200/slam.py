@@ -71,6 +71,7 @@ class SubmapCollection:
         self.submaps: list[SubmapRecord] = []
         self.activeSubmapIdx = 0
         self.numScansMergedInActiveSubmap = 0
+        assert params.numScansOverlap <= 14   # DeviceBackend recycles merge_ clouds through a ring of 16
         self.overlapScansBuffer = collections.deque(maxlen=params.numScansOverlap)   # CircularBuffer, :216
         self.finishedSubmapsIdxs: list[int] = []
         self.adjacency: set[tuple[int, int]] = set()
@@ -264,7 +265,14 @@ class DeviceBackend:
         return res, bool(accepted)     # minMovementBetweenMappingSteps = 0 in every preset: accepted scans are inserted
 
     def last_merge_cloud(self):
-        return self.mapper.lastProcessedScan(merge=True).merge_
+        # ring of pre-allocated clouds (no cudaMalloc per scan); longer than SubmapCollection's overlap buffer, so a buffered cloud is
+        # never overwritten while it can still be replayed into a new submap
+        if not hasattr(self, "_merge_ring"):
+            self._merge_ring = [E.Cloud(self.eng) for _ in range(16)]
+            self._merge_pos = 0
+        c = self._merge_ring[self._merge_pos % len(self._merge_ring)]
+        self._merge_pos += 1
+        return self.mapper.lastProcessedScan(merge_into=c).merge_
 
     def insert_scan(self, sm, cloud, T):
         sm.insertScan(None, cloud, T, isPerformCarving=False)
