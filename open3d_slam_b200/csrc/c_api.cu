@@ -744,6 +744,8 @@ void b2s_submap_destroy(b2s_submap* sm) {
   if (sm->odom_ring) cudaFreeHost(sm->odom_ring);
   if (sm->staging) { sm->staging->xyz.release(); sm->staging->nrm.release(); sm->staging->dn.release(); delete sm->staging; }
   sm->gstate.release(); sm->mstate.release();
+  sm->vkeys.release(); sm->vhead.release(); sm->vstamp.release(); sm->vnext.release(); sm->pstamp.release(); sm->stage_xyz.release();
+  sm->stage_nrm.release(); sm->stage_next.release(); sm->stage_in.release(); sm->touched.release(); sm->dups.release();
   if (sm->cnt_ev) cudaEventDestroy(sm->cnt_ev);
   delete sm;
 }
@@ -808,14 +810,30 @@ int32_t b2s_submap_insert_dense(b2s_handle* h, b2s_submap* sm, const b2s_cloud* 
 int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n) {
   B2S_REQUIRE(h && sm && n, B2S_E_INVALID, "null argument");
   LOCK(h);
-  sm->cloud[0]->n_known = -1;
-  return cloud_count_sync(h, sm->cloud[0], n);
+  // slots in use minus the tombstones the fusion left behind (fuse.cu)
+  B2S_TRY(ensure_pinned(h, 4096));
+  int32_t* pw = reinterpret_cast<int32_t*>(static_cast<char*>(h->pinned) + 1536);
+  B2S_CUDA(cudaMemcpyAsync(pw, sm->cloud[0]->dn.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  B2S_CUDA(cudaMemcpyAsync(pw + 1, sm->mstate.as<int32_t>() + MS_NDEAD, 4, cudaMemcpyDeviceToHost, h->stream));
+  const int32_t rc = check_status(h);   // synchronises
+  *n = (size_t)(pw[0] - pw[1]);
+  return rc;
 }
 
-int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, size_t capacity, size_t* n_out) {
-  B2S_REQUIRE(h && sm, B2S_E_INVALID, "null argument");
-  sm->cloud[0]->n_known = -1;
-  return b2s_cloud_download(h, sm->cloud[0], xyz, normals, capacity, n_out);
+int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm_c, double* xyz, double* normals, size_t capacity, size_t* n_out) {
+  B2S_REQUIRE(h && sm_c, B2S_E_INVALID, "null argument");
+  b2s_submap* sm = const_cast<b2s_submap*>(sm_c);
+  b2s_cloud* view = nullptr;
+  {
+    LOCK(h);
+    sm->cloud[0]->n_known = -1;
+    size_t n = 0;
+    B2S_TRY(cloud_count_sync(h, sm->cloud[0], &n));
+    sm->cloud[0]->n_max = n;
+    B2S_TRY(submap_compact_view(h, sm, &view));   // the live points, in map order
+    view->n_known = -1;
+  }
+  return b2s_cloud_download(h, view, xyz, normals, capacity, n_out);
 }
 
 int32_t b2s_submap_dense_download(b2s_handle* h, const b2s_submap* sm_c, double* xyz, double* normals, int32_t* keys, size_t capacity,
@@ -853,7 +871,8 @@ int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* clo
   B2S_CUDA(cudaMemcpyAsync(m->dn.p, cloud->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
   m->n_max = cloud->n_max; m->n_known = cloud->n_known; m->has_normals = true;
   sm->cnt_pending = false; sm->adds_after_readback = 0;
-  return B2S_OK;
+  B2S_CUDA(cudaMemsetAsync(sm->mstate.as<int32_t>() + MS_NDEAD, 0, 4, h->stream));
+  return fuse_rehash(h, sm);
 }
 
 static int32_t register_to_submap_async(b2s_handle* h, const b2s_cloud* scan, const b2s_submap* sm, const double* sensor_pose_host,

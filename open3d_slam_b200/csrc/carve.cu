@@ -48,12 +48,13 @@ __global__ void __launch_bounds__(CV_THREADS) carve_init_kernel(unsigned long lo
 __global__ void __launch_bounds__(CV_THREADS) carve_insert_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, CropDev crop,
                                                                   double inv, unsigned long long* keys, int32_t* head,
                                                                   int32_t* __restrict__ next, size_t mask, uint32_t* status,
-                                                                  const int32_t* __restrict__ enable) {
+                                                                  const int32_t* __restrict__ enable, int32_t* __restrict__ keep) {
   if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
     next[i] = -1;
+    if (!(x == x)) { keep[i] = 0; continue; }      // tombstone of the fusion (fuse.cu): dropped by the compaction below
     if (!crop_within(crop, x, y, z)) continue;     // getIndicesWithinVolume(*map): only these are candidates
     unsigned long long key;
     if (!cv_key_of(x, y, z, inv, &key)) { atomicOr(status, ST_KEY_OVERFLOW); continue; }
@@ -137,11 +138,13 @@ __global__ void __launch_bounds__(CV_THREADS) carve_commit_kernel(const double* 
   if (threadIdx.x == 0) s_last = (atomicAdd(&mstate[MS_TMP], 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
+    const int dead = mstate[MS_NDEAD];   // tombstones went with the compaction: they are not carved points
     mstate[MS_TMP] = 0;
+    mstate[MS_NDEAD] = 0;
     *d_nmap = n;
-    if (removed) *removed = before - n;
+    if (removed) *removed = before - dead - n;
     mstate[MS_NCARVE] += 1;
-    mstate[MS_CARVED] += before - n;
+    mstate[MS_CARVED] += before - dead - n;
   }
 }
 
@@ -170,7 +173,7 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
   carve_init_kernel<<<grid_for(cap, CV_THREADS), CV_THREADS, 0, h->stream>>>(keys, head, cap, keep, (int)n_max, enable_dev, map->dn.as<int32_t>(),
                                                                              n_eff);
   carve_insert_kernel<<<grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(), crop, inv, keys,
-                                                                                head, next, cap - 1, h->status.as<uint32_t>(), enable_dev);
+                                                                                head, next, cap - 1, h->status.as<uint32_t>(), enable_dev, keep);
   carve_march_kernel<<<grid_for(raw_scan->n_max > 0 ? raw_scan->n_max : 1, CV_THREADS), CV_THREADS, 0, h->stream>>>(
       raw_scan->xyz.as<double>(), raw_scan->dn.as<int32_t>(), T_dev, map->has_normals ? map->nrm.as<double>() : nullptr, keys, head, next,
       cap - 1, prm.voxel_size, inv, prm.max_raytracing_length, prm.truncation_distance, prm.min_dot_product_with_normal, keep, enable_dev);
@@ -187,7 +190,7 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
   h->launches++;
   map->n_known = -1;
   B2S_CUDA(cudaGetLastError());
-  return B2S_OK;
+  return fuse_rehash(h, sm, enable_dev);   // the points moved: the fusion's voxel hash follows
 }
 
 }  // namespace b2s

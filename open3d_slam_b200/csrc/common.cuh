@@ -138,6 +138,17 @@ struct b2s_submap {
   b2s::DevBuf gstate;                 // int32 [0] device step counter, [1] current result slot
   double g_min_fitness = 0.0;
   int g_ignore_fitness = 0;
+  // persistent voxel hash of the map cloud (K-fuse, fuse.cu): map-voxel key -> chain of the map points inside that voxel
+  b2s::DevBuf vkeys;         // uint64 [vcap] packed voxel key, EMPTY = ~0
+  b2s::DevBuf vhead;         // int32 [vcap] first member of the voxel's chain (-1 = none); members >= FUSE_STAGE_BASE are staged scan points
+  b2s::DevBuf vstamp;        // int32 [vcap] stamp of the last insertion that touched the voxel
+  b2s::DevBuf vnext;         // int32 [capacity] chain link of every map point
+  b2s::DevBuf pstamp;        // int32 [capacity] stamp of the insertion that last rewrote the point
+  b2s::DevBuf stage_xyz, stage_nrm, stage_next, stage_in;   // the transformed scan of the insertion in flight
+  b2s::DevBuf touched;       // int32 voxels (table slots) the insertion in flight touched
+  b2s::DevBuf dups;          // int32 [2][FUSE_DUP_CAP] voxels holding more than one map point (ping-pong)
+  size_t vcap = 0;
+  size_t stage_cap = 0;
   // Mapper / SubmapCollection wiring of the device chain (b2s_mapper_options) and its device-side state words (MS_*)
   b2s_mapper_options opts;
   b2s::DevBuf mstate;                 // int32 [MS_WORDS]: gates and counters of the chain, see the MS_* indices below
@@ -157,7 +168,14 @@ enum MapperStateWord {
   MS_NDENSE = 6,      // Submap::nScansInsertedDenseMap_
   MS_NSTEPS = 7, MS_NACCEPT = 8, MS_NCARVE = 9, MS_CARVED = 10, MS_NDCARVE = 11, MS_DCARVED = 12,
   MS_CARVE_N = 13,    // point count the carving compaction works on (0 when carving is skipped)
-  MS_TMP = 14,
+  MS_TMP = 14,        // [14] grid-wide ticket, [15] dense-carve removed count
+  MS_NDEAD = 16,      // tombstones among the map slots (points merged away; xyz = NaN) -- the map holds dn - NDEAD points
+  MS_STAMP = 17,      // stamp of the last committed insertion
+  MS_NTOUCHED = 18,   // voxels touched by the insertion in flight
+  MS_DUPSEL = 19,     // which half of `dups` is current
+  MS_NDUP = 20,       // [20], [21]: entries of the two halves
+  MS_VUSED = 22,      // occupied slots of the voxel table
+  MS_TICKET2 = 23,
   MS_WORDS = 32
 };
 // bumped by every DevBuf re-allocation: a captured graph holds raw pointers of the scratch buffers, so a graph captured
@@ -282,6 +300,13 @@ constexpr int EST_INFORMATION = 3;   // internal estimator code: a single evalua
 int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
 
 int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev);
+// K-fuse bookkeeping (fuse.cu): (re)build the persistent voxel hash from the map cloud (after set_cloud / carving / transform;
+// enable_dev gates it on the device), allocate it, and the tombstone-free view of the map for readers that leave the device
+constexpr int FUSE_STAGE_BASE = 1 << 30;   // chain members >= this are staged scan points (index - FUSE_STAGE_BASE)
+constexpr int FUSE_DUP_CAP = 1 << 16;
+int32_t fuse_reserve(b2s_handle* h, b2s_submap* sm);
+int32_t fuse_rehash(b2s_handle* h, b2s_submap* sm, const int32_t* enable_dev = nullptr);
+int32_t submap_compact_view(b2s_handle* h, b2s_submap* sm, b2s_cloud** view);   // -> sm->cloud[1] holding the live points in map order
 // F2 VoxelHashMap queries on the dense map (fuse.cu)
 int32_t op_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* pts, int32_t* count_dev, double* mean_dev);
 int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts);

@@ -6,14 +6,12 @@
 //         voxelizeWithinCroppingVolume(...)    core/src/helpers.cpp:115-183   (+ AccumulatedPoint :30-70)
 //   F3  Submap::insertScanDenseMap -> VoxelizedPointCloud::insert   core/src/Submap.cpp:77-92, core/src/Voxel.cpp:66-88
 //
-// F1 on the device keeps the reference's semantics exactly: the transformed scan is appended to the map arrays, every
-// point inside the map-builder cropper (centred on the sensor) is keyed by floor(p * (1/v)) on the GLOBAL-origin grid,
-// a stable radix sort groups voxel members in map order, one thread per voxel averages them in that order (an old
-// map point counts as ONE member; normals: mean of non-NaN then normalized()), points outside the cropper pass
-// through untouched.  The result is committed back into the map arrays only when the (device-resident) gate is open,
-// which is how the fitness gate of Mapper::addRangeMeasurement (core/src/Mapper.cpp:151) runs without a host sync.
-// Output order: voxels in Morton order of (key - base), then pass-through points (the reference: pass-through first,
-// then std::unordered_map order -- unspecified, nothing downstream depends on it).
+// F1 on the device keeps the reference's semantics exactly (every in-cropper point of the map is bucketed by
+// floor(p * (1/v)) on the GLOBAL-origin grid, an old map point counts as ONE member, members are summed in map order, normals:
+// mean of non-NaN then normalized(), points outside the cropper pass through untouched) but does the work of one SCAN, not of
+// the whole map: see "K-fuse" below.  Nothing happens unless the (device-resident) gate is open, which is how the gates of
+// Mapper::addRangeMeasurement (core/src/Mapper.cpp:151,170-176) run without a host sync.  Map order: stable slots; new voxels
+// are appended (the reference: pass-through first, then std::unordered_map order -- unspecified, nothing depends on it).
 #include "common.cuh"
 
 namespace b2s {
@@ -22,199 +20,340 @@ constexpr int FZ_THREADS = 256;
 
 int32_t pose_to_device(b2s_handle* h, const double* T, double* dst);  // voxel.cu
 
-// append (optionally duplicated) transformed scan to the map arrays; writes the total into *d_tot
-__global__ void __launch_bounds__(FZ_THREADS) fuse_append_kernel(double* __restrict__ mxyz, double* __restrict__ mnrm,
-                                                                 const int32_t* __restrict__ d_nmap, const double* __restrict__ sxyz,
-                                                                 const double* __restrict__ snrm, const int32_t* __restrict__ d_nscan,
-                                                                 const double* __restrict__ Tdev, const int32_t* __restrict__ gate,
-                                                                 size_t capacity, int32_t* d_tot, uint32_t* status) {
-  const int nmap = *d_nmap;
-  int ns = *d_nscan;
+// ---------------------------------------------------------------------------------------------------------------------
+// K-fuse.  The reference re-buckets EVERY in-cropper point of the whole map on every insertion (helpers.cpp:152-167); here the
+// map keeps a persistent voxel hash (key = floor(p * (1/v)) on the global-origin grid, VoxelHashMap.hpp:47-50; value = the
+// chain of map points inside that voxel), and an insertion only does work proportional to the SCAN:
+//   K1 stage+link   every scan point: transform (o3d_slam::transform, duplication quirk kept), stage, key, find-or-insert the
+//                   voxel, link the staged point into its chain, first toucher of a voxel queues it;
+//   K2 merge        one thread per touched voxel (+ per voxel of the short list of voxels that hold more than one map
+//                   point): AccumulatedPoint over the in-cropper members in map order -- old map points first (each counts as
+//                   ONE member, helpers.cpp:30-70), then the scan points in scan order -- mean, normalized mean normal; the result
+//                   takes the slot of the oldest member (or a fresh slot), merged-away map points become tombstones (NaN),
+//                   out-of-cropper members pass through (a staged one gets a slot of its own), the chain is rebuilt;
+//   K3 renormalize  the reference's pass also rewrites the normal of every UNTOUCHED in-cropper point as normalized(n / 1)
+//                   (helpers.cpp:172), which is not idempotent in floating point: one streaming pass over the map applies it to
+//                   the points K2 did not rewrite, so normals stay bit-faithful; + commit of the counters and the pose.
+// Positions of untouched voxels are unchanged by the reference's pass (mean of one member = p / 1), so the map is identical
+// as a keyed set.  Tombstones are skipped by every reader (NaN never passes a cropper or enters an index) and dropped whenever
+// the map is compacted (carving) or leaves the device.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long FV_EMPTY = ~0ull;
+
+__device__ __forceinline__ unsigned long long fv_pack(int x, int y, int z) {
+  return ((unsigned long long)(unsigned)(x + 1048576) << 42) | ((unsigned long long)(unsigned)(y + 1048576) << 21) |
+         (unsigned long long)(unsigned)(z + 1048576);
+}
+__device__ __forceinline__ unsigned long long fv_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+// getVoxelIdx(p, invVoxelSize): int(floor(p * invSize))   VoxelHashMap.hpp:47-50
+__device__ __forceinline__ bool fv_key(double x, double y, double z, double inv, unsigned long long* key) {
+  const double fx = floor(__dmul_rn(x, inv)), fy = floor(__dmul_rn(y, inv)), fz = floor(__dmul_rn(z, inv));
+  if (!(fabs(fx) < 1048575.0 && fabs(fy) < 1048575.0 && fabs(fz) < 1048575.0)) return false;   // also rejects NaN
+  *key = fv_pack((int)fx, (int)fy, (int)fz);
+  return true;
+}
+// slot of `key`, inserting it when absent (-1: table full)
+__device__ __forceinline__ long long fv_find_or_insert(unsigned long long* keys, int32_t* head, size_t mask, unsigned long long key, int32_t* ms,
+                                                       uint32_t* status) {
+  size_t s = (size_t)fv_hash(key) & mask;
+  for (size_t probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
+    const unsigned long long old = atomicCAS(&keys[s], FV_EMPTY, key);
+    if (old == FV_EMPTY) {
+      if ((size_t)atomicAdd(&ms[MS_VUSED], 1) + 1 > mask - mask / 4) atomicOr(status, ST_HASH_FULL);
+      return (long long)s;
+    }
+    if (old == key) return (long long)s;
+  }
+  atomicOr(status, ST_HASH_FULL);
+  return -1;
+}
+
+struct FuseView {
+  double* mxyz; double* mnrm; int32_t* vnext; int32_t* pstamp;
+  const double* sxyz; const double* snrm; int32_t* snext; const int32_t* sin;
+};
+__device__ __forceinline__ int fv_next(const FuseView& v, int idx) { return idx >= FUSE_STAGE_BASE ? v.snext[idx - FUSE_STAGE_BASE] : v.vnext[idx]; }
+
+// K1
+__global__ void __launch_bounds__(FZ_THREADS) fuse_stage_kernel(const double* __restrict__ sxyz_in, const double* __restrict__ snrm_in,
+                                                                const int32_t* __restrict__ d_nscan, const double* __restrict__ Tdev,
+                                                                const int32_t* __restrict__ gate, CropDev crop, double inv, size_t stage_cap,
+                                                                double* __restrict__ stage_xyz, double* __restrict__ stage_nrm,
+                                                                int32_t* __restrict__ stage_next, int32_t* __restrict__ stage_in,
+                                                                unsigned long long* vkeys, int32_t* vhead, int32_t* vstamp, size_t vmask,
+                                                                int32_t* __restrict__ touched, int32_t* ms, uint32_t* status) {
+  const int ns = *d_nscan;
   const bool open = (gate == nullptr || *gate != 0) && ns > 0;  // Submap.cpp:41-43: empty scan -> nothing happens
-  if (!open) { if (blockIdx.x == 0 && threadIdx.x == 0) *d_tot = 0; return; }
+  if (!open) return;
   double T[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) T[i] = Tdev[i];
   double mx = 0.0;
 #pragma unroll
   for (int i = 0; i < 16; i++) mx = fmax(mx, fabs(T[i] - ((i % 5 == 0) ? 1.0 : 0.0)));
-  const bool ident = mx < 1e-4;  // helpers.cpp:275
-  const size_t total = (size_t)nmap + (size_t)(ident ? 2 : 1) * (size_t)ns;
-  if (total > capacity) { if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(status, ST_CAPACITY); *d_tot = 0; } return; }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *d_tot = (int32_t)total;
-  const size_t b0 = (size_t)nmap, b1 = b0 + (ident ? (size_t)ns : 0);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
-    const double px = sxyz[3 * i], py = sxyz[3 * i + 1], pz = sxyz[3 * i + 2];
-    const double a = snrm[3 * i], b = snrm[3 * i + 1], c = snrm[3 * i + 2];
-    if (ident) {
-      mxyz[3 * (b0 + i)] = px; mxyz[3 * (b0 + i) + 1] = py; mxyz[3 * (b0 + i) + 2] = pz;
-      mnrm[3 * (b0 + i)] = a; mnrm[3 * (b0 + i) + 1] = b; mnrm[3 * (b0 + i) + 2] = c;
+  const bool ident = mx < 1e-4;  // helpers.cpp:275: the untransformed cloud is copied first, every transformed point appended as well
+  const size_t m = (size_t)(ident ? 2 : 1) * (size_t)ns;
+  if (m > stage_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, ST_CAPACITY); return; }
+  const int cur = ms[MS_STAMP] + 1;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (size_t)gridDim.x * blockDim.x) {
+    const bool copy = ident && j < (size_t)ns;
+    const size_t i = (ident && !copy) ? j - (size_t)ns : j;
+    const double px = sxyz_in[3 * i], py = sxyz_in[3 * i + 1], pz = sxyz_in[3 * i + 2];
+    const double a = snrm_in[3 * i], b = snrm_in[3 * i + 1], c = snrm_in[3 * i + 2];
+    double x = px, y = py, z = pz, nx = a, ny = b, nz = c;
+    if (!copy) {
+      const double tx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
+      const double ty = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], px), __dmul_rn(T[5], py)), __dmul_rn(T[6], pz)), T[7]);
+      const double tz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], px), __dmul_rn(T[9], py)), __dmul_rn(T[10], pz)), T[11]);
+      const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[12], px), __dmul_rn(T[13], py)), __dmul_rn(T[14], pz)), T[15]);
+      x = __ddiv_rn(tx, w); y = __ddiv_rn(ty, w); z = __ddiv_rn(tz, w);
+      nx = __dadd_rn(__dadd_rn(__dmul_rn(T[0], a), __dmul_rn(T[1], b)), __dmul_rn(T[2], c));
+      ny = __dadd_rn(__dadd_rn(__dmul_rn(T[4], a), __dmul_rn(T[5], b)), __dmul_rn(T[6], c));
+      nz = __dadd_rn(__dadd_rn(__dmul_rn(T[8], a), __dmul_rn(T[9], b)), __dmul_rn(T[10], c));
     }
-    const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
-    const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], px), __dmul_rn(T[5], py)), __dmul_rn(T[6], pz)), T[7]);
-    const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], px), __dmul_rn(T[9], py)), __dmul_rn(T[10], pz)), T[11]);
-    const double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[12], px), __dmul_rn(T[13], py)), __dmul_rn(T[14], pz)), T[15]);
-    const size_t o = b1 + i;
-    mxyz[3 * o] = __ddiv_rn(x, w); mxyz[3 * o + 1] = __ddiv_rn(y, w); mxyz[3 * o + 2] = __ddiv_rn(z, w);
-    mnrm[3 * o] = __dadd_rn(__dadd_rn(__dmul_rn(T[0], a), __dmul_rn(T[1], b)), __dmul_rn(T[2], c));
-    mnrm[3 * o + 1] = __dadd_rn(__dadd_rn(__dmul_rn(T[4], a), __dmul_rn(T[5], b)), __dmul_rn(T[6], c));
-    mnrm[3 * o + 2] = __dadd_rn(__dadd_rn(__dmul_rn(T[8], a), __dmul_rn(T[9], b)), __dmul_rn(T[10], c));
+    stage_xyz[3 * j] = x; stage_xyz[3 * j + 1] = y; stage_xyz[3 * j + 2] = z;
+    stage_nrm[3 * j] = nx; stage_nrm[3 * j + 1] = ny; stage_nrm[3 * j + 2] = nz;
+    stage_in[j] = crop_within(crop, x, y, z) ? 1 : 0;
+    stage_next[j] = -1;
+    unsigned long long key;
+    if (!(x == x && y == y && z == z)) { stage_in[j] = -1; continue; }   // NaN never survives S1's croppers; dropped here (-1: not linked anywhere)
+    if (!fv_key(x, y, z, inv, &key)) { atomicOr(status, ST_KEY_OVERFLOW); stage_in[j] = -1; continue; }
+    const long long s = fv_find_or_insert(vkeys, vhead, vmask, key, ms, status);
+    if (s < 0) { stage_in[j] = -1; continue; }
+    stage_next[j] = atomicExch(&vhead[s], FUSE_STAGE_BASE + (int)j);
+    if (atomicExch(&vstamp[s], cur) != cur) touched[atomicAdd(&ms[MS_NTOUCHED], 1)] = (int32_t)s;
   }
 }
 
-template <typename K>
-__device__ __forceinline__ K morton3f(uint32_t x, uint32_t y, uint32_t z);
-template <>
-__device__ __forceinline__ uint32_t morton3f<uint32_t>(uint32_t x, uint32_t y, uint32_t z) {
-  return morton_part10(x) | (morton_part10(y) << 1) | (morton_part10(z) << 2);
-}
-template <>
-__device__ __forceinline__ uint64_t morton3f<uint64_t>(uint32_t x, uint32_t y, uint32_t z) {
-  return morton_part21(x) | (morton_part21(y) << 1) | (morton_part21(z) << 2);
-}
-
-// key = Morton(floor(p * inv) - base) for points inside the cropper, sentinel otherwise.
-// base: bounded cropper -> floor((centre - rmax) * inv) - 1 per axis; unbounded -> -2^20 (21-bit keys).
-template <typename K>
-__global__ void __launch_bounds__(FZ_THREADS) fuse_keys_kernel(const double* __restrict__ mxyz, const int32_t* __restrict__ d_tot,
-                                                               CropDev crop, double inv, int bits, int bounded,
-                                                               K* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* status) {
-  const int n = *d_tot;
-  const K invalid = (K)1 << (3 * bits);
-  double bx, by, bz;
-  if (bounded) {
-    double cx = crop.cx, cy = crop.cy, cz = crop.cz;
-    if (crop.pose_dev) { cx = crop.pose_dev[3]; cy = crop.pose_dev[7]; cz = crop.pose_dev[11]; }
-    bx = floor((cx - crop.rmax) * inv) - 1.0; by = floor((cy - crop.rmax) * inv) - 1.0; bz = floor((cz - crop.rmax) * inv) - 1.0;
-  } else { bx = by = bz = -1048576.0; }
-  const double lim = (double)(1u << bits);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double x = mxyz[3 * i], y = mxyz[3 * i + 1], z = mxyz[3 * i + 2];
-    K key = invalid;
-    if (crop_within(crop, x, y, z)) {
-      // getVoxelIdx(p, invVoxelSize): int(floor(p * invSize))   VoxelHashMap.hpp:47-50
-      const double fx = floor(__dmul_rn(x, inv)) - bx, fy = floor(__dmul_rn(y, inv)) - by, fz = floor(__dmul_rn(z, inv)) - bz;
-      if (fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < lim && fy < lim && fz < lim) key = morton3f<K>((uint32_t)fx, (uint32_t)fy, (uint32_t)fz);
-      else atomicOr(status, ST_KEY_OVERFLOW);
+// K2
+__global__ void __launch_bounds__(128) fuse_merge_kernel(const int32_t* __restrict__ gate, const int32_t* __restrict__ d_nscan, CropDev crop,
+                                                         FuseView v, int32_t* vhead, const int32_t* __restrict__ vstamp,
+                                                         const int32_t* __restrict__ touched, int32_t* dups, int32_t* d_nmap, size_t capacity,
+                                                         int32_t* ms, uint32_t* status) {
+  if (!((gate == nullptr || *gate != 0) && *d_nscan > 0)) return;
+  const int cur = ms[MS_STAMP] + 1;
+  const int ntouched = ms[MS_NTOUCHED];
+  const int sel = ms[MS_DUPSEL] & 1;
+  const int ndup = min(ms[MS_NDUP + sel], FUSE_DUP_CAP);
+  const int32_t* dup_cur = dups + (size_t)sel * FUSE_DUP_CAP;
+  int32_t* dup_nxt = dups + (size_t)(sel ^ 1) * FUSE_DUP_CAP;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntouched + ndup; t += gridDim.x * blockDim.x) {
+    int slot;
+    if (t < ntouched) slot = touched[t];
+    else {
+      slot = dup_cur[t - ntouched];
+      if (vstamp[slot] == cur) continue;   // touched by this insertion as well: its own thread deals with it
     }
-    keys[i] = key;
-    vals[i] = (uint32_t)i;
-  }
-}
-
-template <typename K>
-__global__ void __launch_bounds__(FZ_THREADS) fuse_head_kernel(const K* __restrict__ keys, const int32_t* __restrict__ d_tot, int bits,
-                                                               int32_t* __restrict__ head) {
-  const int n = *d_tot;
-  const K invalid = (K)1 << (3 * bits);
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const K k = keys[j];
-    head[j] = (k >= invalid) ? 1 : ((j == 0 || keys[j - 1] != k) ? 1 : 0);  // pass-through points are singleton segments
-  }
-}
-
-template <typename K>
-__global__ void __launch_bounds__(FZ_THREADS) fuse_mean_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                               const int32_t* __restrict__ d_tot, int bits,
-                                                               const int32_t* __restrict__ head, const int32_t* __restrict__ offs,
-                                                               const double* __restrict__ mxyz, const double* __restrict__ mnrm,
-                                                               double* __restrict__ oxyz, double* __restrict__ onrm, int32_t* d_out_n) {
-  const int n = *d_tot;
-  const K invalid = (K)1 << (3 * bits);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *d_out_n = n > 0 ? offs[n] : 0;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    if (!head[j]) continue;
-    const K k = keys[j];
-    const int o = offs[j];
-    if (k >= invalid) {  // outside the cropper: copied through unchanged (helpers.cpp:156-166)
-      const uint32_t i = vals[j];
-      oxyz[3 * o] = mxyz[3 * i]; oxyz[3 * o + 1] = mxyz[3 * i + 1]; oxyz[3 * o + 2] = mxyz[3 * i + 2];
-      onrm[3 * o] = mnrm[3 * i]; onrm[3 * o + 1] = mnrm[3 * i + 1]; onrm[3 * o + 2] = mnrm[3 * i + 2];
-      continue;
+    // pass 1: who is in the bucket?  (a map point counts when it is alive and inside the cropper; a staged one by its flag)
+    int nin = 0, dest = 0x7fffffff;
+    for (int idx = vhead[slot]; idx >= 0; idx = fv_next(v, idx)) {
+      bool in;
+      if (idx >= FUSE_STAGE_BASE) in = v.sin[idx - FUSE_STAGE_BASE] > 0;
+      else {
+        const double x = v.mxyz[3 * (size_t)idx], y = v.mxyz[3 * (size_t)idx + 1], z = v.mxyz[3 * (size_t)idx + 2];
+        in = (x == x) && crop_within(crop, x, y, z);
+        if (in && idx < dest) dest = idx;
+      }
+      nin += in ? 1 : 0;
     }
     double sx = 0, sy = 0, sz = 0, nx = 0, ny = 0, nz = 0;
-    int cnt = 0;
-    for (int t = j; t < n && keys[t] == k; ++t) {
-      const uint32_t i = vals[t];
-      sx = __dadd_rn(sx, mxyz[3 * i]); sy = __dadd_rn(sy, mxyz[3 * i + 1]); sz = __dadd_rn(sz, mxyz[3 * i + 2]);
-      const double a = mnrm[3 * i], b = mnrm[3 * i + 1], c = mnrm[3 * i + 2];
-      if (a == a && b == b && c == c) { nx = __dadd_rn(nx, a); ny = __dadd_rn(ny, b); nz = __dadd_rn(nz, c); }
-      cnt++;
+    if (nin > 0) {
+      // pass 2: AccumulatedPoint in map order: ascending index, map points (< FUSE_STAGE_BASE) before the staged scan points
+      int last = -1;
+      for (int c = 0; c < nin; ++c) {
+        int best = 0x7fffffff;
+        for (int idx = vhead[slot]; idx >= 0; idx = fv_next(v, idx)) {
+          if (idx <= last || idx >= best) continue;
+          bool in;
+          if (idx >= FUSE_STAGE_BASE) in = v.sin[idx - FUSE_STAGE_BASE] > 0;
+          else {
+            const double x = v.mxyz[3 * (size_t)idx], y = v.mxyz[3 * (size_t)idx + 1], z = v.mxyz[3 * (size_t)idx + 2];
+            in = (x == x) && crop_within(crop, x, y, z);
+          }
+          if (in) best = idx;
+        }
+        last = best;
+        const double* px = best >= FUSE_STAGE_BASE ? v.sxyz + 3 * (size_t)(best - FUSE_STAGE_BASE) : v.mxyz + 3 * (size_t)best;
+        const double* pn = best >= FUSE_STAGE_BASE ? v.snrm + 3 * (size_t)(best - FUSE_STAGE_BASE) : v.mnrm + 3 * (size_t)best;
+        sx = __dadd_rn(sx, px[0]); sy = __dadd_rn(sy, px[1]); sz = __dadd_rn(sz, px[2]);
+        const double a = pn[0], b = pn[1], c2 = pn[2];
+        if (a == a && b == b && c2 == c2) { nx = __dadd_rn(nx, a); ny = __dadd_rn(ny, b); nz = __dadd_rn(nz, c2); }
+      }
+      if (dest == 0x7fffffff) {   // a voxel the map did not hold yet: fresh slot
+        dest = atomicAdd(d_nmap, 1);
+        if ((size_t)dest >= capacity) { atomicOr(status, ST_CAPACITY); atomicSub(d_nmap, 1); dest = -1; }
+      }
     }
-    const double c = (double)cnt;
-    oxyz[3 * o] = __ddiv_rn(sx, c); oxyz[3 * o + 1] = __ddiv_rn(sy, c); oxyz[3 * o + 2] = __ddiv_rn(sz, c);
-    double a0 = __ddiv_rn(nx, c), a1 = __ddiv_rn(ny, c), a2 = __ddiv_rn(nz, c);
+    // pass 3: rebuild the chain; merged-away map points die, out-of-cropper members pass through
+    int newhead = -1, survivors = 0;
+    for (int idx = vhead[slot]; idx >= 0;) {
+      const int nxt = fv_next(v, idx);
+      if (idx >= FUSE_STAGE_BASE) {
+        const int j = idx - FUSE_STAGE_BASE;
+        if (v.sin[j] == 0) {   // staged point outside the cropper: copied through unchanged (helpers.cpp:156-166)
+          const int sl = atomicAdd(d_nmap, 1);
+          if ((size_t)sl >= capacity) { atomicOr(status, ST_CAPACITY); atomicSub(d_nmap, 1); }
+          else {
+            for (int k = 0; k < 3; k++) { v.mxyz[3 * (size_t)sl + k] = v.sxyz[3 * (size_t)j + k]; v.mnrm[3 * (size_t)sl + k] = v.snrm[3 * (size_t)j + k]; }
+            v.pstamp[sl] = cur;
+            v.vnext[sl] = newhead; newhead = sl; survivors++;
+          }
+        }
+      } else {
+        const double x = v.mxyz[3 * (size_t)idx], y = v.mxyz[3 * (size_t)idx + 1], z = v.mxyz[3 * (size_t)idx + 2];
+        const bool alive = x == x;
+        const bool in = alive && crop_within(crop, x, y, z);
+        if (in) {
+          if (idx != dest) {   // merged into `dest`: tombstone
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            for (int k = 0; k < 3; k++) { v.mxyz[3 * (size_t)idx + k] = nan; v.mnrm[3 * (size_t)idx + k] = nan; }
+            atomicAdd(&ms[MS_NDEAD], 1);
+          }
+        } else if (alive) { v.vnext[idx] = newhead; newhead = idx; survivors++; }
+      }
+      idx = nxt;
+    }
+    if (nin > 0 && dest >= 0) {
+      const double c = (double)nin;
+      v.mxyz[3 * (size_t)dest] = __ddiv_rn(sx, c); v.mxyz[3 * (size_t)dest + 1] = __ddiv_rn(sy, c); v.mxyz[3 * (size_t)dest + 2] = __ddiv_rn(sz, c);
+      double a0 = __ddiv_rn(nx, c), a1 = __ddiv_rn(ny, c), a2 = __ddiv_rn(nz, c);
+      const double zz = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+      if (zz > 0.0) { const double sn = sqrt(zz); a0 = __ddiv_rn(a0, sn); a1 = __ddiv_rn(a1, sn); a2 = __ddiv_rn(a2, sn); }  // .normalized()
+      v.mnrm[3 * (size_t)dest] = a0; v.mnrm[3 * (size_t)dest + 1] = a1; v.mnrm[3 * (size_t)dest + 2] = a2;
+      v.pstamp[dest] = cur;
+      v.vnext[dest] = newhead; newhead = dest; survivors++;
+    }
+    vhead[slot] = newhead;
+    if (survivors >= 2) {   // more than one map point in this voxel: they merge as soon as both are inside the cropper
+      const int k = atomicAdd(&ms[MS_NDUP + (sel ^ 1)], 1);
+      if (k < FUSE_DUP_CAP) dup_nxt[k] = slot; else atomicOr(status, ST_CAPACITY);
+    }
+  }
+}
+
+// K3: normalized(n / 1) for the in-cropper points this insertion did not rewrite; the last block commits the insertion
+__global__ void __launch_bounds__(FZ_THREADS) fuse_renorm_commit_kernel(const int32_t* __restrict__ gate, const int32_t* __restrict__ d_nscan,
+                                                                        CropDev crop, const double* __restrict__ mxyz, double* __restrict__ mnrm,
+                                                                        const int32_t* __restrict__ pstamp, const int32_t* __restrict__ d_nmap,
+                                                                        int32_t* ms, double* last_pose, const double* __restrict__ Tdev) {
+  if (!((gate == nullptr || *gate != 0) && *d_nscan > 0)) return;
+  const int cur = ms[MS_STAMP] + 1;
+  const int n = *d_nmap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (pstamp[i] == cur) continue;
+    const double x = mxyz[3 * (size_t)i], y = mxyz[3 * (size_t)i + 1], z = mxyz[3 * (size_t)i + 2];
+    if (!(x == x) || !crop_within(crop, x, y, z)) continue;
+    double a0 = mnrm[3 * (size_t)i], a1 = mnrm[3 * (size_t)i + 1], a2 = mnrm[3 * (size_t)i + 2];
+    if (!(a0 == a0 && a1 == a1 && a2 == a2)) { a0 = 0.0; a1 = 0.0; a2 = 0.0; }   // AccumulatedPoint skips NaN normals: the sum stays zero
     const double zz = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-    if (zz > 0.0) { const double sn = sqrt(zz); a0 = __ddiv_rn(a0, sn); a1 = __ddiv_rn(a1, sn); a2 = __ddiv_rn(a2, sn); }  // .normalized()
-    onrm[3 * o] = a0; onrm[3 * o + 1] = a1; onrm[3 * o + 2] = a2;
+    if (zz > 0.0) { const double sn = sqrt(zz); a0 = __ddiv_rn(a0, sn); a1 = __ddiv_rn(a1, sn); a2 = __ddiv_rn(a2, sn); }
+    mnrm[3 * (size_t)i] = a0; mnrm[3 * (size_t)i + 1] = a1; mnrm[3 * (size_t)i + 2] = a2;
+  }
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ms[MS_TICKET2], 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {   // every block has read the stamp: commit
+    const int sel = ms[MS_DUPSEL] & 1;
+    ms[MS_TICKET2] = 0;
+    ms[MS_STAMP] = cur;
+    ms[MS_NTOUCHED] = 0;
+    ms[MS_NDUP + sel] = 0;
+    ms[MS_DUPSEL] = sel ^ 1;
+    ms[MS_NINS] += 1;                                      // Submap::nScansInsertedMap_
+    if (last_pose) for (int i = 0; i < 16; i++) last_pose[i] = Tdev[i];   // mapBuilderCropper_ pose / mapToRangeSensorLastScanInsertion_
   }
 }
 
-// mstate / last_pose: Submap::nScansInsertedMap_ and the pose mapBuilderCropper_ was last set to (Submap.cpp:71,73), which is
-// also Mapper::mapToRangeSensorLastScanInsertion_ (Mapper.cpp:175) -- kept on the device for the chain's own gates
-__global__ void __launch_bounds__(FZ_THREADS) fuse_commit_kernel(const double* __restrict__ oxyz, const double* __restrict__ onrm,
-                                                                 const int32_t* __restrict__ d_out_n, const int32_t* __restrict__ d_tot,
-                                                                 double* __restrict__ mxyz, double* __restrict__ mnrm, int32_t* d_nmap,
-                                                                 int32_t* mstate, double* last_pose, const double* __restrict__ Tdev) {
-  if (*d_tot <= 0) return;  // gate closed, empty scan or capacity error: the map stays as it was
-  const int n = *d_out_n;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *d_nmap = n;
-    if (mstate) mstate[MS_NINS] += 1;
-    if (last_pose) for (int i = 0; i < 16; i++) last_pose[i] = Tdev[i];
+// ---- (re)build of the voxel hash from the map cloud --------------------------------------------------------------------------
+__global__ void fuse_table_clear_kernel(unsigned long long* vkeys, int32_t* vhead, int32_t* vstamp, size_t vcap, int32_t* ms,
+                                        const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vcap; i += (size_t)gridDim.x * blockDim.x) { vkeys[i] = FV_EMPTY; vhead[i] = -1; vstamp[i] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ms[MS_VUSED] = 0; ms[MS_NTOUCHED] = 0; ms[MS_NDUP] = 0; ms[MS_NDUP + 1] = 0; ms[MS_DUPSEL] = 0; ms[MS_STAMP] = 0; }
+}
+__global__ void __launch_bounds__(FZ_THREADS) fuse_table_link_kernel(const double* __restrict__ mxyz, const int32_t* __restrict__ d_nmap, double inv,
+                                                                     unsigned long long* vkeys, int32_t* vhead, size_t vmask, int32_t* __restrict__ vnext,
+                                                                     int32_t* __restrict__ pstamp, int32_t* ms, uint32_t* status,
+                                                                     const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
+  const int n = *d_nmap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    vnext[i] = -1; pstamp[i] = 0;
+    unsigned long long key;
+    if (!fv_key(mxyz[3 * (size_t)i], mxyz[3 * (size_t)i + 1], mxyz[3 * (size_t)i + 2], inv, &key)) continue;   // tombstones / far points stay unlinked
+    const long long s = fv_find_or_insert(vkeys, vhead, vmask, key, ms, status);
+    if (s >= 0) vnext[i] = atomicExch(&vhead[s], i);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += gridDim.x * blockDim.x) { mxyz[i] = oxyz[i]; mnrm[i] = onrm[i]; }
+}
+// voxels whose chain holds more than one point, reported once (by the chain head)
+__global__ void __launch_bounds__(FZ_THREADS) fuse_table_dups_kernel(const unsigned long long* __restrict__ vkeys, const int32_t* __restrict__ vhead,
+                                                                     size_t vcap, const int32_t* __restrict__ vnext, int32_t* dups, int32_t* ms,
+                                                                     uint32_t* status, const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < vcap; s += (size_t)gridDim.x * blockDim.x) {
+    const int hd = vhead[s];
+    if (hd < 0 || vnext[hd] < 0) continue;
+    const int k = atomicAdd(&ms[MS_NDUP], 1);
+    if (k < FUSE_DUP_CAP) dups[k] = (int32_t)s; else atomicOr(status, ST_CAPACITY);
+  }
+  (void)vkeys;
 }
 
-static int bits_for_range(double cells) {
-  int b = 1;
-  while ((double)(1u << b) < cells && b < 22) b++;
-  return b;
-}
-
-template <typename K>
-static int32_t fuse_impl(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev,
-                         const CropDev& crop, double inv, int bits, int bounded, size_t tot_max) {
-  b2s_cloud* map = sm->cloud[0];
-  b2s_cloud* tmp = sm->cloud[1];
-  // scratch is sized once for the submap capacity: growing a device buffer costs a cudaMalloc/cudaFree, i.e. a
-  // device-wide synchronisation that would stall every other chain sharing the GPU
-  const size_t cap = sm->capacity;
-  B2S_TRY(h->keys.ensure(cap * sizeof(K) * 2, h->stream));
-  B2S_TRY(h->vals.ensure(cap * 4 * 2, h->stream));
-  B2S_TRY(h->flags.ensure((cap + 1) * 4, h->stream));
-  B2S_TRY(h->offs.ensure((cap + 2) * 4, h->stream));
-  B2S_TRY(h->tmp_i32.ensure(64, h->stream));
-  int32_t* d_tot = h->tmp_i32.as<int32_t>();
-  int32_t* d_out_n = d_tot + 1;
-  K* keys = h->keys.as<K>(); K* keys_alt = keys + cap;
-  uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + cap;
-  const int sblocks = grid_for(scan->n_max > 0 ? scan->n_max : 1, FZ_THREADS);
-  const int blocks = grid_for(tot_max, FZ_THREADS);
-  { ProfScope prof(h, PK_FUSE);
-  fuse_append_kernel<<<sblocks, FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>(),
-                                                            scan->xyz.as<double>(), scan->nrm.as<double>(), scan->dn.as<int32_t>(), T_dev,
-                                                            gate_dev, sm->capacity, d_tot, h->status.as<uint32_t>());
-  fuse_keys_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), d_tot, crop, inv, bits, bounded, keys, vals,
-                                                            h->status.as<uint32_t>());
-  h->launches += 2; }
-  if constexpr (sizeof(K) == 4) {
-    B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, d_tot, tot_max, 3 * bits + 1));
-  } else {
-    B2S_TRY(radix_sort_pairs_u64(h, keys, vals, keys_alt, vals_alt, d_tot, tot_max, 3 * bits + 1));
-  }
-  ProfScope prof2(h, PK_FUSE);
-  fuse_head_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(keys, d_tot, bits, h->flags.as<int32_t>());
+int32_t fuse_reserve(b2s_handle* h, b2s_submap* sm) {
+  if (sm->vcap) return B2S_OK;
+  size_t vcap = 4096;
+  while (vcap < 2 * sm->capacity) vcap <<= 1;
+  B2S_TRY(sm->vkeys.ensure(vcap * 8, h->stream));
+  B2S_TRY(sm->vhead.ensure(vcap * 4, h->stream));
+  B2S_TRY(sm->vstamp.ensure(vcap * 4, h->stream));
+  B2S_TRY(sm->vnext.ensure((sm->capacity + 1) * 4, h->stream));
+  B2S_TRY(sm->pstamp.ensure((sm->capacity + 1) * 4, h->stream));
+  B2S_TRY(sm->dups.ensure((size_t)2 * FUSE_DUP_CAP * 4, h->stream));
+  sm->vcap = vcap;
+  fuse_table_clear_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), vcap,
+                                                         sm->mstate.as<int32_t>(), nullptr);
   h->launches++;
-  B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_tot, tot_max, nullptr));
-  fuse_mean_kernel<K><<<blocks, FZ_THREADS, 0, h->stream>>>(keys, vals, d_tot, bits, h->flags.as<int32_t>(), h->offs.as<int32_t>(),
-                                                            map->xyz.as<double>(), map->nrm.as<double>(), tmp->xyz.as<double>(),
-                                                            tmp->nrm.as<double>(), d_out_n);
-  fuse_commit_kernel<<<blocks, FZ_THREADS, 0, h->stream>>>(tmp->xyz.as<double>(), tmp->nrm.as<double>(), d_out_n, d_tot,
-                                                           map->xyz.as<double>(), map->nrm.as<double>(), map->dn.as<int32_t>(),
-                                                           sm->mstate.as<int32_t>(), sm->pose.as<double>() + 5 * 16, T_dev);
-  h->launches += 2;
   B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+int32_t fuse_rehash(b2s_handle* h, b2s_submap* sm, const int32_t* enable_dev) {
+  B2S_TRY(fuse_reserve(h, sm));
+  b2s_cloud* map = sm->cloud[0];
+  const size_t n_max = sm->graph_mode ? sm->capacity : (map->n_max > 0 ? map->n_max : 1);
+  int32_t* ms = sm->mstate.as<int32_t>();
+  ProfScope prof(h, PK_FUSE);
+  fuse_table_clear_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), sm->vcap,
+                                                         ms, enable_dev);
+  fuse_table_link_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(),
+                                                                                   1.0 / h->cfg.map_voxel_size, sm->vkeys.as<unsigned long long>(),
+                                                                                   sm->vhead.as<int32_t>(), sm->vcap - 1, sm->vnext.as<int32_t>(),
+                                                                                   sm->pstamp.as<int32_t>(), ms, h->status.as<uint32_t>(), enable_dev);
+  fuse_table_dups_kernel<<<148 * 4, FZ_THREADS, 0, h->stream>>>(sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vcap,
+                                                               sm->vnext.as<int32_t>(), sm->dups.as<int32_t>(), ms, h->status.as<uint32_t>(), enable_dev);
+  h->launches += 3;
+  B2S_CUDA(cudaGetLastError());
+  return B2S_OK;
+}
+
+// live points of the map, in map order, in sm->cloud[1] (readers that leave the device: download, size)
+__global__ void __launch_bounds__(FZ_THREADS) fuse_alive_flags_kernel(const double* __restrict__ mxyz, const int32_t* __restrict__ d_n, int32_t* __restrict__ flags) {
+  const int n = *d_n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const double x = mxyz[3 * (size_t)i]; flags[i] = (x == x) ? 1 : 0; }
+}
+int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, b2s_cloud* out, const int32_t* d_n_override = nullptr);   // voxel.cu
+int32_t submap_compact_view(b2s_handle* h, b2s_submap* sm, b2s_cloud** view) {
+  b2s_cloud* map = sm->cloud[0];
+  const size_t n_max = map->n_max > 0 ? map->n_max : 1;
+  B2S_TRY(h->flags.ensure((n_max + 1) * 4, h->stream));
+  fuse_alive_flags_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(), h->flags.as<int32_t>());
+  h->launches++;
+  B2S_TRY(compact_cloud(h, map, h->flags.as<int32_t>(), sm->cloud[1]));
+  *view = sm->cloud[1];
   return B2S_OK;
 }
 
@@ -223,33 +362,56 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
   b2s_cloud* map = sm->cloud[0];
   const double v = h->cfg.map_voxel_size;
   B2S_REQUIRE(v > 0.0, B2S_E_UNSUPPORTED, "map_voxel_size <= 0 (no voxelisation) is not supported on the device path");
+  B2S_TRY(fuse_reserve(h, sm));
   // host-side upper bound of the map size.  The exact size is read back asynchronously after an insertion (pinned
   // host word + event); once that copy has landed the bound becomes exact-size + what was appended since.
   if (sm->cnt_pending && cudaEventQuery(sm->cnt_ev) == cudaSuccess) {
     map->n_max = (size_t)sm->pinned_cnt[0] + sm->adds_after_readback;
     sm->cnt_pending = false;
   }
-  size_t tot_max = map->n_max + 2 * scan->n_max;
+  const size_t m_max = 2 * (scan->n_max > 0 ? scan->n_max : 1);   // the duplication quirk doubles the scan
+  size_t tot_max = map->n_max + m_max;
   if (sm->graph_mode) tot_max = sm->capacity;   // graph replay: constant launch dimensions, overflow is caught on the device
   if (tot_max > sm->capacity) {
     int32_t n = 0;
     B2S_CUDA(cudaMemcpyAsync(&n, map->dn.p, 4, cudaMemcpyDeviceToHost, h->stream));
     B2S_CUDA(cudaStreamSynchronize(h->stream));
     map->n_max = (size_t)n; map->n_known = n;
-    tot_max = map->n_max + 2 * scan->n_max;
-    B2S_REQUIRE(tot_max <= sm->capacity, B2S_E_CAPACITY, "submap capacity %zu too small for %zu points", sm->capacity, tot_max);
+    tot_max = map->n_max + m_max;
+    if (tot_max > sm->capacity) tot_max = sm->capacity;   // only NEW voxels take slots: a real overflow is caught on the device
+  }
+  if (sm->stage_cap < m_max) {
+    B2S_TRY(sm->stage_xyz.ensure(m_max * 24, h->stream));
+    B2S_TRY(sm->stage_nrm.ensure(m_max * 24, h->stream));
+    B2S_TRY(sm->stage_next.ensure(m_max * 4, h->stream));
+    B2S_TRY(sm->stage_in.ensure(m_max * 4, h->stream));
+    B2S_TRY(sm->touched.ensure(m_max * 4, h->stream));
+    sm->stage_cap = m_max;
   }
   CropDev crop = make_crop(&h->cfg.scan.map_builder_cropper, T_dev);  // Submap.cpp:71 setPose(mapToRangeSensor)
   const double inv = 1.0 / v;
-  const int bounded = (!crop.invert && (crop.kind == B2S_CROP_MAX_RADIUS || crop.kind == B2S_CROP_MINMAX_RADIUS)) ? 1 : 0;
-  const int bits = bounded ? bits_for_range(floor(2.0 * crop.rmax * inv) + 4.0) : 21;
-  B2S_REQUIRE(bits <= 21, B2S_E_INVALID, "map voxel size too small for the cropper radius");
-  int32_t rc = (bits <= 10) ? fuse_impl<uint32_t>(h, sm, scan, T_dev, gate_dev, crop, inv, bits, bounded, tot_max)
-                            : fuse_impl<uint64_t>(h, sm, scan, T_dev, gate_dev, crop, inv, bits, bounded, tot_max);
+  int32_t* ms = sm->mstate.as<int32_t>();
+  FuseView fv{map->xyz.as<double>(), map->nrm.as<double>(), sm->vnext.as<int32_t>(), sm->pstamp.as<int32_t>(), sm->stage_xyz.as<double>(),
+              sm->stage_nrm.as<double>(), sm->stage_next.as<int32_t>(), sm->stage_in.as<int32_t>()};
+  {
+    ProfScope prof(h, PK_FUSE);
+    fuse_stage_kernel<<<grid_for(m_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+        scan->xyz.as<double>(), scan->nrm.as<double>(), scan->dn.as<int32_t>(), T_dev, gate_dev, crop, inv, sm->stage_cap, sm->stage_xyz.as<double>(),
+        sm->stage_nrm.as<double>(), sm->stage_next.as<int32_t>(), sm->stage_in.as<int32_t>(), sm->vkeys.as<unsigned long long>(),
+        sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), sm->vcap - 1, sm->touched.as<int32_t>(), ms, h->status.as<uint32_t>());
+    fuse_merge_kernel<<<grid_for(m_max + 4096, 128), 128, 0, h->stream>>>(gate_dev, scan->dn.as<int32_t>(), crop, fv, sm->vhead.as<int32_t>(),
+                                                                         sm->vstamp.as<int32_t>(), sm->touched.as<int32_t>(), sm->dups.as<int32_t>(),
+                                                                         map->dn.as<int32_t>(), sm->capacity, ms, h->status.as<uint32_t>());
+    fuse_renorm_commit_kernel<<<grid_for(tot_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(gate_dev, scan->dn.as<int32_t>(), crop, map->xyz.as<double>(),
+                                                                                         map->nrm.as<double>(), sm->pstamp.as<int32_t>(),
+                                                                                         map->dn.as<int32_t>(), ms, sm->pose.as<double>() + 5 * 16, T_dev);
+    h->launches += 3;
+  }
   map->n_max = tot_max;   // upper bound only; the exact count lives on the device
   map->n_known = -1;
   map->has_normals = true;
-  if (rc == B2S_OK && !sm->graph_mode) {
+  B2S_CUDA(cudaGetLastError());
+  if (!sm->graph_mode) {
     if (!sm->pinned_cnt) {
       B2S_CUDA(cudaMallocHost(&sm->pinned_cnt, 64));
       B2S_CUDA(cudaEventCreateWithFlags(&sm->cnt_ev, cudaEventDisableTiming));
@@ -260,10 +422,10 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
       sm->cnt_pending = true;
       sm->adds_after_readback = 0;
     } else {
-      sm->adds_after_readback += 2 * scan->n_max;
+      sm->adds_after_readback += m_max;
     }
   }
-  return rc;
+  return B2S_OK;
 }
 
 // =====================================================================================================================

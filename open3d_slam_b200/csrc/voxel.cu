@@ -632,7 +632,7 @@ int32_t op_submap_transform(b2s_handle* h, b2s_submap* sm, const double* T_host)
     h->launches++;
   }
   B2S_CUDA(cudaGetLastError());
-  return B2S_OK;
+  return fuse_rehash(h, sm);   // the points moved into other voxels: the fusion's voxel hash follows
 }
 
 }  // namespace b2s

@@ -82,7 +82,7 @@ int main(void) {
   int fail = 0;
   if (!(worst < 1e-6)) { fprintf(stderr, "transform off by %.3e\n", worst); fail = 1; }
   if (!(res.fitness > 0.999) || res.n_corr < N - 2 || res.iters < 2 || res.iters > 50) { fprintf(stderr, "unexpected fitness / counts\n"); fail = 1; }
-  if (dmax != 0.0 || res.iters != res2.iters) { fprintf(stderr, "b2s_register_host disagrees with b2s_register\n"); fail = 1; }
+  if (dmax > 1e-12 || res.iters != res2.iters) { fprintf(stderr, "b2s_register_host disagrees with b2s_register\n"); fail = 1; }   /* (outlier order: last bits) */
   /* error behaviour: point-to-plane without target normals -> B2S_E_NO_NORMALS with a message; r <= 0 -> B2S_E_INVALID */
   CHECK(b2s_cloud_upload_f64(h, ct, tgt, NULL, N));
   if (b2s_register(h, cs, ct, I, &res) != B2S_E_NO_NORMALS || strlen(b2s_last_error()) == 0) { fprintf(stderr, "missing-normals case not reported\n"); fail = 1; }
