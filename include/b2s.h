@@ -158,6 +158,12 @@ int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* ta
 /* config 4: n independent registrations in one launch (PlaceRecognition.cpp:71,111 iterates them serially) */
 int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sources, const b2s_cloud* const* targets,
                            const double* inits /* n x 16 */, b2s_result* out /* n */);
+/* R3  the correspondence search of [O3D] GetRegistrationResultAndCorrespondences (KDTreeFlann::SearchHybrid(q, r, 1)) on its own:
+ *     for every point of `queries`, moved by T first when T is given, the index of its nearest point of `target` with d^2 < r^2
+ *     (-1 = none; exact, ties -> lower index) and the squared distance (-1 when none).  The correspondence_set_ of a
+ *     RegistrationResult is this call at the result's transformation.  Host arrays hold `capacity` >= query count entries. */
+int32_t b2s_nearest_neighbors(b2s_handle* h, const b2s_cloud* queries, const b2s_cloud* target, double max_correspondence_distance,
+                              const double T_or_null[16], int32_t* index_out, double* d2_out_or_null, size_t capacity, size_t* n_queries);
 /* host-pointer convenience form of R1 used by the C++ shim: uploads, registers, returns. */
 int32_t b2s_register_host(b2s_handle* h, const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_normals,
                           size_t n_tgt, const double init[16], b2s_result* out);
@@ -220,6 +226,9 @@ int32_t b2s_submap_transform(b2s_handle* h, b2s_submap* sm, const double T[16]);
 /* Submap::getMapPointCloud (copy-out)                                       src/Submap.cpp:184-191 */
 int32_t b2s_submap_size(b2s_handle* h, const b2s_submap* sm, size_t* n);
 int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, size_t capacity, size_t* n);
+/* Submap::getMapPointCloudCopy (src/Submap.cpp:187-191) without leaving the device: the map cloud as a b2s_cloud (what place
+ * recognition, the overlap selection and the voxel map of the revisit check read, src/PlaceRecognition.cpp:69,96, src/Submap.cpp:236) */
+int32_t b2s_submap_to_cloud(b2s_handle* h, const b2s_submap* sm, b2s_cloud* out);
 int32_t b2s_submap_dense_download(b2s_handle* h, const b2s_submap* sm, double* xyz, double* normals, int32_t* keys, size_t capacity,
                                   size_t* n);
 int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* cloud);   /* load / initial map */

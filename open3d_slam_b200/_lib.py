@@ -72,7 +72,7 @@ SYMBOLS = [
     "b2s_default_mapper_options", "b2s_submap_set_mapper_options", "b2s_submap_get_mapper_counters",
     "b2s_voxel_map_create", "b2s_voxel_map_destroy", "b2s_voxel_map_clear", "b2s_voxel_map_insert_cloud", "b2s_voxel_map_size",
     "b2s_voxel_map_has_voxel", "b2s_voxel_map_indices_in_voxel", "b2s_mapper_processed_scan",
-    "b2s_cloud_export_device", "b2s_cloud_import_device",
+    "b2s_cloud_export_device", "b2s_cloud_import_device", "b2s_submap_to_cloud", "b2s_nearest_neighbors",
 ]
 PROFILE_KINDS = ["icp", "normals", "radix_sort", "nn_grid_build", "voxel", "fuse", "select", "crop"]
 

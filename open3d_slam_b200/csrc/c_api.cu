@@ -26,6 +26,7 @@ __global__ void f32_to_f64_kernel(const unsigned char* __restrict__ src, size_t 
   }
 }
 
+__global__ void write_i32_kernel(int32_t* p, int32_t v) { *p = v; }
 __global__ void pad_kernel() {}   // B2S_PAD_LAUNCHES=n: n empty launches per scan, to measure what a launch costs the chain (tuning aid)
 
 __global__ void empty_check_kernel(const int32_t* a, const int32_t* b, uint32_t* status) {
@@ -93,6 +94,9 @@ static int32_t check_icp_params(const b2s_icp_params& p) {
   return B2S_OK;
 }
 
+// global working copy of a source of n points (positions + per-point search state); only touched by sources too large for shared memory
+static inline size_t icp_work_bytes(size_t n) { return (n + 1) * 24 + (n + 1) * 4 + 16; }
+
 static void fill_problem(b2s_handle* h, IcpProblem* P, const b2s_cloud* src, const GridIndex* g, const double* init_host,
                          const double* init_dev, double* work, b2s_result* out_dev) {
   memset(P, 0, sizeof(*P));
@@ -103,6 +107,7 @@ static void fill_problem(b2s_handle* h, IcpProblem* P, const b2s_cloud* src, con
   P->tgt_pts = g->pts.as<double>();
   P->tgt_nrm = g->nrm.as<double>();
   P->work_xyz = work;
+  P->work_prev = reinterpret_cast<int32_t*>(work + 3 * (src->n_max + 1));   // callers size the work buffer with icp_work_bytes()
   P->init_dev = init_dev;
   if (init_host) memcpy(P->init, init_host, 128);
   P->max_corr = h->cfg.icp.max_corr_dist;
@@ -264,7 +269,7 @@ static int32_t mapper_step_graph(b2s_handle* h, b2s_submap* sm, const b2s_cloud*
 
 }  // namespace b2s
 
-#define LOCK(h) std::lock_guard<std::mutex> _lk((h)->mu); cudaSetDevice((h)->device)
+#define LOCK(h) std::lock_guard<std::recursive_mutex> _lk((h)->mu); cudaSetDevice((h)->device)
 
 extern "C" {
 
@@ -300,15 +305,23 @@ int32_t b2s_create(const b2s_config* cfg, int32_t device, void* cuda_stream_or_n
   B2S_REQUIRE(h != nullptr, B2S_E_INVALID, "out of host memory");
   h->device = device;
   if (cfg) h->cfg = *cfg; else b2s_default_config(&h->cfg);
-  if (cuda_stream_or_null) { h->stream = (cudaStream_t)cuda_stream_or_null; h->own_stream = false; }
-  else { B2S_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
-  B2S_TRY(h->status.ensure(64, h->stream));
-  B2S_CUDA(cudaMemsetAsync(h->status.p, 0, 64, h->stream));
-  B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream));
-  B2S_TRY(h->slots.ensure(256 * sizeof(b2s_result), h->stream));
-  B2S_CUDA(cudaMemsetAsync(h->slots.p, 0, 256 * sizeof(b2s_result), h->stream));
-  b2s_cloud** tmp[4] = {&h->t0, &h->t1, &h->t2, &h->t3};
-  for (int i = 0; i < 4; i++) { *tmp[i] = new b2s_cloud(); (*tmp[i])->h = h; (*tmp[i])->device = device; B2S_TRY(cloud_reserve(h, *tmp[i], 1, true)); B2S_TRY(cloud_set_count(h, *tmp[i], 0)); }
+  const int32_t rc = [&]() -> int32_t {   // any failure below releases what was built so far (b2s_destroy copes with a partial handle)
+    if (cuda_stream_or_null) { h->stream = (cudaStream_t)cuda_stream_or_null; h->own_stream = false; }
+    else { B2S_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    B2S_TRY(h->status.ensure(64, h->stream));
+    B2S_CUDA(cudaMemsetAsync(h->status.p, 0, 64, h->stream));
+    B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream));
+    B2S_TRY(h->slots.ensure(256 * sizeof(b2s_result), h->stream));
+    B2S_CUDA(cudaMemsetAsync(h->slots.p, 0, 256 * sizeof(b2s_result), h->stream));
+    b2s_cloud** tmp[4] = {&h->t0, &h->t1, &h->t2, &h->t3};
+    for (int i = 0; i < 4; i++) {
+      *tmp[i] = new b2s_cloud(); (*tmp[i])->h = h; (*tmp[i])->device = device;
+      B2S_TRY(cloud_reserve(h, *tmp[i], 1, true));
+      B2S_TRY(cloud_set_count(h, *tmp[i], 0));
+    }
+    return B2S_OK;
+  }();
+  if (rc != B2S_OK) { b2s_destroy(h); return rc; }
   *out = h;
   return B2S_OK;
 }
@@ -316,7 +329,7 @@ int32_t b2s_create(const b2s_config* cfg, int32_t device, void* cuda_stream_or_n
 void b2s_destroy(b2s_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   b2s_cloud* tmp[4] = {h->t0, h->t1, h->t2, h->t3};
   for (int i = 0; i < 4; i++) if (tmp[i]) { tmp[i]->xyz.release(); tmp[i]->nrm.release(); tmp[i]->dn.release(); delete tmp[i]; }
   for (auto* g : h->batch_grids) { g->release(); delete g; }
@@ -324,8 +337,12 @@ void b2s_destroy(b2s_handle* h) {
   DevBuf* bufs[] = {&h->status, &h->scan.state, &h->sort.hist, &h->sort.keys_alt, &h->sort.vals_alt, &h->keys, &h->vals, &h->flags, &h->offs,
                     &h->tmp_i32, &h->tmp_f64, &h->misc, &h->work_xyz, &h->problems, &h->results, &h->slots, &h->poses};
   for (DevBuf* b : bufs) b->release();
+  h->batch_jobs.release();
+  if (h->icp_dbg) cudaFree(h->icp_dbg);
+  for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   if (h->pinned) cudaFreeHost(h->pinned);
-  if (h->own_stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
@@ -543,7 +560,7 @@ int32_t b2s_register(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* ta
   B2S_REQUIRE(source->has_normals || h->cfg.icp.reg_type != B2S_REG_GENERALIZED, B2S_E_NO_NORMALS,
               "GeneralizedIcp on the device derives the covariances from normals: call estimateNormalsOrCovariancesIfNeeded on both clouds");
   B2S_TRY(grid_build(h, &h->grid_a, target, nn_cell(h, h->cfg.icp.max_corr_dist), nullptr, true));
-  B2S_TRY(h->work_xyz.ensure((source->n_max + 1) * 24, h->stream));
+  B2S_TRY(h->work_xyz.ensure(icp_work_bytes(source->n_max), h->stream));
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
   B2S_TRY(h->results.ensure(sizeof(b2s_result), h->stream));
   IcpProblem P;
@@ -576,19 +593,19 @@ int32_t b2s_register_batch(b2s_handle* h, int32_t n, const b2s_cloud* const* sou
       if (h->batch_grids.size() <= (size_t)gi) h->batch_grids.push_back(new GridIndex());
     }
     grid_of[i] = gi;
-    work_total += sources[i]->n_max + 1;
+    work_total += (icp_work_bytes(sources[i]->n_max) + 7) / 8;   // in doubles
     if (sources[i]->n_max > max_src) max_src = sources[i]->n_max;
   }
   // R2 for every distinct target in one set of launches (blockIdx.y = target)
   B2S_TRY(grid_build_batch(h, h->batch_grids.data(), seen.data(), (int)seen.size(), nn_cell(h, h->cfg.icp.max_corr_dist), true));
-  B2S_TRY(h->work_xyz.ensure(work_total * 24, h->stream));
+  B2S_TRY(h->work_xyz.ensure(work_total * 8, h->stream));
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem) * (size_t)n, h->stream));
   B2S_TRY(h->results.ensure(sizeof(b2s_result) * (size_t)n, h->stream));
   size_t woff = 0;
   for (int i = 0; i < n; i++) {
-    fill_problem(h, &probs[i], sources[i], h->batch_grids[grid_of[i]], inits + 16 * (size_t)i, nullptr, h->work_xyz.as<double>() + 3 * woff,
+    fill_problem(h, &probs[i], sources[i], h->batch_grids[grid_of[i]], inits + 16 * (size_t)i, nullptr, h->work_xyz.as<double>() + woff,
                  h->results.as<b2s_result>() + i);
-    woff += sources[i]->n_max + 1;
+    woff += (icp_work_bytes(sources[i]->n_max) + 7) / 8;
   }
   B2S_CUDA(cudaMemcpyAsync(h->problems.p, probs.data(), sizeof(IcpProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   B2S_CUDA(cudaStreamSynchronize(h->stream));  // probs lives on the host stack frame
@@ -680,7 +697,7 @@ int32_t b2s_information_matrix(b2s_handle* h, const b2s_cloud* source, const b2s
   B2S_REQUIRE(max_corr > 0.0, B2S_E_INVALID, "[GetInformationMatrixFromPointClouds] Invalid max_correspondence_distance.");
   LOCK(h);
   B2S_TRY(grid_build(h, &h->grid_a, target, max_corr * 0.25, nullptr, false));
-  B2S_TRY(h->work_xyz.ensure((source->n_max + 1) * 24, h->stream));
+  B2S_TRY(h->work_xyz.ensure(icp_work_bytes(source->n_max), h->stream));
   B2S_TRY(h->results.ensure(sizeof(b2s_result) + 36 * 8 + 64, h->stream));
   IcpProblem P;
   fill_problem(h, &P, source, &h->grid_a, T, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
@@ -693,11 +710,52 @@ int32_t b2s_information_matrix(b2s_handle* h, const b2s_cloud* source, const b2s
   return check_status(h);
 }
 
+int32_t b2s_nearest_neighbors(b2s_handle* h, const b2s_cloud* queries, const b2s_cloud* target, double max_corr, const double T[16], int32_t* index_out,
+                              double* d2_out, size_t capacity, size_t* n_queries) {
+  B2S_REQUIRE(h && queries && target && index_out, B2S_E_INVALID, "null argument");
+  B2S_REQUIRE(max_corr > 0.0, B2S_E_INVALID, "[RegistrationICP] Invalid max_correspondence_distance.");
+  LOCK(h);
+  size_t n = 0;
+  B2S_TRY(cloud_count_sync(h, queries, &n));
+  if (n_queries) *n_queries = n;
+  B2S_REQUIRE(n <= capacity, B2S_E_CAPACITY, "output arrays hold %zu entries, the cloud has %zu points", capacity, n);
+  if (n == 0) return B2S_OK;
+  B2S_TRY(grid_build(h, &h->grid_a, target, nn_cell(h, max_corr), nullptr, false));
+  constexpr size_t CHUNK = 40000;   // what one launch keeps in shared memory (8 CTAs x ~6 000 points)
+  B2S_TRY(h->work_xyz.ensure(icp_work_bytes(CHUNK), h->stream));
+  B2S_TRY(h->results.ensure(sizeof(b2s_result) + 36 * 8 + 64, h->stream));
+  B2S_TRY(h->tmp_i32.ensure((n + 64) * 4, h->stream));
+  B2S_TRY(h->tmp_f64.ensure((n + 1) * 8, h->stream));
+  const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  int32_t* d_cnt = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 14);
+  for (size_t off = 0; off < n; off += CHUNK) {
+    const size_t cnt = n - off < CHUNK ? n - off : CHUNK;
+    write_i32_kernel<<<1, 1, 0, h->stream>>>(d_cnt, (int32_t)cnt);
+    h->launches++;
+    IcpProblem P;
+    fill_problem(h, &P, queries, &h->grid_a, T ? T : I, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
+    P.src_xyz = queries->xyz.as<double>() + 3 * off;
+    P.src_n = d_cnt;
+    P.max_corr = max_corr;
+    P.max_iter = 0;
+    P.estimator = EST_CORRESPONDENCES;
+    P.info_out = nullptr;
+    P.src_n_max = (int32_t)cnt;
+    P.corr_index = h->tmp_i32.as<int32_t>() + off;
+    P.corr_d2 = h->tmp_f64.as<double>() + off;
+    B2S_TRY(icp_launch(h, &P, nullptr, 1, cnt));
+  }
+  B2S_CUDA(cudaMemcpyAsync(index_out, h->tmp_i32.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (d2_out) B2S_CUDA(cudaMemcpyAsync(d2_out, h->tmp_f64.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
 int32_t b2s_register_host(b2s_handle* h, const double* src_xyz, size_t n_src, const double* tgt_xyz, const double* tgt_normals, size_t n_tgt,
                           const double init[16], b2s_result* out) {
   B2S_REQUIRE(h && init && out, B2S_E_INVALID, "null argument");
   B2S_REQUIRE(tgt_normals != nullptr || h->cfg.icp.reg_type != B2S_REG_POINT_TO_PLANE, B2S_E_NO_NORMALS,
               "[RegistrationICP] TransformationEstimationPointToPlane requires target normals");
+  LOCK(h);   // held across the three calls (recursive mutex): another thread cannot touch t2 / t3 in between
   B2S_TRY(b2s_cloud_upload_f64(h, h->t2, src_xyz, nullptr, n_src));
   B2S_TRY(b2s_cloud_upload_f64(h, h->t3, tgt_xyz, tgt_normals, n_tgt));
   return b2s_register(h, h->t2, h->t3, init, out);
@@ -836,6 +894,15 @@ int32_t b2s_submap_download(b2s_handle* h, const b2s_submap* sm_c, double* xyz, 
   return b2s_cloud_download(h, view, xyz, normals, capacity, n_out);
 }
 
+int32_t b2s_submap_to_cloud(b2s_handle* h, const b2s_submap* sm_c, b2s_cloud* out) {
+  B2S_REQUIRE(h && sm_c && out, B2S_E_INVALID, "null argument");
+  b2s_submap* sm = const_cast<b2s_submap*>(sm_c);
+  LOCK(h);
+  b2s_cloud* view = nullptr;
+  B2S_TRY(submap_compact_view(h, sm, &view));            // live points, map order, in the submap's scratch cloud
+  return op_voxel_down_sample(h, view, nullptr, 0.0, out);   // voxel <= 0: plain device copy
+}
+
 int32_t b2s_submap_dense_download(b2s_handle* h, const b2s_submap* sm_c, double* xyz, double* normals, int32_t* keys, size_t capacity,
                                   size_t* n_out) {
   B2S_REQUIRE(h && sm_c, B2S_E_INVALID, "null argument");
@@ -860,13 +927,16 @@ int32_t b2s_submap_dense_download(b2s_handle* h, const b2s_submap* sm_c, double*
 
 int32_t b2s_submap_set_cloud(b2s_handle* h, b2s_submap* sm, const b2s_cloud* cloud) {
   B2S_REQUIRE(h && sm && cloud, B2S_E_INVALID, "null argument");
-  B2S_REQUIRE(cloud->has_normals, B2S_E_NO_NORMALS, "map cloud needs normals");
+  // the point-to-plane and generalized estimators read the map's normals; a point-to-point pipeline may load a map without
+  // (the reference accepts it: isMergeScanValid is only asked of scans) -- "no normal" is stored as NaN
+  B2S_REQUIRE(cloud->has_normals || h->cfg.icp.reg_type == B2S_REG_POINT_TO_POINT, B2S_E_NO_NORMALS, "map cloud needs normals for this registration type");
   B2S_REQUIRE(cloud->n_max <= sm->capacity, B2S_E_CAPACITY, "cloud larger than the submap capacity");
   LOCK(h);
   b2s_cloud* m = sm->cloud[0];
   if (cloud->n_max) {
     B2S_CUDA(cudaMemcpyAsync(m->xyz.p, cloud->xyz.p, cloud->n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
-    B2S_CUDA(cudaMemcpyAsync(m->nrm.p, cloud->nrm.p, cloud->n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
+    if (cloud->has_normals) B2S_CUDA(cudaMemcpyAsync(m->nrm.p, cloud->nrm.p, cloud->n_max * 24, cudaMemcpyDeviceToDevice, h->stream));
+    else B2S_CUDA(cudaMemsetAsync(m->nrm.p, 0xFF, cloud->n_max * 24, h->stream));   // all-ones = NaN
   }
   B2S_CUDA(cudaMemcpyAsync(m->dn.p, cloud->dn.p, 4, cudaMemcpyDeviceToDevice, h->stream));
   m->n_max = cloud->n_max; m->n_known = cloud->n_known; m->has_normals = true;
@@ -884,7 +954,7 @@ static int32_t register_to_submap_async(b2s_handle* h, const b2s_cloud* scan, co
   if (sensor_pose_host) { c.center[0] = sensor_pose_host[3]; c.center[1] = sensor_pose_host[7]; c.center[2] = sensor_pose_host[11]; }
   CropDev patch = make_crop(&c, sensor_pose_dev);
   B2S_TRY(grid_build(h, &h->grid_a, map, nn_cell(h, h->cfg.icp.max_corr_dist), &patch, true));
-  B2S_TRY(h->work_xyz.ensure((scan->n_max + 1) * 24, h->stream));
+  B2S_TRY(h->work_xyz.ensure(icp_work_bytes(scan->n_max), h->stream));
   B2S_TRY(h->problems.ensure(sizeof(IcpProblem), h->stream));
   IcpProblem P;
   fill_problem(h, &P, scan, &h->grid_a, init_host, init_dev, h->work_xyz.as<double>(), out_dev);
@@ -995,6 +1065,7 @@ int32_t b2s_mapper_step_host(b2s_handle* h, b2s_submap* sm, const void* xyz_f32,
                              const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
                              b2s_result* out) {
   B2S_REQUIRE(h && sm && xyz_f32 && odometry_motion && out, B2S_E_INVALID, "null argument");
+  LOCK(h);   // upload + chain + fetch as one unit
   b2s_cloud* dst = sm->graph_mode ? sm->staging : h->t3;
   B2S_REQUIRE(!dst->fixed_cap || n <= dst->fixed_cap, B2S_E_CAPACITY, "scan larger than the staging capacity");
   B2S_TRY(b2s_cloud_upload_f32(h, dst, xyz_f32, n, stride_bytes));
@@ -1007,12 +1078,12 @@ int32_t b2s_mapper_step_host_async(b2s_handle* h, b2s_submap* sm, const void* xy
                                    const double odometry_motion[16], double min_refinement_fitness, int32_t ignore_min_fitness,
                                    b2s_result* out_pinned) {
   B2S_REQUIRE(h && sm && xyz_f32 && odometry_motion && out_pinned, B2S_E_INVALID, "null argument");
+  LOCK(h);   // upload + chain + result copy as one unit
   b2s_cloud* dst = sm->graph_mode ? sm->staging : h->t3;
   B2S_REQUIRE(!dst->fixed_cap || n <= dst->fixed_cap, B2S_E_CAPACITY, "scan larger than the staging capacity");
   B2S_TRY(b2s_cloud_upload_f32(h, dst, xyz_f32, n, stride_bytes));
   const int32_t slot = sm->graph_mode ? (int32_t)(sm->host_step & 255) : 0;
   B2S_TRY(b2s_mapper_step_async(h, sm, dst, odometry_motion, min_refinement_fitness, ignore_min_fitness, slot));
-  LOCK(h);
   B2S_CUDA(cudaMemcpyAsync(out_pinned, h->slots.as<b2s_result>() + slot, sizeof(b2s_result), cudaMemcpyDeviceToHost, h->stream));
   return B2S_OK;
 }

@@ -200,7 +200,7 @@ struct b2s_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  std::mutex mu;
+  std::recursive_mutex mu;            // recursive: the composite host entry points hold it across the calls they chain
   b2s_config cfg;
   unsigned long long cfg_gen = 1;     // bumped by b2s_set_config: captured graphs bake the configuration in
   int64_t launches = 0;
@@ -281,7 +281,8 @@ struct IcpProblem {
   const int32_t* cell_start;
   const double* tgt_pts;    // double4
   const double* tgt_nrm;    // double4
-  double* work_xyz;         // global working copy of the source (used when it does not fit in shared memory)
+  double* work_xyz;         // global working copy of the source (used when it does not fit in shared memory) ...
+  int32_t* work_prev;       // ... and its per-point search state
   const double* init_dev;   // optional device-resident init (overrides init)
   double init[16];
   double max_corr;
@@ -294,8 +295,11 @@ struct IcpProblem {
   double* info_out;         // EST_INFORMATION: 36 doubles, row-major 6x6
   const double* src_nrm;    // B2S_REG_GENERALIZED: source normals (3 x f64 per point, source order)
   double gicp_eps;          // TransformationEstimationForGeneralizedICP::epsilon_ (1e-3)
+  int32_t* corr_index;      // optional: per source point the ORIGINAL index of its final correspondence (-1 = none) ...
+  double* corr_d2;          // ... and its squared distance (correspondence_set_ of the last evaluation)
 };
 constexpr int EST_INFORMATION = 3;   // internal estimator code: a single evaluation that outputs [O3D]'s information matrix
+constexpr int EST_CORRESPONDENCES = 4;   // a single evaluation whose only output is corr_index / corr_d2 (+ fitness, rmse)
 // single_host != nullptr: one registration, the problem travels as a kernel argument (no copy, no sync)
 int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProblem* problems_dev, int n_problems, size_t max_src_points);
 
@@ -329,7 +333,9 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
 int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const double* T_dev, const b2s_cropper* crop,
                         const int32_t* enable_dev = nullptr);
 
-inline int grid_for(size_t n, int threads, int max_blocks = 148 * 16) {
+int grid_cap();   // B2S_GRID_CAP: upper bound of the CTAs of a streaming kernel (tuning knob; default 148 * 16)
+inline int grid_for(size_t n, int threads, int max_blocks = 0) {
+  if (max_blocks <= 0) max_blocks = grid_cap();
   size_t b = (n + (size_t)threads - 1) / (size_t)threads;
   if (b < 1) b = 1;
   if (b > (size_t)max_blocks) b = (size_t)max_blocks;

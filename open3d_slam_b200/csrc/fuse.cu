@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_stage_kernel(const double* __
     const bool copy = ident && j < (size_t)ns;
     const size_t i = (ident && !copy) ? j - (size_t)ns : j;
     const double px = sxyz_in[3 * i], py = sxyz_in[3 * i + 1], pz = sxyz_in[3 * i + 2];
-    const double a = snrm_in[3 * i], b = snrm_in[3 * i + 1], c = snrm_in[3 * i + 2];
+    // a scan without normals (point-to-point pipelines: estimateNormalsOrCovariancesIfNeeded is a no-op there) fuses with "no
+    // normal" = NaN, which AccumulatedPoint skips
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const double a = snrm_in ? snrm_in[3 * i] : qnan, b = snrm_in ? snrm_in[3 * i + 1] : qnan, c = snrm_in ? snrm_in[3 * i + 2] : qnan;
     double x = px, y = py, z = pz, nx = a, ny = b, nz = c;
     if (!copy) {
       const double tx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], px), __dmul_rn(T[1], py)), __dmul_rn(T[2], pz)), T[3]);
@@ -358,7 +361,8 @@ int32_t submap_compact_view(b2s_handle* h, b2s_submap* sm, b2s_cloud** view) {
 }
 
 int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, const double* T_dev, const int32_t* gate_dev) {
-  B2S_REQUIRE(scan->has_normals, B2S_E_NO_NORMALS, "Submap::insertScan: the pre-processed scan must carry normals");
+  B2S_REQUIRE(scan->has_normals || h->cfg.icp.reg_type == B2S_REG_POINT_TO_POINT, B2S_E_NO_NORMALS,
+              "Submap::insertScan: the pre-processed scan must carry normals (isMergeScanValid) unless the registration is point-to-point");
   b2s_cloud* map = sm->cloud[0];
   const double v = h->cfg.map_voxel_size;
   B2S_REQUIRE(v > 0.0, B2S_E_UNSUPPORTED, "map_voxel_size <= 0 (no voxelisation) is not supported on the device path");
@@ -396,7 +400,8 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
   {
     ProfScope prof(h, PK_FUSE);
     fuse_stage_kernel<<<grid_for(m_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
-        scan->xyz.as<double>(), scan->nrm.as<double>(), scan->dn.as<int32_t>(), T_dev, gate_dev, crop, inv, sm->stage_cap, sm->stage_xyz.as<double>(),
+        scan->xyz.as<double>(), scan->has_normals ? scan->nrm.as<double>() : nullptr, scan->dn.as<int32_t>(), T_dev, gate_dev, crop, inv, sm->stage_cap,
+        sm->stage_xyz.as<double>(),
         sm->stage_nrm.as<double>(), sm->stage_next.as<int32_t>(), sm->stage_in.as<int32_t>(), sm->vkeys.as<unsigned long long>(),
         sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), sm->vcap - 1, sm->touched.as<int32_t>(), ms, h->status.as<uint32_t>());
     fuse_merge_kernel<<<grid_for(m_max + 4096, 128), 128, 0, h->stream>>>(gate_dev, scan->dn.as<int32_t>(), crop, fv, sm->vhead.as<int32_t>(),

@@ -33,9 +33,11 @@ namespace cg = cooperative_groups;
 
 namespace b2s {
 
-constexpr int ICP_THREADS = 512;
-constexpr int ICP_WARPS = ICP_THREADS / 32;
 constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
+// threads per CTA by instantiation: the point-to-plane / point-to-point / information kernels keep NO per-thread accumulators
+// (every contribution is warp-reduced at once into a per-warp accumulator in shared memory), fit 64 registers and run 1024
+// threads = 32 warps per SM; the generalized-ICP kernel carries 3x3 covariance algebra per correspondence and stays at 512
+constexpr int icp_threads(int mode) { return mode == 2 ? 512 : 1024; }
 constexpr int ICP_R1 = -1;  // phase 1 is a box query, not a ring walk: phase 2 starts its ring walk at ring 0
 constexpr int ICP_MAX_CLUSTER = 16;   // 8 is the portable limit; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
 
@@ -310,32 +312,52 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
   return true;
 }
 
-constexpr int ICP_FIXED_SMEM_DOUBLES = (ICP_WARPS * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1;   // even: what follows stays 16-byte aligned
-constexpr int ICP_FIXED_SMEM_BYTES = ICP_FIXED_SMEM_DOUBLES * 8 + (int)sizeof(GridHeader) + 16 + 16;   // + header + queue length + mbarrier
+constexpr int icp_fixed_smem_doubles(int threads) { return ((threads / 32) * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1; }   // even: what follows stays 16-byte aligned
+constexpr int icp_fixed_smem_bytes(int threads) { return icp_fixed_smem_doubles(threads) * 8 + (int)sizeof(GridHeader) + 16 + 16; }   // + header + queue length + mbarrier
 constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4;  // working point, previous-neighbour slot, phase-2 queue entry
+
+// ---- contributions of one correspondence to the per-estimator sums ---------------------------------------------------------
+// Every 32 points (one per lane; slot < 0 = no correspondence, contributes zeros) are reduced by a warp butterfly at once and lane 0
+// adds the warp's sum to ITS warp's accumulator in shared memory (wacc, [NACC]).  LANE0 = true: called by lane 0 alone (phase 2,
+// one point per warp), added directly.  No thread keeps accumulators in registers, and the summation order is fixed.
+template <bool LANE0>
+__device__ __forceinline__ void wadd(double* wacc, int k, double v, int lane) {
+  if (LANE0) { wacc[k] += v; return; }
+  v = warp_sum(v);
+  if (lane == 0) wacc[k] += v;
+}
 
 // point-to-point ([O3D] TransformationEstimationPointToPoint = Eigen::umeyama): sums for the means and the cross moments
 //   acc[0..2] = sum source, acc[3..5] = sum target, acc[6 + 3a + b] = sum target_a * source_b
-__device__ __forceinline__ void icp_accumulate_p2p(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz) {
-  const double4 q = g.pts[slot];
-  acc[0] += px; acc[1] += py; acc[2] += pz;
-  acc[3] += q.x; acc[4] += q.y; acc[5] += q.z;
-  acc[6] += q.x * px; acc[7] += q.x * py; acc[8] += q.x * pz;
-  acc[9] += q.y * px; acc[10] += q.y * py; acc[11] += q.y * pz;
-  acc[12] += q.z * px; acc[13] += q.z * py; acc[14] += q.z * pz;
-  acc[27] += d2;
-  acc[28] += 1.0;
+template <bool LANE0>
+__device__ __forceinline__ void icp_contribute_p2p(double* wacc, const GridView& g, int slot, double px, double py, double pz, int lane) {
+  const bool ok = slot >= 0;
+  double4 q = make_double4(0, 0, 0, 0);
+  if (ok) q = g.pts[slot];
+  if (!ok) { px = 0; py = 0; pz = 0; }
+  const double d2 = ok ? dist2_exact(px, py, pz, q.x, q.y, q.z) : 0.0;
+  wadd<LANE0>(wacc, 0, px, lane); wadd<LANE0>(wacc, 1, py, lane); wadd<LANE0>(wacc, 2, pz, lane);
+  wadd<LANE0>(wacc, 3, q.x, lane); wadd<LANE0>(wacc, 4, q.y, lane); wadd<LANE0>(wacc, 5, q.z, lane);
+  wadd<LANE0>(wacc, 6, q.x * px, lane); wadd<LANE0>(wacc, 7, q.x * py, lane); wadd<LANE0>(wacc, 8, q.x * pz, lane);
+  wadd<LANE0>(wacc, 9, q.y * px, lane); wadd<LANE0>(wacc, 10, q.y * py, lane); wadd<LANE0>(wacc, 11, q.y * pz, lane);
+  wadd<LANE0>(wacc, 12, q.z * px, lane); wadd<LANE0>(wacc, 13, q.z * py, lane); wadd<LANE0>(wacc, 14, q.z * pz, lane);
+  wadd<LANE0>(wacc, 27, d2, lane);
+  wadd<LANE0>(wacc, 28, ok ? 1.0 : 0.0, lane);
 }
 
 // information matrix ([O3D] GetInformationMatrixFromPointClouds): first and second moments of the matched TARGET points
 //   acc[0..2] = sum (x, y, z), acc[3..5] = sum (x2, y2, z2), acc[6..8] = sum (xy, xz, yz)
-__device__ __forceinline__ void icp_accumulate_info(double (&acc)[NACC], const GridView& g, int slot, double d2) {
-  const double4 q = g.pts[slot];
-  acc[0] += q.x; acc[1] += q.y; acc[2] += q.z;
-  acc[3] += q.x * q.x; acc[4] += q.y * q.y; acc[5] += q.z * q.z;
-  acc[6] += q.x * q.y; acc[7] += q.x * q.z; acc[8] += q.y * q.z;
-  acc[27] += d2;
-  acc[28] += 1.0;
+template <bool LANE0>
+__device__ __forceinline__ void icp_contribute_info(double* wacc, const GridView& g, int slot, double px, double py, double pz, int lane) {
+  const bool ok = slot >= 0;
+  double4 q = make_double4(0, 0, 0, 0);
+  if (ok) q = g.pts[slot];
+  const double d2 = ok ? dist2_exact(px, py, pz, q.x, q.y, q.z) : 0.0;
+  wadd<LANE0>(wacc, 0, q.x, lane); wadd<LANE0>(wacc, 1, q.y, lane); wadd<LANE0>(wacc, 2, q.z, lane);
+  wadd<LANE0>(wacc, 3, q.x * q.x, lane); wadd<LANE0>(wacc, 4, q.y * q.y, lane); wadd<LANE0>(wacc, 5, q.z * q.z, lane);
+  wadd<LANE0>(wacc, 6, q.x * q.y, lane); wadd<LANE0>(wacc, 7, q.x * q.z, lane); wadd<LANE0>(wacc, 8, q.y * q.z, lane);
+  wadd<LANE0>(wacc, 27, d2, lane);
+  wadd<LANE0>(wacc, 28, ok ? 1.0 : 0.0, lane);
 }
 
 // GTG = sum over matched target points of the three rank-one terms of [O3D]: rows (0,z,-y,1,0,0), (-z,0,x,0,1,0), (y,-x,0,0,0,1)
@@ -400,7 +422,7 @@ __device__ __forceinline__ double det3_dev(const double* M) {
   return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
 }
 
-// Eigen::umeyama without scaling from the accumulated moments (tot as filled by icp_accumulate_p2p, tot[28] = n)
+// Eigen::umeyama without scaling from the accumulated moments (tot as filled by icp_contribute_p2p, tot[28] = n)
 __device__ void umeyama_from_moments(const double* tot, double* Upd) {
   const double one_over_n = 1.0 / tot[28];
   double ms[3], mt[3], sigma[9];
@@ -417,10 +439,15 @@ __device__ void umeyama_from_moments(const double* tot, double* Upd) {
   }
 }
 
-__device__ __forceinline__ void icp_accumulate(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz) {
-  const double4 q = g.pts[slot];
-  const double4 nn = g.nrm[slot];
-  const double r = (px - q.x) * nn.x + (py - q.y) * nn.y + (pz - q.z) * nn.z;
+// point-to-plane ([O3D] TransformationEstimationPointToPlane::ComputeTransformation -> ComputeJTJandJTr): r = (p - q) . n,
+// J = [p x n ; n]
+template <bool LANE0>
+__device__ __forceinline__ void icp_contribute_plane(double* wacc, const GridView& g, int slot, double px, double py, double pz, int lane) {
+  const bool ok = slot >= 0;
+  double4 q = make_double4(0, 0, 0, 0), nn = make_double4(0, 0, 0, 0);
+  if (ok) { q = g.pts[slot]; nn = g.nrm[slot]; }
+  const double d2 = ok ? dist2_exact(px, py, pz, q.x, q.y, q.z) : 0.0;
+  const double r = (px - q.x) * nn.x + (py - q.y) * nn.y + (pz - q.z) * nn.z;   // zero normal for a lane without correspondence: all terms vanish
   double J[6];
   J[0] = py * nn.z - pz * nn.y; J[1] = pz * nn.x - px * nn.z; J[2] = px * nn.y - py * nn.x;
   J[3] = nn.x; J[4] = nn.y; J[5] = nn.z;
@@ -428,11 +455,11 @@ __device__ __forceinline__ void icp_accumulate(double (&acc)[NACC], const GridVi
 #pragma unroll
   for (int a = 0; a < 6; a++)
 #pragma unroll
-    for (int b = a; b < 6; b++) acc[k++] += J[a] * J[b];
+    for (int b = a; b < 6; b++) wadd<LANE0>(wacc, k++, J[a] * J[b], lane);
 #pragma unroll
-  for (int a = 0; a < 6; a++) acc[21 + a] += J[a] * r;
-  acc[27] += d2;
-  acc[28] += 1.0;
+  for (int a = 0; a < 6; a++) wadd<LANE0>(wacc, 21 + a, J[a] * r, lane);
+  wadd<LANE0>(wacc, 27, d2, lane);
+  wadd<LANE0>(wacc, 28, ok ? 1.0 : 0.0, lane);
 }
 
 // ---- Generalized ICP ([O3D] pipelines/registration/GeneralizedICP.cpp) --------------------------------------------
@@ -463,10 +490,16 @@ __device__ __forceinline__ void gicp_cov_from_normal(double nx, double ny, doubl
 
 // one correspondence of TransformationEstimationForGeneralizedICP: M = Ct + R Cs0 R^T, J = M^-1/2 [-skew(p) | I],
 // r = M^-1/2 (p - q); accumulated as J^T J = A^T M^-1 A and J^T r = A^T M^-1 d (the square root only appears squared)
-__device__ __forceinline__ void icp_accumulate_gicp(double (&acc)[NACC], const GridView& g, int slot, double d2, double px, double py, double pz,
-                                                    const double* __restrict__ R, const double* __restrict__ sn, double eps) {
-  const double4 q = g.pts[slot];
-  const double4 nt = g.nrm[slot];
+template <bool LANE0>
+__device__ __forceinline__ void icp_contribute_gicp(double* wacc, const GridView& g, int slot, double px, double py, double pz,
+                                                    const double* __restrict__ R, const double* __restrict__ sn_ptr, double eps, int lane) {
+  const bool ok = slot >= 0;
+  // a lane without correspondence runs the algebra on a harmless stand-in (unit normals) and contributes with weight zero
+  double4 q = make_double4(px, py, pz, 0), nt = make_double4(1, 0, 0, 0);
+  double sn[3] = {1.0, 0.0, 0.0};
+  if (ok) { q = g.pts[slot]; nt = g.nrm[slot]; sn[0] = sn_ptr[0]; sn[1] = sn_ptr[1]; sn[2] = sn_ptr[2]; }
+  const double wgt = ok ? 1.0 : 0.0;
+  const double d2 = ok ? dist2_exact(px, py, pz, q.x, q.y, q.z) : 0.0;
   double Ct[9], Cs0[9], M[9];
   gicp_cov_from_normal(nt.x, nt.y, nt.z, eps, Ct);
   gicp_cov_from_normal(sn[0], sn[1], sn[2], eps, Cs0);
@@ -503,11 +536,11 @@ __device__ __forceinline__ void icp_accumulate_gicp(double (&acc)[NACC], const G
 #pragma unroll
   for (int a = 0; a < 6; a++)
 #pragma unroll
-    for (int b = a; b < 6; b++) acc[k++] += A[a] * MA[b] + A[6 + a] * MA[6 + b] + A[12 + a] * MA[12 + b];
+    for (int b = a; b < 6; b++) wadd<LANE0>(wacc, k++, wgt * (A[a] * MA[b] + A[6 + a] * MA[6 + b] + A[12 + a] * MA[12 + b]), lane);
 #pragma unroll
-  for (int a = 0; a < 6; a++) acc[21 + a] += A[a] * Md[0] + A[6 + a] * Md[1] + A[12 + a] * Md[2];
-  acc[27] += d2;
-  acc[28] += 1.0;
+  for (int a = 0; a < 6; a++) wadd<LANE0>(wacc, 21 + a, wgt * (A[a] * Md[0] + A[6 + a] * Md[1] + A[12 + a] * Md[2]), lane);
+  wadd<LANE0>(wacc, 27, d2, lane);
+  wadd<LANE0>(wacc, 28, wgt, lane);
 }
 
 // `single` carries the problem by value (kernel parameter space) for the one-registration calls, so that no
@@ -518,9 +551,11 @@ __device__ __forceinline__ void icp_accumulate_gicp(double (&acc)[NACC], const G
 //   3 = point-to-plane with search statistics (b2s_debug_icp_clocks): dbg[512 + 8 e + {0,1,2,3}] = candidates scanned in phase 1,
 //       point evaluations, points queued for phase 2, candidates scanned in phase 2 -- per evaluation e < 32, whole cluster
 template <int MODE>
-__global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_constant__ IcpProblem single,
-                                                             const IcpProblem* __restrict__ problems, int smem_pts_cap,
-                                                             long long* dbg) {
+__global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_constant__ IcpProblem single,
+                                                                   const IcpProblem* __restrict__ problems, int smem_pts_cap,
+                                                                   long long* dbg) {
+  constexpr int THREADS = icp_threads(MODE);
+  constexpr int WARPS = THREADS / 32;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const unsigned csize = cluster.num_blocks();
@@ -528,17 +563,17 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   const bool dbg_on = dbg != nullptr && blockIdx.y == 0 && crank == 0 && threadIdx.x == 0;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_red = reinterpret_cast<double*>(smem_raw);  // [ICP_WARPS][NACC]
-  double* s_part = s_red + ICP_WARPS * NACC;            // [2][NACC]  (read by the other CTAs through DSMEM)
+  double* s_wacc = reinterpret_cast<double*>(smem_raw); // [WARPS][NACC]  per-warp accumulators (lane 0 of the warp owns its row)
+  double* s_part = s_wacc + WARPS * NACC;               // [2][NACC]  (read by the other CTAs through DSMEM)
   double* s_tot = s_part + 2 * NACC;                    // [NACC]
   double* s_U = s_tot + NACC;                           // [16] update of the current iteration
   double* s_T = s_U + 16;                               // [16] accumulated transformation
   double* s_misc = s_T + 16;                            // [0] prev fitness [1] prev rmse [2] done [3] apply
-  GridHeader* s_g = reinterpret_cast<GridHeader*>(smem_raw + ICP_FIXED_SMEM_DOUBLES * 8);
+  GridHeader* s_g = reinterpret_cast<GridHeader*>(smem_raw + icp_fixed_smem_doubles(THREADS) * 8);
   int* s_qn = reinterpret_cast<int*>(s_g + 1);          // phase-2 queue length (16 bytes reserved)
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_qn + 4);   // mbarrier of the bulk-async staging (16 bytes reserved)
-  double* s_pts = reinterpret_cast<double*>(smem_raw + ICP_FIXED_SMEM_BYTES);    // 16-byte aligned
-  int* s_prev = reinterpret_cast<int*>(s_pts + 3 * (size_t)smem_pts_cap);  // previous neighbour slot per point (warm start)
+  double* s_pts = reinterpret_cast<double*>(smem_raw + icp_fixed_smem_bytes(THREADS));    // 16-byte aligned
+  int* s_prev = reinterpret_cast<int*>(s_pts + 3 * (size_t)smem_pts_cap);  // neighbour slot per point (state between the phases, warm start)
   int* s_queue = s_prev + smem_pts_cap;                                    // local indices of points left to phase 2
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -548,6 +583,8 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   const int cnt = hi - lo;
   const bool in_smem = chunk <= smem_pts_cap;   // uniform over the cluster (phase 2 shares work across CTAs)
   double* work = in_smem ? s_pts : (P.work_xyz + 3 * (size_t)lo);
+  // per-point state: >= -1 = slot of the correspondence (-1: none); <= -2 = queued for phase 2, -(slot + 3) = best seen so far
+  int* prev = in_smem ? s_prev : (P.work_prev + lo);
 
   if (tid == 0) {
     *s_g = *P.ghdr;
@@ -558,6 +595,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
     *s_qn = 0;
     if (in_smem) { mbar_init(s_bar, 1); mbar_fence_init(); }
   }
+  for (int i = tid; i < WARPS * NACC; i += THREADS) s_wacc[i] = 0.0;
   __syncthreads();
   {  // stage this CTA's chunk of the source cloud
     const double* src = P.src_xyz + 3 * (size_t)lo;
@@ -572,11 +610,11 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
           bulk_copy_g2s(reinterpret_cast<char*>(s_pts) + off, reinterpret_cast<const char*>(src) + off, min(32768u, total - off), s_bar);
       }
       if ((cnt & 1) && tid < 3) s_pts[3 * (cnt - 1) + tid] = src[3 * (cnt - 1) + tid];   // odd tail point
-      for (int i = tid; i < cnt; i += ICP_THREADS) s_prev[i] = -1;
       if (total > 0) mbar_wait_parity(s_bar, 0);
     } else {
-      for (int i = tid; i < 3 * cnt; i += ICP_THREADS) work[i] = src[i];
+      for (int i = tid; i < 3 * cnt; i += THREADS) work[i] = src[i];
     }
+    for (int i = tid; i < cnt; i += THREADS) prev[i] = -1;
   }
   __syncthreads();
 
@@ -593,7 +631,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
   constexpr bool COUNT = MODE == 3;
   int n_scanned1 = 0, n_evals1 = 0, n_queued = 0, n_scanned2 = 0;
   const bool p2p = MODE == 1 && P.estimator == B2S_REG_POINT_TO_POINT;
-  const bool info = MODE == 1 && P.estimator == EST_INFORMATION;   // one evaluation, output = 6x6 information matrix
+  const bool corr_only = MODE == 1 && P.estimator == EST_CORRESPONDENCES;
+  const bool info = MODE == 1 && (P.estimator == EST_INFORMATION || corr_only);   // one evaluation, output = 6x6 information matrix
+  double* wacc = s_wacc + warp * NACC;
 
   for (int e = 0;; ++e) {
     if (dbg_on && e < 64) dbg[4 * e] = clock64();
@@ -601,34 +641,20 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
     long long t_start = 0;
     if (bal_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const bool apply = s_misc[3] != 0.0;
-    double U[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) U[i] = s_U[i];
-    double RT[9];   // GICP: rotation of the accumulated transformation = what [O3D] has applied to the source covariances so far
-    if (GICP) {
-      const bool moved = e > 0 || apply;   // identity init is not applied at all (isIdentity), like the covariance transform
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) RT[3 * i + j] = moved ? s_T[4 * i + j] : (i == j ? 1.0 : 0.0);
-    }
 
-    double acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
-
-    // ---- phase 1: one thread per point ----
-    for (int i = tid; i < cnt; i += ICP_THREADS) {
+    // ---- phase 1a: correspondence search, one thread per point (nothing but the search state lives in registers) ----
+    for (int i = tid; i < cnt; i += THREADS) {
       double px = work[3 * i], py = work[3 * i + 1], pz = work[3 * i + 2];
       if (apply) {  // [O3D] TransformPoints with w == 1 exactly for a rigid update; same association as Eigen's product
-        const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(U[0], px), __dmul_rn(U[1], py)), __dmul_rn(U[2], pz)), U[3]);
-        const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(U[4], px), __dmul_rn(U[5], py)), __dmul_rn(U[6], pz)), U[7]);
-        const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(U[8], px), __dmul_rn(U[9], py)), __dmul_rn(U[10], pz)), U[11]);
+        const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[0], px), __dmul_rn(s_U[1], py)), __dmul_rn(s_U[2], pz)), s_U[3]);
+        const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[4], px), __dmul_rn(s_U[5], py)), __dmul_rn(s_U[6], pz)), s_U[7]);
+        const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[8], px), __dmul_rn(s_U[9], py)), __dmul_rn(s_U[10], pz)), s_U[11]);
         px = x; py = y; pz = z;
         work[3 * i] = px; work[3 * i + 1] = py; work[3 * i + 2] = pz;
       }
       NNState st;
-      bool done = nn_phase1(g, px, py, pz, r2, in_smem ? s_prev[i] : -1, st);
+      const int hint = prev[i];
+      bool done = nn_phase1(g, px, py, pz, r2, hint >= 0 ? hint : -1, st);
       if (!done && !in_smem) {  // no queue for clouds that overflow shared memory: finish serially
         int cx, cy, cz;
         cell_of(g, px, py, pz, cx, cy, cz);
@@ -641,23 +667,35 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
         }
         done = true;
       }
-      if (in_smem) s_prev[i] = st.bslot;
+      prev[i] = done ? st.bslot : -(st.bslot + 3);
       if (COUNT) { n_scanned1 += st.scanned; n_evals1++; n_queued += done ? 0 : 1; }
-      if (done) {
-        if (st.bslot >= 0) {
-          if (GICP) icp_accumulate_gicp(acc, g, st.bslot, st.best, px, py, pz, RT, P.src_nrm + 3 * (size_t)(lo + i), P.gicp_eps);
-          else if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz);
-          else if (info) icp_accumulate_info(acc, g, st.bslot, st.best);
-          else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
-        }
-      } else {
-        s_queue[atomicAdd(s_qn, 1)] = i;
-      }
+      if (!done) s_queue[atomicAdd(s_qn, 1)] = i;
     }
     __syncthreads();
+    // ---- phase 1b: the sums, 32 points per warp step, every term warp-reduced into the warp's shared-memory accumulator ----
+    double RT[9];   // GICP: rotation of the accumulated transformation = what [O3D] has applied to the source covariances so far
+    if (GICP) {
+      const bool moved = e > 0 || apply;   // identity init is not applied at all (isIdentity), like the covariance transform
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) RT[3 * i + j] = moved ? s_T[4 * i + j] : (i == j ? 1.0 : 0.0);
+    }
+    {
+      for (int base = warp * 32; base < cnt; base += THREADS) {
+        const int i = base + lane;
+        int slot = -1;
+        double px = 0.0, py = 0.0, pz = 0.0;
+        if (i < cnt) { slot = prev[i]; px = work[3 * i]; py = work[3 * i + 1]; pz = work[3 * i + 2]; }   // queued points (<= -2) are phase 2's
+        if (GICP) icp_contribute_gicp<false>(wacc, g, slot, px, py, pz, RT, P.src_nrm + 3 * (size_t)(lo + (i < cnt ? i : 0)), P.gicp_eps, lane);
+        else if (p2p) icp_contribute_p2p<false>(wacc, g, slot, px, py, pz, lane);
+        else if (info) icp_contribute_info<false>(wacc, g, slot, px, py, pz, lane);
+        else icp_contribute_plane<false>(wacc, g, slot, px, py, pz, lane);
+      }
+    }
     long long t_p1 = 0;
     if (bal_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_p1));
-    // ---- phase 2: one warp per point that needs rings beyond ICP_R1 ----
+    // ---- phase 2: one warp per point that needs more than phase 1's box ----
     // The unresolved points cluster spatially (map frontier), i.e. in one or two CTAs of the Morton-ordered source:
     // the queues of ALL CTAs are therefore drained by ALL warps of the cluster, through distributed shared memory.
     // The sums are cluster totals anyway, so a point may be accumulated by any CTA.
@@ -667,7 +705,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
       qoff[0] = 0;
 #pragma unroll
       for (int r = 0; r < ICP_MAX_CLUSTER; r++) qoff[r + 1] = qoff[r] + ((unsigned)r < csize ? *cluster.map_shared_rank(s_qn, r) : 0);
-      for (int gi = (int)crank * ICP_WARPS + warp; gi < qoff[ICP_MAX_CLUSTER]; gi += (int)csize * ICP_WARPS) {
+      for (int gi = (int)crank * WARPS + warp; gi < qoff[ICP_MAX_CLUSTER]; gi += (int)csize * WARPS) {
         int r = 0;
 #pragma unroll
         for (int k = 1; k < ICP_MAX_CLUSTER; k++) if (gi >= qoff[k]) r = k;
@@ -678,7 +716,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
         const double px = rw[3 * i], py = rw[3 * i + 1], pz = rw[3 * i + 2];
         NNState st;
         st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
-        const int hs = rp[i];  // best of the box query (or the seed), -1 when nothing was in range
+        const int hs = -rp[i] - 3;  // best of the box query (or the seed), -1 when nothing was in range
         if (hs >= 0) {
           const double4 p = g.pts[hs];
           st.best = dist2_exact(px, py, pz, p.x, p.y, p.z); st.bidx = (int)__double_as_longlong(p.w); st.bslot = hs;
@@ -689,10 +727,10 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
         if (lane == 0) {
           rp[i] = st.bslot;
           if (st.bslot >= 0) {
-            if (GICP) icp_accumulate_gicp(acc, g, st.bslot, st.best, px, py, pz, RT, P.src_nrm + 3 * (size_t)(min(r * chunk, n) + i), P.gicp_eps);
-            else if (p2p) icp_accumulate_p2p(acc, g, st.bslot, st.best, px, py, pz);
-            else if (info) icp_accumulate_info(acc, g, st.bslot, st.best);
-            else icp_accumulate(acc, g, st.bslot, st.best, px, py, pz);
+            if (GICP) icp_contribute_gicp<true>(wacc, g, st.bslot, px, py, pz, RT, P.src_nrm + 3 * (size_t)(min(r * chunk, n) + i), P.gicp_eps, 0);
+            else if (p2p) icp_contribute_p2p<true>(wacc, g, st.bslot, px, py, pz, 0);
+            else if (info) icp_contribute_info<true>(wacc, g, st.bslot, px, py, pz, 0);
+            else icp_contribute_plane<true>(wacc, g, st.bslot, px, py, pz, 0);
           }
         }
       }
@@ -717,17 +755,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
         d[0] = t_p1 - t_start; d[1] = t_p2 - t_p1; d[2] = *s_qn; d[3] = cnt;   // ns, ns, queue length, points
       }
     }
-    // warp tree -> CTA tree (fixed order => run-to-run deterministic)
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-      const double v = warp_sum(acc[i]);
-      if (lane == 0) s_red[warp * NACC + i] = v;
-    }
+    // per-warp accumulators -> CTA partial (fixed order => run-to-run deterministic up to who drained which phase-2 entry)
     __syncthreads();
     const int buf = e & 1;
     if (tid < NACC) {
       double v = 0.0;
-      for (int w = 0; w < ICP_WARPS; w++) v += s_red[w * NACC + tid];
+      for (int w = 0; w < WARPS; w++) { v += s_wacc[w * NACC + tid]; s_wacc[w * NACC + tid] = 0.0; }
       s_part[buf * NACC + tid] = v;
     }
     cluster.sync();
@@ -798,7 +831,24 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) icp_kernel(const __grid_consta
     }
     if (dbg_on && e < 64) dbg[4 * e + 3] = clock64();
     __syncthreads();
-    if (s_misc[2] != 0.0) break;
+    if (s_misc[2] != 0.0) {
+      // correspondence_set_ of the final evaluation: every CTA reports its own chunk (phase 2 wrote its results into the owners'
+      // per-point state before the cluster barrier above)
+      if (MODE == 1 && P.corr_index != nullptr) {
+        for (int i = tid; i < cnt; i += THREADS) {
+          const int sl = prev[i];
+          int oi = -1; double d2 = -1.0;
+          if (sl >= 0) {
+            const double4 q = g.pts[sl];
+            oi = (int)__double_as_longlong(q.w);
+            d2 = dist2_exact(work[3 * i], work[3 * i + 1], work[3 * i + 2], q.x, q.y, q.z);
+          }
+          P.corr_index[lo + i] = oi;
+          if (P.corr_d2) P.corr_d2[lo + i] = d2;
+        }
+      }
+      break;
+    }
   }
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
@@ -840,8 +890,10 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   const int estimator = single_host ? single_host->estimator : h->cfg.icp.reg_type;   // uniform over a batch
   int csize = 1;
   const int cmax = icp_max_cluster();
-  while (csize < cmax && (size_t)csize * ICP_THREADS * (csize >= 8 ? 1 : 2) < max_src_points) csize *= 2;
-  const int fixed = ICP_FIXED_SMEM_BYTES;
+  const int mode = estimator == B2S_REG_GENERALIZED ? 2 : (estimator == B2S_REG_POINT_TO_PLANE ? (h->icp_dbg ? 3 : 0) : 1);
+  const int threads = icp_threads(mode);
+  while (csize < cmax && (size_t)csize * threads < max_src_points) csize *= 2;
+  const int fixed = icp_fixed_smem_bytes(threads);
   {
     // a batch that already fills the GPU is served better by small clusters (one CTA per SM is resident either way, and
     // every evaluation pays its barriers and reduction once per cluster): shrink while the chunk still fits shared memory
@@ -862,7 +914,7 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(csize, n_problems, 1);
-  cfg.blockDim = dim3(ICP_THREADS, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)dyn_smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];

@@ -674,10 +674,14 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       __syncwarp();
       if (nc > NS2_CAP) { if (lane == 0) atomicAdd(queue_n + 2, 1); break; }   // too dense for the buffer: general kernel
       // ---- candidates -> registers (round-robin), statistics ----
+      // nc is uniform over the warp, so is the number of 32-candidate chunks in use: every chunk loop below stops there
+      // (the loops stay fully unrolled -- the register arrays need static indices -- but the unused tail is branched over)
+      const int nch = (nc + 31) >> 5;
       double d[NS2_CHUNKS]; int idx[NS2_CHUNKS], sl[NS2_CHUNKS];
       double dmax = 0.0;
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
+        if (c >= nch) break;
         const int t = c * 32 + lane;
         d[c] = INFINITY; idx[c] = 0x7fffffff; sl[c] = -1;
         if (t < nc) { d[c] = s_d[wib][t]; idx[c] = s_i[wib][t]; sl[c] = s_s[wib][t]; dmax = fmax(dmax, d[c]); }
@@ -693,6 +697,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         int bin[NS2_CHUNKS];
 #pragma unroll
         for (int c = 0; c < NS2_CHUNKS; c++) {
+          if (c >= nch) break;
           bin[c] = 32;
           if (sl[c] >= 0) { bin[c] = min(31, (int)(d[c] * scale)); atomicAdd(&s_hist[wib][bin[c]], 1); }
         }
@@ -708,6 +713,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
           double bd = INFINITY; int bi = 0x7fffffff;
 #pragma unroll
           for (int c = 0; c < NS2_CHUNKS; c++) {
+            if (c >= nch) break;
             const bool in_bin = bin[c] == B;
             const bool after = d[c] > ld || (d[c] == ld && idx[c] > li);
             const bool better = d[c] < bd || (d[c] == bd && idx[c] < bi);
@@ -723,8 +729,10 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         }
         td = ld; ti = li;
 #pragma unroll
-        for (int c = 0; c < NS2_CHUNKS; c++)
+        for (int c = 0; c < NS2_CHUNKS; c++) {
+          if (c >= nch) break;
           if (bin[c] > B || (bin[c] == B && (d[c] > td || (d[c] == td && idx[c] > ti)))) sl[c] = -1;
+        }
       }
       // ---- exact?  every candidate kept lies strictly inside the guaranteed ball (radius sqrt(lim2) <= distance to the
       // nearest block face), so k kept candidates contain the true k nearest; fewer than k is final only when the
@@ -733,6 +741,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       // ---- cumulants of the selected candidates, butterfly sum over the warp ----
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
+        if (c >= nch) break;
         if (sl[c] >= 0) {
           const double4 p = pts[sl[c]];
           c9[0] += p.x; c9[1] += p.y; c9[2] += p.z;

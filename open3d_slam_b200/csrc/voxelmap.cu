@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(VM_THREADS) vm_fill_kernel(const double* __res
 
 }  // namespace b2s
 
-#define VM_LOCK(h) std::lock_guard<std::mutex> _lk((h)->mu); cudaSetDevice((h)->device)
+#define VM_LOCK(h) std::lock_guard<std::recursive_mutex> _lk((h)->mu); cudaSetDevice((h)->device)
 
 extern "C" {
 

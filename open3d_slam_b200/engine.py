@@ -355,6 +355,18 @@ def getInformationMatrixFromPointClouds(eng: Engine, source: Cloud, target: Clou
     return G
 
 
+def nearestNeighbors(eng: Engine, queries: Cloud, target: Cloud, maxCorrespondenceDistance: float, T=None):
+    """The correspondence search of [O3D] RegistrationICP on its own (KDTreeFlann::SearchHybrid(q, r, 1) per query): index of the
+    nearest target point with d^2 < r^2 (-1 = none), squared distance.  correspondence_set_ = this at the result's transformation."""
+    n = len(queries)
+    idx = np.full(max(n, 1), -1, dtype=np.int32); d2 = np.full(max(n, 1), -1.0)
+    m = C.c_size_t()
+    Tm = _mat(T) if T is not None else None
+    L.check(L.lib().b2s_nearest_neighbors(eng._h, queries._c, target._c, C.c_double(maxCorrespondenceDistance), _pd(Tm) if Tm is not None else None,
+                                          idx.ctypes.data_as(C.POINTER(C.c_int32)), _pd(d2), C.c_size_t(len(idx)), C.byref(m)))
+    return idx[:n], d2[:n]
+
+
 class CloudRegistration:
     def registerClouds(self, source: Cloud, target: Cloud, init) -> RegistrationResult:  # pragma: no cover - abstract
         raise NotImplementedError
@@ -529,6 +541,12 @@ class Submap:
         xyz = np.empty((n, 3)); nrm = np.empty((n, 3)); m = C.c_size_t()
         L.check(L.lib().b2s_submap_download(self.eng._h, self._s, _pd(xyz), _pd(nrm), C.c_size_t(n), C.byref(m)))
         return xyz[:m.value], nrm[:m.value]
+
+    def toCloud(self, out: "Cloud | None" = None) -> "Cloud":
+        """getMapPointCloudCopy without leaving the device"""
+        out = out if out is not None else Cloud(self.eng)
+        L.check(L.lib().b2s_submap_to_cloud(self.eng._h, self._s, out._c))
+        return out
 
     def getDenseMap(self, capacity=1 << 22):
         xyz = np.empty((capacity, 3)); keys = np.empty((capacity, 3), dtype=np.int32); m = C.c_size_t()

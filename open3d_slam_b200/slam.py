@@ -294,8 +294,7 @@ class DeviceBackend:
             vm = E.VoxelMap(self.eng, v, 1 << 18)
             self._voxel_maps[id(sm)] = vm
         vm.clear()
-        xyz, nrm = sm.getMapPointCloud()
-        c = self.eng.cloud(xyz, nrm)
+        c = sm.toCloud()
         vm.insertCloud(VOXEL_MAP_LAYER, c)
         c.free()
 
@@ -309,8 +308,7 @@ class DeviceBackend:
 
     # -- loop-closure refinement
     def submap_as_cloud(self, sm):
-        xyz, nrm = sm.getMapPointCloud()
-        return self.eng.cloud(xyz, nrm)
+        return sm.toCloud()
 
     def overlap(self, source, target, T0, voxel, min_pts):
         return E.computeOverlappingClouds(self.eng, source, target, T0, voxel, min_pts)

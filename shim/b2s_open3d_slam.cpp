@@ -212,11 +212,13 @@ RegistrationResult ScanToMapIcpB200::scanToMapRegistration(const PointCloud& sca
 #else
   const PointCloud& map = activeSubmap.getMapPointCloud();
 #endif
-  DeviceCloud dscan(h, scan, false), dmap(h, map, true);
+  // the scan goes up WITH its normals when it has them: the generalized estimator derives the source covariances from them
+  // ([O3D] InitializePointCloudForGeneralizedICP), exactly the match_ normals the reference's own preprocess left on the cloud
+  DeviceCloud dscan(h, scan, true), dmap(h, map, true);
   b2s_submap* sm = nullptr;
   int32_t rc = b2s_submap_create(h, map.points_.size() + 1, &sm);
   if (rc != B2S_OK) b2sThrow(rc);
-  rc = b2s_submap_set_cloud(h, sm, dmap.c);
+  rc = b2s_submap_set_cloud(h, sm, dmap.c);   // a map without normals is accepted for PointToPointIcp only (like the reference)
   double Ts[16], Tg[16];
   toRowMajor(mapToRangeSensor.matrix(), Ts);
   toRowMajor(initialGuess.matrix(), Tg);
@@ -225,6 +227,114 @@ RegistrationResult ScanToMapIcpB200::scanToMapRegistration(const PointCloud& sca
   b2s_submap_destroy(sm);
   if (rc != B2S_OK) b2sThrow(rc);
   return toResult(r);
+}
+
+RegistrationResult ScanToMapIcpB200::scanToMapRegistration(const PointCloud& scan, const SubmapB200& activeSubmap, const Transform& mapToRangeSensor,
+                                                           const Transform& initialGuess) const {
+  b2s_handle* h = activeSubmap.engine();   // the submap's own handle: the map never leaves the device
+  int32_t rc = b2s_set_config(h, &cfg_);
+  if (rc != B2S_OK) b2sThrow(rc);
+  DeviceCloud dscan(h, scan, true);
+  double Ts[16], Tg[16];
+  toRowMajor(mapToRangeSensor.matrix(), Ts);
+  toRowMajor(initialGuess.matrix(), Tg);
+  b2s_result r;
+  rc = b2s_register_to_submap(h, dscan.c, activeSubmap.handle(), Ts, Tg, &r);   // B2S_E_EMPTY == "map patch size is zero" (:60)
+  if (rc != B2S_OK) b2sThrow(rc);
+  return toResult(r);
+}
+
+// ---- SubmapB200 -----------------------------------------------------------------------------------------------------------
+SubmapB200::SubmapB200(const MapperParameters& p, size_t capacityPoints)
+    : cfg_(b2sConfigFrom(p.scanMatcher_.icp_, &p.scanProcessing_, &p.mapBuilder_)), mapBuilder_(p.mapBuilder_), denseMapBuilder_(p.denseMapBuilder_) {
+  cfg_.dense_voxel_size = p.denseMapBuilder_.mapVoxelSize_;
+  switch (p.scanMatcher_.scanToMapRegType_) {
+    case ScanToMapRegistrationType::PointToPointIcp: cfg_.icp.reg_type = B2S_REG_POINT_TO_POINT; break;
+    case ScanToMapRegistrationType::GeneralizedIcp: cfg_.icp.reg_type = B2S_REG_GENERALIZED; break;
+    default: cfg_.icp.reg_type = B2S_REG_POINT_TO_PLANE; break;
+  }
+  h_ = b2sThreadHandle(cfg_);
+  const int32_t rc = b2s_submap_create(h_, capacityPoints, &sm_);
+  if (rc != B2S_OK) b2sThrow(rc);
+}
+
+SubmapB200::~SubmapB200() { b2s_submap_destroy(sm_); }
+
+bool SubmapB200::insertScan(const PointCloud& rawScan, const PointCloud& preProcessedScan, const Transform& mapToRangeSensor, bool isPerformCarving) {
+  if (preProcessedScan.IsEmpty()) return true;   // Submap.cpp:41-43
+  double Ts[16], Tc[16];
+  toRowMajor(mapToRangeSensor.matrix(), Ts);
+  int32_t rc = B2S_OK;
+  if (isPerformCarving && nScansInsertedMap_ % static_cast<size_t>(mapBuilder_.carving_.carveSpaceEveryNscans_) == 1 && !isEmpty()) {   // Submap.cpp:111
+    DeviceCloud raw(h_, rawScan, false);
+    toRowMajor(cropperPose_.matrix(), Tc);
+    const b2s_carving_params prm = {mapBuilder_.carving_.voxelSize_, mapBuilder_.carving_.maxRaytracingLength_, mapBuilder_.carving_.truncationDistance_,
+                                    mapBuilder_.carving_.minDotProductWithNormal_, mapBuilder_.carving_.neighborhoodRadiusDenseMap_};
+    rc = b2s_submap_carve(h_, sm_, raw.c, Ts, Tc, &prm, nullptr);
+    if (rc != B2S_OK) b2sThrow(rc);
+  }
+  DeviceCloud scan(h_, preProcessedScan, true);
+  rc = b2s_submap_insert(h_, sm_, scan.c, Ts);   // transform (duplication quirk kept), append, voxelizeWithinCroppingVolume
+  if (rc != B2S_OK) b2sThrow(rc);
+  cropperPose_ = mapToRangeSensor;
+  ++nScansInsertedMap_;
+  cacheValid_ = false;
+  return true;
+}
+
+bool SubmapB200::insertScanDenseMap(const PointCloud& rawScan, const Transform& mapToRangeSensor, bool isPerformCarving) {
+  DeviceCloud raw(h_, rawScan, false);
+  double Ts[16];
+  toRowMajor(mapToRangeSensor.matrix(), Ts);
+  const b2s_cropper crop = toCropper(denseMapBuilder_.cropper_);
+  int32_t rc = b2s_submap_insert_dense(h_, sm_, raw.c, Ts, &crop);
+  if (rc != B2S_OK) b2sThrow(rc);
+  if (isPerformCarving && nScansInsertedDenseMap_ % static_cast<size_t>(denseMapBuilder_.carving_.carveSpaceEveryNscans_) == 1) {   // Submap.cpp:127
+    const double sensor[3] = {mapToRangeSensor.matrix()(0, 3), mapToRangeSensor.matrix()(1, 3), mapToRangeSensor.matrix()(2, 3)};   // .translation()
+    const b2s_carving_params prm = {denseMapBuilder_.carving_.voxelSize_, denseMapBuilder_.carving_.maxRaytracingLength_,
+                                    denseMapBuilder_.carving_.truncationDistance_, denseMapBuilder_.carving_.minDotProductWithNormal_,
+                                    denseMapBuilder_.carving_.neighborhoodRadiusDenseMap_};
+    rc = b2s_dense_carve(h_, sm_, raw.c, sensor, &prm, nullptr);   // the reference hands over the RAW scan with the map-frame position (:88)
+    if (rc != B2S_OK) b2sThrow(rc);
+  }
+  ++nScansInsertedDenseMap_;
+  return true;
+}
+
+void SubmapB200::transform(const Transform& T) {
+  double Tm[16];
+  toRowMajor(T.matrix(), Tm);
+  const int32_t rc = b2s_submap_transform(h_, sm_, Tm);
+  if (rc != B2S_OK) b2sThrow(rc);
+  cacheValid_ = false;
+}
+
+bool SubmapB200::isEmpty() const {
+  size_t n = 0;
+  const int32_t rc = b2s_submap_size(h_, sm_, &n);
+  if (rc != B2S_OK) b2sThrow(rc);
+  return n == 0;
+}
+
+const PointCloud& SubmapB200::getMapPointCloud() const {
+  if (!cacheValid_) {   // ROS publishers, saving and place recognition read the map a few times per second at most
+    size_t n = 0;
+    int32_t rc = b2s_submap_size(h_, sm_, &n);
+    if (rc != B2S_OK) b2sThrow(rc);
+    cache_.points_.resize(n);
+    cache_.normals_.resize(n);
+    rc = b2s_submap_download(h_, sm_, n ? cache_.points_.front().data() : nullptr, n ? cache_.normals_.front().data() : nullptr, n, &n);
+    if (rc != B2S_OK) b2sThrow(rc);
+    cacheValid_ = true;
+  }
+  return cache_;
+}
+
+void SubmapB200::setMapPointCloud(const PointCloud& cloud) {
+  DeviceCloud d(h_, cloud, true);
+  const int32_t rc = b2s_submap_set_cloud(h_, sm_, d.c);
+  if (rc != B2S_OK) b2sThrow(rc);
+  cacheValid_ = false;
 }
 
 void ScanToMapIcpB200::prepareInitialMap(PointCloud* map) const {

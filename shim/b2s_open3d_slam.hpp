@@ -61,9 +61,47 @@ class RegistrationIcpGeneralizedB200 : public CloudRegistration {
 void carveB200(const PointCloud& rawScan, const Transform& mapToRangeSensor, const Transform& cropperPose, const MapBuilderParameters& p,
                PointCloud* map);
 
+// The map side of o3d_slam::Submap, device-resident: what a maintainer puts behind Submap's own methods (one member,
+// `std::unique_ptr<SubmapB200> device_`).  Same method names and argument meaning as the methods it replaces:
+//     Submap::insertScan            src/Submap.cpp:39-75     (transform, carve every N insertions, append, voxelize within the cropper)
+//     Submap::insertScanDenseMap    src/Submap.cpp:77-92
+//     Submap::transform             src/Submap.cpp:94-107
+//     Submap::getMapPointCloud      src/Submap.cpp:184-186   (download on demand, cached until the next change)
+//     Submap::isEmpty               src/Submap.cpp:221-223
+// The b2s_submap lives on the handle of the thread that created the SubmapB200 (the mapping thread).
+class SubmapB200 {
+ public:
+  SubmapB200(const MapperParameters& p, size_t capacityPoints = 2000000);
+  ~SubmapB200();
+  SubmapB200(const SubmapB200&) = delete;
+  SubmapB200& operator=(const SubmapB200&) = delete;
+  bool insertScan(const PointCloud& rawScan, const PointCloud& preProcessedScan, const Transform& mapToRangeSensor, bool isPerformCarving);
+  bool insertScanDenseMap(const PointCloud& rawScan, const Transform& mapToRangeSensor, bool isPerformCarving);
+  void transform(const Transform& T);
+  const PointCloud& getMapPointCloud() const;
+  bool isEmpty() const;
+  void setMapPointCloud(const PointCloud& cloud);           // initial map (SlamWrapper::setInitialMap)
+  b2s_submap* handle() const { return sm_; }
+  b2s_handle* engine() const { return h_; }
+
+ private:
+  b2s_config cfg_;
+  MapBuilderParameters mapBuilder_;
+  MapBuilderParameters denseMapBuilder_;
+  b2s_handle* h_ = nullptr;
+  b2s_submap* sm_ = nullptr;
+  size_t nScansInsertedMap_ = 0, nScansInsertedDenseMap_ = 0;
+  Transform cropperPose_ = Transform::Identity();           // mapBuilderCropper_'s pose: set after every insertion (Submap.cpp:71)
+  mutable PointCloud cache_;
+  mutable bool cacheValid_ = false;
+};
+
 class ScanToMapIcpB200 : public ScanToMapRegistration {
  public:
   explicit ScanToMapIcpB200(const MapperParameters& p);
+  // device-resident variant: no upload of the map, the patch crop and the index build run on the resident cloud
+  RegistrationResult scanToMapRegistration(const PointCloud& scan, const SubmapB200& activeSubmap, const Transform& mapToRangeSensor,
+                                           const Transform& initialGuess) const;
   ProcessedScans processForScanMatchingAndMerging(const PointCloud& in, const Transform& mapToRangeSensor) const final;
   RegistrationResult scanToMapRegistration(const PointCloud& scan, const Submap& activeSubmap, const Transform& mapToRangeSensor,
                                            const Transform& initialGuess) const final;

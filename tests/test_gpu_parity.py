@@ -648,6 +648,7 @@ def test_edge_cases_empty_inputs_and_capacity(engine_factory):
     small = E.Submap(eng, 2000)
     with pytest.raises(L.B2SError) as ei:
         small.insertScan(None, ps.merge_, np.eye(4))
+        small.size()      # only NEW voxels take slots, so the overflow is detected on the device and raised at the next synchronising call
     assert ei.value.code == L.E_CAPACITY
     # invalid parameters are refused like the reference's asserts (CloudRegistration.cpp:50-51, [O3D] r <= 0)
     with pytest.raises(L.B2SError):

@@ -64,3 +64,50 @@ def test_two_ranks_shard_and_gather():
         assert tmax == 11.0                                                           # MAX over ranks
         shards[rank] = mine
     assert sorted(shards[0] + shards[1]) == list(range(N_PAIRS)) and not set(shards[0]) & set(shards[1])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# shared registration targets: built once by the owner, broadcast to the ranks that register against them
+# ----------------------------------------------------------------------------------------------------------------------
+N_UNITS = 5
+
+
+def _unit(u):
+    rng = np.random.default_rng(100 + u)
+    n = 50 + 17 * u
+    return rng.normal(size=(n, 3)), rng.normal(size=(n, 3))
+
+
+def _bcast_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist_
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist_.init_process_group("gloo", rank=rank, world_size=world)
+    from open3d_slam_b200 import dist
+    local = {u: tuple(torch.from_numpy(a) for a in _unit(u)) for u in range(N_UNITS) if dist.owner_of(u, world) == rank}
+    needed = [0, 1, 4] if rank == 0 else [1, 2, 3]
+    got, recv = dist.broadcast_point_sets(local, N_UNITS, world, rank, None, needed)
+    dist_.barrier()
+    q.put((rank, {u: (x.numpy().copy(), n.numpy().copy()) for u, (x, n) in got.items()}, recv, sorted(local)))
+    dist_.destroy_process_group()
+
+
+def test_two_ranks_broadcast_shared_targets():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, sets, recv, owned in got:
+        assert owned == [u for u in range(N_UNITS) if u % 2 == rank]                   # round-robin ownership
+        assert sorted(sets) == ([0, 1, 4] if rank == 0 else [1, 2, 3])                 # only what the rank registers against
+        for u, (x, n) in sets.items():
+            rx, rn = _unit(u)
+            assert np.array_equal(x, rx) and np.array_equal(n, rn)                      # bit-exact payload
+        foreign = [u for u in range(N_UNITS) if u % 2 != rank]
+        assert recv == sum(_unit(u)[0].size * 8 * 2 for u in foreign)                  # bytes that crossed the wire into this rank
