@@ -505,14 +505,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2s", choices=["b2s", "reference"])
-    ap.add_argument("--chains", type=int, default=8, help="independent odometry chains per GPU")
+    ap.add_argument("--chains", type=int, default=16, help="independent odometry chains per GPU")
     ap.add_argument("--scans-per-step", type=int, default=64, help="scans every chain advances per step (timed region = steps x this)")
     ap.add_argument("--ratio", type=float, default=0.3, help="scan_processing.downsampling_ratio (Lua default 0.3)")
     ap.add_argument("--cpu-sample", type=int, default=12, help="scans in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config4 / config5 runs")
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--sweep", default="1,4,16,32", help="other chain counts measured at N = 1")
+    ap.add_argument("--sweep", default="1,4,8,32", help="other chain counts measured at N = 1")
     ap.add_argument("--map-capacity", type=int, default=760_000, help="points a chain's submap can hold")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads issuing the chains' launches (0 = auto: 1 with graph replay, 8 eager)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per scan")

@@ -333,7 +333,9 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
 int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, const double* T_host, const double* T_dev, const b2s_cropper* crop,
                         const int32_t* enable_dev = nullptr);
 
-int grid_cap();   // B2S_GRID_CAP: upper bound of the CTAs of a streaming kernel (tuning knob; default 148 * 16)
+// upper bound of the CTAs of a streaming kernel: 2 per SM (B2S_GRID_CAP overrides).  Measured at 16 concurrent chains: 148 .. 592
+// CTAs give 9.1 - 9.2 k registrations/s, 2368 (the round-1 value) 8.1 k -- few fat CTAs leave the SMs to the other chains' kernels
+int grid_cap();
 inline int grid_for(size_t n, int threads, int max_blocks = 0) {
   if (max_blocks <= 0) max_blocks = grid_cap();
   size_t b = (n + (size_t)threads - 1) / (size_t)threads;

@@ -178,6 +178,14 @@ __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double q
   }
   const double radm = sqrt(rad2) * (1.0 + 1e-12) + 1e-300;
   if (radm > 2.0 * g.cell) return false;
+  if (seeded) {
+    // a seeded box of more than a dozen cells (a neighbour more than ~half a cell away) is a long serial walk for one thread and
+    // would set the duration of the whole phase: those points are finished by a warp each in phase 2 instead
+    const int ex = (int)(floor((qx + radm - g.ox) * g.inv) - floor((qx - radm - g.ox) * g.inv)) + 1;
+    const int ey = (int)(floor((qy + radm - g.oy) * g.inv) - floor((qy - radm - g.oy) * g.inv)) + 1;
+    const int ez = (int)(floor((qz + radm - g.oz) * g.inv) - floor((qz - radm - g.oz) * g.inv)) + 1;
+    if (ex * ey * ez > 12) return false;
+  }
   if (!seeded) {
     // stage A: a half-cell box first (at most 2 x 2 x 2 cells instead of 3 x 3 x 3).  Every point within half a cell edge of
     // the query lies inside it, so a hit at that distance is already exact -- which is the case for almost every inlier
@@ -314,7 +322,7 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
 
 constexpr int icp_fixed_smem_doubles(int threads) { return ((threads / 32) * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1; }   // even: what follows stays 16-byte aligned
 constexpr int icp_fixed_smem_bytes(int threads) { return icp_fixed_smem_doubles(threads) * 8 + (int)sizeof(GridHeader) + 16 + 16; }   // + header + queue length + mbarrier
-constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4;  // working point, previous-neighbour slot, phase-2 queue entry
+constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4 + 4;  // working point, neighbour slot / search state, phase-2 queue entry, empty-neighbourhood slack
 
 // ---- contributions of one correspondence to the per-estimator sums ---------------------------------------------------------
 // Every 32 points (one per lane; slot < 0 = no correspondence, contributes zeros) are reduced by a warp butterfly at once and lane 0
@@ -575,6 +583,11 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
   double* s_pts = reinterpret_cast<double*>(smem_raw + icp_fixed_smem_bytes(THREADS));    // 16-byte aligned
   int* s_prev = reinterpret_cast<int*>(s_pts + 3 * (size_t)smem_pts_cap);  // neighbour slot per point (state between the phases, warm start)
   int* s_queue = s_prev + smem_pts_cap;                                    // local indices of points left to phase 2
+  // Certificate of an empty neighbourhood: a point for which phase 2 found NOTHING within r + m keeps slack[i] = (distance to the
+  // nearest target) - r >= 0 (m when there is none within r + m).  Every later evaluation moves the point by |U p - p|; while the
+  // accumulated motion stays below the slack no target can have come within r, so the point is known to have no correspondence
+  // without searching again (outliers at the map frontier would otherwise repeat the most expensive search of all, every evaluation).
+  float* s_slack = reinterpret_cast<float*>(s_queue + smem_pts_cap);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *P.src_n;
@@ -614,7 +627,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
     } else {
       for (int i = tid; i < 3 * cnt; i += THREADS) work[i] = src[i];
     }
-    for (int i = tid; i < cnt; i += THREADS) prev[i] = -1;
+    for (int i = tid; i < cnt; i += THREADS) { prev[i] = -1; if (in_smem) s_slack[i] = 0.0f; }
   }
   __syncthreads();
 
@@ -645,15 +658,22 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
     // ---- phase 1a: correspondence search, one thread per point (nothing but the search state lives in registers) ----
     for (int i = tid; i < cnt; i += THREADS) {
       double px = work[3 * i], py = work[3 * i + 1], pz = work[3 * i + 2];
+      double moved = 0.0;
       if (apply) {  // [O3D] TransformPoints with w == 1 exactly for a rigid update; same association as Eigen's product
         const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[0], px), __dmul_rn(s_U[1], py)), __dmul_rn(s_U[2], pz)), s_U[3]);
         const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[4], px), __dmul_rn(s_U[5], py)), __dmul_rn(s_U[6], pz)), s_U[7]);
         const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[8], px), __dmul_rn(s_U[9], py)), __dmul_rn(s_U[10], pz)), s_U[11]);
+        moved = sqrt((x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz));
         px = x; py = y; pz = z;
         work[3 * i] = px; work[3 * i + 1] = py; work[3 * i + 2] = pz;
       }
-      NNState st;
       const int hint = prev[i];
+      if (in_smem && hint == -1) {   // no correspondence last time: still provably none?
+        const float left = s_slack[i] - (float)(moved * (1.0 + 1e-6)) - 1e-7f;   // float rounding only ever shortens the slack
+        s_slack[i] = left > 0.0f ? left : 0.0f;
+        if (left > 0.0f) { if (COUNT) n_evals1++; continue; }   // prev[i] stays -1
+      }
+      NNState st;
       bool done = nn_phase1(g, px, py, pz, r2, hint >= 0 ? hint : -1, st);
       if (!done && !in_smem) {  // no queue for clouds that overflow shared memory: finish serially
         int cx, cy, cz;
@@ -722,8 +742,19 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
           st.best = dist2_exact(px, py, pz, p.x, p.y, p.z); st.bidx = (int)__double_as_longlong(p.w); st.bslot = hs;
           if (!(st.best < r2)) { st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; }
         }
+        // without a seed the search reaches a margin beyond r: what it finds there is no correspondence (d2 < r2 is strict), but
+        // it tells how far the point is from getting one
+        const double margin = 0.25 * g.cell;
+        const bool unseeded = st.bslot < 0;
+        if (unseeded) st.best = (P.max_corr + margin) * (P.max_corr + margin);
         nn_phase2_warp(g, px, py, pz, st);
         if (COUNT) n_scanned2 += st.scanned;
+        if (unseeded && st.bslot >= 0 && !(st.best < r2)) {   // nearest target lies in the margin shell: none within r, slack = distance - r
+          if (lane == 0) cluster.map_shared_rank(s_slack, r)[i] = (float)fmax((sqrt(st.best) - P.max_corr) * (1.0 - 1e-6) - 1e-7, 0.0);
+          st.bslot = -1;
+        } else if (unseeded && st.bslot < 0) {
+          if (lane == 0) cluster.map_shared_rank(s_slack, r)[i] = (float)(margin * (1.0 - 1e-6));
+        }
         if (lane == 0) {
           rp[i] = st.bslot;
           if (st.bslot >= 0) {

@@ -21,8 +21,8 @@ const char* get_error() { return g_err; }
 
 unsigned long long g_alloc_generation = 1;
 int grid_cap() {
-  static const int v = getenv("B2S_GRID_CAP") ? atoi(getenv("B2S_GRID_CAP")) : 148 * 16;
-  return v > 0 ? v : 148 * 16;
+  static const int v = getenv("B2S_GRID_CAP") ? atoi(getenv("B2S_GRID_CAP")) : 148 * 2;
+  return v > 0 ? v : 148 * 2;
 }
 thread_local bool g_capturing = false;
 thread_local bool g_capture_broken = false;
