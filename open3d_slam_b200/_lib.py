@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2s.so")
+LIB_PATH = os.environ.get("B2S_LIB") or os.path.join(_HERE, "libb2s.so")   # B2S_LIB: an A/B build of the same library (tuning aid)
 
 OK, E_INVALID, E_CUDA, E_EMPTY, E_NO_NORMALS, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 CROP_NONE, CROP_MAX_RADIUS, CROP_MIN_RADIUS, CROP_MINMAX_RADIUS, CROP_CYLINDER = 0, 1, 2, 3, 4

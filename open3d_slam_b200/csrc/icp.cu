@@ -37,7 +37,10 @@ constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
 // threads per CTA by instantiation: the point-to-plane / point-to-point / information kernels keep NO per-thread accumulators
 // (every contribution is warp-reduced at once into a per-warp accumulator in shared memory), fit 64 registers and run 1024
 // threads = 32 warps per SM; the generalized-ICP kernel carries 3x3 covariance algebra per correspondence and stays at 512
-constexpr int icp_threads(int mode) { return mode == 2 ? 512 : 1024; }
+#ifndef B2S_ICP_PLANE_THREADS
+#define B2S_ICP_PLANE_THREADS 1024   // A/B knob of the build (make alt builds libb2s_alt.so with 512)
+#endif
+constexpr int icp_threads(int mode) { return mode == 2 ? 512 : B2S_ICP_PLANE_THREADS; }
 constexpr int ICP_R1 = -1;  // phase 1 is a box query, not a ring walk: phase 2 starts its ring walk at ring 0
 constexpr int ICP_MAX_CLUSTER = 16;   // 8 is the portable limit; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
 
@@ -178,14 +181,6 @@ __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double q
   }
   const double radm = sqrt(rad2) * (1.0 + 1e-12) + 1e-300;
   if (radm > 2.0 * g.cell) return false;
-  if (seeded) {
-    // a seeded box of more than a dozen cells (a neighbour more than ~half a cell away) is a long serial walk for one thread and
-    // would set the duration of the whole phase: those points are finished by a warp each in phase 2 instead
-    const int ex = (int)(floor((qx + radm - g.ox) * g.inv) - floor((qx - radm - g.ox) * g.inv)) + 1;
-    const int ey = (int)(floor((qy + radm - g.oy) * g.inv) - floor((qy - radm - g.oy) * g.inv)) + 1;
-    const int ez = (int)(floor((qz + radm - g.oz) * g.inv) - floor((qz - radm - g.oz) * g.inv)) + 1;
-    if (ex * ey * ez > 12) return false;
-  }
   if (!seeded) {
     // stage A: a half-cell box first (at most 2 x 2 x 2 cells instead of 3 x 3 x 3).  Every point within half a cell edge of
     // the query lies inside it, so a hit at that distance is already exact -- which is the case for almost every inlier

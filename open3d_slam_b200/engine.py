@@ -722,6 +722,60 @@ def scanToMapRegistrationFactory(eng: Engine, p: MapperParameters) -> ScanToMapR
     raise RuntimeError("scanToMapRegistrationFactory: unknown type of registration scan to map")
 
 
+@dataclass
+class OdometryParameters:
+    """include/open3d_slam/Parameters.hpp:155-159 (scanMatcher_ + scanProcessing_); defaults = the Lua odometry block"""
+    scanMatcher: CloudRegistrationParameters = field(default_factory=CloudRegistrationParameters)
+    scanProcessing: ScanProcessingParameters = field(default_factory=ScanProcessingParameters)
+    seed: int = 0
+
+
+class LidarOdometry:
+    """src/Odometry.cpp:19-79 -- scan-to-scan odometry: preprocess = crop -> voxelize -> estimateNormalsOrCovariancesIfNeeded ->
+    RandomDownSample; addRangeScan registers the PREVIOUS pre-processed cloud (source) against the new one (target) from Identity
+    and accumulates odomToRangeSensorCumulative_ *= result^-1.  Host control flow here, every stage on the device."""
+
+    def __init__(self, eng: Engine, params: OdometryParameters | None = None):
+        self.eng = eng
+        self.params_ = params or OdometryParameters()
+        self.cloudRegistration_ = cloudRegistrationFactory(eng, self.params_.scanMatcher)
+        self.cloudPrev_: Cloud | None = None
+        self.odomToRangeSensorCumulative_ = np.eye(4)
+        self.buffer = []            # odomToRangeSensorBuffer_ (timestamp, transform)
+        self.lastResult: RegistrationResult | None = None
+
+    def preprocess(self, cloud: Cloud) -> Cloud:   # :25-30
+        sp = self.params_.scanProcessing
+        c = crop(self.eng, cloud, sp.cropper.to_c())
+        v = voxelize(self.eng, c, sp.voxelSize)
+        self.cloudRegistration_.estimateNormalsOrCovariancesIfNeeded(v)
+        out = random_down_sample(self.eng, v, sp.downSamplingRatio, self.params_.seed)
+        c.free(); v.free()
+        return out
+
+    def addRangeScan(self, cloud: Cloud, timestamp=None) -> bool:   # :32-79
+        pre = self.preprocess(cloud)
+        if self.cloudPrev_ is None or len(self.cloudPrev_) == 0:
+            self.cloudPrev_ = pre
+            self.buffer.append((timestamp, self.odomToRangeSensorCumulative_.copy()))
+            return True
+        result = self.cloudRegistration_.registerClouds(self.cloudPrev_, pre, np.eye(4))
+        self.lastResult = result
+        isOdomOkay = result.fitness_ > 0.1   # "todo magic" in the reference
+        if not isOdomOkay:
+            if len(pre) > 0:
+                self.cloudPrev_.free(); self.cloudPrev_ = pre
+            return False
+        self.odomToRangeSensorCumulative_ = self.odomToRangeSensorCumulative_ @ np.linalg.inv(result.transformation_)
+        self.cloudPrev_.free()
+        self.cloudPrev_ = pre
+        self.buffer.append((timestamp, self.odomToRangeSensorCumulative_.copy()))
+        return True
+
+    def getOdomToRangeSensor(self) -> np.ndarray:
+        return self.odomToRangeSensorCumulative_.copy()
+
+
 class Mapper:
     """Host control flow of Mapper::addRangeMeasurement (src/Mapper.cpp:101-181), single active submap, no carving.
     The odometry prediction is supplied per call as `odometryMotion` (odomToRangeSensorPrev^-1 * odomToRangeSensor)."""

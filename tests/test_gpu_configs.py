@@ -152,6 +152,39 @@ def test_chain_minimum_motion_gate_and_carving_schedule(engine_factory, graph):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# LidarOdometry: the scan-to-scan chain (config 1's real call site)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_lidar_odometry_scan_to_scan_chain(engine_factory):
+    """src/Odometry.cpp:25-79: preprocess (crop -> voxelize -> normals -> RandomDownSample), registerClouds(previous, current, I),
+    cumulative *= result^-1 -- against the same chain over the oracle, 8 scans of the loop."""
+    op = E.OdometryParameters(seed=5)
+    op.scanMatcher.icp = E.IcpParameters(maxNumIter=50, maxCorrespondenceDistance=1.0, knn=20, maxDistanceKnn=3.0)
+    p = E.MapperParameters(seed=5); p.icp = op.scanMatcher.icp
+    eng = engine_factory(p)
+    odo = E.LidarOdometry(eng, op)
+    lp = W.ClosedLoop()
+    crop = O.cropper("MinMaxRadius", 2.0, 30.0)
+    prev = None; cum = np.eye(4)
+    for k in range(8):
+        raw = lp.scan(k, seed=40 + k)
+        ok = odo.addRangeScan(eng.cloud(raw))
+        cx, _ = O.crop(crop, raw.astype(np.float64))
+        vx, _ = O.voxel_down_sample(cx, 0.1)
+        vn = O.estimate_normals(vx, 20, 3.0)
+        sx, sn = O.random_down_sample(vx, 0.3, 5, vn)
+        if prev is not None:
+            ref = O.registration_icp_p2plane(prev[0], sx, sn, 1.0, np.eye(4), max_iter=50)
+            g = odo.lastResult
+            assert ok and g.iters == ref.iters and g.n_corr == ref.n_corr
+            assert rel_rot(g.transformation_, ref.T) < 1e-8 and rel_trans(g.transformation_, ref.T) < 1e-8     # north star: 1e-4
+            cum = cum @ np.linalg.inv(ref.T)
+        prev = (sx, sn)
+    assert np.abs(odo.getOdomToRangeSensor() - cum).max() < 1e-7
+    gt = np.linalg.inv(lp.pose(0)) @ lp.pose(7)
+    assert np.linalg.norm(odo.getOdomToRangeSensor()[:3, 3] - gt[:3, 3]) < 0.1      # and it is odometry: 3.5 m travelled, < 10 cm off
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # config 5: the full mapper over a segment of the trajectory
 # ----------------------------------------------------------------------------------------------------------------------
 def test_config5_segment_full_mapper(engine_factory):
