@@ -130,7 +130,8 @@ static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud*
   if (sp.voxel_size > 0.0) B2S_TRY(op_voxel_down_sample(h, raw, has_crop ? &wide : nullptr, sp.voxel_size, h->t0));
   else if (has_crop) B2S_TRY(op_crop(h, raw, wide, h->t0));
   else B2S_TRY(op_voxel_down_sample(h, raw, nullptr, 0.0, h->t0));
-  const double cell_hint = sp.voxel_size > 0.0 ? 4.0 * sp.voxel_size : 0.0;
+  static const double cell_factor = getenv("B2S_NORMALS_CELL_FACTOR") ? atof(getenv("B2S_NORMALS_CELL_FACTOR")) : 4.0;   // tuning knob: index cell = factor x voxel
+  const double cell_hint = sp.voxel_size > 0.0 ? cell_factor * sp.voxel_size : 0.0;
   if (sp.downsampling_ratio < 1.0) {
     // reference order: normals for every voxel point, then RandomDownSample.  The selection only depends on the point
     // positions, so select first and estimate normals for the survivors only (neighbours still from the full cloud).

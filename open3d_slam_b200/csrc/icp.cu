@@ -41,6 +41,7 @@ constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
 #define B2S_ICP_PLANE_THREADS 1024   // A/B knob of the build (make alt builds libb2s_alt.so with 512)
 #endif
 constexpr int icp_threads(int mode) { return mode == 2 ? 512 : B2S_ICP_PLANE_THREADS; }
+constexpr int ICP_TILE = 64;   // points per tile of the source cloud (tile t belongs to CTA t % cluster size)
 constexpr int ICP_R1 = -1;  // phase 1 is a box query, not a ring walk: phase 2 starts its ring walk at ring 0
 constexpr int ICP_MAX_CLUSTER = 16;   // 8 is the portable limit; 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
 
@@ -147,7 +148,11 @@ __device__ __forceinline__ void cell_of(const GridView& g, double qx, double qy,
   cz = (int)fmin(fmax(floor((qz - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
 }
 
-// every cell overlapping the box [q - rad, q + rad]: one contiguous slot range per (y, z) row
+// every cell overlapping the box [q - rad, q + rad]: one contiguous slot range per (y, z) row.
+// The walk is software-pipelined, because one thread's search is nothing but a chain of L2 round trips: the slot ranges of FOUR
+// rows are fetched at once (8 independent loads), their candidates are then addressed as one flat sequence and fetched four at a
+// time (x, y, z only: 24 bytes) before any of them is looked at.  The original index of a candidate (the tie-breaker of equal
+// distances) is only read when two distances are exactly equal; st.bidx is NOT maintained here (phase 1 never needs it).
 __device__ __forceinline__ void nn_scan_box(const GridView& g, double qx, double qy, double qz, double rad, NNState& st) {
   const int ix0 = (int)fmin(fmax(floor((qx - rad - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
   const int ix1 = (int)fmin(fmax(floor((qx + rad - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
@@ -155,11 +160,44 @@ __device__ __forceinline__ void nn_scan_box(const GridView& g, double qx, double
   const int iy1 = (int)fmin(fmax(floor((qy + rad - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
   const int iz0 = (int)fmin(fmax(floor((qz - rad - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
   const int iz1 = (int)fmin(fmax(floor((qz + rad - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
-  for (int z = iz0; z <= iz1; ++z)
-    for (int y = iy0; y <= iy1; ++y) {
-      const int row = (z * g.ny + y) * g.nx;
-      nn_scan_range(g.pts, g.cs[row + ix0], g.cs[row + ix1 + 1], qx, qy, qz, st);
+  int y = iy0, z = iz0;
+  while (z <= iz1) {
+    int rs[4], rn[4];   // first slot of each of the next four rows, inclusive prefix of their sizes
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int a = 0, b = 0;
+      if (z <= iz1) {
+        const int row = (z * g.ny + y) * g.nx;
+        a = g.cs[row + ix0]; b = g.cs[row + ix1 + 1];
+        if (++y > iy1) { y = iy0; ++z; }
+      }
+      rs[u] = a; rn[u] = b - a;
     }
+    rn[1] += rn[0]; rn[2] += rn[1]; rn[3] += rn[2];
+    const int total = rn[3];
+    st.scanned += total;
+    for (int c0 = 0; c0 < total; c0 += 4) {
+      int j[4]; double cx[4], cy[4], cz[4];
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const int c = min(c0 + v, total - 1);
+        j[v] = c < rn[0] ? rs[0] + c : (c < rn[1] ? rs[1] + (c - rn[0]) : (c < rn[2] ? rs[2] + (c - rn[1]) : rs[3] + (c - rn[2])));
+        const double2 xy = *reinterpret_cast<const double2*>(&g.pts[j[v]]);
+        cx[v] = xy.x; cy[v] = xy.y; cz[v] = g.pts[j[v]].z;
+      }
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        if (c0 + v < total) {
+          const double d = dist2_exact(qx, qy, qz, cx[v], cy[v], cz[v]);
+          if (d < st.best) { st.best = d; st.bslot = j[v]; }
+          else if (d == st.best && st.bslot >= 0 && j[v] != st.bslot) {   // exact tie: the lower original index wins
+            const int ia = (int)__double_as_longlong(g.pts[j[v]].w), ib = (int)__double_as_longlong(g.pts[st.bslot].w);
+            if (ia < ib) st.bslot = j[v];
+          }
+        }
+      }
+    }
+  }
 }
 
 // phase 1 (one thread): BOX QUERY.  The previous iteration's neighbour (`hint`, -1 = none) is almost always still the
@@ -209,17 +247,28 @@ __device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, dou
   const int iz0 = (int)fmin(fmax(floor((qz - radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
   const int iz1 = (int)fmin(fmax(floor((qz + radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
   const int ny_ = iy1 - iy0 + 1, nrows = ny_ * (iz1 - iz0 + 1);
-  for (int t = lane; t < nrows; t += 32) {
-    const int y = iy0 + t % ny_, z = iz0 + t / ny_;
-    const double gz = slab_gap(qz, g.oz, g.cell, z, g.nz, g.eps);
-    const double gy = slab_gap(qy, g.oy, g.cell, y, g.ny, g.eps);
-    const double g2 = gz * gz + gy * gy;
-    if (g2 > st.best) continue;
-    const double xr = sqrt(fmax(st.best - g2, 0.0)) * (1.0 + 1e-12) + g.eps;
-    const int xa = (int)fmin(fmax(floor((qx - xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
-    const int xb = (int)fmin(fmax(floor((qx + xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
-    const int row = (z * g.ny + y) * g.nx;
-    nn_scan_range(g.pts, g.cs[row + xa], g.cs[row + xb + 1], qx, qy, qz, st);
+  for (int t0 = lane; t0 < nrows; t0 += 128) {   // four rows per lane and trip: their slot ranges are fetched together (8 independent loads)
+    int ra[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = t0 + 32 * u;
+      ra[u] = 0; rb[u] = 0;
+      if (t < nrows) {
+        const int y = iy0 + t % ny_, z = iz0 + t / ny_;
+        const double gz = slab_gap(qz, g.oz, g.cell, z, g.nz, g.eps);
+        const double gy = slab_gap(qy, g.oy, g.cell, y, g.ny, g.eps);
+        const double g2 = gz * gz + gy * gy;
+        if (!(g2 > st.best)) {
+          const double xr = sqrt(fmax(st.best - g2, 0.0)) * (1.0 + 1e-12) + g.eps;
+          const int xa = (int)fmin(fmax(floor((qx - xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+          const int xb = (int)fmin(fmax(floor((qx + xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
+          const int row = (z * g.ny + y) * g.nx;
+          ra[u] = g.cs[row + xa]; rb[u] = g.cs[row + xb + 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) nn_scan_range(g.pts, ra[u], rb[u], qx, qy, qz, st);
   }
   // lexicographic (d2, index) minimum over the lanes; a lane without a hit carries slot -1
 #pragma unroll
@@ -328,6 +377,45 @@ __device__ __forceinline__ void wadd(double* wacc, int k, double v, int lane) {
   if (LANE0) { wacc[k] += v; return; }
   v = warp_sum(v);
   if (lane == 0) wacc[k] += v;
+}
+
+// Warp sums of 32 values at once with the butterfly exchanges TRANSPOSED: at distance 16 the two halves of the warp split the values
+// between them (a lane keeps the half it will finish and receives its partner's copy of that half), at distance 8 the quarters do,
+// ... -- 16 + 8 + 4 + 2 + 1 = 31 exchanges instead of 32 x 5, and lane l ends up with the total of value l.  Every partial sum adds
+// the same two operands as the plain butterfly at that distance (fp addition commutes), so each total is bit-identical to warp_sum.
+// val(k): value k of the calling lane, evaluated on demand (keeps the live set at the 16 partial sums of the first stage).
+template <class F>
+__device__ __forceinline__ double warp_sum32_transposed(F val, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  double a[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const double lo = val(k), hi = val(k + 16);
+      a[k] = (up ? hi : lo) + __shfl_xor_sync(FULL, up ? lo : hi, 16);
+    }
+  }
+  double b[8];
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) b[k] = (up ? a[k + 8] : a[k]) + __shfl_xor_sync(FULL, up ? a[k] : a[k + 8], 8);
+  }
+  double c[4];
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = (up ? b[k + 4] : b[k]) + __shfl_xor_sync(FULL, up ? b[k] : b[k + 4], 4);
+  }
+  double d[2];
+  {
+    const bool up = (lane & 2) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) d[k] = (up ? c[k + 2] : c[k]) + __shfl_xor_sync(FULL, up ? c[k] : c[k + 2], 2);
+  }
+  const bool up = (lane & 1) != 0;
+  return (up ? d[1] : d[0]) + __shfl_xor_sync(FULL, up ? d[0] : d[1], 1);
 }
 
 // point-to-point ([O3D] TransformationEstimationPointToPoint = Eigen::umeyama): sums for the means and the cross moments
@@ -454,15 +542,27 @@ __device__ __forceinline__ void icp_contribute_plane(double* wacc, const GridVie
   double J[6];
   J[0] = py * nn.z - pz * nn.y; J[1] = pz * nn.x - px * nn.z; J[2] = px * nn.y - py * nn.x;
   J[3] = nn.x; J[4] = nn.y; J[5] = nn.z;
-  int k = 0;
+  const double cnt1 = ok ? 1.0 : 0.0;
+  auto val = [&](int k) -> double {   // k is a compile-time constant at every call site (fully unrolled)
+    // upper triangle of J^T J row by row: row a starts at 6a - a(a-1)/2
+    if (k < 6) return J[0] * J[k];
+    if (k < 11) return J[1] * J[k - 5];
+    if (k < 15) return J[2] * J[k - 9];
+    if (k < 18) return J[3] * J[k - 12];
+    if (k < 20) return J[4] * J[k - 14];
+    if (k < 21) return J[5] * J[5];
+    if (k < 27) return J[k - 21] * r;
+    if (k == 27) return d2;
+    if (k == 28) return cnt1;
+    return 0.0;
+  };
+  if (LANE0) {
 #pragma unroll
-  for (int a = 0; a < 6; a++)
-#pragma unroll
-    for (int b = a; b < 6; b++) wadd<LANE0>(wacc, k++, J[a] * J[b], lane);
-#pragma unroll
-  for (int a = 0; a < 6; a++) wadd<LANE0>(wacc, 21 + a, J[a] * r, lane);
-  wadd<LANE0>(wacc, 27, d2, lane);
-  wadd<LANE0>(wacc, 28, ok ? 1.0 : 0.0, lane);
+    for (int k = 0; k < NACC; k++) wacc[k] += val(k);
+  } else {
+    const double tot = warp_sum32_transposed(val, lane);
+    if (lane < NACC) wacc[lane] += tot;
+  }
 }
 
 // ---- Generalized ICP ([O3D] pipelines/registration/GeneralizedICP.cpp) --------------------------------------------
@@ -535,15 +635,24 @@ __device__ __forceinline__ void icp_contribute_gicp(double* wacc, const GridView
     for (int c = 0; c < 6; c++) MA[6 * r + c] = Mi[3 * r] * A[c] + Mi[3 * r + 1] * A[6 + c] + Mi[3 * r + 2] * A[12 + c];
     Md[r] = Mi[3 * r] * dd[0] + Mi[3 * r + 1] * dd[1] + Mi[3 * r + 2] * dd[2];
   }
-  int k = 0;
+  double v[NACC];
+  {
+    int k = 0;
 #pragma unroll
-  for (int a = 0; a < 6; a++)
+    for (int a = 0; a < 6; a++)
 #pragma unroll
-    for (int b = a; b < 6; b++) wadd<LANE0>(wacc, k++, wgt * (A[a] * MA[b] + A[6 + a] * MA[6 + b] + A[12 + a] * MA[12 + b]), lane);
+      for (int b = a; b < 6; b++) v[k++] = wgt * (A[a] * MA[b] + A[6 + a] * MA[6 + b] + A[12 + a] * MA[12 + b]);
 #pragma unroll
-  for (int a = 0; a < 6; a++) wadd<LANE0>(wacc, 21 + a, wgt * (A[a] * Md[0] + A[6 + a] * Md[1] + A[12 + a] * Md[2]), lane);
-  wadd<LANE0>(wacc, 27, d2, lane);
-  wadd<LANE0>(wacc, 28, wgt, lane);
+    for (int a = 0; a < 6; a++) v[21 + a] = wgt * (A[a] * Md[0] + A[6 + a] * Md[1] + A[12 + a] * Md[2]);
+    v[27] = d2; v[28] = wgt;
+  }
+  if (LANE0) {
+#pragma unroll
+    for (int k = 0; k < NACC; k++) wacc[k] += v[k];
+  } else {
+    const double tot = warp_sum32_transposed([&](int k) -> double { return k < NACC ? v[k] : 0.0; }, lane);
+    if (lane < NACC) wacc[lane] += tot;
+  }
 }
 
 // `single` carries the problem by value (kernel parameter space) for the one-registration calls, so that no
@@ -586,13 +695,21 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *P.src_n;
-  const int chunk = (((n + (int)csize - 1) / (int)csize) + 1) & ~1;   // even: every chunk starts on a 16-byte boundary of the 24-byte points
-  const int lo = min((int)crank * chunk, n), hi = min(lo + chunk, n);
-  const int cnt = hi - lo;
+  // The source cloud is dealt out in TILES of ICP_TILE consecutive points, tile t to CTA t % csize: the cloud is Morton-ordered, so
+  // a contiguous split would hand whole regions (the sparse far range, the map frontier) to single CTAs and the cluster would wait
+  // for the unluckiest one at every barrier; tiles keep the locality inside a warp and spread the regions over all CTAs.
+  const int ntiles = (n + ICP_TILE - 1) / ICP_TILE;
+  const int chunk = ((ntiles + (int)csize - 1) / (int)csize) * ICP_TILE;   // capacity, uniform over the cluster
+  const int my_tiles = (int)crank < ntiles ? (ntiles - (int)crank + (int)csize - 1) / (int)csize : 0;
+  const bool has_last = my_tiles > 0 && ((ntiles - 1) % (int)csize) == (int)crank;   // the (possibly partial) last tile is mine
+  const int cnt = my_tiles * ICP_TILE - (has_last ? ntiles * ICP_TILE - n : 0);
   const bool in_smem = chunk <= smem_pts_cap;   // uniform over the cluster (phase 2 shares work across CTAs)
-  double* work = in_smem ? s_pts : (P.work_xyz + 3 * (size_t)lo);
+  // local index -> index in the source cloud (of CTA `r`), and -> index in the working arrays (local in shared memory, global otherwise)
+  auto gidx_of = [csize](int i, int r) { return ((i / ICP_TILE) * (int)csize + r) * ICP_TILE + (i % ICP_TILE); };
+  auto widx = [&](int i) { return in_smem ? i : gidx_of(i, (int)crank); };
+  double* work = in_smem ? s_pts : P.work_xyz;
   // per-point state: >= -1 = slot of the correspondence (-1: none); <= -2 = queued for phase 2, -(slot + 3) = best seen so far
-  int* prev = in_smem ? s_prev : (P.work_prev + lo);
+  int* prev = in_smem ? s_prev : P.work_prev;
 
   if (tid == 0) {
     *s_g = *P.ghdr;
@@ -605,24 +722,30 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
   }
   for (int i = tid; i < WARPS * NACC; i += THREADS) s_wacc[i] = 0.0;
   __syncthreads();
-  {  // stage this CTA's chunk of the source cloud
-    const double* src = P.src_xyz + 3 * (size_t)lo;
+  {  // stage this CTA's tiles of the source cloud
     if (in_smem) {
-      // one elected thread hands the chunk to the bulk-async copy engine (cp.async.bulk global -> shared, 48 bytes per pair of
-      // points keeps every transfer a multiple of 16 bytes); completion is counted in bytes on the mbarrier
-      const int cnt_even = cnt & ~1;
-      const uint32_t total = 24u * (uint32_t)cnt_even;
+      // one elected thread hands every full tile to the bulk-async copy engine (cp.async.bulk global -> shared, 24 * ICP_TILE bytes
+      // each: a multiple of 16 at a 16-byte aligned offset); completion is counted in bytes on the mbarrier
+      const int full_tiles = my_tiles - ((has_last && (n % ICP_TILE) != 0) ? 1 : 0);
+      const uint32_t total = (uint32_t)full_tiles * (24u * ICP_TILE);
       if (tid == 0 && total > 0) {
         mbar_arrive_expect_tx(s_bar, total);
-        for (uint32_t off = 0; off < total; off += 32768u)
-          bulk_copy_g2s(reinterpret_cast<char*>(s_pts) + off, reinterpret_cast<const char*>(src) + off, min(32768u, total - off), s_bar);
+        for (int t = 0; t < full_tiles; t++)
+          bulk_copy_g2s(reinterpret_cast<char*>(s_pts) + (size_t)t * (24 * ICP_TILE),
+                        reinterpret_cast<const char*>(P.src_xyz) + (size_t)(t * (int)csize + (int)crank) * (24 * ICP_TILE), 24u * ICP_TILE, s_bar);
       }
-      if ((cnt & 1) && tid < 3) s_pts[3 * (cnt - 1) + tid] = src[3 * (cnt - 1) + tid];   // odd tail point
+      for (int i = full_tiles * ICP_TILE + tid; i < cnt; i += THREADS) {   // the partial last tile
+        const size_t gi = (size_t)gidx_of(i, (int)crank);
+        s_pts[3 * i] = P.src_xyz[3 * gi]; s_pts[3 * i + 1] = P.src_xyz[3 * gi + 1]; s_pts[3 * i + 2] = P.src_xyz[3 * gi + 2];
+      }
       if (total > 0) mbar_wait_parity(s_bar, 0);
     } else {
-      for (int i = tid; i < 3 * cnt; i += THREADS) work[i] = src[i];
+      for (int i = tid; i < cnt; i += THREADS) {
+        const size_t gi = (size_t)gidx_of(i, (int)crank);
+        work[3 * gi] = P.src_xyz[3 * gi]; work[3 * gi + 1] = P.src_xyz[3 * gi + 1]; work[3 * gi + 2] = P.src_xyz[3 * gi + 2];
+      }
     }
-    for (int i = tid; i < cnt; i += THREADS) { prev[i] = -1; if (in_smem) s_slack[i] = 0.0f; }
+    for (int i = tid; i < cnt; i += THREADS) { prev[widx(i)] = -1; if (in_smem) s_slack[i] = 0.0f; }
   }
   __syncthreads();
 
@@ -652,7 +775,8 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
 
     // ---- phase 1a: correspondence search, one thread per point (nothing but the search state lives in registers) ----
     for (int i = tid; i < cnt; i += THREADS) {
-      double px = work[3 * i], py = work[3 * i + 1], pz = work[3 * i + 2];
+      const int wi = widx(i);
+      double px = work[3 * wi], py = work[3 * wi + 1], pz = work[3 * wi + 2];
       double moved = 0.0;
       if (apply) {  // [O3D] TransformPoints with w == 1 exactly for a rigid update; same association as Eigen's product
         const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[0], px), __dmul_rn(s_U[1], py)), __dmul_rn(s_U[2], pz)), s_U[3]);
@@ -660,9 +784,9 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[8], px), __dmul_rn(s_U[9], py)), __dmul_rn(s_U[10], pz)), s_U[11]);
         moved = sqrt((x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz));
         px = x; py = y; pz = z;
-        work[3 * i] = px; work[3 * i + 1] = py; work[3 * i + 2] = pz;
+        work[3 * wi] = px; work[3 * wi + 1] = py; work[3 * wi + 2] = pz;
       }
-      const int hint = prev[i];
+      const int hint = prev[wi];
       if (in_smem && hint == -1) {   // no correspondence last time: still provably none?
         const float left = s_slack[i] - (float)(moved * (1.0 + 1e-6)) - 1e-7f;   // float rounding only ever shortens the slack
         s_slack[i] = left > 0.0f ? left : 0.0f;
@@ -671,6 +795,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
       NNState st;
       bool done = nn_phase1(g, px, py, pz, r2, hint >= 0 ? hint : -1, st);
       if (!done && !in_smem) {  // no queue for clouds that overflow shared memory: finish serially
+        if (st.bslot >= 0) st.bidx = (int)__double_as_longlong(g.pts[st.bslot].w);   // the box walk does not track it
         int cx, cy, cz;
         cell_of(g, px, py, pz, cx, cy, cz);
         for (int R = ICP_R1 + 1;; ++R) {
@@ -682,7 +807,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         }
         done = true;
       }
-      prev[i] = done ? st.bslot : -(st.bslot + 3);
+      prev[wi] = done ? st.bslot : -(st.bslot + 3);
       if (COUNT) { n_scanned1 += st.scanned; n_evals1++; n_queued += done ? 0 : 1; }
       if (!done) s_queue[atomicAdd(s_qn, 1)] = i;
     }
@@ -701,8 +826,8 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         const int i = base + lane;
         int slot = -1;
         double px = 0.0, py = 0.0, pz = 0.0;
-        if (i < cnt) { slot = prev[i]; px = work[3 * i]; py = work[3 * i + 1]; pz = work[3 * i + 2]; }   // queued points (<= -2) are phase 2's
-        if (GICP) icp_contribute_gicp<false>(wacc, g, slot, px, py, pz, RT, P.src_nrm + 3 * (size_t)(lo + (i < cnt ? i : 0)), P.gicp_eps, lane);
+        if (i < cnt) { const int wi = widx(i); slot = prev[wi]; px = work[3 * wi]; py = work[3 * wi + 1]; pz = work[3 * wi + 2]; }   // queued points (<= -2) are phase 2's
+        if (GICP) icp_contribute_gicp<false>(wacc, g, slot, px, py, pz, RT, P.src_nrm + 3 * (size_t)gidx_of(i < cnt ? i : 0, (int)crank), P.gicp_eps, lane);
         else if (p2p) icp_contribute_p2p<false>(wacc, g, slot, px, py, pz, lane);
         else if (info) icp_contribute_info<false>(wacc, g, slot, px, py, pz, lane);
         else icp_contribute_plane<false>(wacc, g, slot, px, py, pz, lane);
@@ -716,15 +841,15 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
     // The sums are cluster totals anyway, so a point may be accumulated by any CTA.
     if (in_smem) {
       cluster.sync();  // every queue is complete
-      int qoff[ICP_MAX_CLUSTER + 1];
-      qoff[0] = 0;
+      // queue lengths of the cluster's CTAs: lane r reads CTA r's counter, the warp scans them (no per-thread offset table)
+      int qinc = lane < (int)csize ? *cluster.map_shared_rank(s_qn, lane) : 0;
 #pragma unroll
-      for (int r = 0; r < ICP_MAX_CLUSTER; r++) qoff[r + 1] = qoff[r] + ((unsigned)r < csize ? *cluster.map_shared_rank(s_qn, r) : 0);
-      for (int gi = (int)crank * WARPS + warp; gi < qoff[ICP_MAX_CLUSTER]; gi += (int)csize * WARPS) {
-        int r = 0;
-#pragma unroll
-        for (int k = 1; k < ICP_MAX_CLUSTER; k++) if (gi >= qoff[k]) r = k;
-        const int li = gi - qoff[r];
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, qinc, o); if (lane >= o) qinc += v; }
+      const int qtotal = __shfl_sync(0xffffffffu, qinc, 31);
+      for (int gi = (int)crank * WARPS + warp; gi < qtotal; gi += (int)csize * WARPS) {
+        const unsigned before = __ballot_sync(0xffffffffu, qinc <= gi);   // CTAs whose queues end at or before entry gi (a prefix of the lanes)
+        const int r = __popc(before);
+        const int li = gi - (r > 0 ? __shfl_sync(0xffffffffu, qinc, r - 1) : 0);
         const int i = cluster.map_shared_rank(s_queue, r)[li];
         const double* rw = cluster.map_shared_rank(s_pts, r);
         int* rp = cluster.map_shared_rank(s_prev, r);
@@ -753,7 +878,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         if (lane == 0) {
           rp[i] = st.bslot;
           if (st.bslot >= 0) {
-            if (GICP) icp_contribute_gicp<true>(wacc, g, st.bslot, px, py, pz, RT, P.src_nrm + 3 * (size_t)(min(r * chunk, n) + i), P.gicp_eps, 0);
+            if (GICP) icp_contribute_gicp<true>(wacc, g, st.bslot, px, py, pz, RT, P.src_nrm + 3 * (size_t)gidx_of(i, r), P.gicp_eps, 0);
             else if (p2p) icp_contribute_p2p<true>(wacc, g, st.bslot, px, py, pz, 0);
             else if (info) icp_contribute_info<true>(wacc, g, st.bslot, px, py, pz, 0);
             else icp_contribute_plane<true>(wacc, g, st.bslot, px, py, pz, 0);
@@ -862,15 +987,17 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
       // per-point state before the cluster barrier above)
       if (MODE == 1 && P.corr_index != nullptr) {
         for (int i = tid; i < cnt; i += THREADS) {
-          const int sl = prev[i];
+          const int wi = widx(i);
+          const int sl = prev[wi];
           int oi = -1; double d2 = -1.0;
           if (sl >= 0) {
             const double4 q = g.pts[sl];
             oi = (int)__double_as_longlong(q.w);
-            d2 = dist2_exact(work[3 * i], work[3 * i + 1], work[3 * i + 2], q.x, q.y, q.z);
+            d2 = dist2_exact(work[3 * wi], work[3 * wi + 1], work[3 * wi + 2], q.x, q.y, q.z);
           }
-          P.corr_index[lo + i] = oi;
-          if (P.corr_d2) P.corr_d2[lo + i] = d2;
+          const int gi = gidx_of(i, (int)crank);
+          P.corr_index[gi] = oi;
+          if (P.corr_d2) P.corr_d2[gi] = d2;
         }
       }
       break;
@@ -880,6 +1007,11 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
 }
 
 constexpr int ICP_DYN_SMEM = 200 * 1024;
+
+static size_t icp_chunk_points(size_t n, int csize) {   // per-CTA capacity in points, as icp_kernel computes it
+  const size_t ntiles = (n + ICP_TILE - 1) / ICP_TILE;
+  return ((ntiles + (size_t)csize - 1) / (size_t)csize) * ICP_TILE;
+}
 
 // the opt-in attributes are per DEVICE (a process may hold handles on several GPUs): one flag per device, set under a lock
 static std::mutex g_icp_attr_mu;
@@ -926,14 +1058,13 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
     const size_t smem_pts = (size_t)((ICP_DYN_SMEM - fixed) / ICP_BYTES_PER_POINT) - 64;
     static const int forced = getenv("B2S_ICP_BATCH_CSIZE") ? atoi(getenv("B2S_ICP_BATCH_CSIZE")) : 0;
     if (n_problems > 1 && forced > 0) csize = forced;
-    else while (csize > 1 && (size_t)n_problems * (size_t)csize > 148 * 2 && (max_src_points + csize / 2 - 1) / (csize / 2) <= smem_pts) csize /= 2;
+    else while (csize > 1 && (size_t)n_problems * (size_t)csize > 148 * 2 && icp_chunk_points(max_src_points, csize / 2) <= smem_pts) csize /= 2;
   }
   // shared memory is sized for THIS launch's chunk only: whatever is not claimed stays L1, and the candidate gathers of
   // neighbouring queries hit the same lines (4 target points per 128-byte line)
   int pts_cap = (ICP_DYN_SMEM - fixed) / ICP_BYTES_PER_POINT;
   {
-    const size_t chunk = (((max_src_points + (size_t)csize - 1) / (size_t)csize) + 1) & ~(size_t)1;   // even, like the kernel's
-    const size_t want = ((chunk + 63) / 64) * 64 + 64;
+    const size_t want = icp_chunk_points(max_src_points, csize) + 64;   // the kernel's capacity per CTA
     if (want < (size_t)pts_cap) pts_cap = (int)want;
   }
   const int dyn_smem = fixed + pts_cap * ICP_BYTES_PER_POINT;

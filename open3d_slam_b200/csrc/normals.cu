@@ -559,6 +559,55 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select_kernel(const GridHe
   }
 }
 
+// Butterfly sum of 9 values over the warp with the exchanges TRANSPOSED: at distance 16 the two halves of the warp split the values
+// between them (each lane keeps the half it will finish and receives the partner's copy of it), at distance 8 the quarters do, and so
+// on -- 8 + 4 + 2 + 1 + 1 = 16 exchanges instead of 9 x 5.  Every partial sum is the same pair of operands the plain xor butterfly
+// adds at that distance (fp addition commutes), so the totals are bit-identical to it.  On return lane l holds the total of value
+// l >> 1 in v[0] (values 9..15 are padding).
+__device__ __forceinline__ void warp_sum9_transposed(double (&v)[9], int lane) {
+  const unsigned FULL = 0xffffffffu;
+  double a[8];
+  {  // distance 16: lower half keeps 0..7, upper half keeps 8..15 (only 8 is real)
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double hi = k == 0 ? v[8] : 0.0;                 // value 8 + k
+      const double send = up ? v[k] : hi;
+      const double recv = __shfl_xor_sync(FULL, send, 16);
+      a[k] = (up ? hi : v[k]) + recv;
+    }
+  }
+  double b[4];
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double send = up ? a[k] : a[k + 4];
+      const double recv = __shfl_xor_sync(FULL, send, 8);
+      b[k] = (up ? a[k + 4] : a[k]) + recv;
+    }
+  }
+  double c[2];
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const double send = up ? b[k] : b[k + 2];
+      const double recv = __shfl_xor_sync(FULL, send, 4);
+      c[k] = (up ? b[k + 2] : b[k]) + recv;
+    }
+  }
+  double d;
+  {
+    const bool up = (lane & 2) != 0;
+    const double send = up ? c[0] : c[1];
+    const double recv = __shfl_xor_sync(FULL, send, 2);
+    d = (up ? c[1] : c[0]) + recv;
+  }
+  d += __shfl_xor_sync(FULL, d, 1);
+  v[0] = d;
+}
+
 // Second-generation fast path: same GATHER -> SELECT-BY-COUNTING -> BUTTERFLY pipeline as normals_select_kernel, but the
 // gathered candidates go through a per-warp shared-memory buffer, which lets the block radius R grow (1, 2, 3 cells)
 // until the k-th neighbour provably lies inside the block: dense areas finish at R = 1, sparse far-range areas at
@@ -566,6 +615,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select_kernel(const GridHe
 constexpr int NS2_CAP = 256;
 constexpr int NS2_CHUNKS = NS2_CAP / 32;
 constexpr int NS2_RMAX = 3;
+constexpr int NS2_ROWS = 320;   // row-table entries per warp: (2 R + 1)^2 rows of the largest block, rounded up to 32 (R = 8 -> 289)
 
 __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
                                                                      const double4* __restrict__ pts, int knn, double radius,
@@ -577,8 +627,8 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
   __shared__ int s_i[NK_THREADS / 32][NS2_CAP];
   __shared__ int s_s[NK_THREADS / 32][NS2_CAP];
   __shared__ int s_hist[NK_THREADS / 32][32];
-  __shared__ int s_ra[NK_THREADS / 32][64];   // first slot of every (y, z) row of the current block ((2*3+1)^2 = 49 rows at most)
-  __shared__ int s_rp[NK_THREADS / 32][65];   // exclusive prefix of the row sizes
+  __shared__ int s_ra[NK_THREADS / 32][NS2_ROWS];       // first slot of every (y, z) row of the current block
+  __shared__ int s_rp[NK_THREADS / 32][NS2_ROWS + 1];   // exclusive prefix of the row sizes
   if (threadIdx.x == 0) g = *hdr;
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -617,7 +667,14 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       const int n1b = __shfl_sync(0xffffffffu, n1, 0), n2b = __shfl_sync(0xffffffffu, n2, 0);
       if (n1b < 3 * knn && n2b <= NS2_CAP) Rstart = 2;
     }
-    for (int R = Rstart; R <= NS2_RMAX && !resolved; ++R) {
+    // Block radii tried: Rstart .. NS2_RMAX, then -- for the sparse queries that are still open (isolated far-range points, whose k
+    // neighbours lie further apart than any certified ball of a small block) -- ONE block that covers the whole search radius, if its
+    // rows fit the table: everything within the radius is then in the buffer and the answer is final even with fewer than k members.
+    const int Rfull = (int)ceil(radius * g.inv_cell);
+    const bool full_fits = Rfull > NS2_RMAX && (2 * Rfull + 1) * (2 * Rfull + 1) <= NS2_ROWS;
+    constexpr int R_NONE = 1 << 20;
+    for (int R = Rstart; !resolved && R != R_NONE; R = (R < NS2_RMAX ? R + 1 : (full_fits && R == NS2_RMAX ? Rfull : R_NONE))) {
+      const bool last_try = R > NS2_RMAX || (R == NS2_RMAX && !full_fits);
       // ---- gather the (2R+1)^3 block into shared memory (valid = inside the radius), rows resolved by the lanes ----
       const int side = 2 * R + 1;
       const int x0 = max(cx - R, 0), x1 = min(cx + R, nx - 1);
@@ -657,7 +714,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         const int t = t0 + lane;
         double dd = INFINITY; int ii = 0x7fffffff, j = -1;
         if (t < total) {
-          int lo = 0, hi = nrows;   // first index whose prefix exceeds t; s_rp[nrows] = total > t
+          int lo = 0, hi = side * side;   // first index whose prefix exceeds t; s_rp[side * side] = total > t (the padding rows are empty)
           while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_rp[wib][mid] > t) hi = mid; else lo = mid + 1; }
           const int r = lo - 1;
           j = s_ra[wib][r] + (t - s_rp[wib][r]);
@@ -678,20 +735,19 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       // (the loops stay fully unrolled -- the register arrays need static indices -- but the unused tail is branched over)
       const int nch = (nc + 31) >> 5;
       double d[NS2_CHUNKS]; int idx[NS2_CHUNKS], sl[NS2_CHUNKS];
-      double dmax = 0.0;
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
         if (c >= nch) break;
         const int t = c * 32 + lane;
         d[c] = INFINITY; idx[c] = 0x7fffffff; sl[c] = -1;
-        if (t < nc) { d[c] = s_d[wib][t]; idx[c] = s_i[wib][t]; sl[c] = s_s[wib][t]; dmax = fmax(dmax, d[c]); }
+        if (t < nc) { d[c] = s_d[wib][t]; idx[c] = s_i[wib][t]; sl[c] = s_s[wib][t]; }
       }
       __syncwarp();
       need = min(knn, nc);
       double td = INFINITY; int ti = 0x7fffffff;
       if (nc > knn) {   // k-th smallest (d2, index) by counting: 32-bin histogram over d2, then arg-min rounds in one bin
-        dmax = warp_max(dmax);
-        const double scale = dmax > 0.0 ? 32.0 / dmax : 0.0;
+        // every candidate kept lies below lim2 (finite: lim2 <= radius^2), so that is the histogram's range -- no maximum to reduce
+        const double scale = lim2 > 0.0 ? 32.0 / lim2 : 0.0;
         s_hist[wib][lane] = 0;
         __syncwarp();
         int bin[NS2_CHUNKS];
@@ -708,26 +764,29 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         const int B = __ffs(__ballot_sync(0xffffffffu, cumh >= need)) - 1;
         const int below = B > 0 ? __shfl_sync(0xffffffffu, cumh, B - 1) : 0;
         const int m = need - below;
-        double ld = -1.0; int li = -1;
-        for (int round = 0; round < m; ++round) {
-          double bd = INFINITY; int bi = 0x7fffffff;
+        // the m-th smallest (d2, index) of bin B by counting: its members go back to the (now free) candidate buffer, every lane ranks
+        // one of them against all the others -- the keys are distinct, so exactly one member has rank m - 1
+        int nb = 0;
 #pragma unroll
-          for (int c = 0; c < NS2_CHUNKS; c++) {
-            if (c >= nch) break;
-            const bool in_bin = bin[c] == B;
-            const bool after = d[c] > ld || (d[c] == ld && idx[c] > li);
-            const bool better = d[c] < bd || (d[c] == bd && idx[c] < bi);
-            if (in_bin && after && better) { bd = d[c]; bi = idx[c]; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-          }
-          ld = bd; li = bi;
+        for (int c = 0; c < NS2_CHUNKS; c++) {
+          if (c >= nch) break;
+          const bool in_bin = bin[c] == B;
+          const unsigned bm = __ballot_sync(0xffffffffu, in_bin);
+          if (in_bin) { const int pos = nb + __popc(bm & lt_mask); s_d[wib][pos] = d[c]; s_i[wib][pos] = idx[c]; }
+          nb += __popc(bm);
         }
-        td = ld; ti = li;
+        __syncwarp();
+        for (int base = 0; base < nb; base += 32) {
+          const int t = base + lane;
+          double md = INFINITY; int mi = 0x7fffffff, rank = -1;
+          if (t < nb) {
+            md = s_d[wib][t]; mi = s_i[wib][t]; rank = 0;
+            for (int u = 0; u < nb; u++) { const double od = s_d[wib][u]; const int oi = s_i[wib][u]; rank += (od < md || (od == md && oi < mi)) ? 1 : 0; }
+          }
+          const unsigned hit = __ballot_sync(0xffffffffu, rank == m - 1);
+          if (hit) { const int src = __ffs(hit) - 1; td = __shfl_sync(0xffffffffu, md, src); ti = __shfl_sync(0xffffffffu, mi, src); break; }
+        }
+        __syncwarp();   // the buffer is written again by the next block radius
 #pragma unroll
         for (int c = 0; c < NS2_CHUNKS; c++) {
           if (c >= nch) break;
@@ -737,7 +796,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       // ---- exact?  every candidate kept lies strictly inside the guaranteed ball (radius sqrt(lim2) <= distance to the
       // nearest block face), so k kept candidates contain the true k nearest; fewer than k is final only when the
       // block covers the whole search radius ----
-      if (!(nc >= knn || b2 > r2)) continue;         // grow the block
+      if (!(nc >= knn || b2 > r2)) { if (last_try) break; continue; }   // grow the block
       // ---- cumulants of the selected candidates, butterfly sum over the warp ----
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
@@ -749,23 +808,18 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
           c9[6] += p.y * p.y; c9[7] += p.y * p.z; c9[8] += p.z * p.z;
         }
       }
-#pragma unroll
-      for (int t = 0; t < 9; t++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c9[t] += __shfl_xor_sync(0xffffffffu, c9[t], o);
-      }
+      warp_sum9_transposed(c9, lane);   // lane l now holds the warp total of cumulant l >> 1 in c9[0] (l < 18)
       resolved = true;
-      if (lane == 0 && R > 1) atomicAdd(queue_n + 2 + R, 1);   // statistics (B2S_DEBUG_NORMALS): resolved at R = 2 / 3
+      if (lane == 0 && R > 1) atomicAdd(queue_n + 2 + min(R, 3), 1);   // statistics (B2S_DEBUG_NORMALS): resolved at R = 2 / at R >= 3
     }
     if (!resolved) {
       if (lane == 0) { queue[atomicAdd(queue_n, 1)] = s; cum[10 * (size_t)tq + 9] = -1.0; }
       continue;
     }
     {
-      double v = (double)need;   // lane 9 writes the neighbour count, lanes 0..8 one cumulant each (all lanes hold the sums)
-#pragma unroll
-      for (int t = 0; t < 9; t++) if (lane == t) v = c9[t];
-      if (lane < 10) cum[10 * (size_t)tq + lane] = v;
+      // lanes 0, 2, .., 16 hold one cumulant each (see warp_sum9_transposed), lane 18 writes the neighbour count
+      const int slot = lane >> 1;
+      if (!(lane & 1) && slot < 10) cum[10 * (size_t)tq + slot] = slot < 9 ? c9[0] : (double)need;
     }
   }
 }
