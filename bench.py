@@ -24,6 +24,7 @@ Chains are independent trajectories (one b2s handle / CUDA stream each), the uni
 from __future__ import annotations
 
 import argparse
+import copy
 import ctypes
 import json
 import os
@@ -353,6 +354,16 @@ def run_b2s_arm(args):
             if n == 1:
                 latency_ms = per_scan_step
         sweep_out[str(chains)] = {"registrations_per_s": value, "ms_per_scan_step": ms_total / (K * S)}
+    # latency mode: one chain alone with the registration spread over 16 SMs instead of 8 (b2s_config.icp_cluster_ctas; the default
+    # of 8 is the throughput setting the headline is measured with -- 16-SM clusters of many concurrent chains queue behind each other)
+    latency16_ms = None
+    if sweep and 1 in sweep:
+        p16 = copy.deepcopy(params); p16.icpClusterCtas = 16
+        engs[0].set_parameters(p16)
+        timed_region(one_resident, 1, 1, 8)
+        latency16_ms = float(np.median(timed_region(one_resident, 1, 4, 24))) / 24.0
+        engs[0].set_parameters(params)
+        timed_region(one_resident, 1, 1, 4)
 
     # ---------------- e2e: host buffers in, results out, every scan ----------------
     pinned = [[torch.from_numpy(scans[s][k]).pin_memory() for k in range(Lp)] for s in range(sets)]
@@ -489,7 +500,7 @@ def run_b2s_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
                         "min_fitness_last_scan": e2e_fit, "final_pose_err_m": e2e_err},
                 "gpu_launches": int(launches),
-                "single_chain_latency_ms": latency_ms, "chain_sweep": sweep_out or None,
+                "single_chain_latency_ms": latency_ms, "single_chain_latency_ms_16sm": latency16_ms, "chain_sweep": sweep_out or None,
                 "roofline": roofline, "profile_chain0": profile, "cpu_baseline": cpu}
         line.update(extras)
         print(json.dumps(line), flush=True)

@@ -93,6 +93,9 @@ typedef struct b2s_config {
   double map_voxel_size;       /* map_builder.map_voxel_size (Parameters.hpp:94) */
   double dense_voxel_size;     /* dense_map_builder.map_voxel_size */
   double nn_cell_size;         /* 0 = automatic (max_corr_dist / 4) : cell edge of the nearest-neighbour grid */
+  int32_t icp_cluster_ctas;    /* 0 = automatic: CTAs (= SMs) one registration may spread over: 8 suits many concurrent registrations
+                                * (throughput), 16 a single stream of scans (latency); rounded down to a power of two, at most 16 */
+  int32_t reserved_;
 } b2s_config;
 
 /* open3d::pipelines::registration::RegistrationResult as read by the callers

@@ -34,7 +34,7 @@ class ScanParams(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("icp", IcpParams), ("scan", ScanParams), ("map_voxel_size", C.c_double), ("dense_voxel_size", C.c_double),
-                ("nn_cell_size", C.c_double)]
+                ("nn_cell_size", C.c_double), ("icp_cluster_ctas", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Result(C.Structure):

@@ -288,6 +288,8 @@ void b2s_default_config(b2s_config* cfg) {
   cfg->map_voxel_size = 0.1;
   cfg->dense_voxel_size = 0.05;
   cfg->nn_cell_size = 0.0;
+  cfg->icp_cluster_ctas = 0;
+  cfg->reserved_ = 0;
 }
 
 const char* b2s_last_error(void) { return get_error(); }

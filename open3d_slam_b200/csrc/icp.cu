@@ -38,7 +38,7 @@ constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
 // (every contribution is warp-reduced at once into a per-warp accumulator in shared memory), fit 64 registers and run 1024
 // threads = 32 warps per SM; the generalized-ICP kernel carries 3x3 covariance algebra per correspondence and stays at 512
 #ifndef B2S_ICP_PLANE_THREADS
-#define B2S_ICP_PLANE_THREADS 1024   // A/B knob of the build (make alt builds libb2s_alt.so with 512)
+#define B2S_ICP_PLANE_THREADS 768   // threads per CTA of the point-to-plane / point-to-point instantiations (80 registers); measured on B200: 768 beats 512 and 1024 on latency and throughput (make alt ALT_THREADS=... builds libb2s_alt<N>.so for A/B runs)
 #endif
 constexpr int icp_threads(int mode) { return mode == 2 ? 512 : B2S_ICP_PLANE_THREADS; }
 constexpr int ICP_TILE = 64;   // points per tile of the source cloud (tile t belongs to CTA t % cluster size)
@@ -83,7 +83,9 @@ struct GridView {
 };
 
 struct NNState {
-  double best;
+  double best;     // d2 of the best candidate so far (or the search limit while bslot < 0)
+  double second;   // d2 of the best OTHER candidate seen (inf: none) -- with `gb` the raw material of the gap certificate
+  double gb;       // every target that was NOT looked at lies further than this from the query (distance, not squared)
   int bidx, bslot;
   int scanned;   // candidates looked at (only read by the counting instantiation, icp_kernel<3>)
 };
@@ -103,7 +105,12 @@ __device__ __forceinline__ void nn_scan_range(const double4* __restrict__ pts, i
     const double4 p = pts[j];
     const double d = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
     const int idx = (int)__double_as_longlong(p.w);
-    if (d < st.best || (d == st.best && st.bslot >= 0 && idx < st.bidx)) { st.best = d; st.bidx = idx; st.bslot = j; }
+    if (d < st.best || (d == st.best && st.bslot >= 0 && idx < st.bidx)) {
+      if (st.bslot >= 0) st.second = st.best;
+      st.best = d; st.bidx = idx; st.bslot = j;
+    } else if (j != st.bslot && d < st.second) {
+      st.second = d;
+    }
   }
 }
 
@@ -189,15 +196,31 @@ __device__ __forceinline__ void nn_scan_box(const GridView& g, double qx, double
       for (int v = 0; v < 4; v++) {
         if (c0 + v < total) {
           const double d = dist2_exact(qx, qy, qz, cx[v], cy[v], cz[v]);
-          if (d < st.best) { st.best = d; st.bslot = j[v]; }
-          else if (d == st.best && st.bslot >= 0 && j[v] != st.bslot) {   // exact tie: the lower original index wins
-            const int ia = (int)__double_as_longlong(g.pts[j[v]].w), ib = (int)__double_as_longlong(g.pts[st.bslot].w);
-            if (ia < ib) st.bslot = j[v];
+          if (d < st.best) {
+            if (st.bslot >= 0) st.second = st.best;
+            st.best = d; st.bslot = j[v];
+          } else if (j[v] != st.bslot) {
+            if (d < st.second) st.second = d;
+            if (d == st.best && st.bslot >= 0) {   // exact tie: the lower original index wins
+              const int ia = (int)__double_as_longlong(g.pts[j[v]].w), ib = (int)__double_as_longlong(g.pts[st.bslot].w);
+              if (ia < ib) st.bslot = j[v];
+            }
           }
         }
       }
     }
   }
+  // the block of cells just walked: whatever was not looked at lies beyond its faces (faces on the grid border have nothing behind
+  // them: outside points were clamped INTO the border cells)
+  double gb = INFINITY;
+  if (ix0 > 0) gb = fmin(gb, qx - (g.ox + (double)ix0 * g.cell));
+  if (ix1 < g.nx - 1) gb = fmin(gb, (g.ox + (double)(ix1 + 1) * g.cell) - qx);
+  if (iy0 > 0) gb = fmin(gb, qy - (g.oy + (double)iy0 * g.cell));
+  if (iy1 < g.ny - 1) gb = fmin(gb, (g.oy + (double)(iy1 + 1) * g.cell) - qy);
+  if (iz0 > 0) gb = fmin(gb, qz - (g.oz + (double)iz0 * g.cell));
+  if (iz1 < g.nz - 1) gb = fmin(gb, (g.oz + (double)(iz1 + 1) * g.cell) - qz);
+  if (gb != INFINITY) gb = fmax(gb - g.eps, 0.0);
+  st.gb = gb;
 }
 
 // phase 1 (one thread): BOX QUERY.  The previous iteration's neighbour (`hint`, -1 = none) is almost always still the
@@ -208,7 +231,7 @@ __device__ __forceinline__ void nn_scan_box(const GridView& g, double qx, double
 // Cell indices use the same floor((v - o) * inv) expression as the index build, which is monotone in v, so no point
 // inside the box can sit in a cell outside the index range.  Returns true when st holds the exact answer.
 __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double qy, double qz, double r2, int hint, NNState& st) {
-  st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
+  st.best = r2; st.second = INFINITY; st.gb = 0.0; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
   if (!(qx == qx && qy == qy && qz == qz)) return true;
   double rad2 = fmin(r2, g.cell * g.cell);
   bool seeded = false;
@@ -236,12 +259,14 @@ __device__ __forceinline__ bool nn_phase1(const GridView& g, double qx, double q
 
 // phase 2 (one warp, all lanes with the same query): continues from ring ICP_R1 + 1 with the rows of each ring spread
 // over the lanes.  st must hold the phase-1 state; on return every lane holds the exact answer.
-__device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, double qy, double qz, NNState& st) {
+__device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, double qy, double qz, double clip2, NNState& st) {
   // One pass over the box that encloses the sphere of the seed distance (or of the correspondence radius when there is
   // no seed): the (y, z) rows of the box are independent, so they are spread over the lanes and every lane clips its
   // row's x-run to the sphere.  No ring-by-ring termination tests, one warp reduction at the end.
   const int lane = threadIdx.x & 31;
-  const double radm = sqrt(st.best) * (1.0 + 1e-12) + 1e-300;   // st.best = seed distance^2, or r^2 when unseeded
+  // clip2: FIXED square radius of the ball that is searched completely (it does not shrink with the best candidate, so that on
+  // return every target within sqrt(clip2) has been looked at: the guarantee behind the gap certificate)
+  const double radm = sqrt(clip2) * (1.0 + 1e-12) + 1e-300;
   const int iy0 = (int)fmin(fmax(floor((qy - radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
   const int iy1 = (int)fmin(fmax(floor((qy + radm - g.oy) * g.inv), 0.0), (double)(g.ny - 1));
   const int iz0 = (int)fmin(fmax(floor((qz - radm - g.oz) * g.inv), 0.0), (double)(g.nz - 1));
@@ -258,8 +283,8 @@ __device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, dou
         const double gz = slab_gap(qz, g.oz, g.cell, z, g.nz, g.eps);
         const double gy = slab_gap(qy, g.oy, g.cell, y, g.ny, g.eps);
         const double g2 = gz * gz + gy * gy;
-        if (!(g2 > st.best)) {
-          const double xr = sqrt(fmax(st.best - g2, 0.0)) * (1.0 + 1e-12) + g.eps;
+        if (!(g2 > clip2)) {
+          const double xr = sqrt(fmax(clip2 - g2, 0.0)) * (1.0 + 1e-12) + g.eps;
           const int xa = (int)fmin(fmax(floor((qx - xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
           const int xb = (int)fmin(fmax(floor((qx + xr - g.ox) * g.inv), 0.0), (double)(g.nx - 1));
           const int row = (z * g.ny + y) * g.nx;
@@ -271,6 +296,8 @@ __device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, dou
     for (int u = 0; u < 4; u++) nn_scan_range(g.pts, ra[u], rb[u], qx, qy, qz, st);
   }
   // lexicographic (d2, index) minimum over the lanes; a lane without a hit carries slot -1
+  const double my_best = st.best, my_second = st.second;
+  const int my_slot = st.bslot;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double od = __shfl_xor_sync(0xffffffffu, st.best, o);
@@ -279,6 +306,12 @@ __device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, dou
     const bool take = os >= 0 && (st.bslot < 0 || od < st.best || (od == st.best && oi < st.bidx));
     if (take) { st.best = od; st.bidx = oi; st.bslot = os; }
   }
+  // the best OTHER candidate: every lane's runner-up, and every lane's own best unless that is the winner itself
+  double sec = my_second;
+  if (my_slot >= 0 && my_slot != st.bslot) sec = fmin(sec, my_best);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sec = fmin(sec, __shfl_xor_sync(0xffffffffu, sec, o));
+  st.second = sec;
 }
 
 // ---- small fp64 linear algebra on one thread, registers only -----------------------------------------------------
@@ -366,7 +399,7 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
 
 constexpr int icp_fixed_smem_doubles(int threads) { return ((threads / 32) * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1; }   // even: what follows stays 16-byte aligned
 constexpr int icp_fixed_smem_bytes(int threads) { return icp_fixed_smem_doubles(threads) * 8 + (int)sizeof(GridHeader) + 16 + 16; }   // + header + queue length + mbarrier
-constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4 + 4;  // working point, neighbour slot / search state, phase-2 queue entry, empty-neighbourhood slack
+constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4 + 4;  // working point, neighbour slot / search state, phase-2 queue entry, certificate slack
 
 // ---- contributions of one correspondence to the per-estimator sums ---------------------------------------------------------
 // Every 32 points (one per lane; slot < 0 = no correspondence, contributes zeros) are reduced by a warp butterfly at once and lane 0
@@ -687,10 +720,14 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
   double* s_pts = reinterpret_cast<double*>(smem_raw + icp_fixed_smem_bytes(THREADS));    // 16-byte aligned
   int* s_prev = reinterpret_cast<int*>(s_pts + 3 * (size_t)smem_pts_cap);  // neighbour slot per point (state between the phases, warm start)
   int* s_queue = s_prev + smem_pts_cap;                                    // local indices of points left to phase 2
-  // Certificate of an empty neighbourhood: a point for which phase 2 found NOTHING within r + m keeps slack[i] = (distance to the
-  // nearest target) - r >= 0 (m when there is none within r + m).  Every later evaluation moves the point by |U p - p|; while the
-  // accumulated motion stays below the slack no target can have come within r, so the point is known to have no correspondence
-  // without searching again (outliers at the map frontier would otherwise repeat the most expensive search of all, every evaluation).
+  // CERTIFICATES (slack[i], a distance).  Every evaluation moves point i by m_i = |U p - p|; a search result stays valid while the
+  // accumulated motion is provably too small to change it:
+  //   * no correspondence (state -1): slack = (distance to the nearest target) - r.  While the motion stays below it no target can
+  //     have come within r (outliers at the map frontier would otherwise repeat the most expensive search of all, every evaluation);
+  //   * a correspondence (state >= 0): slack = (lower bound of the distance to every other target) - (distance to the neighbour).
+  //     While TWICE the motion stays below it the neighbour is still the unique nearest target: the evaluation costs one distance.
+  // ICP converges geometrically, so after the first two or three evaluations almost every point is certified and the correspondence
+  // search all but disappears.  Both tests are conservative (rounded against the certificate), never approximate.
   float* s_slack = reinterpret_cast<float*>(s_queue + smem_pts_cap);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -792,6 +829,24 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         s_slack[i] = left > 0.0f ? left : 0.0f;
         if (left > 0.0f) { if (COUNT) n_evals1++; continue; }   // prev[i] stays -1
       }
+      if (in_smem && hint >= 0) {   // a correspondence last time: still provably the same target?
+        // slack = (lower bound of the distance to every OTHER target) - (distance to the neighbour) when it was last searched.  A move
+        // by m brings the neighbour at most m further and every other target at most m closer: while 2 m stays below the slack
+        // the neighbour is still the unique nearest target, and the search is replaced by one distance evaluation.
+        const float left = s_slack[i] - (float)(2.0 * moved * (1.0 + 1e-6)) - 1e-7f;
+        if (left > 0.0f) {
+          const double4 q = g.pts[hint];
+          const double d = dist2_exact(px, py, pz, q.x, q.y, q.z);
+          if (d < r2) {
+            s_slack[i] = left;
+          } else {   // the nearest target has left the correspondence radius: nothing is within it (and stays so for sqrt(d) - r)
+            prev[wi] = -1;
+            s_slack[i] = (float)fmax((sqrt(d) - P.max_corr) * (1.0 - 1e-6) - 1e-7, 0.0);
+          }
+          if (COUNT) n_evals1++;
+          continue;
+        }
+      }
       NNState st;
       bool done = nn_phase1(g, px, py, pz, r2, hint >= 0 ? hint : -1, st);
       if (!done && !in_smem) {  // no queue for clouds that overflow shared memory: finish serially
@@ -808,6 +863,11 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         done = true;
       }
       prev[wi] = done ? st.bslot : -(st.bslot + 3);
+      if (in_smem) {   // gap certificate of the answer: runner-up among the cells walked, or the walked block's nearest face
+        float sl = 0.0f;
+        if (done && st.bslot >= 0) sl = (float)fmax((fmin(sqrt(st.second), st.gb) - sqrt(st.best)) * (1.0 - 1e-6) - 1e-7, 0.0);
+        s_slack[i] = sl;
+      }
       if (COUNT) { n_scanned1 += st.scanned; n_evals1++; n_queued += done ? 0 : 1; }
       if (!done) s_queue[atomicAdd(s_qn, 1)] = i;
     }
@@ -855,26 +915,32 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         int* rp = cluster.map_shared_rank(s_prev, r);
         const double px = rw[3 * i], py = rw[3 * i + 1], pz = rw[3 * i + 2];
         NNState st;
-        st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
+        st.best = r2; st.second = INFINITY; st.gb = 0.0; st.bidx = 0x7fffffff; st.bslot = -1; st.scanned = 0;
         const int hs = -rp[i] - 3;  // best of the box query (or the seed), -1 when nothing was in range
         if (hs >= 0) {
           const double4 p = g.pts[hs];
           st.best = dist2_exact(px, py, pz, p.x, p.y, p.z); st.bidx = (int)__double_as_longlong(p.w); st.bslot = hs;
           if (!(st.best < r2)) { st.best = r2; st.bidx = 0x7fffffff; st.bslot = -1; }
         }
-        // without a seed the search reaches a margin beyond r: what it finds there is no correspondence (d2 < r2 is strict), but
-        // it tells how far the point is from getting one
+        // The ball searched completely reaches a margin beyond the seed distance (beyond r without a seed).  What lies in the margin
+        // is never the answer, but it is what the certificates are made of: the runner-up bounds how far the point may move before
+        // the neighbour can change, the nearest target beyond r how far before a point without correspondence can get one.
         const double margin = 0.25 * g.cell;
         const bool unseeded = st.bslot < 0;
-        if (unseeded) st.best = (P.max_corr + margin) * (P.max_corr + margin);
-        nn_phase2_warp(g, px, py, pz, st);
+        const double rc = (unseeded ? P.max_corr : sqrt(st.best)) + margin;
+        if (unseeded) st.best = rc * rc;
+        nn_phase2_warp(g, px, py, pz, rc * rc, st);
         if (COUNT) n_scanned2 += st.scanned;
+        float sl;
         if (unseeded && st.bslot >= 0 && !(st.best < r2)) {   // nearest target lies in the margin shell: none within r, slack = distance - r
-          if (lane == 0) cluster.map_shared_rank(s_slack, r)[i] = (float)fmax((sqrt(st.best) - P.max_corr) * (1.0 - 1e-6) - 1e-7, 0.0);
+          sl = (float)fmax((sqrt(st.best) - P.max_corr) * (1.0 - 1e-6) - 1e-7, 0.0);
           st.bslot = -1;
         } else if (unseeded && st.bslot < 0) {
-          if (lane == 0) cluster.map_shared_rank(s_slack, r)[i] = (float)(margin * (1.0 - 1e-6));
+          sl = (float)(margin * (1.0 - 1e-6));
+        } else {   // a correspondence: gap to the runner-up, or to the edge of the searched ball
+          sl = (float)fmax((fmin(sqrt(st.second), rc) - sqrt(st.best)) * (1.0 - 1e-6) - 1e-7, 0.0);
         }
+        if (lane == 0) cluster.map_shared_rank(s_slack, r)[i] = sl;
         if (lane == 0) {
           rp[i] = st.bslot;
           if (st.bslot >= 0) {
@@ -1017,8 +1083,9 @@ static size_t icp_chunk_points(size_t n, int csize) {   // per-CTA capacity in p
 static std::mutex g_icp_attr_mu;
 static bool g_icp_attr_set[64] = {false};
 
-static int icp_max_cluster() {   // B2S_ICP_MAX_CLUSTER=16 spreads one registration over 16 SMs (non-portable cluster size)
-  static const int v = getenv("B2S_ICP_MAX_CLUSTER") ? atoi(getenv("B2S_ICP_MAX_CLUSTER")) : 8;
+static int icp_max_cluster(const b2s_handle* h) {   // 16 spreads one registration over 16 SMs (non-portable cluster size)
+  static const int env = getenv("B2S_ICP_MAX_CLUSTER") ? atoi(getenv("B2S_ICP_MAX_CLUSTER")) : 0;
+  const int v = h->cfg.icp_cluster_ctas > 0 ? h->cfg.icp_cluster_ctas : (env > 0 ? env : 8);
   return v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1)));
 }
 
@@ -1047,7 +1114,7 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   }
   const int estimator = single_host ? single_host->estimator : h->cfg.icp.reg_type;   // uniform over a batch
   int csize = 1;
-  const int cmax = icp_max_cluster();
+  const int cmax = icp_max_cluster(h);
   const int mode = estimator == B2S_REG_GENERALIZED ? 2 : (estimator == B2S_REG_POINT_TO_PLANE ? (h->icp_dbg ? 3 : 0) : 1);
   const int threads = icp_threads(mode);
   while (csize < cmax && (size_t)csize * threads < max_src_points) csize *= 2;

@@ -98,6 +98,7 @@ class MapperParameters:
     minMovementBetweenMappingSteps: float = 0.0
     seed: int = 0            # replaces std::random_device of [O3D] RandomDownSample
     nnCellSize: float = 0.0  # engine knob: NN grid cell (0 = maxCorrespondenceDistance / 4)
+    icpClusterCtas: int = 0  # engine knob: SMs one registration spreads over (0 = automatic; 8 = throughput, 16 = latency)
 
     def to_config(self) -> L.Config:
         types = {"PointToPlaneIcp": L.REG_POINT_TO_PLANE, "PointToPointIcp": L.REG_POINT_TO_POINT, "GeneralizedIcp": L.REG_GENERALIZED}
@@ -120,6 +121,7 @@ class MapperParameters:
         cfg.map_voxel_size = float(self.mapBuilder.mapVoxelSize)
         cfg.dense_voxel_size = float(self.denseMapVoxelSize)
         cfg.nn_cell_size = float(self.nnCellSize)
+        cfg.icp_cluster_ctas = int(self.icpClusterCtas)
         return cfg
 
 

@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(L.Result) == 152
     assert C.sizeof(L.Cropper) == 64
     assert C.sizeof(L.IcpParams) == 48
-    assert C.sizeof(L.Config) == C.sizeof(L.IcpParams) + C.sizeof(L.ScanParams) + 24
+    assert C.sizeof(L.Config) == C.sizeof(L.IcpParams) + C.sizeof(L.ScanParams) + 32   # 3 doubles + icp_cluster_ctas + reserved_
 
 
 def test_default_config_is_the_lua_default():
