@@ -521,24 +521,28 @@ int32_t b2s_cloud_copy(b2s_handle* h, const b2s_cloud* src, b2s_cloud* dst) {
 int32_t b2s_crop(b2s_handle* h, const b2s_cloud* in, const b2s_cropper* cropper, b2s_cloud* out) {
   B2S_REQUIRE(h && in && cropper && out && in != out, B2S_E_INVALID, "bad argument");
   LOCK(h);
+  WideGridScope wide(in->n_max);
   return op_crop(h, in, make_crop(cropper), out);
 }
 
 int32_t b2s_voxel_down_sample(b2s_handle* h, const b2s_cloud* in, double voxel_size, b2s_cloud* out) {
   B2S_REQUIRE(h && in && out && in != out, B2S_E_INVALID, "bad argument");
   LOCK(h);
+  WideGridScope wide(in->n_max);
   return op_voxel_down_sample(h, in, nullptr, voxel_size, out);
 }
 
 int32_t b2s_estimate_normals(b2s_handle* h, b2s_cloud* cloud, int32_t knn, double radius) {
   B2S_REQUIRE(h && cloud, B2S_E_INVALID, "null argument");
   LOCK(h);
+  WideGridScope wide(cloud->n_max);
   return op_estimate_normals(h, cloud, knn, radius, h->cfg.scan.voxel_size > 0.0 ? 4.0 * h->cfg.scan.voxel_size : 0.0);
 }
 
 int32_t b2s_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t seed, b2s_cloud* out) {
   B2S_REQUIRE(h && in && out && in != out, B2S_E_INVALID, "bad argument");
   LOCK(h);
+  WideGridScope wide(in->n_max);
   return op_random_down_sample(h, in, ratio, seed, out);
 }
 
@@ -724,7 +728,7 @@ int32_t b2s_nearest_neighbors(b2s_handle* h, const b2s_cloud* queries, const b2s
   B2S_REQUIRE(n <= capacity, B2S_E_CAPACITY, "output arrays hold %zu entries, the cloud has %zu points", capacity, n);
   if (n == 0) return B2S_OK;
   B2S_TRY(grid_build(h, &h->grid_a, target, nn_cell(h, max_corr), nullptr, false));
-  constexpr size_t CHUNK = 40000;   // what one launch keeps in shared memory (8 CTAs x ~6 000 points)
+  constexpr size_t CHUNK = 36864;   // what one launch keeps in shared memory (8 CTAs x 72 tiles of 64 points at 40 bytes per point)
   B2S_TRY(h->work_xyz.ensure(icp_work_bytes(CHUNK), h->stream));
   B2S_TRY(h->results.ensure(sizeof(b2s_result) + 36 * 8 + 64, h->stream));
   B2S_TRY(h->tmp_i32.ensure((n + 64) * 4, h->stream));
@@ -738,6 +742,7 @@ int32_t b2s_nearest_neighbors(b2s_handle* h, const b2s_cloud* queries, const b2s
     IcpProblem P;
     fill_problem(h, &P, queries, &h->grid_a, T ? T : I, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
     P.src_xyz = queries->xyz.as<double>() + 3 * off;
+    P.work_prev = reinterpret_cast<int32_t*>(h->work_xyz.as<double>() + 3 * (CHUNK + 1));   // the work buffer is sized for a chunk, not for the cloud
     P.src_n = d_cnt;
     P.max_corr = max_corr;
     P.max_iter = 0;

@@ -336,6 +336,13 @@ int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, con
 // upper bound of the CTAs of a streaming kernel: 2 per SM (B2S_GRID_CAP overrides).  Measured at 16 concurrent chains: 148 .. 592
 // CTAs give 9.1 - 9.2 k registrations/s, 2368 (the round-1 value) 8.1 k -- few fat CTAs leave the SMs to the other chains' kernels
 int grid_cap();
+// The stand-alone operators (voxel down-sample, normals, crop of ONE large cloud: config 3) are not sharing the GPU with other chains'
+// kernels: for the duration of such a call the cap is lifted so that a 2^20-point cloud fills every SM.
+struct WideGridScope {
+  explicit WideGridScope(size_t n);
+  ~WideGridScope();
+  bool on;
+};
 inline int grid_for(size_t n, int threads, int max_blocks = 0) {
   if (max_blocks <= 0) max_blocks = grid_cap();
   size_t b = (n + (size_t)threads - 1) / (size_t)threads;

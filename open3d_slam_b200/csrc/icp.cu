@@ -399,7 +399,7 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
 
 constexpr int icp_fixed_smem_doubles(int threads) { return ((threads / 32) * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1; }   // even: what follows stays 16-byte aligned
 constexpr int icp_fixed_smem_bytes(int threads) { return icp_fixed_smem_doubles(threads) * 8 + (int)sizeof(GridHeader) + 16 + 16; }   // + header + queue length + mbarrier
-constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4 + 4;  // working point, neighbour slot / search state, phase-2 queue entry, certificate slack
+constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4 + 4 + 4;  // working point, neighbour slot / search state, phase-2 queue entry, certificate slack, search-list entry
 
 // ---- contributions of one correspondence to the per-estimator sums ---------------------------------------------------------
 // Every 32 points (one per lane; slot < 0 = no correspondence, contributes zeros) are reduced by a warp butterfly at once and lane 0
@@ -729,6 +729,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
   // ICP converges geometrically, so after the first two or three evaluations almost every point is certified and the correspondence
   // search all but disappears.  Both tests are conservative (rounded against the certificate), never approximate.
   float* s_slack = reinterpret_cast<float*>(s_queue + smem_pts_cap);
+  int* s_list = reinterpret_cast<int*>(s_slack + smem_pts_cap);   // points that need a search in this evaluation (s_qn[1] = how many)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = *P.src_n;
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
     for (int i = 0; i < 16; i++) { s_T[i] = init[i]; s_U[i] = init[i]; }
     s_misc[0] = 0.0; s_misc[1] = 0.0; s_misc[2] = 0.0;
     s_misc[3] = mat4_is_identity_dev(init) ? 0.0 : 1.0;  // [O3D]: if (!init.isIdentity()) pcd.Transform(init)
-    *s_qn = 0;
+    s_qn[0] = 0; s_qn[1] = 0;
     if (in_smem) { mbar_init(s_bar, 1); mbar_fence_init(); }
   }
   for (int i = tid; i < WARPS * NACC; i += THREADS) s_wacc[i] = 0.0;
@@ -810,43 +811,72 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
     if (bal_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     const bool apply = s_misc[3] != 0.0;
 
-    // ---- phase 1a: correspondence search, one thread per point (nothing but the search state lives in registers) ----
-    for (int i = tid; i < cnt; i += THREADS) {
-      const int wi = widx(i);
-      double px = work[3 * wi], py = work[3 * wi + 1], pz = work[3 * wi + 2];
-      double moved = 0.0;
-      if (apply) {  // [O3D] TransformPoints with w == 1 exactly for a rigid update; same association as Eigen's product
-        const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[0], px), __dmul_rn(s_U[1], py)), __dmul_rn(s_U[2], pz)), s_U[3]);
-        const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[4], px), __dmul_rn(s_U[5], py)), __dmul_rn(s_U[6], pz)), s_U[7]);
-        const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[8], px), __dmul_rn(s_U[9], py)), __dmul_rn(s_U[10], pz)), s_U[11]);
-        moved = sqrt((x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz));
-        px = x; py = y; pz = z;
-        work[3 * wi] = px; work[3 * wi + 1] = py; work[3 * wi + 2] = pz;
-      }
-      const int hint = prev[wi];
-      if (in_smem && hint == -1) {   // no correspondence last time: still provably none?
-        const float left = s_slack[i] - (float)(moved * (1.0 + 1e-6)) - 1e-7f;   // float rounding only ever shortens the slack
-        s_slack[i] = left > 0.0f ? left : 0.0f;
-        if (left > 0.0f) { if (COUNT) n_evals1++; continue; }   // prev[i] stays -1
-      }
-      if (in_smem && hint >= 0) {   // a correspondence last time: still provably the same target?
-        // slack = (lower bound of the distance to every OTHER target) - (distance to the neighbour) when it was last searched.  A move
-        // by m brings the neighbour at most m further and every other target at most m closer: while 2 m stays below the slack
-        // the neighbour is still the unique nearest target, and the search is replaced by one distance evaluation.
-        const float left = s_slack[i] - (float)(2.0 * moved * (1.0 + 1e-6)) - 1e-7f;
-        if (left > 0.0f) {
-          const double4 q = g.pts[hint];
-          const double d = dist2_exact(px, py, pz, q.x, q.y, q.z);
-          if (d < r2) {
-            s_slack[i] = left;
-          } else {   // the nearest target has left the correspondence radius: nothing is within it (and stays so for sqrt(d) - r)
-            prev[wi] = -1;
-            s_slack[i] = (float)fmax((sqrt(d) - P.max_corr) * (1.0 - 1e-6) - 1e-7, 0.0);
+    // ---- phase 1a: move the points, settle what the certificates settle, search the rest ----
+    // Sweep A touches every point: apply the update, then (certificates) decide whether the previous answer still stands.  Points
+    // that need a search are COMPACTED into a list (warp-aggregated append), so that sweep B runs the search with full warps: in the
+    // later evaluations a few percent of the points search, and scattered over all warps they would make every warp walk the whole
+    // search path (and wait for its L2 round trips) for one or two live lanes.
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int base = warp * 32; base < cnt; base += THREADS) {
+      const int i = base + lane;
+      bool need = false;
+      if (i < cnt) {
+        const int wi = widx(i);
+        double px = work[3 * wi], py = work[3 * wi + 1], pz = work[3 * wi + 2];
+        double moved = 0.0;
+        if (apply) {  // [O3D] TransformPoints with w == 1 exactly for a rigid update; same association as Eigen's product
+          const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[0], px), __dmul_rn(s_U[1], py)), __dmul_rn(s_U[2], pz)), s_U[3]);
+          const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[4], px), __dmul_rn(s_U[5], py)), __dmul_rn(s_U[6], pz)), s_U[7]);
+          const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(s_U[8], px), __dmul_rn(s_U[9], py)), __dmul_rn(s_U[10], pz)), s_U[11]);
+          moved = sqrt((x - px) * (x - px) + (y - py) * (y - py) + (z - pz) * (z - pz));
+          px = x; py = y; pz = z;
+          work[3 * wi] = px; work[3 * wi + 1] = py; work[3 * wi + 2] = pz;
+        }
+        need = true;
+        if (in_smem) {
+          const int hint = prev[wi];
+          if (hint == -1) {   // no correspondence last time: still provably none?
+            const float left = s_slack[i] - (float)(moved * (1.0 + 1e-6)) - 1e-7f;   // float rounding only ever shortens the slack
+            s_slack[i] = left > 0.0f ? left : 0.0f;
+            if (left > 0.0f) need = false;   // prev[i] stays -1
+          } else if (hint >= 0) {   // a correspondence last time: still provably the same target?
+            // slack = (lower bound of the distance to every OTHER target) - (distance to the neighbour) when it was last searched.  A
+            // move by m brings the neighbour at most m further and every other target at most m closer: while 2 m stays below the
+            // slack the neighbour is still the unique nearest target, and the search is replaced by one distance evaluation.
+            const float left = s_slack[i] - (float)(2.0 * moved * (1.0 + 1e-6)) - 1e-7f;
+            if (left > 0.0f) {
+              const double4 q = g.pts[hint];
+              const double d = dist2_exact(px, py, pz, q.x, q.y, q.z);
+              if (d < r2) {
+                s_slack[i] = left;
+              } else {   // the nearest target has left the correspondence radius: nothing is within it (and stays so for sqrt(d) - r)
+                prev[wi] = -1;
+                s_slack[i] = (float)fmax((sqrt(d) - P.max_corr) * (1.0 - 1e-6) - 1e-7, 0.0);
+              }
+              need = false;
+            }
           }
-          if (COUNT) n_evals1++;
-          continue;
+          if (COUNT && !need) n_evals1++;
         }
       }
+      if (in_smem) {
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+          int pos = 0;
+          if (lane == 0) pos = atomicAdd(&s_qn[1], __popc(m));
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (need) s_list[pos + __popc(m & lt_mask)] = i;
+        }
+      }
+    }
+    __syncthreads();
+    // Sweep B: one thread per listed point (without shared-memory residency there is no list: every point, no certificates)
+    const int n_search = in_smem ? s_qn[1] : cnt;
+    for (int t = tid; t < n_search; t += THREADS) {
+      const int i = in_smem ? s_list[t] : t;
+      const int wi = widx(i);
+      const double px = work[3 * wi], py = work[3 * wi + 1], pz = work[3 * wi + 2];
+      const int hint = prev[wi];
       NNState st;
       bool done = nn_phase1(g, px, py, pz, r2, hint >= 0 ? hint : -1, st);
       if (!done && !in_smem) {  // no queue for clouds that overflow shared memory: finish serially
@@ -981,7 +1011,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
       s_part[buf * NACC + tid] = v;
     }
     cluster.sync();
-    if (tid == 0) *s_qn = 0;   // only after the barrier: peers read this queue during their phase 2
+    if (tid == 0) { s_qn[0] = 0; s_qn[1] = 0; }   // only after the barrier: peers read this queue during their phase 2
     if (tid < NACC) {
       double v = 0.0;
       for (unsigned r = 0; r < csize; r++) {

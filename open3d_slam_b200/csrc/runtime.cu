@@ -20,10 +20,14 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 unsigned long long g_alloc_generation = 1;
+static thread_local int g_grid_cap_override = 0;
 int grid_cap() {
+  if (g_grid_cap_override > 0) return g_grid_cap_override;
   static const int v = getenv("B2S_GRID_CAP") ? atoi(getenv("B2S_GRID_CAP")) : 148 * 2;
   return v > 0 ? v : 148 * 2;
 }
+WideGridScope::WideGridScope(size_t n) : on(n >= ((size_t)1 << 19) && g_grid_cap_override == 0) { if (on) g_grid_cap_override = 148 * 16; }
+WideGridScope::~WideGridScope() { if (on) g_grid_cap_override = 0; }
 thread_local bool g_capturing = false;
 thread_local bool g_capture_broken = false;
 

@@ -38,6 +38,31 @@ def lua_params(**kw):
     return p
 
 
+def test_icp_source_larger_than_shared_memory(engine_factory):
+    """A source cloud too large for the cluster's shared memory (8 CTAs x ~4.9 k points) takes the kernel's other path: working copy
+    and per-point state in global memory, no phase-2 queue, no certificates.  Same answers as the oracle."""
+    rng = np.random.default_rng(11)
+    n_t, n_s = 30_000, 60_000
+    tgt = np.c_[rng.uniform(-8, 8, (n_t, 2)), 0.05 * rng.standard_normal(n_t)]
+    tgt[: n_t // 3] = np.c_[rng.uniform(-8, 8, n_t // 3), np.full(n_t // 3, 8.0) + 0.05 * rng.standard_normal(n_t // 3), rng.uniform(0, 4, n_t // 3)]
+    tgt[n_t // 3: 2 * n_t // 3, 0] = -8.0 + 0.05 * rng.standard_normal(2 * n_t // 3 - n_t // 3)
+    tgt[n_t // 3: 2 * n_t // 3, 2] = rng.uniform(0, 4, 2 * n_t // 3 - n_t // 3)
+    nrm = O.estimate_normals(tgt, 10, 1.0)
+    T_true = synth.se3(0.01, -0.015, 0.02, (0.06, -0.04, 0.03))
+    pick = rng.integers(0, n_t, n_s)
+    src = (tgt[pick] + 0.01 * rng.standard_normal((n_s, 3)) - T_true[:3, 3]) @ T_true[:3, :3]      # inverse motion of noisy target samples
+    p = lua_params()
+    p.icp.maxCorrespondenceDistance = 0.5
+    p.icp.maxNumIter = 4
+    eng = engine_factory(p)
+    reg = E.cloudRegistrationFactory(eng, E.CloudRegistrationParameters(icp=p.icp))
+    res = reg.registerClouds(eng.cloud(src), eng.cloud(tgt, nrm), np.eye(4))
+    ref = O.registration_icp_p2plane(src, tgt, nrm, 0.5, np.eye(4), max_iter=4)
+    assert res.iters == ref.iters and res.n_corr == ref.n_corr
+    assert abs(res.fitness_ - ref.fitness) < 1e-12
+    assert rel_rot(res.transformation_, ref.T) < 1e-9 and rel_trans(res.transformation_, ref.T) < 1e-9
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # R1-R5: config 1 -- scan-to-scan point-to-plane ICP on the 2k-pt three-plane cloud
 # ----------------------------------------------------------------------------------------------------------------------
