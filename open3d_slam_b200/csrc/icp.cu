@@ -315,65 +315,57 @@ __device__ __forceinline__ void nn_phase2_warp(const GridView& g, double qx, dou
 }
 
 // ---- small fp64 linear algebra on one thread, registers only -----------------------------------------------------
-#define B2S_SWAP(u, v) { const double _t = (u); (u) = (v); (v) = _t; }
 
-// A x = b, A symmetric 6x6 (full storage a[6][6]).  LDL^T with symmetric pivoting on the largest |diagonal|, the
-// scheme Eigen's LDLT uses for [O3D] SolveLinearSystemPSD (no determinant / PSD check on this call path).  Every loop
-// is fully unrolled and every index static: pivot swaps are predicated register moves, nothing goes to local memory.
-__device__ __forceinline__ void ldlt6_solve_reg(double (&a)[6][6], double (&b)[6], double (&x)[6]) {
+// A x = b, A symmetric 6x6.  LDL^T with symmetric pivoting on the largest |diagonal|, the scheme Eigen's LDLT uses for [O3D]
+// SolveLinearSystemPSD (no determinant / PSD check on this call path).  ONE thread, the matrix in shared memory with dynamic
+// indices: a pivot swap is a real (and rare) exchange of one row and one column.  (The round-1 version kept everything in
+// registers with select-based swaps so that nothing went to local memory -- and spent most of its ~2000 instructions on the
+// selects: 4 us per evaluation with every other thread of the cluster waiting.)
+// a: 36 doubles (row-major, full storage), b: 6 doubles; the solution is left in b.
+__device__ __forceinline__ void ldlt6_solve_smem(double* a, double* b) {
   int piv[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) {
     int p = k;
-    double best = fabs(a[k][k]);
+    double best = fabs(a[7 * k]);
 #pragma unroll
-    for (int i = k + 1; i < 6; i++) { const double v = fabs(a[i][i]); if (v > best) { best = v; p = i; } }
+    for (int i = k + 1; i < 6; i++) { const double v = fabs(a[7 * i]); if (v > best) { best = v; p = i; } }
     piv[k] = p;
-#pragma unroll
-    for (int i = k + 1; i < 6; i++) {
-      // data-flow selects, not branches: a branchy "if (p == i) swap" chain gets re-rolled by the compiler into
-      // dynamically indexed (local-memory) accesses
-      const bool sw = (p == i);
-#pragma unroll
-      for (int j = 0; j < 6; j++) { const double u = a[k][j], v = a[i][j]; a[k][j] = sw ? v : u; a[i][j] = sw ? u : v; }
-#pragma unroll
-      for (int j = 0; j < 6; j++) { const double u = a[j][k], v = a[j][i]; a[j][k] = sw ? v : u; a[j][i] = sw ? u : v; }
-      { const double u = b[k], v = b[i]; b[k] = sw ? v : u; b[i] = sw ? u : v; }
+    if (p != k) {
+      for (int j = 0; j < 6; j++) { const double u = a[6 * k + j]; a[6 * k + j] = a[6 * p + j]; a[6 * p + j] = u; }
+      for (int j = 0; j < 6; j++) { const double u = a[6 * j + k]; a[6 * j + k] = a[6 * j + p]; a[6 * j + p] = u; }
+      { const double u = b[k]; b[k] = b[p]; b[p] = u; }
     }
-    const double d = a[k][k];
+    const double d = a[7 * k];
     if (d != 0.0) {
 #pragma unroll
-      for (int i = k + 1; i < 6; i++) a[i][k] /= d;
+      for (int i = k + 1; i < 6; i++) a[6 * i + k] /= d;
 #pragma unroll
       for (int i = k + 1; i < 6; i++)
 #pragma unroll
         for (int j = k + 1; j <= i; j++) {
-          a[i][j] -= a[i][k] * d * a[j][k];
-          a[j][i] = a[i][j];
+          const double v = a[6 * i + j] - a[6 * i + k] * d * a[6 * j + k];
+          a[6 * i + j] = v;
+          a[6 * j + i] = v;
         }
     }
   }
-  double y[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) y[i] = b[i];
 #pragma unroll
   for (int i = 0; i < 6; i++)
 #pragma unroll
-    for (int j = 0; j < i; j++) y[i] -= a[i][j] * y[j];
+    for (int j = 0; j < i; j++) b[i] -= a[6 * i + j] * b[j];
 #pragma unroll
-  for (int i = 0; i < 6; i++) { const double d = a[i][i]; y[i] = (fabs(d) > 2.2250738585072014e-308) ? y[i] / d : 0.0; }
+  for (int i = 0; i < 6; i++) { const double d = a[7 * i]; b[i] = (fabs(d) > 2.2250738585072014e-308) ? b[i] / d : 0.0; }
 #pragma unroll
   for (int i = 5; i >= 0; i--)
 #pragma unroll
-    for (int j = i + 1; j < 6; j++) y[i] -= a[j][i] * y[j];
+    for (int j = i + 1; j < 6; j++) b[i] -= a[6 * j + i] * b[j];
   // undo the permutation: apply the recorded transpositions in reverse order
 #pragma unroll
   for (int k = 5; k >= 0; k--) {
-#pragma unroll
-    for (int i = k + 1; i < 6; i++) { const bool sw = (piv[k] == i); const double u = y[k], v = y[i]; y[k] = sw ? v : u; y[i] = sw ? u : v; }
+    const int p = piv[k];
+    if (p != k) { const double u = b[k]; b[k] = b[p]; b[p] = u; }
   }
-#pragma unroll
-  for (int i = 0; i < 6; i++) x[i] = y[i];
 }
 
 // [O3D] TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x[3..5]
@@ -397,7 +389,7 @@ __device__ bool mat4_is_identity_dev(const double* T) {  // Eigen isIdentity(1e-
   return true;
 }
 
-constexpr int icp_fixed_smem_doubles(int threads) { return ((threads / 32) * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 1) & ~1; }   // even: what follows stays 16-byte aligned
+constexpr int icp_fixed_smem_doubles(int threads) { return ((threads / 32) * NACC + 2 * NACC + NACC + 16 + 16 + 8 + 42 + 1) & ~1; }   // even: what follows stays 16-byte aligned
 constexpr int icp_fixed_smem_bytes(int threads) { return icp_fixed_smem_doubles(threads) * 8 + (int)sizeof(GridHeader) + 16 + 16; }   // + header + queue length + mbarrier
 constexpr int ICP_BYTES_PER_POINT = 24 + 4 + 4 + 4 + 4;  // working point, neighbour slot / search state, phase-2 queue entry, certificate slack, search-list entry
 
@@ -714,6 +706,7 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
   double* s_U = s_tot + NACC;                           // [16] update of the current iteration
   double* s_T = s_U + 16;                               // [16] accumulated transformation
   double* s_misc = s_T + 16;                            // [0] prev fitness [1] prev rmse [2] done [3] apply
+  double* s_A = s_misc + 8;                             // [36 + 6] the 6x6 system of the solve
   GridHeader* s_g = reinterpret_cast<GridHeader*>(smem_raw + icp_fixed_smem_doubles(THREADS) * 8);
   int* s_qn = reinterpret_cast<int*>(s_g + 1);          // phase-2 queue length (16 bytes reserved)
   unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_qn + 4);   // mbarrier of the bulk-async staging (16 bytes reserved)
@@ -1038,17 +1031,19 @@ __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_
         if (c > 0.0 && p2p) {
           umeyama_from_moments(s_tot, Upd);
         } else if (c > 0.0) {
-          double A[6][6], b[6], x[6];
+          double x[6];
           {
             int k = 0;
 #pragma unroll
             for (int a = 0; a < 6; a++)
 #pragma unroll
-              for (int bb = a; bb < 6; bb++) { A[a][bb] = s_tot[k]; A[bb][a] = s_tot[k]; k++; }
+              for (int bb = a; bb < 6; bb++) { s_A[6 * a + bb] = s_tot[k]; s_A[6 * bb + a] = s_tot[k]; k++; }
           }
 #pragma unroll
-          for (int a = 0; a < 6; a++) b[a] = -s_tot[21 + a];
-          ldlt6_solve_reg(A, b, x);
+          for (int a = 0; a < 6; a++) s_A[36 + a] = -s_tot[21 + a];
+          ldlt6_solve_smem(s_A, s_A + 36);
+#pragma unroll
+          for (int a = 0; a < 6; a++) x[a] = s_A[36 + a];
           vec6_to_mat4_dev(x, Upd);
         } else {  // [O3D] ComputeTransformation: corres.empty() -> Identity
 #pragma unroll

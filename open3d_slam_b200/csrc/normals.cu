@@ -612,12 +612,15 @@ __device__ __forceinline__ void warp_sum9_transposed(double (&v)[9], int lane) {
 // gathered candidates go through a per-warp shared-memory buffer, which lets the block radius R grow (1, 2, 3 cells)
 // until the k-th neighbour provably lies inside the block: dense areas finish at R = 1, sparse far-range areas at
 // R = 2 or 3, and only what is still unresolved (or holds more than NS2_CAP candidates) goes to normals_phase2_kernel.
+#ifndef B2S_NS2_MINBLOCKS
+#define B2S_NS2_MINBLOCKS 8   // resident CTAs per SM the select kernel is compiled for (8 -> 64 registers; A/B knob of the build)
+#endif
 constexpr int NS2_CAP = 256;
 constexpr int NS2_CHUNKS = NS2_CAP / 32;
 constexpr int NS2_RMAX = 3;
 constexpr int NS2_ROWS = 320;   // row-table entries per warp: (2 R + 1)^2 rows of the largest block, rounded up to 32 (R = 8 -> 289)
 
-__global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
+__global__ void __launch_bounds__(NK_THREADS, B2S_NS2_MINBLOCKS) normals_select2_kernel(const GridHeader* __restrict__ hdr, const int32_t* __restrict__ cs,
                                                                      const double4* __restrict__ pts, int knn, double radius,
                                                                      const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
                                                                      int32_t* __restrict__ queue, int32_t* queue_n,
@@ -734,13 +737,15 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
       // nc is uniform over the warp, so is the number of 32-candidate chunks in use: every chunk loop below stops there
       // (the loops stay fully unrolled -- the register arrays need static indices -- but the unused tail is branched over)
       const int nch = (nc + 31) >> 5;
-      double d[NS2_CHUNKS]; int idx[NS2_CHUNKS], sl[NS2_CHUNKS];
+      // only the keys live in registers; a candidate's slot stays in the shared buffer until the cumulants need it, and its
+      // histogram bin is recomputed where it is used (one multiply) -- registers, i.e. resident warps, are what this kernel is short of
+      double d[NS2_CHUNKS]; int idx[NS2_CHUNKS];
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
         if (c >= nch) break;
         const int t = c * 32 + lane;
-        d[c] = INFINITY; idx[c] = 0x7fffffff; sl[c] = -1;
-        if (t < nc) { d[c] = s_d[wib][t]; idx[c] = s_i[wib][t]; sl[c] = s_s[wib][t]; }
+        d[c] = INFINITY; idx[c] = 0x7fffffff;
+        if (t < nc) { d[c] = s_d[wib][t]; idx[c] = s_i[wib][t]; }
       }
       __syncwarp();
       need = min(knn, nc);
@@ -750,12 +755,10 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
         const double scale = lim2 > 0.0 ? 32.0 / lim2 : 0.0;
         s_hist[wib][lane] = 0;
         __syncwarp();
-        int bin[NS2_CHUNKS];
 #pragma unroll
         for (int c = 0; c < NS2_CHUNKS; c++) {
           if (c >= nch) break;
-          bin[c] = 32;
-          if (sl[c] >= 0) { bin[c] = min(31, (int)(d[c] * scale)); atomicAdd(&s_hist[wib][bin[c]], 1); }
+          if (c * 32 + lane < nc) atomicAdd(&s_hist[wib][min(31, (int)(d[c] * scale))], 1);
         }
         __syncwarp();
         int cumh = s_hist[wib][lane];
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
 #pragma unroll
         for (int c = 0; c < NS2_CHUNKS; c++) {
           if (c >= nch) break;
-          const bool in_bin = bin[c] == B;
+          const bool in_bin = c * 32 + lane < nc && min(31, (int)(d[c] * scale)) == B;
           const unsigned bm = __ballot_sync(0xffffffffu, in_bin);
           if (in_bin) { const int pos = nb + __popc(bm & lt_mask); s_d[wib][pos] = d[c]; s_i[wib][pos] = idx[c]; }
           nb += __popc(bm);
@@ -787,12 +790,8 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
           if (hit) { const int src = __ffs(hit) - 1; td = __shfl_sync(0xffffffffu, md, src); ti = __shfl_sync(0xffffffffu, mi, src); break; }
         }
         __syncwarp();   // the buffer is written again by the next block radius
-#pragma unroll
-        for (int c = 0; c < NS2_CHUNKS; c++) {
-          if (c >= nch) break;
-          if (bin[c] > B || (bin[c] == B && (d[c] > td || (d[c] == td && idx[c] > ti)))) sl[c] = -1;
-        }
       }
+      // (td, ti) = the k-th smallest key (inf when there are at most k candidates): the selected set is every key up to it
       // ---- exact?  every candidate kept lies strictly inside the guaranteed ball (radius sqrt(lim2) <= distance to the
       // nearest block face), so k kept candidates contain the true k nearest; fewer than k is final only when the
       // block covers the whole search radius ----
@@ -801,8 +800,9 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select2_kernel(const GridH
 #pragma unroll
       for (int c = 0; c < NS2_CHUNKS; c++) {
         if (c >= nch) break;
-        if (sl[c] >= 0) {
-          const double4 p = pts[sl[c]];
+        const int t = c * 32 + lane;
+        if (t < nc && (d[c] < td || (d[c] == td && idx[c] <= ti))) {
+          const double4 p = pts[s_s[wib][t]];
           c9[0] += p.x; c9[1] += p.y; c9[2] += p.z;
           c9[3] += p.x * p.x; c9[4] += p.x * p.y; c9[5] += p.x * p.z;
           c9[6] += p.y * p.y; c9[7] += p.y * p.z; c9[8] += p.z * p.z;

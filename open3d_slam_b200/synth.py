@@ -82,7 +82,8 @@ def lidar_scan(scene: Scene, pose: np.ndarray, n_beams=64, n_az=1024, max_range=
     with np.errstate(divide="ignore", invalid="ignore"):
         t = (scene.ground_z - o[2]) / d[:, 2]
     t = np.where((t > 0) & np.isfinite(t), t, np.inf)
-    hx = o[0] + t * d[:, 0]; hy = o[1] + t * d[:, 1]
+    with np.errstate(invalid="ignore"):   # inf * 0 for rays parallel to the plane: those rows are rejected below
+        hx = o[0] + t * d[:, 0]; hy = o[1] + t * d[:, 1]
     okg = (np.abs(hx) <= scene.half_x) & (np.abs(hy) <= scene.half_y)
     t_best = np.minimum(t_best, np.where(okg, t, np.inf))
     # walls
@@ -92,7 +93,8 @@ def lidar_scan(scene: Scene, pose: np.ndarray, n_beams=64, n_az=1024, max_range=
             t = (val - o[axis]) / d[:, axis]
         t = np.where((t > 0) & np.isfinite(t), t, np.inf)
         oth = 1 - axis
-        ho = o[oth] + t * d[:, oth]; hz = o[2] + t * d[:, 2]
+        with np.errstate(invalid="ignore"):
+            ho = o[oth] + t * d[:, oth]; hz = o[2] + t * d[:, 2]
         ok = (np.abs(ho) <= other_half) & (hz >= scene.ground_z) & (hz <= scene.ground_z + scene.wall_h)
         t_best = np.minimum(t_best, np.where(ok, t, np.inf))
     # cylinders (infinite in z, clipped to wall height)

@@ -1,6 +1,7 @@
 """Summaries of ncu outputs for profiles/ (run here on the CPU box; ncu reads the reports without a GPU).
   python tools/summarize_ncu.py launches <launches.csv> <out.md> [title]
-  python tools/summarize_ncu.py report <file.ncu-rep> <out.md> [title]"""
+  python tools/summarize_ncu.py report <file.ncu-rep> <out.md> [title]
+  python tools/summarize_ncu.py table <file.ncu-rep | raw.csv> <out.md> [title]     one row per launch, the columns the round's analysis uses"""
 import collections
 import csv
 import subprocess
@@ -49,7 +50,49 @@ def report(path, out, title):
                     f.write(f"| `{h}` | {v} |\n")
 
 
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except Exception:  # noqa: BLE001
+        return float("nan")
+
+
+def table(path, out, title):
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader([l for l in raw.splitlines() if not l.startswith("==")]))
+    hdr, units = rows[0], rows[1]
+    unit = dict(zip(hdr, units))
+    stall_cols = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+    tot_dur = tot_sm = 0.0
+    lines = []
+    for vals in rows[2:]:
+        d = dict(zip(hdr, vals))
+        dur = _num(d["gpu__time_duration.sum"]) * (1e-3 if unit.get("gpu__time_duration.sum") == "ns" else 1.0)
+        dr, dw = _num(d.get("dram__bytes_read.sum", "nan")), _num(d.get("dram__bytes_write.sum", "nan"))
+        scale = {"byte": 1e-3, "Kbyte": 1.0, "Mbyte": 1e3, "Gbyte": 1e6}
+        dr *= scale.get(unit.get("dram__bytes_read.sum"), 1.0); dw *= scale.get(unit.get("dram__bytes_write.sum"), 1.0)
+        st = sorted(((_num(d[c]), c[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for c in stall_cols if d.get(c)), reverse=True)
+        sm_act = _num(d.get("sm__cycles_active.sum", "nan"))
+        tot_dur += dur; tot_sm += sm_act if sm_act == sm_act else 0.0
+        lines.append("| `%s` | %s | %s | %s | %.1f | %.0f | %.1f | %.1f | %.0f | %.0f | %.0f | %.0f | %s |" % (
+            d["Kernel Name"].split("(")[0][-44:], d.get("launch__grid_size", "?"), d.get("launch__block_size", "?"), d.get("launch__registers_per_thread", "?"),
+            dur, _num(d["smsp__inst_executed.sum"]) / 1e3, _num(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+            _num(d["smsp__thread_inst_executed_per_inst_executed.ratio"]), sm_act / 1e3, dr + dw, _num(d.get("l1tex__t_sector_hit_rate.pct", "nan")),
+            _num(d.get("lts__t_sector_hit_rate.pct", "nan")), ", ".join("%s %.1f" % (n, v) for v, n in st[:2])))
+    with open(out, "w") as f:
+        f.write(f"# {title}\n\nSource: `ncu --set full --clock-control none`, one row per launch in launch order (times are cold-cache and serialised).  "
+                "inst = warp instructions executed (thousands); issue = `smsp__issue_active` % of peak; thr/inst = active threads per warp instruction; "
+                "SM-act = `sm__cycles_active.sum` (thousand cycles summed over the SMs: what the launch costs a GPU shared with other chains); "
+                "DRAM = bytes read + written (KB); stalls = the two largest `warps_issue_stalled_*_per_issue_active` ratios.\n\n"
+                "| kernel | grid | block | regs | µs | inst k | issue % | thr/inst | SM-act k | DRAM KB | L1 hit % | L2 hit % | top stalls |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|\n")
+        f.write("\n".join(lines))
+        f.write(f"\n\ntotal {tot_dur:.1f} µs, {tot_sm / 1e3:.0f} k SM-active cycles over {len(lines)} launches\n")
+
+
 if __name__ == "__main__":
     mode, path, out = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else path
-    (launches if mode == "launches" else report)(path, out, title)
+    {"launches": launches, "report": report, "table": table}[mode](path, out, title)
