@@ -900,8 +900,12 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
   // exact instantiations for the knn values the reference's presets use (Lua default 20, C++ struct default 5,
   // place-recognition normals 10); any other knn <= 32 takes the generic variants
   if (ring_limit == -1) {   // default: gather + select (one warp per query), stragglers to the general warp kernel
+    // one warp per query, grid-stride (B2S_NS2_GRID: A/B knob of the grid size)
+    static const int ns2_grid_env = getenv("B2S_NS2_GRID") ? atoi(getenv("B2S_NS2_GRID")) : 0;
+    // measured at 16 chains / 1 chain: 2368 CTAs 10.21 k/s, 0.600 ms; 592: 10.28 k/s, 0.619 ms; 296: 10.41 k/s, 0.640 ms -> the large grid stays
+    const int ns2_cap = ns2_grid_env > 0 ? ns2_grid_env : 148 * 16;
     int wblocks = (int)((n_max + (NK_THREADS / 32) - 1) / (NK_THREADS / 32));
-    if (wblocks > 148 * 16) wblocks = 148 * 16;
+    if (wblocks > ns2_cap) wblocks = ns2_cap;
     if (wblocks < 1) wblocks = 1;
     B2S_TRY(h->tmp_f64.ensure((n_max + 1) * 80, h->stream));
     double* cum = h->tmp_f64.as<double>();

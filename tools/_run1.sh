@@ -1,4 +1,5 @@
 set -x
-md5sum open3d_slam_b200/*.so > gpurun_out/r2l_md5.txt
-python -m pytest tests -q -m gpu 2>&1 | tail -5 > gpurun_out/r2l_tests.log
-python bench.py --no-extras --no-cpu-baseline --sweep 1 > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err
+for g in 2368 592 1184 296 592 2368; do
+B2S_NS2_GRID=$g python bench.py --no-extras --no-cpu-baseline --sweep 1 > gpurun_out/r2m_bench_$g.json 2> gpurun_out/r2m_bench_$g.err
+cp gpurun_out/r2m_bench_$g.json gpurun_out/r2m_bench_${g}_$RANDOM.json
+done
