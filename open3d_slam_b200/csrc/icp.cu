@@ -7,24 +7,27 @@
 // (the headline path carries no code of the others), 1 point-to-point + information matrix, 2 generalized ICP.
 //
 // Mapping to the machine:
-//   * one thread-block CLUSTER (1..8 CTAs, one per SM) per registration, blockIdx.y = registration in the batch;
-//   * the working copy of the source cloud lives in shared memory for the whole loop (each CTA owns a contiguous
-//     chunk) and is advanced by the per-iteration update like [O3D] pcd.Transform(update);
-//   * exact nearest neighbour with the strict d2 < r2 cut through the dense grid of grid_index.cu, in two phases:
-//       phase 1, one thread per point: BOX QUERY -- the cells overlapping [q - d, q + d], one contiguous slot range per
-//                (y, z) row, with d = distance to the previous evaluation's neighbour (kept per point in shared
-//                memory); without a neighbour to start from (first evaluation) a half-cell box, then a one-cell box;
-//       phase 2, one WARP per unresolved point (outliers / empty neighbourhoods, queued in shared memory): the rows
-//                of the box around the search sphere are spread over the 32 lanes, then a warp lexicographic-min;
-//                the queues of all CTAs are drained by all warps of the cluster through distributed shared memory.
+//   * one thread-block CLUSTER (1..8 CTAs, one per SM; 16 on request) per registration, blockIdx.y = registration in the batch;
+//   * the working copy of the source cloud lives in shared memory for the whole loop and is advanced by the per-iteration update
+//     like [O3D] pcd.Transform(update); the cloud is dealt out in tiles of 64 points, tile t to CTA t % cluster size, every full
+//     tile staged by one bulk-async copy (cp.async.bulk + mbarrier);
+//   * exact nearest neighbour with the strict d2 < r2 cut through the dense grid of grid_index.cu.  Per evaluation:
+//       sweep A, every point: apply the update; CERTIFICATES decide whether the previous answer provably still stands (one distance
+//                evaluation instead of a search); the points that need a search are compacted into a list;
+//       sweep B, one thread per listed point: BOX QUERY -- the cells overlapping [q - d, q + d], one contiguous slot range per
+//                (y, z) row, with d = distance to the previous evaluation's neighbour; without a neighbour to start from (first
+//                evaluation) a half-cell box, then a one-cell box; four rows / four candidates in flight per thread;
+//       phase 2, one WARP per unresolved point (outliers / empty neighbourhoods, queued in shared memory): the rows of the box
+//                around the search sphere are spread over the 32 lanes, then a warp lexicographic-min; the queues of all CTAs
+//                are drained by all warps of the cluster through distributed shared memory.
 //     Ties -> lower target index.  Gathers hit the L2-resident target.
-//   * per-thread fp64 accumulation of 29 sums (plane / GICP: 21 JtJ + 6 Jtr; point-to-point: means + cross moments;
-//     information: target moments; + sum d2 + count), warp-shuffle tree, CTA tree, then a DSMEM exchange: every CTA
-//     reads all cluster partials in rank order and redundantly computes the update (6x6 LDLT with diagonal pivoting,
-//     fully unrolled into registers; or umeyama with a one-thread Jacobi SVD), so one cluster barrier per iteration
-//     is enough and no host round trip ever happens;
-//   * all arithmetic fp64; distances and the point transform use explicitly rounded ops (no FMA contraction) so
-//     that correspondences are bit-identical to the CPU oracle.
+//   * the 29 sums (plane / GICP: 21 JtJ + 6 Jtr; point-to-point: means + cross moments; information: target moments; + sum d2 +
+//     count) are never per-thread state: each warp reduces the terms of 32 points at once (transposed butterfly, lane k ends up
+//     with term k) into its row of a shared-memory accumulator; rows -> CTA partial -> DSMEM exchange: every CTA reads all cluster
+//     partials in rank order and redundantly computes the update (6x6 LDLT with diagonal pivoting, or umeyama with a one-thread
+//     Jacobi SVD), so no host round trip ever happens;
+//   * all arithmetic fp64; distances and the point transform use explicitly rounded ops (no FMA contraction) so that
+//     correspondences are bit-identical to the CPU oracle.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -35,10 +38,10 @@ namespace b2s {
 
 constexpr int NACC = 29;  // 21 upper-triangular JtJ + 6 Jtr + sum d2 + count
 // threads per CTA by instantiation: the point-to-plane / point-to-point / information kernels keep NO per-thread accumulators
-// (every contribution is warp-reduced at once into a per-warp accumulator in shared memory), fit 64 registers and run 1024
-// threads = 32 warps per SM; the generalized-ICP kernel carries 3x3 covariance algebra per correspondence and stays at 512
+// (every contribution is warp-reduced at once into a per-warp accumulator in shared memory) and run 768 threads = 24 warps per SM
+// at 80 registers; the generalized-ICP kernel carries 3x3 covariance algebra per correspondence and stays at 512 threads
 #ifndef B2S_ICP_PLANE_THREADS
-#define B2S_ICP_PLANE_THREADS 768   // threads per CTA of the point-to-plane / point-to-point instantiations (80 registers); measured on B200: 768 beats 512 and 1024 on latency and throughput (make alt ALT_THREADS=... builds libb2s_alt<N>.so for A/B runs)
+#define B2S_ICP_PLANE_THREADS 768   // measured on B200: 768 beats 512 and 1024 on latency and throughput (make alt ALT_THREADS=... builds libb2s_alt<N>.so for A/B runs)
 #endif
 constexpr int icp_threads(int mode) { return mode == 2 ? 512 : B2S_ICP_PLANE_THREADS; }
 constexpr int ICP_TILE = 64;   // points per tile of the source cloud (tile t belongs to CTA t % cluster size)

@@ -2,14 +2,17 @@
 // (core/src/CloudRegistration.cpp:49-56) = [O3D] EstimateNormals(KDTreeSearchParamHybrid(radius, knn)) +
 // NormalizeNormals + OrientNormalsTowardsCameraLocation(0,0,0).
 //
-// One WARP per query point.  The warp walks the dense grid (grid_index.cu) ring by ring; each 32-candidate chunk of a
-// cell row is one coalesced 128-bit load per lane; the current k best (k <= 32) are kept as a sorted list with ONE
-// entry per lane, and a qualifying candidate is inserted with a single shuffle-up step.  Search stops as soon as the
-// k-th distance is below the distance to the unvisited shell (exact k-NN), or the shell is beyond the radius.
-// The covariance is then accumulated in the neighbour order the reference uses (ascending distance, nanoflann's
-// result order) with the reference's single-pass cumulant formula in explicitly rounded fp64, the neighbour
-// coordinates being broadcast across the warp by shuffles; lane 0 runs the analytic 3x3 eigen-solver
-// ([O3D] FastEigen3x3, geometrictools RobustEigenSymmetric3x3) and writes the oriented unit normal.
+// One WARP per query point, three kernels (default path):
+//   normals_select2_kernel  gathers the (2R+1)^3 block of grid cells (grid_index.cu) around the query into a per-warp shared-memory
+//                           buffer, R grown until the k-th neighbour provably lies inside the block (ball-within-bounds, like a
+//                           KD-tree), selects the k nearest by counting (32-bin histogram of d2 + exact ranking of the boundary
+//                           bin; ties -> lower index) and sums the nine cumulants with a transposed warp butterfly;
+//   normals_finish_kernel   one thread per query: analytic 3x3 eigen-solver ([O3D] FastEigen3x3, geometrictools
+//                           RobustEigenSymmetric3x3), normalise, orient;
+//   normals_phase2_kernel   the few queries the block gather cannot certify (more than NS2_CAP candidates, or a search radius the
+//                           row table cannot cover): ring walk with a sorted k-best list, one entry per lane, shuffle insert.
+// The neighbour SET is the oracle's exactly; the cumulants are summed in butterfly order instead of ascending-distance order, which
+// moves the normal by < 1e-9.  A thread-per-query variant (normals_kernel<K>) is kept behind B2S_NORMALS_RING_LIMIT for comparison.
 #include "common.cuh"
 
 namespace b2s {

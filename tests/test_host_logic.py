@@ -75,6 +75,17 @@ def test_bench_reference_arm_smoke():
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
         assert k in line
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    # both arms describe the workload with the SAME function of the SAME flags (the driver compares the two `config` objects)
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": make_config(args)') == 2          # one per arm, nothing arm-specific inside
+    ns = argparse.Namespace(chains=2, scans_per_step=64, ratio=0.3)
+    cfg = bench.make_config(ns)
+    assert cfg == line["config"] or {k: v for k, v in cfg.items() if k != "chains_per_gpu"} == {k: v for k, v in line["config"].items() if k != "chains_per_gpu"}
+    assert set(cfg) == set(line["config"])
 
 
 def test_reference_side_shim_type_checks():
