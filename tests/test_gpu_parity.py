@@ -38,6 +38,31 @@ def lua_params(**kw):
     return p
 
 
+def test_icp_sixteen_sm_clusters_give_the_same_registration(engine_factory):
+    """b2s_config.icp_cluster_ctas = 16 (latency mode: one registration over 16 SMs, non-portable cluster size) must change nothing but
+    the summation order: same iterations / correspondences, T to 1e-10 of the default 8-SM clusters, on a scan-sized source."""
+    sc = synth.Scene(); poses = synth.loop_trajectory(8)
+    results = []
+    for ctas in (0, 16, 4):
+        p = lua_params()
+        p.icpClusterCtas = ctas
+        eng = engine_factory(p)
+        icp = E.ScanToMapIcp(eng)
+        sm = E.Submap(eng, 400_000)
+        for k in range(3):
+            ps = icp.processForScanMatchingAndMerging(eng.cloud(synth.lidar_scan(sc, poses[k], seed=k)))
+            sm.insertScan(None, ps.merge_, np.linalg.inv(poses[0]) @ poses[k])
+        ps = icp.processForScanMatchingAndMerging(eng.cloud(synth.lidar_scan(sc, poses[3], seed=3)))
+        assert len(ps.match_) > 8 * 768                      # enough points for the launch to pick the largest cluster allowed
+        guess = np.linalg.inv(poses[0]) @ poses[3] @ synth.se3(0.004, -0.003, 0.01, (0.03, -0.02, 0.01))
+        results.append(icp.scanToMapRegistration(ps.match_, sm, np.linalg.inv(poses[0]) @ poses[2], guess))
+    a = results[0]
+    for b in results[1:]:
+        assert a.iters == b.iters and a.n_corr == b.n_corr and abs(a.fitness_ - b.fitness_) < 1e-14
+        assert np.abs(a.transformation_ - b.transformation_).max() < 1e-10
+    assert a.fitness_ > 0.9
+
+
 def test_icp_source_larger_than_shared_memory(engine_factory):
     """A source cloud too large for the cluster's shared memory (8 CTAs x ~4.9 k points) takes the kernel's other path: working copy
     and per-point state in global memory, no phase-2 queue, no certificates.  Same answers as the oracle."""
