@@ -20,21 +20,26 @@ int32_t dense_init(b2s_handle* h, b2s_submap* sm, size_t cap, double voxel);
 int32_t dense_to_cloud(b2s_handle* h, b2s_submap* sm, double* d_xyz, int32_t* d_keys, int32_t* d_out_n);
 
 __global__ void f32_to_f64_kernel(const unsigned char* __restrict__ src, size_t stride, int n, double* __restrict__ dst) {
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
     dst[3 * i] = (double)p[0]; dst[3 * i + 1] = (double)p[1]; dst[3 * i + 2] = (double)p[2];
   }
 }
 
-__global__ void write_i32_kernel(int32_t* p, int32_t v) { *p = v; }
-__global__ void pad_kernel() {}   // B2S_PAD_LAUNCHES=n: n empty launches per scan, to measure what a launch costs the chain (tuning aid)
+__global__ void write_i32_kernel(int32_t* p, int32_t v) {
+  pdl_wait(); *p = v; }
+__global__ void pad_kernel() {
+  pdl_wait();}   // B2S_PAD_LAUNCHES=n: n empty launches per scan, to measure what a launch costs the chain (tuning aid)
 
 __global__ void empty_check_kernel(const int32_t* a, const int32_t* b, uint32_t* status) {
+  pdl_wait();
   if (*a <= 0 || *b <= 0) atomicOr(status, ST_EMPTY);
 }
 
 // guess = pose * odom ; (row-major 4x4)
 __global__ void compose_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
+  pdl_wait();
   const int i = threadIdx.x >> 2, j = threadIdx.x & 3;
   if (threadIdx.x < 16) {
     double s = 0.0;
@@ -55,6 +60,7 @@ struct GateArgs {
 };
 __global__ void mapper_gate_kernel(const b2s_result* __restrict__ res, GateArgs a, double* pose, int32_t* ms, const int32_t* __restrict__ map_n,
                                    b2s_result* slots, const int32_t* __restrict__ gstate) {
+  pdl_wait();
   if (threadIdx.x != 0) return;
   const bool accepted = a.ignore_fitness || !(res->fitness < a.min_fitness);
   if (accepted) for (int i = 0; i < 16; i++) pose[i] = res->T[i];
@@ -78,6 +84,7 @@ __global__ void mapper_gate_kernel(const b2s_result* __restrict__ res, GateArgs 
 }
 // end of a step that fed the dense map: ++nScansInsertedDenseMap_ (Submap.cpp:90)
 __global__ void mapper_post_kernel(int32_t* ms) {
+  pdl_wait();
   if (threadIdx.x == 0 && ms[MS_DENSE]) ms[MS_NDENSE] += 1;
 }
 
@@ -146,10 +153,10 @@ static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud*
   b2s_cropper c1 = sp.scan_matcher_cropper;
   c1.center[0] = c1.center[1] = c1.center[2] = 0.0;   // ScanToMapRegistration.cpp:47 setPose(Identity)
   B2S_TRY(op_crop(h, merge, make_crop(&c1), match));
-  empty_check_kernel<<<1, 1, 0, h->stream>>>(merge->dn.as<int32_t>(), match->dn.as<int32_t>(), h->status.as<uint32_t>());
+  launch_pdl(empty_check_kernel, 1, 1, 0, h->stream, merge->dn.as<int32_t>(), match->dn.as<int32_t>(), h->status.as<uint32_t>());
   h->launches++;
   static const int pad = getenv("B2S_PAD_LAUNCHES") ? atoi(getenv("B2S_PAD_LAUNCHES")) : 0;
-  for (int i = 0; i < pad; i++) pad_kernel<<<1, 32, 0, h->stream>>>();
+  for (int i = 0; i < pad; i++) launch_pdl(pad_kernel, 1, 32, 0, h->stream);
   return B2S_OK;
 }
 
@@ -157,6 +164,7 @@ static int32_t process_scan_impl(b2s_handle* h, const b2s_cloud* raw, b2s_cloud*
 // first node of the chain: takes the step number from a device counter, fetches that step's odometry motion from the
 // host-written ring (pinned, device-mapped) and publishes the result slot of this step
 __global__ void graph_begin_kernel(const double* __restrict__ ring, int32_t* gstate, double* __restrict__ odom) {
+  pdl_wait();
   const int step = gstate[0];
   if (threadIdx.x < 16) odom[threadIdx.x] = ring[(step & 63) * 16 + threadIdx.x];
   __syncthreads();
@@ -172,7 +180,7 @@ static int32_t mapper_chain_tail(b2s_handle* h, b2s_submap* sm, const b2s_cloud*
   GateArgs ga;
   ga.min_fitness = min_fitness; ga.min_move = o.min_movement_between_mapping_steps; ga.ignore_fitness = ignore_fitness;
   ga.carve_on = o.carve_enabled; ga.carve_n = o.carve_every_n_scans; ga.dense_on = o.dense_enabled; ga.dcarve_n = o.dense_carve_every_n_scans; ga.pad = 0;
-  mapper_gate_kernel<<<1, 32, 0, h->stream>>>(res, ga, pose_state, ms, sm->cloud[0]->dn.as<int32_t>(), slots, gstate);
+  launch_pdl(mapper_gate_kernel, 1, 32, 0, h->stream, res, ga, pose_state, ms, sm->cloud[0]->dn.as<int32_t>(), slots, gstate);
   h->launches++;
   if (o.carve_enabled) {   // Submap::insertScan: carve BEFORE the scan is appended, cropper still at the pose of the last insertion
     B2S_REQUIRE(o.carving.voxel_size > 0.0, B2S_E_INVALID, "carving voxel size must be > 0");
@@ -189,7 +197,7 @@ static int32_t mapper_chain_tail(b2s_handle* h, b2s_submap* sm, const b2s_cloud*
     if (o.dense_carve_every_n_scans > 0)
       B2S_TRY(op_dense_carve(h, sm, raw_scan, nullptr, pose_state, o.dense_carving.neighborhood_radius_dense_map, o.dense_carving.truncation_distance,
                              o.dense_carving.max_raytracing_length, ms + MS_TMP + 1, ms + MS_DCARVE));
-    mapper_post_kernel<<<1, 32, 0, h->stream>>>(ms);
+    launch_pdl(mapper_post_kernel, 1, 32, 0, h->stream, ms);
     h->launches++;
   }
   return B2S_OK;
@@ -203,10 +211,10 @@ static int32_t mapper_chain_graphable(b2s_handle* h, b2s_submap* sm) {
   b2s_result* res = h->results.as<b2s_result>();
   double* ring_dev = nullptr;
   B2S_CUDA(cudaHostGetDevicePointer(&ring_dev, sm->odom_ring, 0));
-  graph_begin_kernel<<<1, 32, 0, h->stream>>>(ring_dev, gstate, odom);
+  launch_pdl(graph_begin_kernel, 1, 32, 0, h->stream, ring_dev, gstate, odom);
   h->launches++;
   B2S_TRY(process_scan_impl(h, sm->staging, h->t1, h->t2));
-  compose_kernel<<<1, 32, 0, h->stream>>>(pose_state, odom, guess);
+  launch_pdl(compose_kernel, 1, 32, 0, h->stream, pose_state, odom, guess);
   h->launches++;
   B2S_TRY(::register_to_submap_async(h, h->t2, sm, nullptr, pose_state, nullptr, guess, res));
   return mapper_chain_tail(h, sm, sm->staging, h->t1, res, sm->g_min_fitness, sm->g_ignore_fitness, h->slots.as<b2s_result>(), gstate);
@@ -442,7 +450,7 @@ int32_t b2s_cloud_upload_f32(b2s_handle* h, b2s_cloud* c, const void* xyz, size_
   B2S_TRY(h->tmp_f64.ensure(n * stride_bytes + 16, h->stream));
   if (n) {
     B2S_CUDA(cudaMemcpyAsync(h->tmp_f64.p, xyz, n * stride_bytes, cudaMemcpyHostToDevice, h->stream));
-    f32_to_f64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->tmp_f64.as<unsigned char>(), stride_bytes, (int)n, c->xyz.as<double>());
+    launch_pdl(f32_to_f64_kernel, grid_for(n, 256), 256, 0, h->stream, h->tmp_f64.as<unsigned char>(), stride_bytes, (int)n, c->xyz.as<double>());
     h->launches++;
   }
   c->has_normals = false;
@@ -737,7 +745,7 @@ int32_t b2s_nearest_neighbors(b2s_handle* h, const b2s_cloud* queries, const b2s
   int32_t* d_cnt = reinterpret_cast<int32_t*>(h->status.as<uint32_t>() + 14);
   for (size_t off = 0; off < n; off += CHUNK) {
     const size_t cnt = n - off < CHUNK ? n - off : CHUNK;
-    write_i32_kernel<<<1, 1, 0, h->stream>>>(d_cnt, (int32_t)cnt);
+    launch_pdl(write_i32_kernel, 1, 1, 0, h->stream, d_cnt, (int32_t)cnt);
     h->launches++;
     IcpProblem P;
     fill_problem(h, &P, queries, &h->grid_a, T ? T : I, nullptr, h->work_xyz.as<double>(), h->results.as<b2s_result>());
@@ -995,7 +1003,7 @@ int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* ra
   b2s_result* res = h->slots.as<b2s_result>() + slot;
   B2S_TRY(process_scan_impl(h, raw_scan, h->t1, h->t2));                      // Mapper.cpp:139
   B2S_TRY(pose_to_device(h, odometry_motion, odom));
-  compose_kernel<<<1, 32, 0, h->stream>>>(pose_state, odom, guess);           // Mapper.cpp:130-137
+  launch_pdl(compose_kernel, 1, 32, 0, h->stream, pose_state, odom, guess);           // Mapper.cpp:130-137
   h->launches++;
   B2S_TRY(register_to_submap_async(h, h->t2, sm, nullptr, pose_state, nullptr, guess, res));  // Mapper.cpp:140-141
   return mapper_chain_tail(h, sm, raw_scan, h->t1, res, min_refinement_fitness, ignore_min_fitness, nullptr, nullptr);   // Mapper.cpp:151-177

@@ -38,6 +38,7 @@ __device__ __forceinline__ bool cv_key_of(double x, double y, double z, double i
 __global__ void __launch_bounds__(CV_THREADS) carve_init_kernel(unsigned long long* __restrict__ keys, int32_t* __restrict__ head, size_t cap,
                                                                 int32_t* __restrict__ keep, int n_max, const int32_t* __restrict__ enable,
                                                                 const int32_t* __restrict__ d_nmap, int32_t* n_eff) {
+  pdl_wait();
   const bool on = enable == nullptr || *enable != 0;
   if (n_eff && blockIdx.x == 0 && threadIdx.x == 0) *n_eff = on ? *d_nmap : 0;
   if (!on) return;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(CV_THREADS) carve_insert_kernel(const double* 
                                                                   double inv, unsigned long long* keys, int32_t* head,
                                                                   int32_t* __restrict__ next, size_t mask, uint32_t* status,
                                                                   const int32_t* __restrict__ enable, int32_t* __restrict__ keep) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(CV_THREADS) carve_march_kernel(const double* _
                                                                  const int32_t* __restrict__ next, size_t mask, double voxel, double inv,
                                                                  double max_len, double trunc, double min_dot, int32_t* keep,
                                                                  const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   const int n = *d_nscan;
   double T[16];
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(CV_THREADS) carve_commit_kernel(const double* 
                                                                   const int32_t* __restrict__ d_after, double* __restrict__ mxyz,
                                                                   double* __restrict__ mnrm, int32_t* d_nmap, int32_t* removed,
                                                                   const int32_t* __restrict__ enable, int32_t* mstate) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) { if (removed && blockIdx.x == 0 && threadIdx.x == 0) *removed = 0; return; }
   const int before = *d_nmap, n = *d_after;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n; i += gridDim.x * blockDim.x) { mxyz[i] = txyz[i]; if (mnrm) mnrm[i] = tnrm[i]; }
@@ -170,11 +174,11 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
   int32_t* n_eff = ms + MS_CARVE_N;
   const double inv = 1.0 / prm.voxel_size;   // fromVoxelSize (VoxelHashMap.hpp:43-45)
   ProfScope prof(h, PK_FUSE);
-  carve_init_kernel<<<grid_for(cap, CV_THREADS), CV_THREADS, 0, h->stream>>>(keys, head, cap, keep, (int)n_max, enable_dev, map->dn.as<int32_t>(),
+  launch_pdl(carve_init_kernel, grid_for(cap, CV_THREADS), CV_THREADS, 0, h->stream, keys, head, cap, keep, (int)n_max, enable_dev, map->dn.as<int32_t>(),
                                                                              n_eff);
-  carve_insert_kernel<<<grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(), crop, inv, keys,
+  launch_pdl(carve_insert_kernel, grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream, map->xyz.as<double>(), map->dn.as<int32_t>(), crop, inv, keys,
                                                                                 head, next, cap - 1, h->status.as<uint32_t>(), enable_dev, keep);
-  carve_march_kernel<<<grid_for(raw_scan->n_max > 0 ? raw_scan->n_max : 1, CV_THREADS), CV_THREADS, 0, h->stream>>>(
+  launch_pdl(carve_march_kernel, grid_for(raw_scan->n_max > 0 ? raw_scan->n_max : 1, CV_THREADS), CV_THREADS, 0, h->stream, 
       raw_scan->xyz.as<double>(), raw_scan->dn.as<int32_t>(), T_dev, map->has_normals ? map->nrm.as<double>() : nullptr, keys, head, next,
       cap - 1, prm.voxel_size, inv, prm.max_raytracing_length, prm.truncation_distance, prm.min_dot_product_with_normal, keep, enable_dev);
   h->launches += 3;
@@ -183,7 +187,7 @@ int32_t op_submap_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw_scan
   const int32_t rc = compact_cloud(h, map, keep, tmp, n_eff);   // order-preserving (removeByIds = SelectByIndex(invert))
   map->n_max = keep_n_max;
   B2S_TRY(rc);
-  carve_commit_kernel<<<grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream>>>(tmp->xyz.as<double>(), tmp->nrm.as<double>(),
+  launch_pdl(carve_commit_kernel, grid_for(n_max, CV_THREADS), CV_THREADS, 0, h->stream, tmp->xyz.as<double>(), tmp->nrm.as<double>(),
                                                                                tmp->dn.as<int32_t>(), map->xyz.as<double>(),
                                                                                map->has_normals ? map->nrm.as<double>() : nullptr,
                                                                                map->dn.as<int32_t>(), removed_dev, enable_dev, ms);

@@ -351,6 +351,24 @@ inline int grid_for(size_t n, int threads, int max_blocks = 0) {
   return (int)b;
 }
 
+bool pdl_enabled();   // runtime.cu: B2S_PDL=0 switches the attribute off (A/B)
+
+#ifdef __CUDACC__
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute (see pdl_wait)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);   // errors surface through cudaGetLastError / the next B2S_CUDA, like <<<>>>
+}
+#endif
+
 }  // namespace b2s
 
 // ------------------------------------------------------------------------------------------------
@@ -358,6 +376,12 @@ inline int grid_for(size_t n, int threads, int max_blocks = 0) {
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 namespace b2s {
+
+// Programmatic dependent launch: every kernel of the library starts with this wait and every launch carries the programmatic-stream-
+// serialization attribute, so a kernel's launch (scheduling, CTA distribution, its own prologue up to here) overlaps the tail of its
+// predecessor in the stream instead of starting after it -- a scan is a chain of 42 kernels of 3-50 us.  Past the wait the predecessor
+// grid has completed and its writes are visible, so nothing else changes.  Without the launch attribute the instruction is a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // order-preserving map double -> uint64 so that atomicMin/atomicMax work on doubles
 __host__ __device__ inline unsigned long long ord_encode(double v) {

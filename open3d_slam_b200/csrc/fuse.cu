@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_stage_kernel(const double* __
                                                                 int32_t* __restrict__ stage_next, int32_t* __restrict__ stage_in,
                                                                 unsigned long long* vkeys, int32_t* vhead, int32_t* vstamp, size_t vmask,
                                                                 int32_t* __restrict__ touched, int32_t* ms, uint32_t* status) {
+  pdl_wait();
   const int ns = *d_nscan;
   const bool open = (gate == nullptr || *gate != 0) && ns > 0;  // Submap.cpp:41-43: empty scan -> nothing happens
   if (!open) return;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(128) fuse_merge_kernel(const int32_t* __restri
                                                          FuseView v, int32_t* vhead, const int32_t* __restrict__ vstamp,
                                                          const int32_t* __restrict__ touched, int32_t* dups, int32_t* d_nmap, size_t capacity,
                                                          int32_t* ms, uint32_t* status) {
+  pdl_wait();
   if (!((gate == nullptr || *gate != 0) && *d_nscan > 0)) return;
   const int cur = ms[MS_STAMP] + 1;
   const int ntouched = ms[MS_NTOUCHED];
@@ -242,6 +244,7 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_renorm_commit_kernel(const in
                                                                         CropDev crop, const double* __restrict__ mxyz, double* __restrict__ mnrm,
                                                                         const int32_t* __restrict__ pstamp, const int32_t* __restrict__ d_nmap,
                                                                         int32_t* ms, double* last_pose, const double* __restrict__ Tdev) {
+  pdl_wait();
   if (!((gate == nullptr || *gate != 0) && *d_nscan > 0)) return;
   const int cur = ms[MS_STAMP] + 1;
   const int n = *d_nmap;
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_renorm_commit_kernel(const in
 // ---- (re)build of the voxel hash from the map cloud --------------------------------------------------------------------------
 __global__ void fuse_table_clear_kernel(unsigned long long* vkeys, int32_t* vhead, int32_t* vstamp, size_t vcap, int32_t* ms,
                                         const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vcap; i += (size_t)gridDim.x * blockDim.x) { vkeys[i] = FV_EMPTY; vhead[i] = -1; vstamp[i] = 0; }
   if (blockIdx.x == 0 && threadIdx.x == 0) { ms[MS_VUSED] = 0; ms[MS_NTOUCHED] = 0; ms[MS_NDUP] = 0; ms[MS_NDUP + 1] = 0; ms[MS_DUPSEL] = 0; ms[MS_STAMP] = 0; }
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_table_link_kernel(const doubl
                                                                      unsigned long long* vkeys, int32_t* vhead, size_t vmask, int32_t* __restrict__ vnext,
                                                                      int32_t* __restrict__ pstamp, int32_t* ms, uint32_t* status,
                                                                      const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   const int n = *d_nmap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -296,6 +301,7 @@ __global__ void __launch_bounds__(FZ_THREADS) fuse_table_link_kernel(const doubl
 __global__ void __launch_bounds__(FZ_THREADS) fuse_table_dups_kernel(const unsigned long long* __restrict__ vkeys, const int32_t* __restrict__ vhead,
                                                                      size_t vcap, const int32_t* __restrict__ vnext, int32_t* dups, int32_t* ms,
                                                                      uint32_t* status, const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < vcap; s += (size_t)gridDim.x * blockDim.x) {
     const int hd = vhead[s];
@@ -317,7 +323,7 @@ int32_t fuse_reserve(b2s_handle* h, b2s_submap* sm) {
   B2S_TRY(sm->pstamp.ensure((sm->capacity + 1) * 4, h->stream));
   B2S_TRY(sm->dups.ensure((size_t)2 * FUSE_DUP_CAP * 4, h->stream));
   sm->vcap = vcap;
-  fuse_table_clear_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), vcap,
+  launch_pdl(fuse_table_clear_kernel, 148 * 4, 256, 0, h->stream, sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), vcap,
                                                          sm->mstate.as<int32_t>(), nullptr);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
@@ -330,13 +336,13 @@ int32_t fuse_rehash(b2s_handle* h, b2s_submap* sm, const int32_t* enable_dev) {
   const size_t n_max = sm->graph_mode ? sm->capacity : (map->n_max > 0 ? map->n_max : 1);
   int32_t* ms = sm->mstate.as<int32_t>();
   ProfScope prof(h, PK_FUSE);
-  fuse_table_clear_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), sm->vcap,
+  launch_pdl(fuse_table_clear_kernel, 148 * 4, 256, 0, h->stream, sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), sm->vcap,
                                                          ms, enable_dev);
-  fuse_table_link_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(),
+  launch_pdl(fuse_table_link_kernel, grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream, map->xyz.as<double>(), map->dn.as<int32_t>(),
                                                                                    1.0 / h->cfg.map_voxel_size, sm->vkeys.as<unsigned long long>(),
                                                                                    sm->vhead.as<int32_t>(), sm->vcap - 1, sm->vnext.as<int32_t>(),
                                                                                    sm->pstamp.as<int32_t>(), ms, h->status.as<uint32_t>(), enable_dev);
-  fuse_table_dups_kernel<<<148 * 4, FZ_THREADS, 0, h->stream>>>(sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vcap,
+  launch_pdl(fuse_table_dups_kernel, 148 * 4, FZ_THREADS, 0, h->stream, sm->vkeys.as<unsigned long long>(), sm->vhead.as<int32_t>(), sm->vcap,
                                                                sm->vnext.as<int32_t>(), sm->dups.as<int32_t>(), ms, h->status.as<uint32_t>(), enable_dev);
   h->launches += 3;
   B2S_CUDA(cudaGetLastError());
@@ -345,6 +351,7 @@ int32_t fuse_rehash(b2s_handle* h, b2s_submap* sm, const int32_t* enable_dev) {
 
 // live points of the map, in map order, in sm->cloud[1] (readers that leave the device: download, size)
 __global__ void __launch_bounds__(FZ_THREADS) fuse_alive_flags_kernel(const double* __restrict__ mxyz, const int32_t* __restrict__ d_n, int32_t* __restrict__ flags) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { const double x = mxyz[3 * (size_t)i]; flags[i] = (x == x) ? 1 : 0; }
 }
@@ -353,7 +360,7 @@ int32_t submap_compact_view(b2s_handle* h, b2s_submap* sm, b2s_cloud** view) {
   b2s_cloud* map = sm->cloud[0];
   const size_t n_max = map->n_max > 0 ? map->n_max : 1;
   B2S_TRY(h->flags.ensure((n_max + 1) * 4, h->stream));
-  fuse_alive_flags_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(map->xyz.as<double>(), map->dn.as<int32_t>(), h->flags.as<int32_t>());
+  launch_pdl(fuse_alive_flags_kernel, grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream, map->xyz.as<double>(), map->dn.as<int32_t>(), h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(compact_cloud(h, map, h->flags.as<int32_t>(), sm->cloud[1]));
   *view = sm->cloud[1];
@@ -399,15 +406,15 @@ int32_t op_submap_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, c
               sm->stage_nrm.as<double>(), sm->stage_next.as<int32_t>(), sm->stage_in.as<int32_t>()};
   {
     ProfScope prof(h, PK_FUSE);
-    fuse_stage_kernel<<<grid_for(m_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+    launch_pdl(fuse_stage_kernel, grid_for(m_max, FZ_THREADS), FZ_THREADS, 0, h->stream, 
         scan->xyz.as<double>(), scan->has_normals ? scan->nrm.as<double>() : nullptr, scan->dn.as<int32_t>(), T_dev, gate_dev, crop, inv, sm->stage_cap,
         sm->stage_xyz.as<double>(),
         sm->stage_nrm.as<double>(), sm->stage_next.as<int32_t>(), sm->stage_in.as<int32_t>(), sm->vkeys.as<unsigned long long>(),
         sm->vhead.as<int32_t>(), sm->vstamp.as<int32_t>(), sm->vcap - 1, sm->touched.as<int32_t>(), ms, h->status.as<uint32_t>());
-    fuse_merge_kernel<<<grid_for(m_max + 4096, 128), 128, 0, h->stream>>>(gate_dev, scan->dn.as<int32_t>(), crop, fv, sm->vhead.as<int32_t>(),
+    launch_pdl(fuse_merge_kernel, grid_for(m_max + 4096, 128), 128, 0, h->stream, gate_dev, scan->dn.as<int32_t>(), crop, fv, sm->vhead.as<int32_t>(),
                                                                          sm->vstamp.as<int32_t>(), sm->touched.as<int32_t>(), sm->dups.as<int32_t>(),
                                                                          map->dn.as<int32_t>(), sm->capacity, ms, h->status.as<uint32_t>());
-    fuse_renorm_commit_kernel<<<grid_for(tot_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(gate_dev, scan->dn.as<int32_t>(), crop, map->xyz.as<double>(),
+    launch_pdl(fuse_renorm_commit_kernel, grid_for(tot_max, FZ_THREADS), FZ_THREADS, 0, h->stream, gate_dev, scan->dn.as<int32_t>(), crop, map->xyz.as<double>(),
                                                                                          map->nrm.as<double>(), sm->pstamp.as<int32_t>(),
                                                                                          map->dn.as<int32_t>(), ms, sm->pose.as<double>() + 5 * 16, T_dev);
     h->launches += 3;
@@ -476,6 +483,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dense_insert_kernel(const double* 
                                                                   unsigned long long* __restrict__ keys, double* __restrict__ sums,
                                                                   int32_t* __restrict__ cnts, size_t cap, int32_t* used, uint32_t* status,
                                                                   const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   double T[16];
@@ -499,6 +507,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dense_insert_kernel(const double* 
 }
 
 __global__ void dense_init_kernel(unsigned long long* keys, double* sums, int32_t* cnts, size_t cap, int32_t* used) {
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     keys[i] = DENSE_EMPTY; cnts[i] = 0;
     for (int k = 0; k < 6; k++) sums[6 * i + k] = 0.0;
@@ -512,7 +521,7 @@ int32_t dense_init(b2s_handle* h, b2s_submap* sm, size_t cap, double voxel) {
   B2S_TRY(sm->dense_cnt.ensure(cap * 4, h->stream));
   B2S_TRY(sm->dense_used.ensure(16, h->stream));
   sm->dense_cap = cap; sm->dense_voxel = voxel;
-  dense_init_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
+  launch_pdl(dense_init_kernel, 148 * 4, 256, 0, h->stream, sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
                                                     sm->dense_cnt.as<int32_t>(), cap, sm->dense_used.as<int32_t>());
   h->launches++;
   B2S_CUDA(cudaGetLastError());
@@ -533,7 +542,7 @@ int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, con
   memset(&c0, 0, sizeof(c0));
   if (crop) c0 = *crop;
   c0.center[0] = c0.center[1] = c0.center[2] = 0.0;  // Submap.cpp:78 setPose(Identity)
-  dense_insert_kernel<<<grid_for(raw->n_max > 0 ? raw->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+  launch_pdl(dense_insert_kernel, grid_for(raw->n_max > 0 ? raw->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream, 
       raw->xyz.as<double>(), raw->dn.as<int32_t>(), Td, make_crop(&c0), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(),
       sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, sm->dense_used.as<int32_t>(), h->status.as<uint32_t>(), enable_dev);
   h->launches++;
@@ -543,11 +552,13 @@ int32_t op_dense_insert(b2s_handle* h, b2s_submap* sm, const b2s_cloud* raw, con
 
 // VoxelizedPointCloud::toPointCloud (Voxel.cpp:90-115): flags -> scan -> gather of sum / count
 __global__ void dense_flags_kernel(const int32_t* __restrict__ cnts, size_t cap, int32_t* __restrict__ flags) {
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) flags[i] = cnts[i] > 0 ? 1 : 0;
 }
 __global__ void dense_gather_kernel(const unsigned long long* __restrict__ keys, const double* __restrict__ sums,
                                     const int32_t* __restrict__ cnts, size_t cap, const int32_t* __restrict__ flags,
                                     const int32_t* __restrict__ offs, double* __restrict__ oxyz, int32_t* __restrict__ okeys, int32_t* out_n) {
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = offs[cap];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     if (!flags[i]) continue;
@@ -564,10 +575,10 @@ int32_t dense_to_cloud(b2s_handle* h, b2s_submap* sm, double* d_xyz, int32_t* d_
   const size_t cap = sm->dense_cap;
   B2S_TRY(h->flags.ensure((cap + 1) * 4, h->stream));
   B2S_TRY(h->offs.ensure((cap + 2) * 4, h->stream));
-  dense_flags_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_cnt.as<int32_t>(), cap, h->flags.as<int32_t>());
+  launch_pdl(dense_flags_kernel, 148 * 4, 256, 0, h->stream, sm->dense_cnt.as<int32_t>(), cap, h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), nullptr, cap, nullptr));
-  dense_gather_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
+  launch_pdl(dense_gather_kernel, 148 * 4, 256, 0, h->stream, sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
                                                       sm->dense_cnt.as<int32_t>(), cap, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_xyz,
                                                       d_keys, d_out_n);
   h->launches++;
@@ -599,6 +610,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dense_query_kernel(const double* _
                                                                  const unsigned long long* __restrict__ keys, const double* __restrict__ sums,
                                                                  const int32_t* __restrict__ cnts, size_t cap, int32_t* __restrict__ count_out,
                                                                  double* __restrict__ mean_out) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const long long s = dense_find(keys, cap, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], inv);
@@ -614,6 +626,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dense_query_kernel(const double* _
 __global__ void __launch_bounds__(FZ_THREADS) dense_remove_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double inv,
                                                                   const unsigned long long* __restrict__ keys, double* __restrict__ sums,
                                                                   int32_t* __restrict__ cnts, size_t cap) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const long long s = dense_find(keys, cap, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], inv);
@@ -624,6 +637,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dense_remove_kernel(const double* 
 }
 
 __global__ void dense_count_kernel(const int32_t* __restrict__ cnts, size_t cap, int32_t* out) {
+  pdl_wait();
   int c = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) c += cnts[i] > 0;
   c = warp_sum_i(c);
@@ -632,7 +646,7 @@ __global__ void dense_count_kernel(const int32_t* __restrict__ cnts, size_t cap,
 
 int32_t op_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* pts, int32_t* count_dev, double* mean_dev) {
   B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
-  dense_query_kernel<<<grid_for(pts->n_max > 0 ? pts->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+  launch_pdl(dense_query_kernel, grid_for(pts->n_max > 0 ? pts->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream, 
       pts->xyz.as<double>(), pts->dn.as<int32_t>(), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
       sm->dense_cnt.as<int32_t>(), sm->dense_cap, count_dev, mean_dev);
   h->launches++;
@@ -642,7 +656,7 @@ int32_t op_dense_query(b2s_handle* h, const b2s_submap* sm, const b2s_cloud* pts
 
 int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts) {
   B2S_REQUIRE(sm->dense_cap > 0, B2S_E_INVALID, "dense map not initialised");
-  dense_remove_kernel<<<grid_for(pts->n_max > 0 ? pts->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(
+  launch_pdl(dense_remove_kernel, grid_for(pts->n_max > 0 ? pts->n_max : 1, FZ_THREADS), FZ_THREADS, 0, h->stream, 
       pts->xyz.as<double>(), pts->dn.as<int32_t>(), 1.0 / sm->dense_voxel, sm->dense_keys.as<unsigned long long>(), sm->dense_sum.as<double>(),
       sm->dense_cnt.as<int32_t>(), sm->dense_cap);
   h->launches++;
@@ -653,7 +667,7 @@ int32_t op_dense_remove(b2s_handle* h, b2s_submap* sm, const b2s_cloud* pts) {
 int32_t op_dense_count(b2s_handle* h, const b2s_submap* sm, int32_t* out_dev) {
   B2S_CUDA(cudaMemsetAsync(out_dev, 0, 4, h->stream));
   if (sm->dense_cap == 0) return B2S_OK;
-  dense_count_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_cnt.as<int32_t>(), sm->dense_cap, out_dev);
+  launch_pdl(dense_count_kernel, 148 * 4, 256, 0, h->stream, sm->dense_cnt.as<int32_t>(), sm->dense_cap, out_dev);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
@@ -684,6 +698,7 @@ __device__ __forceinline__ long long dense_find_key(const unsigned long long* __
 __global__ void __launch_bounds__(FZ_THREADS) dcarve_first_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double inv,
                                                                   unsigned long long* keys, int32_t* first, size_t mask,
                                                                   int32_t* __restrict__ slot_of, const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -701,6 +716,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dcarve_first_kernel(const double* 
 
 __global__ void dcarve_init_kernel(unsigned long long* keys, int32_t* first, size_t cap, int32_t* rm, size_t dense_cap,
                                    const int32_t* __restrict__ enable, int32_t* removed) {
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0 && removed) *removed = 0;
   if (enable != nullptr && *enable == 0) return;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) { keys[i] = DENSE_EMPTY; first[i] = 0x7fffffff; }
@@ -714,6 +730,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dcarve_march_kernel(const double* 
                                                                   double max_len, const unsigned long long* __restrict__ dkeys,
                                                                   const int32_t* __restrict__ dcnt, size_t dcap, int32_t* __restrict__ rm,
                                                                   const int32_t* __restrict__ enable) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   if (sensor_dev) { sx = sensor_dev[3]; sy = sensor_dev[7]; sz = sensor_dev[11]; }   // mapToRangeSensor.translation()
   const int n = *d_n;
@@ -759,6 +776,7 @@ __global__ void __launch_bounds__(FZ_THREADS) dcarve_march_kernel(const double* 
 
 __global__ void dcarve_apply_kernel(const int32_t* __restrict__ rm, size_t cap, double* __restrict__ sums, int32_t* __restrict__ cnts, int32_t* removed,
                                     const int32_t* __restrict__ enable, int32_t* mstate) {
+  pdl_wait();
   if (enable != nullptr && *enable == 0) return;
   if (mstate && blockIdx.x == 0 && threadIdx.x == 0) mstate[MS_NDCARVE] += 1;
   int c = 0;
@@ -789,14 +807,14 @@ int32_t op_dense_carve(b2s_handle* h, b2s_submap* sm, const b2s_cloud* scan, con
   const double voxel = sm->dense_voxel;
   const double s0 = sensor ? sensor[0] : 0.0, s1 = sensor ? sensor[1] : 0.0, s2 = sensor ? sensor[2] : 0.0;
   ProfScope prof(h, PK_FUSE);
-  dcarve_init_kernel<<<148 * 8, 256, 0, h->stream>>>(keys, first, cap, rm, sm->dense_cap, enable_dev, removed_dev);
-  dcarve_first_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), 1.0 / voxel, keys, first,
+  launch_pdl(dcarve_init_kernel, 148 * 8, 256, 0, h->stream, keys, first, cap, rm, sm->dense_cap, enable_dev, removed_dev);
+  launch_pdl(dcarve_first_kernel, grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream, scan->xyz.as<double>(), scan->dn.as<int32_t>(), 1.0 / voxel, keys, first,
                                                                                 cap - 1, slot_of, enable_dev);
-  dcarve_march_kernel<<<grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream>>>(scan->xyz.as<double>(), scan->dn.as<int32_t>(), slot_of, first, s0, s1, s2,
+  launch_pdl(dcarve_march_kernel, grid_for(n_max, FZ_THREADS), FZ_THREADS, 0, h->stream, scan->xyz.as<double>(), scan->dn.as<int32_t>(), slot_of, first, s0, s1, s2,
                                                                                 sensor_dev, voxel, radius, trunc, max_len,
                                                                                 sm->dense_keys.as<unsigned long long>(), sm->dense_cnt.as<int32_t>(),
                                                                                 sm->dense_cap, rm, enable_dev);
-  dcarve_apply_kernel<<<148 * 8, 256, 0, h->stream>>>(rm, sm->dense_cap, sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), removed_dev, enable_dev,
+  launch_pdl(dcarve_apply_kernel, 148 * 8, 256, 0, h->stream, rm, sm->dense_cap, sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), removed_dev, enable_dev,
                                                       sm->mstate.as<int32_t>());
   h->launches += 4;
   B2S_CUDA(cudaGetLastError());

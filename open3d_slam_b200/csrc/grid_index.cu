@@ -15,6 +15,7 @@ namespace b2s {
 constexpr int GB_THREADS = 256;
 
 __global__ void grid_bbox_init_kernel(unsigned long long* bbox) {
+  pdl_wait();
   int t = threadIdx.x;
   if (t < 3) bbox[t] = ord_encode(INFINITY);
   else if (t < 6) bbox[t] = ord_encode(-INFINITY);
@@ -47,6 +48,7 @@ __device__ __forceinline__ void grid_bbox_body(const double* __restrict__ xyz, c
 
 __global__ void __launch_bounds__(GB_THREADS) grid_bbox_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                                CropDev crop, int use_crop, unsigned long long* bbox) {
+  pdl_wait();
   grid_bbox_body(xyz, d_n, crop, use_crop, bbox);
 }
 
@@ -74,6 +76,7 @@ __device__ void grid_header_body(const unsigned long long* bbox, double cell, in
 }
 
 __global__ void grid_header_kernel(const unsigned long long* bbox, double cell, int cap_cells, GridHeader* hdr) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   grid_header_body(bbox, cell, cap_cells, hdr);
 }
@@ -87,6 +90,7 @@ __device__ __forceinline__ int grid_cell_of(const GridHeader& g, double x, doubl
 }
 
 __global__ void grid_zero_kernel(const GridHeader* hdr, int32_t* counts) {
+  pdl_wait();
   const int nc = hdr->ncell + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) counts[i] = 0;
 }
@@ -109,6 +113,7 @@ __device__ __forceinline__ void grid_count_body(const double* __restrict__ xyz, 
 __global__ void __launch_bounds__(GB_THREADS) grid_count_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                                 CropDev crop, int use_crop, const GridHeader* __restrict__ hdr,
                                                                 int32_t* counts, int32_t* __restrict__ rank) {
+  pdl_wait();
   grid_count_body(xyz, d_n, crop, use_crop, hdr, counts, rank);
 }
 
@@ -136,6 +141,7 @@ __global__ void __launch_bounds__(GB_THREADS) grid_scatter_kernel(const double* 
                                                                   const int32_t* __restrict__ cell_start,
                                                                   const int32_t* __restrict__ rank, double4* __restrict__ pts,
                                                                   double4* __restrict__ onrm) {
+  pdl_wait();
   grid_scatter_body(xyz, nrm, d_n, hdr, cell_start, rank, pts, onrm);
 }
 
@@ -147,31 +153,37 @@ struct GridJob {
 };
 
 __global__ void gridb_init_kernel(const GridJob* __restrict__ jobs, int njobs) {
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= njobs * 6) return;
   const int t = j % 6;
   jobs[j / 6].bbox[t] = t < 3 ? ord_encode(INFINITY) : ord_encode(-INFINITY);
 }
 __global__ void __launch_bounds__(GB_THREADS) gridb_bbox_kernel(const GridJob* __restrict__ jobs) {
+  pdl_wait();
   const GridJob j = jobs[blockIdx.y];
   CropDev none; none.kind = 0; none.invert = 0; none.pose_dev = nullptr;
   grid_bbox_body(j.xyz, j.d_n, none, 0, j.bbox);
 }
 __global__ void gridb_header_kernel(const GridJob* __restrict__ jobs, int njobs, double cell) {
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < njobs) grid_header_body(jobs[j].bbox, cell, jobs[j].cap_cells, jobs[j].hdr);
 }
 __global__ void gridb_zero_kernel(const GridJob* __restrict__ jobs) {
+  pdl_wait();
   const GridJob j = jobs[blockIdx.y];
   const int nc = j.hdr->ncell + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) j.counts[i] = 0;
 }
 __global__ void __launch_bounds__(GB_THREADS) gridb_count_kernel(const GridJob* __restrict__ jobs) {
+  pdl_wait();
   const GridJob j = jobs[blockIdx.y];
   CropDev none; none.kind = 0; none.invert = 0; none.pose_dev = nullptr;
   grid_count_body(j.xyz, j.d_n, none, 0, j.hdr, j.counts, j.rank);
 }
 __global__ void __launch_bounds__(GB_THREADS) gridb_scatter_kernel(const GridJob* __restrict__ jobs) {
+  pdl_wait();
   const GridJob j = jobs[blockIdx.y];
   grid_scatter_body(j.xyz, j.nrm, j.d_n, j.hdr, j.starts, j.rank, j.pts, j.onrm);
 }
@@ -216,15 +228,15 @@ int32_t grid_build(b2s_handle* h, GridIndex* g, const b2s_cloud* cloud, double c
   const int32_t* d_n = cloud->dn.as<int32_t>();
   GridHeader* hdr = g->hdr.as<GridHeader>();
   ProfScope prof(h, PK_GRID);
-  grid_bbox_init_kernel<<<1, 32, 0, h->stream>>>(g->bbox.as<unsigned long long>());
-  grid_bbox_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(), d_n, cd, use_crop, g->bbox.as<unsigned long long>());
-  grid_header_kernel<<<1, 32, 0, h->stream>>>(g->bbox.as<unsigned long long>(), cell, g->cap_cells, hdr);
-  grid_zero_kernel<<<148 * 4, 256, 0, h->stream>>>(hdr, counts);
-  grid_count_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(), d_n, cd, use_crop, hdr, counts, g->rank.as<int32_t>());
+  launch_pdl(grid_bbox_init_kernel, 1, 32, 0, h->stream, g->bbox.as<unsigned long long>());
+  launch_pdl(grid_bbox_kernel, blocks, GB_THREADS, 0, h->stream, cloud->xyz.as<double>(), d_n, cd, use_crop, g->bbox.as<unsigned long long>());
+  launch_pdl(grid_header_kernel, 1, 32, 0, h->stream, g->bbox.as<unsigned long long>(), cell, g->cap_cells, hdr);
+  launch_pdl(grid_zero_kernel, 148 * 4, 256, 0, h->stream, hdr, counts);
+  launch_pdl(grid_count_kernel, blocks, GB_THREADS, 0, h->stream, cloud->xyz.as<double>(), d_n, cd, use_crop, hdr, counts, g->rank.as<int32_t>());
   h->launches += 5;
   // scan over ncell (device-known) counts; launch sized for the capacity
   B2S_TRY(scan_exclusive_i32(h, counts, starts, &hdr->ncell, (size_t)g->cap_cells, nullptr));
-  grid_scatter_kernel<<<blocks, GB_THREADS, 0, h->stream>>>(cloud->xyz.as<double>(),
+  launch_pdl(grid_scatter_kernel, blocks, GB_THREADS, 0, h->stream, cloud->xyz.as<double>(),
                                                             (with_normals && cloud->has_normals) ? cloud->nrm.as<double>() : nullptr, d_n,
                                                             hdr, starts, g->rank.as<int32_t>(), g->pts.as<double4>(),
                                                             with_normals ? g->nrm.as<double4>() : nullptr);
@@ -297,14 +309,14 @@ int32_t grid_build_batch(b2s_handle* h, GridIndex* const* g, const b2s_cloud* co
   int bx = grid_for(max_pts, GB_THREADS, 148 * 2);   // x blocks per job; y = job
   const dim3 gpts((unsigned)bx, (unsigned)n);
   ProfScope prof(h, PK_GRID);
-  gridb_init_kernel<<<(n * 6 + 127) / 128, 128, 0, h->stream>>>(dj, n);
-  gridb_bbox_kernel<<<gpts, GB_THREADS, 0, h->stream>>>(dj);
-  gridb_header_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(dj, n, cell);
-  gridb_zero_kernel<<<dim3(148, (unsigned)n), 256, 0, h->stream>>>(dj);
-  gridb_count_kernel<<<gpts, GB_THREADS, 0, h->stream>>>(dj);
+  launch_pdl(gridb_init_kernel, (n * 6 + 127) / 128, 128, 0, h->stream, dj, n);
+  launch_pdl(gridb_bbox_kernel, gpts, GB_THREADS, 0, h->stream, dj);
+  launch_pdl(gridb_header_kernel, (n + 127) / 128, 128, 0, h->stream, dj, n, cell);
+  launch_pdl(gridb_zero_kernel, dim3(148, (unsigned)n), 256, 0, h->stream, dj);
+  launch_pdl(gridb_count_kernel, gpts, GB_THREADS, 0, h->stream, dj);
   h->launches += 5;
   B2S_TRY(scan_exclusive_i32_batch(h, ds, n, max_cells));
-  gridb_scatter_kernel<<<gpts, GB_THREADS, 0, h->stream>>>(dj);
+  launch_pdl(gridb_scatter_kernel, gpts, GB_THREADS, 0, h->stream, dj);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;

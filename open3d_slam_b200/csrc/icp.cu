@@ -694,6 +694,7 @@ template <int MODE>
 __global__ void __launch_bounds__(icp_threads(MODE), 1) icp_kernel(const __grid_constant__ IcpProblem single,
                                                                    const IcpProblem* __restrict__ problems, int smem_pts_cap,
                                                                    long long* dbg) {
+  pdl_wait();
   constexpr int THREADS = icp_threads(MODE);
   constexpr int WARPS = THREADS / 32;
   cg::cluster_group cluster = cg::this_cluster();
@@ -1169,11 +1170,13 @@ int32_t icp_launch(b2s_handle* h, const IcpProblem* single_host, const IcpProble
   cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)dyn_smem;
   cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   ProfScope prof(h, PK_ICP);
   if (estimator == B2S_REG_GENERALIZED) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<2>, single, problems_dev, pts_cap, h->icp_dbg));
   else if (estimator == B2S_REG_POINT_TO_PLANE && h->icp_dbg) B2S_CUDA(cudaLaunchKernelEx(&cfg, icp_kernel<3>, single, problems_dev, pts_cap, h->icp_dbg));

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_kernel(const GridHeader* _
                                                              int32_t* __restrict__ queue, int32_t* queue_n,
                                                              const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
                                                              double* __restrict__ out_nrm) {
+  pdl_wait();
   __shared__ GridHeader g;
   if (threadIdx.x == 0) g = *hdr;
   __syncthreads();
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_phase2_kernel(const GridHe
                                                                     const double4* __restrict__ pts, int knn, double radius,
                                                                     const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_n,
                                                                     double* __restrict__ out_nrm) {
+  pdl_wait();
   __shared__ GridHeader g;
   if (threadIdx.x == 0) g = *hdr;
   __syncthreads();
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(NK_THREADS) normals_select_kernel(const GridHe
                                                                     const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
                                                                     int32_t* __restrict__ queue, int32_t* queue_n,
                                                                     double* __restrict__ cum) {
+  pdl_wait();
   __shared__ GridHeader g;
   __shared__ int s_hist[NK_THREADS / 32][32];
   if (threadIdx.x == 0) g = *hdr;
@@ -628,6 +631,7 @@ __global__ void __launch_bounds__(NK_THREADS, B2S_NS2_MINBLOCKS) normals_select2
                                                                      const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
                                                                      int32_t* __restrict__ queue, int32_t* queue_n,
                                                                      double* __restrict__ cum) {
+  pdl_wait();
   __shared__ GridHeader g;
   __shared__ double s_d[NK_THREADS / 32][NS2_CAP];
   __shared__ int s_i[NK_THREADS / 32][NS2_CAP];
@@ -831,6 +835,7 @@ __global__ void __launch_bounds__(NK_THREADS, B2S_NS2_MINBLOCKS) normals_select2
 __global__ void __launch_bounds__(NK_THREADS) normals_finish_kernel(const GridHeader* __restrict__ hdr, const double4* __restrict__ pts,
                                                                     const int32_t* __restrict__ qlist, const int32_t* __restrict__ qcount,
                                                                     const double* __restrict__ cum, double* __restrict__ out_nrm) {
+  pdl_wait();
   const int nq = qlist ? *qcount : hdr->n;
   for (int tq = blockIdx.x * blockDim.x + threadIdx.x; tq < nq; tq += gridDim.x * blockDim.x) {
     const double kkd = cum[10 * (size_t)tq + 9];
@@ -847,12 +852,14 @@ __global__ void __launch_bounds__(NK_THREADS) normals_finish_kernel(const GridHe
 }
 
 
-__global__ void zero_i32_kernel(int32_t* p) { for (int i = 0; i < 6; i++) p[i] = 0; }
+__global__ void zero_i32_kernel(int32_t* p) {
+  pdl_wait(); for (int i = 0; i < 6; i++) p[i] = 0; }
 
 // query list = grid slots whose original point is flagged; warp-aggregated append keeps neighbouring slots together
 __global__ void __launch_bounds__(NK_THREADS) normals_qlist_kernel(const GridHeader* __restrict__ hdr, const double4* __restrict__ pts,
                                                                    const int32_t* __restrict__ flags, int32_t* __restrict__ qlist,
                                                                    int32_t* qcount) {
+  pdl_wait();
   const int n = hdr->n;
   const int lane = threadIdx.x & 31;
   const int n_round = (n + 31) & ~31;
@@ -895,9 +902,9 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
   const int32_t* cs = grid_starts(&h->grid_b);
   const double4* pts = h->grid_b.pts.as<double4>();
   double* out = c->nrm.as<double>();
-  zero_i32_kernel<<<1, 1, 0, h->stream>>>(qn);
+  launch_pdl(zero_i32_kernel, 1, 1, 0, h->stream, qn);
   if (flags) {
-    normals_qlist_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(hdr, pts, flags, qlist, qn + 1);
+    launch_pdl(normals_qlist_kernel, blocks, NK_THREADS, 0, h->stream, hdr, pts, flags, qlist, qn + 1);
     h->launches++;
   }
   // exact instantiations for the knn values the reference's presets use (Lua default 20, C++ struct default 5,
@@ -913,15 +920,15 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
     B2S_TRY(h->tmp_f64.ensure((n_max + 1) * 80, h->stream));
     double* cum = h->tmp_f64.as<double>();
     static const bool use_v1 = getenv("B2S_NORMALS_SELECT_V1") != nullptr;   // A/B knob: fixed 3x3x3 block, register gather
-    if (use_v1) normals_select_kernel<<<wblocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, qlist, qcount, queue, qn, cum);
-    else normals_select2_kernel<<<wblocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, qlist, qcount, queue, qn, cum);
-    normals_finish_kernel<<<blocks, NK_THREADS, 0, h->stream>>>(hdr, pts, qlist, qcount, cum, out);
+    if (use_v1) launch_pdl(normals_select_kernel, wblocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, qlist, qcount, queue, qn, cum);
+    else launch_pdl(normals_select2_kernel, wblocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, qlist, qcount, queue, qn, cum);
+    launch_pdl(normals_finish_kernel, blocks, NK_THREADS, 0, h->stream, hdr, pts, qlist, qcount, cum, out);
     h->launches++;
-  } else if (knn == 20) normals_kernel<20, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
-  else if (knn == 10) normals_kernel<10, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
-  else if (knn == 5) normals_kernel<5, true><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
-  else if (knn <= 16) normals_kernel<16, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
-  else normals_kernel<32, false><<<blocks, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  } else if (knn == 20) launch_pdl(normals_kernel<20, true>, blocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else if (knn == 10) launch_pdl(normals_kernel<10, true>, blocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else if (knn == 5) launch_pdl(normals_kernel<5, true>, blocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else if (knn <= 16) launch_pdl(normals_kernel<16, false>, blocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
+  else launch_pdl(normals_kernel<32, false>, blocks, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, ring_limit, queue, qn, qlist, qcount, out);
   static const bool dbg_counts = getenv("B2S_DEBUG_NORMALS") != nullptr;
   if (dbg_counts) {   // debug aid: how many queries the fast path left to the general kernel
     int32_t hq[6] = {0, 0, 0, 0, 0, 0};
@@ -933,7 +940,7 @@ int32_t op_estimate_normals(b2s_handle* h, b2s_cloud* c, int knn, double radius,
     fprintf(stderr, "[b2s normals] indexed %d queries %d fallback %d cell %.3f dims %dx%dx%d\n", gh.n, flags ? hq[1] : gh.n, hq[0], gh.cell,
             gh.dims[0], gh.dims[1], gh.dims[2]);
   }
-  normals_phase2_kernel<<<148 * 4, NK_THREADS, 0, h->stream>>>(hdr, cs, pts, knn, radius, queue, qn, out);
+  launch_pdl(normals_phase2_kernel, 148 * 4, NK_THREADS, 0, h->stream, hdr, cs, pts, knn, radius, queue, qn, out);
   h->launches += 3;
   c->has_normals = true;
   B2S_CUDA(cudaGetLastError());

@@ -26,6 +26,7 @@ __device__ __forceinline__ unsigned long long ov_hash(unsigned long long k) {
 }
 
 __global__ void __launch_bounds__(OV_THREADS) ov_init_kernel(unsigned long long* __restrict__ keys, int32_t* __restrict__ cnt, size_t cap) {
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     keys[i] = OV_EMPTY; cnt[2 * i] = 0; cnt[2 * i + 1] = 0;
   }
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(OV_THREADS) ov_init_kernel(unsigned long long*
 __global__ void __launch_bounds__(OV_THREADS) ov_insert_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                                const double* __restrict__ Tdev, int which, double inv, unsigned long long* keys,
                                                                int32_t* cnt, size_t mask, int32_t* __restrict__ slot_of, uint32_t* status) {
+  pdl_wait();
   const int n = *d_n;
   double T[16];
 #pragma unroll
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(OV_THREADS) ov_insert_kernel(const double* __r
 
 __global__ void __launch_bounds__(OV_THREADS) ov_flags_kernel(const int32_t* __restrict__ d_n, const int32_t* __restrict__ slot_of,
                                                               const int32_t* __restrict__ cnt, int min_pts, int32_t* __restrict__ keep) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int s = slot_of[i];
@@ -88,13 +91,13 @@ int32_t op_overlap(b2s_handle* h, const b2s_cloud* source, const b2s_cloud* targ
   int32_t* keep_t = keep_s + ns + 1;
   const double inv = 1.0 / voxel;   // VoxelMap(Eigen::Vector3d::Constant(voxelSize)) -> fromVoxelSize
   ProfScope prof(h, PK_FUSE);
-  ov_init_kernel<<<grid_for(cap, OV_THREADS), OV_THREADS, 0, h->stream>>>(keys, cnt, cap);
-  ov_insert_kernel<<<grid_for(nt, OV_THREADS), OV_THREADS, 0, h->stream>>>(target->xyz.as<double>(), target->dn.as<int32_t>(), nullptr, 1, inv, keys,
+  launch_pdl(ov_init_kernel, grid_for(cap, OV_THREADS), OV_THREADS, 0, h->stream, keys, cnt, cap);
+  launch_pdl(ov_insert_kernel, grid_for(nt, OV_THREADS), OV_THREADS, 0, h->stream, target->xyz.as<double>(), target->dn.as<int32_t>(), nullptr, 1, inv, keys,
                                                                           cnt, cap - 1, slot_t, h->status.as<uint32_t>());
-  ov_insert_kernel<<<grid_for(ns, OV_THREADS), OV_THREADS, 0, h->stream>>>(source->xyz.as<double>(), source->dn.as<int32_t>(), T_dev, 0, inv, keys,
+  launch_pdl(ov_insert_kernel, grid_for(ns, OV_THREADS), OV_THREADS, 0, h->stream, source->xyz.as<double>(), source->dn.as<int32_t>(), T_dev, 0, inv, keys,
                                                                           cnt, cap - 1, slot_s, h->status.as<uint32_t>());
-  ov_flags_kernel<<<grid_for(ns, OV_THREADS), OV_THREADS, 0, h->stream>>>(source->dn.as<int32_t>(), slot_s, cnt, min_pts, keep_s);
-  ov_flags_kernel<<<grid_for(nt, OV_THREADS), OV_THREADS, 0, h->stream>>>(target->dn.as<int32_t>(), slot_t, cnt, min_pts, keep_t);
+  launch_pdl(ov_flags_kernel, grid_for(ns, OV_THREADS), OV_THREADS, 0, h->stream, source->dn.as<int32_t>(), slot_s, cnt, min_pts, keep_s);
+  launch_pdl(ov_flags_kernel, grid_for(nt, OV_THREADS), OV_THREADS, 0, h->stream, target->dn.as<int32_t>(), slot_t, cnt, min_pts, keep_t);
   h->launches += 5;
   B2S_TRY(compact_cloud(h, source, keep_s, source_overlap));   // SelectByIndex on the ORIGINAL (untransformed) source
   B2S_TRY(compact_cloud(h, target, keep_t, target_overlap));

@@ -28,6 +28,10 @@ int grid_cap() {
 }
 WideGridScope::WideGridScope(size_t n) : on(n >= ((size_t)1 << 19) && g_grid_cap_override == 0) { if (on) g_grid_cap_override = 148 * 16; }
 WideGridScope::~WideGridScope() { if (on) g_grid_cap_override = 0; }
+bool pdl_enabled() {
+  static const bool on = !(getenv("B2S_PDL") && atoi(getenv("B2S_PDL")) == 0);
+  return on;
+}
 thread_local bool g_capturing = false;
 thread_local bool g_capture_broken = false;
 
@@ -215,11 +219,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_kernel(const int32
                                                                      const int32_t* __restrict__ d_n, int32_t n_host,
                                                                      unsigned long long* state, int32_t* tile_counter,
                                                                      int32_t* d_total) {
+  pdl_wait();
   scan_lookback_body(in, out, d_n, n_host, state, tile_counter, d_total);
 }
 
 // blockIdx.y = job: independent scans of different arrays in one launch (batched index builds)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_lookback_batch_kernel(const ScanJob* __restrict__ jobs) {
+  pdl_wait();
   const ScanJob j = jobs[blockIdx.y];
   scan_lookback_body(j.in, j.out, j.d_n, 0, j.state, j.counter, nullptr);
 }
@@ -234,7 +240,7 @@ size_t scan_state_bytes(size_t n_max) {
 int32_t scan_exclusive_i32_batch(b2s_handle* h, const ScanJob* jobs_dev, int njobs, size_t n_max) {
   int ntiles = (int)((n_max + SCAN_TILE - 1) / SCAN_TILE);
   if (ntiles < 1) ntiles = 1;
-  scan_lookback_batch_kernel<<<dim3(ntiles, njobs), SCAN_THREADS, 0, h->stream>>>(jobs_dev);
+  launch_pdl(scan_lookback_batch_kernel, dim3(ntiles, njobs), SCAN_THREADS, 0, h->stream, jobs_dev);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
@@ -248,7 +254,7 @@ static int32_t scan_impl(b2s_handle* h, const int32_t* in, int32_t* out, const i
   B2S_CUDA(cudaMemsetAsync(h->scan.state.p, 0, (size_t)ntiles * 8 + 64, h->stream));
   unsigned long long* st = h->scan.state.as<unsigned long long>();
   int32_t* counter = reinterpret_cast<int32_t*>(st + ntiles);
-  scan_lookback_kernel<<<ntiles, SCAN_THREADS, 0, h->stream>>>(in, out, d_n, n_host, st, counter, d_total);
+  launch_pdl(scan_lookback_kernel, ntiles, SCAN_THREADS, 0, h->stream, in, out, d_n, n_host, st, counter, d_total);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
@@ -269,6 +275,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K* __restrict__ keys, const int32_t* __restrict__ d_n, int shift,
                                                              int32_t* __restrict__ hist, int nblocks) {
+  pdl_wait();
   __shared__ int s_h[256];
   s_h[threadIdx.x] = 0;
   __syncthreads();
@@ -288,6 +295,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restr
                                                                 K* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                                 const int32_t* __restrict__ d_n, int shift,
                                                                 const int32_t* __restrict__ offs, int nblocks) {
+  pdl_wait();
   __shared__ int s_cnt[RS_WARPS][256];
   __shared__ int s_base[256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -352,6 +360,7 @@ template <typename K>
 __global__ void __cluster_dims__(CS_CTAS, 1, 1) __launch_bounds__(CS_THREADS, 1)
     cluster_sort_kernel(K* __restrict__ keys_a, uint32_t* __restrict__ vals_a, K* __restrict__ keys_b, uint32_t* __restrict__ vals_b,
                         const int32_t* __restrict__ d_n, int passes) {
+  pdl_wait();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -457,7 +466,7 @@ static int32_t cluster_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& k
     attr = true;
   }
   ProfScope prof(h, PK_SORT);
-  cluster_sort_kernel<K><<<CS_CTAS, CS_THREADS, smem, h->stream>>>(keys, vals, keys_alt, vals_alt, d_n, passes);
+  launch_pdl(cluster_sort_kernel<K>, CS_CTAS, CS_THREADS, smem, h->stream, keys, vals, keys_alt, vals_alt, d_n, passes);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   if (passes & 1) {
@@ -490,10 +499,10 @@ static int32_t radix_sort_impl(b2s_handle* h, K*& keys, uint32_t*& vals, K*& key
   ProfScope prof(h, PK_SORT);
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
-    rs_hist_kernel<K><<<nblocks, RS_THREADS, 0, h->stream>>>(keys, d_n, shift, hist, nblocks);
+    launch_pdl(rs_hist_kernel<K>, nblocks, RS_THREADS, 0, h->stream, keys, d_n, shift, hist, nblocks);
     h->launches++;
     B2S_TRY(scan_impl(h, hist, offs, nullptr, (int32_t)hist_n, hist_n, nullptr));
-    rs_scatter_kernel<K><<<nblocks, RS_THREADS, 0, h->stream>>>(keys, vals, keys_alt, vals_alt, d_n, shift, offs, nblocks);
+    launch_pdl(rs_scatter_kernel<K>, nblocks, RS_THREADS, 0, h->stream, keys, vals, keys_alt, vals_alt, d_n, shift, offs, nblocks);
     h->launches++;
     K* tk = keys; keys = keys_alt; keys_alt = tk;
     uint32_t* tv = vals; vals = vals_alt; vals_alt = tv;

@@ -19,6 +19,7 @@ constexpr int VX_THREADS = 256;
 
 // ---- bbox of the points that pass the cropper (shared with grid_index.cu) ------------------------------------------
 __global__ void bbox_init_kernel(unsigned long long* bbox, int32_t* kept) {
+  pdl_wait();
   int t = threadIdx.x;
   if (t < 3) bbox[t] = ord_encode(INFINITY);
   else if (t < 6) bbox[t] = ord_encode(-INFINITY);
@@ -27,6 +28,7 @@ __global__ void bbox_init_kernel(unsigned long long* bbox, int32_t* kept) {
 
 __global__ void __launch_bounds__(VX_THREADS) bbox_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, CropDev crop,
                                                           int use_crop, unsigned long long* bbox) {
+  pdl_wait();
   const int n = *d_n;
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -52,15 +54,16 @@ __global__ void __launch_bounds__(VX_THREADS) bbox_kernel(const double* __restri
 
 int32_t bbox_reduce(b2s_handle* h, const double* xyz, const int32_t* d_n, size_t n_max, const CropDev* crop, unsigned long long* bbox) {
   CropDev cd = crop ? *crop : make_crop(nullptr);
-  bbox_init_kernel<<<1, 32, 0, h->stream>>>(bbox, nullptr);
-  bbox_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(xyz, d_n, cd, crop ? 1 : 0, bbox);
+  launch_pdl(bbox_init_kernel, 1, 32, 0, h->stream, bbox, nullptr);
+  launch_pdl(bbox_kernel, grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream, xyz, d_n, cd, crop ? 1 : 0, bbox);
   h->launches += 2;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
 }
 
 // ---- cloud helpers ----------------------------------------------------------------------------------------------------
-__global__ void set_count_kernel(int32_t* dn, int32_t n) { *dn = n; }
+__global__ void set_count_kernel(int32_t* dn, int32_t n) {
+  pdl_wait(); *dn = n; }
 
 int32_t cloud_reserve(b2s_handle* h, b2s_cloud* c, size_t n, bool normals) {
   size_t m = n > 0 ? n : 1;
@@ -71,7 +74,7 @@ int32_t cloud_reserve(b2s_handle* h, b2s_cloud* c, size_t n, bool normals) {
 }
 int32_t cloud_set_count(b2s_handle* h, b2s_cloud* c, size_t n) {
   B2S_TRY(c->dn.ensure(4, h->stream, true));
-  set_count_kernel<<<1, 1, 0, h->stream>>>(c->dn.as<int32_t>(), (int32_t)n);
+  launch_pdl(set_count_kernel, 1, 1, 0, h->stream, c->dn.as<int32_t>(), (int32_t)n);
   h->launches++;
   c->n_known = (long long)n;
   c->n_max = c->fixed_cap ? c->fixed_cap : n;
@@ -81,6 +84,7 @@ int32_t cloud_set_count(b2s_handle* h, b2s_cloud* c, size_t n) {
 // ---- P1: order-preserving crop (flags -> scan -> scatter) -----------------------------------------------------------
 __global__ void __launch_bounds__(VX_THREADS) crop_flags_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                                 CropDev crop, int32_t* __restrict__ flags) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     flags[i] = crop_within(crop, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]) ? 1 : 0;
@@ -90,6 +94,7 @@ __global__ void __launch_bounds__(VX_THREADS) compact_kernel(const double* __res
                                                              const int32_t* __restrict__ d_n, const int32_t* __restrict__ flags,
                                                              const int32_t* __restrict__ offs, double* __restrict__ oxyz,
                                                              double* __restrict__ onrm, int32_t* out_n) {
+  pdl_wait();
   const int n = *d_n;
   if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = offs[n];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -107,7 +112,7 @@ int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, 
   B2S_TRY(h->offs.ensure((n_max + 2) * 4, h->stream));
   B2S_TRY(cloud_reserve(h, out, n_max, in->has_normals));
   B2S_TRY(scan_exclusive_i32(h, flags, h->offs.as<int32_t>(), d_n, n_max, nullptr));
-  compact_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(
+  launch_pdl(compact_kernel, grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream, 
       in->xyz.as<double>(), in->has_normals ? in->nrm.as<double>() : nullptr, d_n, flags, h->offs.as<int32_t>(),
       out->xyz.as<double>(), in->has_normals ? out->nrm.as<double>() : nullptr, out->dn.as<int32_t>());
   h->launches++;
@@ -121,7 +126,7 @@ int32_t compact_cloud(b2s_handle* h, const b2s_cloud* in, const int32_t* flags, 
 int32_t op_crop(b2s_handle* h, const b2s_cloud* in, const CropDev& crop, b2s_cloud* out) {
   const size_t n_max = in->n_max;
   B2S_TRY(h->flags.ensure((n_max + 1) * 4, h->stream));
-  crop_flags_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), in->dn.as<int32_t>(), crop,
+  launch_pdl(crop_flags_kernel, grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream, in->xyz.as<double>(), in->dn.as<int32_t>(), crop,
                                                                                h->flags.as<int32_t>());
   h->launches++;
   return compact_cloud(h, in, h->flags.as<int32_t>(), out);
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_keys_kernel(const double* __
                                                                 CropDev crop, int use_crop, const unsigned long long* __restrict__ bbox,
                                                                 double voxel, int bits, K* __restrict__ keys, uint32_t* __restrict__ vals,
                                                                 uint32_t* status) {
+  pdl_wait();
   const int n = *d_n;
   const K invalid = (K)1 << (3 * bits);
   // [O3D] voxel_min_bound = GetMinBound() - voxel_size * 0.5
@@ -169,6 +175,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_keys_kernel(const double* __
 template <typename K>
 __global__ void __launch_bounds__(VX_THREADS) seg_head_kernel(const K* __restrict__ keys, const int32_t* __restrict__ d_n, int bits,
                                                               int singletons_for_invalid, int32_t* __restrict__ head) {
+  pdl_wait();
   const int n = *d_n;
   const K invalid = (K)1 << (3 * bits);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(VX_THREADS) voxel_mean_kernel(const K* __restr
                                                                 const int32_t* __restrict__ offs, const double* __restrict__ xyz,
                                                                 const double* __restrict__ nrm, double* __restrict__ oxyz,
                                                                 double* __restrict__ onrm, int32_t* out_n) {
+  pdl_wait();
   const int n = *d_n;
   if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = offs[n];
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -231,7 +239,7 @@ static int32_t voxel_impl(b2s_handle* h, const b2s_cloud* in, const CropDev* cro
   const int blocks = grid_for(n_max, VX_THREADS);
   CropDev cd = crop ? *crop : make_crop(nullptr);
   { ProfScope prof(h, PK_VOXEL);
-  voxel_keys_kernel<K><<<blocks, VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), d_n, cd, crop ? 1 : 0, h->misc.as<unsigned long long>(),
+  launch_pdl(voxel_keys_kernel<K>, blocks, VX_THREADS, 0, h->stream, in->xyz.as<double>(), d_n, cd, crop ? 1 : 0, h->misc.as<unsigned long long>(),
                                                              voxel, bits, keys, vals, h->status.as<uint32_t>());
   h->launches++; }
   if constexpr (sizeof(K) == 4) {
@@ -240,10 +248,10 @@ static int32_t voxel_impl(b2s_handle* h, const b2s_cloud* in, const CropDev* cro
     B2S_TRY(radix_sort_pairs_u64(h, keys, vals, keys_alt, vals_alt, d_n, n_max, 3 * bits + 1));
   }
   ProfScope prof2(h, PK_VOXEL);
-  seg_head_kernel<K><<<blocks, VX_THREADS, 0, h->stream>>>(keys, d_n, bits, 0, h->flags.as<int32_t>());
+  launch_pdl(seg_head_kernel<K>, blocks, VX_THREADS, 0, h->stream, keys, d_n, bits, 0, h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), d_n, n_max, nullptr));
-  voxel_mean_kernel<K><<<blocks, VX_THREADS, 0, h->stream>>>(keys, vals, d_n, h->flags.as<int32_t>(), h->offs.as<int32_t>(),
+  launch_pdl(voxel_mean_kernel<K>, blocks, VX_THREADS, 0, h->stream, keys, vals, d_n, h->flags.as<int32_t>(), h->offs.as<int32_t>(),
                                                              in->xyz.as<double>(), in->has_normals ? in->nrm.as<double>() : nullptr,
                                                              out->xyz.as<double>(), in->has_normals ? out->nrm.as<double>() : nullptr,
                                                              out->dn.as<int32_t>());
@@ -302,6 +310,7 @@ __device__ __forceinline__ uint32_t select_hash(uint32_t seed, double x, double 
 __global__ void __launch_bounds__(VX_THREADS) select_keys_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, uint32_t seed,
                                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                                  int32_t* __restrict__ flags) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     keys[i] = select_hash(seed, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
@@ -311,6 +320,7 @@ __global__ void __launch_bounds__(VX_THREADS) select_keys_kernel(const double* _
 }
 __global__ void __launch_bounds__(VX_THREADS) select_mark_kernel(const int32_t* __restrict__ d_n, double ratio, const uint32_t* __restrict__ vals,
                                                                  int32_t* __restrict__ flags) {
+  pdl_wait();
   const int n = *d_n;
   size_t k = (size_t)((double)n * ratio);  // [O3D]: size_t(points_.size() * sampling_ratio)
   if (k > (size_t)n) k = (size_t)n;
@@ -324,6 +334,7 @@ __global__ void __launch_bounds__(VX_THREADS) select_mark_kernel(const int32_t* 
 constexpr int SK_THREADS = 1024;
 __global__ void __launch_bounds__(SK_THREADS) select_kth_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ d_n,
                                                                 double ratio, uint32_t* __restrict__ sel) {
+  pdl_wait();
   __shared__ int s_hist[256];
   __shared__ int s_scan[8];
   __shared__ uint32_t s_prefix;
@@ -368,6 +379,7 @@ __global__ void __launch_bounds__(SK_THREADS) select_kth_kernel(const uint32_t* 
 
 __global__ void __launch_bounds__(VX_THREADS) select_mark_kth_kernel(const int32_t* __restrict__ d_n, const uint32_t* __restrict__ keys,
                                                                      const uint32_t* __restrict__ sel, int32_t* __restrict__ flags) {
+  pdl_wait();
   const int n = *d_n;
   const uint32_t kth = sel[0], need = sel[1], cnt_eq = sel[2], k = sel[3];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -401,7 +413,7 @@ int32_t select_flags(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t 
   uint32_t* keys = h->keys.as<uint32_t>(); uint32_t* keys_alt = keys + n_max;
   uint32_t* vals = h->vals.as<uint32_t>(); uint32_t* vals_alt = vals + n_max;
   const int blocks = grid_for(n_max, VX_THREADS);
-  select_keys_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), in->dn.as<int32_t>(), seed, keys, vals,
+  launch_pdl(select_keys_kernel, blocks, VX_THREADS, 0, h->stream, in->xyz.as<double>(), in->dn.as<int32_t>(), seed, keys, vals,
                                                            h->flags.as<int32_t>());
   h->launches++;
   static const bool sort_select = getenv("B2S_SELECT_SORT") != nullptr;   // A/B knob: the full sort this replaced
@@ -409,14 +421,14 @@ int32_t select_flags(b2s_handle* h, const b2s_cloud* in, double ratio, uint32_t 
     ProfScope prof(h, PK_SELECT);
     B2S_TRY(h->misc.ensure(256, h->stream));
     uint32_t* sel = h->misc.as<uint32_t>() + 32;   // words 0..11 of misc hold the voxel bounding box
-    select_kth_kernel<<<1, SK_THREADS, 0, h->stream>>>(keys, in->dn.as<int32_t>(), ratio, sel);
-    select_mark_kth_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), keys, sel, h->flags.as<int32_t>());
+    launch_pdl(select_kth_kernel, 1, SK_THREADS, 0, h->stream, keys, in->dn.as<int32_t>(), ratio, sel);
+    launch_pdl(select_mark_kth_kernel, blocks, VX_THREADS, 0, h->stream, in->dn.as<int32_t>(), keys, sel, h->flags.as<int32_t>());
     h->launches += 2;
     B2S_CUDA(cudaGetLastError());
     return B2S_OK;
   }
   B2S_TRY(radix_sort_pairs_u32(h, keys, vals, keys_alt, vals_alt, in->dn.as<int32_t>(), n_max, 32));
-  select_mark_kernel<<<blocks, VX_THREADS, 0, h->stream>>>(in->dn.as<int32_t>(), ratio, vals, h->flags.as<int32_t>());
+  launch_pdl(select_mark_kernel, blocks, VX_THREADS, 0, h->stream, in->dn.as<int32_t>(), ratio, vals, h->flags.as<int32_t>());
   h->launches++;
   B2S_CUDA(cudaGetLastError());
   return B2S_OK;
@@ -450,6 +462,7 @@ int32_t op_random_down_sample(b2s_handle* h, const b2s_cloud* in, double ratio, 
 __global__ void __launch_bounds__(VX_THREADS) transform_kernel(const double* __restrict__ xyz, const double* __restrict__ nrm,
                                                                const int32_t* __restrict__ d_n, const double* __restrict__ Tdev,
                                                                double* __restrict__ oxyz, double* __restrict__ onrm, int32_t* out_n) {
+  pdl_wait();
   const int n = *d_n;
   double T[16];
 #pragma unroll
@@ -481,13 +494,14 @@ __global__ void __launch_bounds__(VX_THREADS) transform_kernel(const double* __r
 
 __global__ void write_pose_kernel(double* dst, double t0, double t1, double t2, double t3, double t4, double t5, double t6, double t7,
                                   double t8, double t9, double t10, double t11, double t12, double t13, double t14, double t15) {
+  pdl_wait();
   dst[0] = t0; dst[1] = t1; dst[2] = t2; dst[3] = t3; dst[4] = t4; dst[5] = t5; dst[6] = t6; dst[7] = t7;
   dst[8] = t8; dst[9] = t9; dst[10] = t10; dst[11] = t11; dst[12] = t12; dst[13] = t13; dst[14] = t14; dst[15] = t15;
 }
 
 // copies a host 4x4 into a device slot without a staging buffer (the values travel as kernel arguments)
 int32_t pose_to_device(b2s_handle* h, const double* T, double* dst) {
-  write_pose_kernel<<<1, 1, 0, h->stream>>>(dst, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8], T[9], T[10], T[11], T[12], T[13],
+  launch_pdl(write_pose_kernel, 1, 1, 0, h->stream, dst, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8], T[9], T[10], T[11], T[12], T[13],
                                             T[14], T[15]);
   h->launches++;
   B2S_CUDA(cudaGetLastError());
@@ -500,7 +514,7 @@ int32_t op_transform(b2s_handle* h, const b2s_cloud* in, const double* T_host, b
   B2S_TRY(h->poses.ensure(64 * 16 * 8, h->stream, true));
   double* Td = h->poses.as<double>() + 16 * 63;  // slot 63: scratch pose for standalone transforms
   B2S_TRY(pose_to_device(h, T_host, Td));
-  transform_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(),
+  launch_pdl(transform_kernel, grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream, in->xyz.as<double>(),
                                                                               in->has_normals ? in->nrm.as<double>() : nullptr,
                                                                               in->dn.as<int32_t>(), Td, out->xyz.as<double>(),
                                                                               in->has_normals ? out->nrm.as<double>() : nullptr,
@@ -521,6 +535,7 @@ int32_t op_transform(b2s_handle* h, const b2s_cloud* in, const double* T_host, b
 __global__ void __launch_bounds__(VX_THREADS) undistort_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, double vx, double vy,
                                                                double vz, double wr, double wp, double wy, double duration, int clockwise,
                                                                double* __restrict__ out, int32_t* out_n) {
+  pdl_wait();
   const int n = *d_n;
   if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = n;
   const double two_pi = 2.0 * 3.14159265358979323846;
@@ -559,7 +574,7 @@ int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, 
   const size_t n_max = in->n_max > 0 ? in->n_max : 1;
   B2S_TRY(cloud_reserve(h, out, n_max, false));
   ProfScope prof(h, PK_CROP);
-  undistort_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(in->xyz.as<double>(), in->dn.as<int32_t>(), lin_vel[0], lin_vel[1],
+  launch_pdl(undistort_kernel, grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream, in->xyz.as<double>(), in->dn.as<int32_t>(), lin_vel[0], lin_vel[1],
                                                                               lin_vel[2], ang_vel_rpy[0], ang_vel_rpy[1], ang_vel_rpy[2],
                                                                               scan_duration, clockwise, out->xyz.as<double>(), out->dn.as<int32_t>());
   h->launches++;
@@ -576,6 +591,7 @@ int32_t op_undistort(b2s_handle* h, const b2s_cloud* in, const double* lin_vel, 
 struct Mat4 { double m[16]; };
 __global__ void __launch_bounds__(VX_THREADS) o3d_transform_inplace_kernel(double* __restrict__ xyz, double* __restrict__ nrm,
                                                                            const int32_t* __restrict__ d_n, Mat4 M) {
+  pdl_wait();
   const int n = *d_n;
   const double* T = M.m;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -593,7 +609,8 @@ __global__ void __launch_bounds__(VX_THREADS) o3d_transform_inplace_kernel(doubl
     }
   }
 }
-__global__ void pose_right_multiply_kernel(double* pose, Mat4 M) {   // pose = pose * T (row-major), one thread
+__global__ void pose_right_multiply_kernel(double* pose, Mat4 M) {
+  pdl_wait();   // pose = pose * T (row-major), one thread
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double P[16], R[16];
   for (int i = 0; i < 16; i++) P[i] = pose[i];
@@ -607,6 +624,7 @@ __global__ void pose_right_multiply_kernel(double* pose, Mat4 M) {   // pose = p
 }
 // VoxelizedPointCloud::transform (core/src/Voxel.cpp:49-64): the transform is applied to the position SUM, keys stay
 __global__ void dense_transform_kernel(double* __restrict__ sums, const int32_t* __restrict__ cnts, size_t cap, Mat4 M) {
+  pdl_wait();
   const double* T = M.m;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     if (cnts[i] <= 0) continue;
@@ -622,13 +640,13 @@ int32_t op_submap_transform(b2s_handle* h, b2s_submap* sm, const double* T_host)
   for (int i = 0; i < 16; i++) M.m[i] = T_host[i];
   b2s_cloud* map = sm->cloud[0];
   const size_t n_max = map->n_max > 0 ? map->n_max : 1;
-  o3d_transform_inplace_kernel<<<grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream>>>(map->xyz.as<double>(),
+  launch_pdl(o3d_transform_inplace_kernel, grid_for(n_max, VX_THREADS), VX_THREADS, 0, h->stream, map->xyz.as<double>(),
                                                                                           map->has_normals ? map->nrm.as<double>() : nullptr,
                                                                                           map->dn.as<int32_t>(), M);
-  pose_right_multiply_kernel<<<1, 32, 0, h->stream>>>(sm->pose.as<double>(), M);
+  launch_pdl(pose_right_multiply_kernel, 1, 32, 0, h->stream, sm->pose.as<double>(), M);
   h->launches += 2;
   if (sm->dense_cap > 0) {
-    dense_transform_kernel<<<148 * 4, 256, 0, h->stream>>>(sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, M);
+    launch_pdl(dense_transform_kernel, 148 * 4, 256, 0, h->stream, sm->dense_sum.as<double>(), sm->dense_cnt.as<int32_t>(), sm->dense_cap, M);
     h->launches++;
   }
   B2S_CUDA(cudaGetLastError());

@@ -69,6 +69,7 @@ __device__ __forceinline__ long long vm_find(const unsigned long long* __restric
 }
 
 __global__ void __launch_bounds__(VM_THREADS) vm_clear_kernel(unsigned long long* keys, int32_t* head, int32_t* cnt, size_t cap, int32_t* used) {
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
     keys[i] = VM_EMPTY;
     for (int l = 0; l < VM_LAYERS; l++) { head[(size_t)l * cap + i] = -1; cnt[(size_t)l * cap + i] = 0; }
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(VM_THREADS) vm_insert_kernel(const double* __r
                                                                double iz, int layer, unsigned long long* keys, int32_t* head, int32_t* cnt,
                                                                int32_t* __restrict__ next, int32_t* __restrict__ eidx, size_t cap, size_t entries_cap,
                                                                int32_t* used, uint32_t* status) {
+  pdl_wait();
   const int n = *d_n;
   const size_t mask = cap - 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(VM_THREADS) vm_insert_kernel(const double* __r
 // (isSwitchingSubmapsConsistant: p = mapToRangeSensor * scan.points_[i], an isometry applied as R p + t)
 __global__ void __launch_bounds__(VM_THREADS) vm_has_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n,
                                                             const double* __restrict__ Tdev, VmView v, int32_t* __restrict__ flags, int32_t* hits) {
+  pdl_wait();
   const int n = *d_n;
   double T[12];
   if (Tdev) {
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(VM_THREADS) vm_has_kernel(const double* __rest
 // getIndicesInVoxel(layer, p), batched: first the list lengths ...
 __global__ void __launch_bounds__(VM_THREADS) vm_count_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ d_n, VmView v, int layer,
                                                               const int32_t* __restrict__ cnt, size_t cap, int32_t* __restrict__ out) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned long long key;
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(VM_THREADS) vm_fill_kernel(const double* __res
                                                              const int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                              const int32_t* __restrict__ eidx, size_t cap, const int32_t* __restrict__ offs,
                                                              int32_t* __restrict__ out) {
+  pdl_wait();
   const int n = *d_n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned long long key;
@@ -188,7 +193,7 @@ int32_t b2s_voxel_map_create(b2s_handle* h, const double voxel_size[3], size_t c
   if (rc == B2S_OK) rc = vm->cnt.ensure(cap * 4 * VM_LAYERS, h->stream);
   if (rc == B2S_OK) rc = vm->used.ensure(64, h->stream);
   if (rc != B2S_OK) { vm->keys.release(); vm->head.release(); vm->cnt.release(); vm->used.release(); delete vm; return rc; }
-  vm_clear_kernel<<<148 * 4, VM_THREADS, 0, h->stream>>>(vm->keys.as<unsigned long long>(), vm->head.as<int32_t>(), vm->cnt.as<int32_t>(), cap,
+  launch_pdl(vm_clear_kernel, 148 * 4, VM_THREADS, 0, h->stream, vm->keys.as<unsigned long long>(), vm->head.as<int32_t>(), vm->cnt.as<int32_t>(), cap,
                                                          vm->used.as<int32_t>());
   h->launches++;
   *out = vm;
@@ -207,7 +212,7 @@ void b2s_voxel_map_destroy(b2s_voxel_map* vm) {
 int32_t b2s_voxel_map_clear(b2s_handle* h, b2s_voxel_map* vm) {
   B2S_REQUIRE(h && vm, B2S_E_INVALID, "null argument");
   VM_LOCK(h);
-  vm_clear_kernel<<<148 * 4, VM_THREADS, 0, h->stream>>>(vm->keys.as<unsigned long long>(), vm->head.as<int32_t>(), vm->cnt.as<int32_t>(), vm->cap,
+  launch_pdl(vm_clear_kernel, 148 * 4, VM_THREADS, 0, h->stream, vm->keys.as<unsigned long long>(), vm->head.as<int32_t>(), vm->cnt.as<int32_t>(), vm->cap,
                                                          vm->used.as<int32_t>());
   h->launches++;
   vm->entries_bound = 0;
@@ -225,7 +230,7 @@ int32_t b2s_voxel_map_insert_cloud(b2s_handle* h, b2s_voxel_map* vm, int32_t lay
   B2S_TRY(vm->next.ensure(want * 4, h->stream, true));
   B2S_TRY(vm->eidx.ensure(want * 4, h->stream, true));
   const size_t ecap = (vm->next.cap < vm->eidx.cap ? vm->next.cap : vm->eidx.cap) / 4;
-  vm_insert_kernel<<<grid_for(n_max, VM_THREADS), VM_THREADS, 0, h->stream>>>(
+  launch_pdl(vm_insert_kernel, grid_for(n_max, VM_THREADS), VM_THREADS, 0, h->stream, 
       cloud->xyz.as<double>(), cloud->dn.as<int32_t>(), vm->inv[0], vm->inv[1], vm->inv[2], layer, vm->keys.as<unsigned long long>(),
       vm->head.as<int32_t>(), vm->cnt.as<int32_t>(), vm->next.as<int32_t>(), vm->eidx.as<int32_t>(), vm->cap, ecap, vm->used.as<int32_t>(),
       h->status.as<uint32_t>());
@@ -265,7 +270,7 @@ int32_t b2s_voxel_map_has_voxel(b2s_handle* h, const b2s_voxel_map* vm, const b2
     Td = slot;
   }
   VmView v{vm->inv[0], vm->inv[1], vm->inv[2], vm->cap - 1, vm->keys.as<unsigned long long>()};
-  vm_has_kernel<<<grid_for(n_max, VM_THREADS), VM_THREADS, 0, h->stream>>>(points->xyz.as<double>(), points->dn.as<int32_t>(), Td, v,
+  launch_pdl(vm_has_kernel, grid_for(n_max, VM_THREADS), VM_THREADS, 0, h->stream, points->xyz.as<double>(), points->dn.as<int32_t>(), Td, v,
                                                                           flags_or_null ? d_flags : nullptr, d_hits);
   h->launches++;
   B2S_TRY(ensure_pinned(h, 4096));
@@ -288,7 +293,7 @@ int32_t b2s_voxel_map_indices_in_voxel(b2s_handle* h, const b2s_voxel_map* vm, i
   B2S_TRY(h->flags.ensure((nm + 1) * 4, h->stream));
   B2S_TRY(h->offs.ensure((nm + 2) * 4, h->stream));
   VmView v{vm->inv[0], vm->inv[1], vm->inv[2], vm->cap - 1, vm->keys.as<unsigned long long>()};
-  vm_count_kernel<<<grid_for(nm, VM_THREADS), VM_THREADS, 0, h->stream>>>(points->xyz.as<double>(), points->dn.as<int32_t>(), v, layer,
+  launch_pdl(vm_count_kernel, grid_for(nm, VM_THREADS), VM_THREADS, 0, h->stream, points->xyz.as<double>(), points->dn.as<int32_t>(), v, layer,
                                                                          vm->cnt.as<int32_t>(), vm->cap, h->flags.as<int32_t>());
   h->launches++;
   B2S_TRY(scan_exclusive_i32(h, h->flags.as<int32_t>(), h->offs.as<int32_t>(), points->dn.as<int32_t>(), nm, nullptr));
@@ -304,7 +309,7 @@ int32_t b2s_voxel_map_indices_in_voxel(b2s_handle* h, const b2s_voxel_map* vm, i
   B2S_CUDA(cudaMemcpyAsync(offsets, h->offs.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
   if (indices && total > 0) {
     B2S_TRY(h->tmp_i32.ensure(((size_t)total + 64) * 4, h->stream));
-    vm_fill_kernel<<<grid_for(nm, VM_THREADS), VM_THREADS, 0, h->stream>>>(points->xyz.as<double>(), points->dn.as<int32_t>(), v, layer,
+    launch_pdl(vm_fill_kernel, grid_for(nm, VM_THREADS), VM_THREADS, 0, h->stream, points->xyz.as<double>(), points->dn.as<int32_t>(), v, layer,
                                                                           vm->head.as<int32_t>(), vm->next.as<int32_t>(), vm->eidx.as<int32_t>(),
                                                                           vm->cap, h->offs.as<int32_t>(), h->tmp_i32.as<int32_t>());
     h->launches++;
