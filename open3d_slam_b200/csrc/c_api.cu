@@ -996,6 +996,7 @@ int32_t b2s_mapper_step_async(b2s_handle* h, b2s_submap* sm, const b2s_cloud* ra
   B2S_REQUIRE(h && sm && raw_scan && odometry_motion, B2S_E_INVALID, "null argument");
   B2S_REQUIRE(slot >= 0 && slot < 256, B2S_E_INVALID, "slot out of range");
   LOCK(h);
+  PdlScope pdl;   // the chain's launches (eager and captured) overlap their predecessors' tails: see pdl_wait in common.cuh
   if (sm->graph_mode) return mapper_step_graph(h, sm, raw_scan, odometry_motion, slot);
   double* pose_state = sm->pose.as<double>();        // mapToRangeSensor_ (== mapToRangeSensorPrev_ in steady state)
   double* odom = pose_state + 32;

@@ -28,10 +28,13 @@ int grid_cap() {
 }
 WideGridScope::WideGridScope(size_t n) : on(n >= ((size_t)1 << 19) && g_grid_cap_override == 0) { if (on) g_grid_cap_override = 148 * 16; }
 WideGridScope::~WideGridScope() { if (on) g_grid_cap_override = 0; }
+static thread_local int g_pdl_depth = 0;
 bool pdl_enabled() {
   static const bool on = !(getenv("B2S_PDL") && atoi(getenv("B2S_PDL")) == 0);
-  return on;
+  return on && g_pdl_depth > 0;
 }
+PdlScope::PdlScope() { g_pdl_depth++; }
+PdlScope::~PdlScope() { g_pdl_depth--; }
 thread_local bool g_capturing = false;
 thread_local bool g_capture_broken = false;
 
